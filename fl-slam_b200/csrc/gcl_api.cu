@@ -1,0 +1,441 @@
+// gcl_api.cu -- the C ABI declared in include/gcl_b200.h: argument checks, launch planning, error text.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gcl_internal.cuh"
+
+using namespace gcl;
+
+static std::string g_create_error;
+
+#define GCL_REQUIRE(h, cond, msg)                  \
+  do {                                             \
+    if (!(cond)) {                                 \
+      (h)->err = std::string(__func__) + ": " + (msg); \
+      return GCL_ERR_ARG;                          \
+    }                                              \
+  } while (0)
+
+static int cuda_fail(gcl_handle h, const char* fn, cudaError_t e) {
+  h->err = std::string(fn) + ": CUDA error: " + cudaGetErrorString(e);
+  return GCL_ERR_CUDA;
+}
+#define GCL_CUDA(h, expr)                                   \
+  do {                                                      \
+    cudaError_t e__ = (expr);                               \
+    if (e__ != cudaSuccess) return cuda_fail(h, __func__, e__); \
+  } while (0)
+
+static bool fixed_shift_ok(double tau, int precision) {
+  // exp arguments lie in [-2/tau, 0] with the shift 1/tau; keep them far from fp32 / fp64 underflow
+  return (2.0 / tau) <= (precision == GCL_F64 ? 600.0 : 60.0);
+}
+
+extern "C" {
+
+int gcl_abi_version(void) { return GCL_ABI_VERSION; }
+
+int gcl_create(int device, gcl_handle* out) {
+  if (!out) { g_create_error = "gcl_create: out is NULL"; return GCL_ERR_ARG; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("gcl_create: no CUDA device: ") + cudaGetErrorString(e);
+    return GCL_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) { g_create_error = "gcl_create: device index out of range"; return GCL_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("gcl_create: cudaSetDevice: ") + cudaGetErrorString(e); return GCL_ERR_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = std::string("gcl_create: ") + cudaGetErrorString(e); return GCL_ERR_CUDA; }
+  if (prop.major < 10) {
+    g_create_error = "gcl_create: this library is built for sm_100a only (found compute capability " +
+                     std::to_string(prop.major) + "." + std::to_string(prop.minor) + ")";
+    return GCL_ERR_UNSUPPORTED;
+  }
+  gcl_handle h = new gcl_handle_s();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return GCL_OK;
+}
+
+void gcl_destroy(gcl_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->d_buf) cudaFree(h->d_buf);
+  if (h->h_buf) cudaFreeHost(h->h_buf);
+  delete h;
+}
+
+const char* gcl_last_error(gcl_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int gcl_device_sm_count(gcl_handle h) { return h ? h->sm_count : 0; }
+int64_t gcl_launch_count(gcl_handle h) { return h ? h->launches : 0; }
+
+size_t gcl_partial_record_doubles(int n_bins) { return (size_t)GCL_NM * n_bins + GCL_NCERT; }
+size_t gcl_stats_record_doubles(int n_bins) { return (size_t)StatsLayout(n_bins).total(); }
+
+int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_bins, int precision) {
+  (void)n_bins; (void)precision;
+  const int sms = h ? h->sm_count : 148;
+  if (n_jobs < 1) n_jobs = 1;
+  // enough CTAs to cover the SMs once, never less than one tile (256 rows) of work per CTA
+  int64_t by_rows = (max_sel_rows + 255) / 256;
+  if (by_rows < 1) by_rows = 1;
+  int64_t want = (sms + n_jobs - 1) / n_jobs;
+  if (want < 1) want = 1;
+  int64_t c = want < by_rows ? want : by_rows;
+  return (int)c;
+}
+
+int gcl_scan_moments(gcl_handle h, void* stream, const gcl_job* jobs_dev, const gcl_job* job_host, int n_jobs,
+                     int ctas_per_job, int layout, int precision, const double* bin_dirs, int n_bins, double tau,
+                     const double* origin_host, double eps_mass, double* partials) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_jobs >= 1, "n_jobs must be >= 1");
+  GCL_REQUIRE(h, (jobs_dev != nullptr) != (job_host != nullptr), "exactly one of jobs_dev / job_by_value_host must be given");
+  GCL_REQUIRE(h, jobs_dev || n_jobs == 1, "a by-value job implies n_jobs == 1");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS, "n_bins must be in [1, 1024]");
+  GCL_REQUIRE(h, tau > 0.0, "tau must be > 0 (the reference ships no default, SURVEY.md 0.4)");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  GCL_REQUIRE(h, layout == GCL_LAYOUT_REF_F64 || layout == GCL_LAYOUT_PACKED_F32, "unknown layout");
+  GCL_REQUIRE(h, !(precision == GCL_F64 && layout == GCL_LAYOUT_PACKED_F32), "fp64 mode needs the fp64 reference layout");
+  GCL_REQUIRE(h, ctas_per_job >= 1 && ctas_per_job <= 65535, "ctas_per_job out of range");
+  GCL_REQUIRE(h, bin_dirs && origin_host && partials, "NULL pointer");
+  if (job_host) {
+    GCL_REQUIRE(h, job_host->n_raw >= 0 && job_host->n_points_cap >= 1, "job: n_raw >= 0 and n_points_cap >= 1 required");
+    GCL_REQUIRE(h, job_host->n_raw == 0 || (job_host->points && job_host->weights), "job: NULL points / weights");
+  }
+  ScanParams P;
+  memset(&P, 0, sizeof(P));
+  P.jobs = jobs_dev;
+  if (job_host) P.job = *job_host;
+  P.c.origin[0] = origin_host[0]; P.c.origin[1] = origin_host[1]; P.c.origin[2] = origin_host[2];
+  P.c.eps_mass = eps_mass;
+  P.bin_dirs = bin_dirs;
+  P.partials = partials;
+  P.rec_doubles = (int64_t)gcl_partial_record_doubles(n_bins);
+  P.tau = tau;
+  P.n_bins = n_bins;
+  int G, L, chunks;
+  plan_bins(n_bins, precision, &G, &L, &chunks);
+  P.lanes = L; P.n_chunks = chunks;
+  P.layout = layout;
+  P.fixed_shift = fixed_shift_ok(tau, precision) ? 1 : 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_scan_moments(P, n_jobs, ctas_per_job, precision, G, GCL_NM, false, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
+int gcl_reduce_finalize(gcl_handle h, void* stream, const double* parts, int n_parts, int64_t part_stride,
+                        int64_t job_stride, const gcl_job* jobs_dev, const gcl_job* job_host, int n_jobs, int n_bins,
+                        const double* bin_dirs, double tau, const double* origin_host, double eps_psd, double eps_mass,
+                        int finalize, double* reduced, double* stats) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_jobs >= 1 && n_parts >= 1, "n_jobs and n_parts must be >= 1");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS, "n_bins must be in [1, 1024]");
+  GCL_REQUIRE(h, parts && reduced, "parts and reduced must be given");
+  GCL_REQUIRE(h, !finalize || (stats && bin_dirs && origin_host && tau > 0.0), "finalize needs stats, bin_dirs, origin and tau > 0");
+  GCL_REQUIRE(h, !finalize || ((jobs_dev != nullptr) != (job_host != nullptr)), "finalize needs the jobs (device array or one by value)");
+  FinalizeParams P;
+  memset(&P, 0, sizeof(P));
+  P.parts = parts; P.n_parts = n_parts; P.part_stride = part_stride; P.job_stride = job_stride;
+  P.jobs = jobs_dev;
+  if (job_host) P.job = *job_host;
+  P.n_bins = n_bins; P.nmom = GCL_NM; P.bin_dirs = bin_dirs; P.tau = tau;
+  if (origin_host) { P.origin[0] = origin_host[0]; P.origin[1] = origin_host[1]; P.origin[2] = origin_host[2]; }
+  P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.finalize = finalize; P.from_resp = 0;
+  P.reduced = reduced; P.stats = stats;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_reduce_finalize(P, n_jobs, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
+int gcl_map_derived_stats(gcl_handle h, void* stream, const double* S_dir, const double* N_dir, const double* N_pos,
+                          const double* sum_p, const double* sum_ppT, int n_bins, double eps_mass, double eps_psd, double* out) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_bins >= 1, "n_bins must be >= 1");
+  GCL_REQUIRE(h, S_dir && N_dir && N_pos && sum_p && sum_ppT && out, "NULL pointer");
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_map_derived(S_dir, N_dir, N_pos, sum_p, sum_ppT, n_bins, eps_mass, eps_psd, out, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
+int gcl_pose_evidence(gcl_handle h, void* stream, const double* stats, int64_t stats_stride, const double* map_S_dir,
+                      const double* map_S_dir_scatter, const double* map_N_dir, const double* map_N_pos,
+                      const double* map_derived, const double* pose_pred, const double* R_hat_override, int n_jobs, int n_bins,
+                      double eps_psd, double eps_mass, int do_rotation, int do_translation, double* evidence) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_jobs >= 1 && n_bins >= 1, "n_jobs and n_bins must be >= 1");
+  GCL_REQUIRE(h, stats && map_S_dir && map_S_dir_scatter && map_N_dir && pose_pred && evidence, "NULL pointer");
+  GCL_REQUIRE(h, !do_translation || (map_N_pos && map_derived), "translation needs map_N_pos and map_derived");
+  GCL_REQUIRE(h, do_rotation || !do_translation || R_hat_override, "translation without rotation needs R_hat_override");
+  EvidenceParams P;
+  P.stats = stats; P.stats_stride = stats_stride;
+  P.map_S_dir = map_S_dir; P.map_S_dir_scatter = map_S_dir_scatter; P.map_N_dir = map_N_dir; P.map_N_pos = map_N_pos;
+  P.map_derived = map_derived; P.pose_pred = pose_pred; P.R_hat_override = R_hat_override; P.n_bins = n_bins;
+  P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.do_rotation = do_rotation; P.do_translation = do_translation;
+  P.evidence = evidence;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_pose_evidence(P, n_jobs, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
+int gcl_point_budget_resample(gcl_handle h, void* stream, const double* points, const double* timestamps, const double* weights,
+                              const uint8_t* ring, const uint8_t* tag, int64_t n_input, int32_t cap, double eps_mass,
+                              double* points_out, double* timestamps_out, double* weights_out, uint8_t* ring_out,
+                              uint8_t* tag_out, double* scalars_out, double* workspace) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_input >= 0 && cap >= 1, "n_input >= 0 and n_points_cap >= 1 required");
+  GCL_REQUIRE(h, n_input == 0 || (points && timestamps && weights), "NULL input");
+  GCL_REQUIRE(h, points_out && timestamps_out && weights_out && ring_out && tag_out && scalars_out && workspace, "NULL output");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_point_budget(points, timestamps, weights, ring, tag, n_input, cap, eps_mass, points_out, timestamps_out,
+                              weights_out, ring_out, tag_out, scalars_out, workspace, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+int gcl_deskew_constant_twist(gcl_handle h, void* stream, const double* points, const double* timestamps, const double* weights,
+                              int64_t n, double t0, double t1, const double* xi_host, double eps_mass, double* points_out,
+                              double* weights_out, double* scalars_out, double* workspace) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && xi_host, "n >= 0 and xi_body required");
+  GCL_REQUIRE(h, n == 0 || (points && timestamps && weights && points_out && weights_out), "NULL array");
+  GCL_REQUIRE(h, scalars_out && workspace, "NULL scalars / workspace");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_deskew(points, timestamps, weights, n, t0, t1, xi_host, eps_mass, points_out, weights_out, scalars_out,
+                        workspace, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+int gcl_ray_directions(gcl_handle h, void* stream, const double* points, int64_t n, const double* origin_host, double eps_mass,
+                       double* dirs_out) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && origin_host && (n == 0 || (points && dirs_out)), "bad arguments");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_ray_dirs(points, n, origin_host, eps_mass, dirs_out, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+int gcl_bin_soft_assign(gcl_handle h, void* stream, const double* point_dirs, int64_t n, const double* bin_dirs, int n_bins,
+                        double tau, double eps_mass, double* responsibilities, double* scalars_out, double* workspace) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && n_bins >= 1 && n_bins <= 4096, "n >= 0 and 1 <= n_bins <= 4096 required");
+  GCL_REQUIRE(h, tau > 0.0, "tau must be > 0");
+  GCL_REQUIRE(h, bin_dirs && scalars_out && workspace && (n == 0 || (point_dirs && responsibilities)), "NULL pointer");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_soft_assign(point_dirs, n, bin_dirs, n_bins, tau, eps_mass, responsibilities, scalars_out, workspace,
+                             (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+static int mm_ctas(gcl_handle h, int64_t n) {
+  int64_t c = (n + 255) / 256;
+  if (c < 1) c = 1;
+  if (c > 2 * h->sm_count) c = 2 * h->sm_count;
+  return (int)c;
+}
+
+size_t gcl_moment_match_workspace_doubles(gcl_handle h, int64_t n, int n_bins) {
+  if (!h) return 0;
+  const size_t rec = (size_t)28 * n_bins + GCL_NCERT;
+  return rec * (size_t)mm_ctas(h, n) + rec;
+}
+
+int gcl_scan_bin_moment_match(gcl_handle h, void* stream, const double* points, const double* point_cov, const double* weights,
+                              const double* resp, const double* point_lambda, const double* origin_host, int64_t n, int n_bins,
+                              double eps_psd, double eps_mass, double* stats, double* workspace) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && n_bins >= 1 && n_bins <= GCL_MAX_BINS, "n >= 0 and 1 <= n_bins <= 1024 required");
+  GCL_REQUIRE(h, n < (int64_t)1 << 31, "n too large for the materialised-responsibility operator");
+  GCL_REQUIRE(h, origin_host && stats && workspace && (n == 0 || (points && weights && resp)), "NULL pointer");
+  const int ctas = mm_ctas(h, n);
+  const int64_t rec = (int64_t)28 * n_bins + GCL_NCERT;
+  ScanParams P;
+  memset(&P, 0, sizeof(P));
+  P.job.points = points; P.job.weights = weights; P.job.point_lambda = point_lambda;
+  P.job.n_raw = n; P.job.n_points_cap = (int32_t)(n > 0 ? n : 1); P.job.sel_begin = 0; P.job.sel_end = -1;
+  P.c.origin[0] = origin_host[0]; P.c.origin[1] = origin_host[1]; P.c.origin[2] = origin_host[2];
+  P.c.eps_mass = eps_mass;
+  P.resp = resp; P.point_cov = point_cov;
+  P.partials = workspace;
+  P.rec_doubles = rec;
+  P.tau = 1.0; P.n_bins = n_bins;
+  int G, L, chunks;
+  plan_bins(n_bins, GCL_F64, &G, &L, &chunks);
+  P.lanes = L; P.n_chunks = chunks; P.layout = GCL_LAYOUT_REF_F64; P.fixed_shift = 1;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_scan_moments(P, 1, ctas, GCL_F64, G, 28, true, (cudaStream_t)stream));
+  FinalizeParams F;
+  memset(&F, 0, sizeof(F));
+  F.parts = workspace; F.n_parts = ctas; F.part_stride = rec; F.job_stride = 0;
+  F.job = P.job; F.n_bins = n_bins; F.nmom = 28; F.tau = 1.0;
+  F.eps_psd = eps_psd; F.eps_mass = eps_mass; F.finalize = 1; F.from_resp = 1;
+  F.reduced = workspace + (size_t)rec * ctas; F.stats = stats;
+  GCL_CUDA(h, launch_reduce_finalize(F, 1, (cudaStream_t)stream));
+  h->launches += 2;
+  return GCL_OK;
+}
+
+int gcl_kappa_from_resultant(gcl_handle h, void* stream, const double* R_bar, int64_t n, double eps_r, int d, double r0,
+                             double tau, double* kappa_out) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && (n == 0 || (R_bar && kappa_out)), "bad arguments");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_kappa(R_bar, n, eps_r, d, r0, tau, kappa_out, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+int gcl_fibonacci_atlas(gcl_handle h, void* stream, int n_bins, double eps_mass, double* dirs_out) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_bins >= 1 && dirs_out, "n_bins >= 1 and an output buffer required");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_atlas(n_bins, eps_mass, dirs_out, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+int gcl_map_update(gcl_handle h, void* stream, const double* stats, const double* R_world, const double* t_world, int n_bins,
+                   double forgetting, double* S_dir, double* S_dir_scatter, double* N_dir, double* N_pos, double* sum_p,
+                   double* sum_ppT) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_bins >= 1 && stats && R_world && t_world && S_dir && S_dir_scatter && N_dir && N_pos && sum_p && sum_ppT,
+              "bad arguments");
+  GCL_REQUIRE(h, forgetting > 0.0 && forgetting <= 1.0, "forgetting factor must be in (0, 1]");
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_map_update(stats, R_world, t_world, n_bins, forgetting, S_dir, S_dir_scatter, N_dir, N_pos, sum_p,
+                                sum_ppT, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
+int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps, const double* weights,
+                        int64_t n, double t0, void* packed_xyzt, float* packed_w) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n >= 0 && (n == 0 || (points && timestamps && weights && packed_xyzt && packed_w)), "bad arguments");
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, op_pack(points, timestamps, weights, n, t0, packed_xyzt, packed_w, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
+// ---- reference-facing call with HOST buffers -------------------------------------------------------------------------------
+static int ensure_buffers(gcl_handle h, size_t dbytes, size_t hbytes) {
+  if (!h->stream) GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (dbytes > h->d_bytes) {
+    if (h->d_buf) cudaFree(h->d_buf);
+    h->d_buf = nullptr; h->d_bytes = 0;
+    GCL_CUDA(h, cudaMalloc(&h->d_buf, dbytes));
+    h->d_bytes = dbytes;
+  }
+  if (hbytes > h->h_bytes) {
+    if (h->h_buf) cudaFreeHost(h->h_buf);
+    h->h_buf = nullptr; h->h_bytes = 0;
+    GCL_CUDA(h, cudaMallocHost(&h->h_buf, hbytes));
+    h->h_bytes = hbytes;
+  }
+  return GCL_OK;
+}
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
+                                 const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1,
+                                 const double* xi_host, const double* pose_host, int n_hyp, const double* origin_host,
+                                 const double* bins_host, int n_bins, double tau, int precision, const double* mS_dir,
+                                 const double* mS_sc, const double* mN_dir, const double* mN_pos, const double* msum_p,
+                                 const double* msum_ppT, double eps_psd, double eps_mass, double* stats_host,
+                                 double* evidence_host) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
+  GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
+  GCL_REQUIRE(h, xi_host && pose_host && origin_host && bins_host && stats_host && evidence_host, "NULL pointer");
+  GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  cudaSetDevice(h->device);
+  const size_t B = n_bins, H = n_hyp, n = (size_t)n_raw;
+  int64_t stride = (n_raw + cap - 1) / cap; if (stride < 1) stride = 1;
+  const int64_t n_sel = (n_raw + stride - 1) / stride;
+  const int ctas = gcl_plan_ctas_per_job(h, n_hyp, n_sel, n_bins, precision);
+  const size_t rec = gcl_partial_record_doubles(n_bins), srec = gcl_stats_record_doubles(n_bins);
+  // one pinned staging block (inputs) and one device block, carved identically
+  const size_t o_pts = 0, o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), o_bins = al(o_w + n * 8);
+  const size_t o_map = al(o_bins + B * 24);                    // S_dir 3B, S_sc 9B, N_dir B, N_pos B, sum_p 3B, sum_ppT 9B
+  const size_t o_pose = al(o_map + B * 26 * 8), o_jobs = al(o_pose + H * 48), in_end = al(o_jobs + H * sizeof(gcl_job));
+  const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
+  const size_t o_evid = al(o_stats + H * srec * 8), o_mder = al(o_evid + H * GCL_EVID_DOUBLES * 8);
+  const size_t d_end = al(o_mder + B * 16 * 8);
+  const size_t out_bytes = H * srec * 8 + H * GCL_EVID_DOUBLES * 8;
+  int rc = ensure_buffers(h, d_end, in_end + al(out_bytes));
+  if (rc != GCL_OK) return rc;
+  unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
+  unsigned char* db = static_cast<unsigned char*>(h->d_buf);
+  cudaStream_t st = h->stream;
+  memcpy(hb + o_pts, points_host, n * 24);
+  memcpy(hb + o_ts, timestamps_host, n * 8);
+  memcpy(hb + o_w, weights_host, n * 8);
+  memcpy(hb + o_bins, bins_host, B * 24);
+  double* hm = reinterpret_cast<double*>(hb + o_map);
+  memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
+  memcpy(hm + 13 * B, mN_pos, B * 8); memcpy(hm + 14 * B, msum_p, B * 24); memcpy(hm + 17 * B, msum_ppT, B * 72);
+  memcpy(hb + o_pose, pose_host, H * 48);
+  gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
+  for (int i = 0; i < n_hyp; ++i) {
+    gcl_job& j = hj[i];
+    memset(&j, 0, sizeof(j));
+    j.points = db + o_pts; j.timestamps = db + o_ts; j.weights = db + o_w; j.point_lambda = nullptr;
+    j.n_raw = n_raw; j.n_points_cap = cap; j.sel_begin = 0; j.sel_end = -1;
+    j.scan_start_time = t0; j.scan_end_time = t1;
+    for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host[i * 6 + k];
+  }
+  GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, st));
+  const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
+  const double* dm = reinterpret_cast<const double*>(db + o_map);
+  const gcl_job* d_jobs = reinterpret_cast<const gcl_job*>(db + o_jobs);
+  double* d_parts = reinterpret_cast<double*>(db + o_parts);
+  double* d_red = reinterpret_cast<double*>(db + o_red);
+  double* d_stats = reinterpret_cast<double*>(db + o_stats);
+  double* d_evid = reinterpret_cast<double*>(db + o_evid);
+  double* d_mder = reinterpret_cast<double*>(db + o_mder);
+  rc = gcl_scan_moments(h, st, d_jobs, nullptr, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host,
+                        eps_mass, d_parts);
+  if (rc != GCL_OK) return rc;
+  rc = gcl_reduce_finalize(h, st, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
+                           origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
+  if (rc != GCL_OK) return rc;
+  rc = gcl_map_derived_stats(h, st, dm, dm + 12 * B, dm + 13 * B, dm + 14 * B, dm + 17 * B, n_bins, eps_mass, eps_psd, d_mder);
+  if (rc != GCL_OK) return rc;
+  rc = gcl_pose_evidence(h, st, d_stats, (int64_t)srec, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, d_mder,
+                         reinterpret_cast<const double*>(db + o_pose), nullptr, n_hyp, n_bins, eps_psd, eps_mass, 1, 1, d_evid);
+  if (rc != GCL_OK) return rc;
+  // stats and evidence are adjacent on the device only up to alignment: two copies into the pinned out block
+  unsigned char* hout = hb + in_end;
+  GCL_CUDA(h, cudaMemcpyAsync(hout, d_stats, H * srec * 8, cudaMemcpyDeviceToHost, st));
+  GCL_CUDA(h, cudaMemcpyAsync(hout + H * srec * 8, d_evid, H * GCL_EVID_DOUBLES * 8, cudaMemcpyDeviceToHost, st));
+  GCL_CUDA(h, cudaStreamSynchronize(st));
+  memcpy(stats_host, hout, H * srec * 8);
+  memcpy(evidence_host, hout + H * srec * 8, H * GCL_EVID_DOUBLES * 8);
+  return GCL_OK;
+}
+
+}  // extern "C"

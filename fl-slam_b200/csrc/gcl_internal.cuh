@@ -1,0 +1,123 @@
+// gcl_internal.cuh -- declarations shared by the translation units of libgcl_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/gcl_b200.h"
+#include "gcl_math.cuh"
+
+#ifndef GCL_USE_FFMA2
+#define GCL_USE_FFMA2 1  // packed fp32 FMA (fma.rn.f32x2, sm_100+); 0 = two scalar FFMAs (for A/B timing)
+#endif
+
+struct gcl_handle_s {
+  int device = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string err;
+  // resources of the *_host entry point (allocated on first use, grown on demand)
+  cudaStream_t stream = nullptr;
+  void* d_buf = nullptr; size_t d_bytes = 0;
+  void* h_buf = nullptr; size_t h_bytes = 0;
+};
+
+namespace gcl {
+
+struct ScanConst {
+  double origin[3];
+  double eps_mass;
+  float xi32[6];  // single-job fp32 copy of the twist (jobs array: converted per CTA instead)
+};
+
+struct ScanParams {
+  const gcl_job* jobs;  // device array or nullptr
+  gcl_job job;          // used when jobs == nullptr
+  ScanConst c;
+  const double* bin_dirs;  // (B,3) device
+  const double* resp;      // (N,B) device, FROM_RESP variant only
+  const double* point_cov; // (N,3,3) device, FROM_RESP variant only (may be nullptr => zeros)
+  double* partials;
+  int64_t rec_doubles;
+  double tau;
+  int n_bins;
+  int lanes;        // L
+  int n_chunks;     // bin chunks of G*L
+  int layout;
+  int fixed_shift;
+};
+
+void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_out);
+size_t scan_moments_smem_bytes(int precision, int G, int L, int n_chunks, int nmom);
+cudaError_t launch_scan_moments(const ScanParams& P, int n_jobs, int ctas_per_job, int precision, int G, int nmom,
+                                bool from_resp, cudaStream_t stream);
+
+struct FinalizeParams {
+  const double* parts;
+  int n_parts;
+  int64_t part_stride, job_stride;
+  const gcl_job* jobs;
+  gcl_job job;
+  int n_bins, nmom;
+  const double* bin_dirs;
+  double tau;
+  double origin[3];
+  double eps_psd, eps_mass;
+  int finalize;
+  int from_resp;  // standalone moment match: no resample / deskew / soft-assign scalars
+  double* reduced;
+  double* stats;
+};
+cudaError_t launch_reduce_finalize(const FinalizeParams& P, int n_jobs, cudaStream_t stream);
+
+struct EvidenceParams {
+  const double* stats;
+  int64_t stats_stride;
+  const double *map_S_dir, *map_S_dir_scatter, *map_N_dir, *map_N_pos, *map_derived;
+  const double* pose_pred;
+  const double* R_hat_override;
+  int n_bins;
+  double eps_psd, eps_mass;
+  int do_rotation, do_translation;
+  double* evidence;
+};
+cudaError_t launch_pose_evidence(const EvidenceParams& P, int n_jobs, cudaStream_t stream);
+cudaError_t launch_map_derived(const double* S_dir, const double* N_dir, const double* N_pos, const double* sum_p,
+                               const double* sum_ppT, int n_bins, double eps_mass, double eps_psd, double* out,
+                               cudaStream_t stream);
+cudaError_t launch_map_update(const double* stats, const double* R, const double* t, int n_bins, double forgetting,
+                              double* S_dir, double* S_dir_scatter, double* N_dir, double* N_pos, double* sum_p,
+                              double* sum_ppT, cudaStream_t stream);
+
+// standalone operators (gcl_ops.cu)
+cudaError_t op_point_budget(const double* pts, const double* ts, const double* w, const uint8_t* ring, const uint8_t* tag,
+                            int64_t n, int cap, double eps, double* pts_out, double* ts_out, double* w_out,
+                            uint8_t* ring_out, uint8_t* tag_out, double* scalars, double* ws, cudaStream_t st, int* launches);
+cudaError_t op_deskew(const double* pts, const double* ts, const double* w, int64_t n, double t0, double t1, const double* xi,
+                      double eps, double* pts_out, double* w_out, double* scalars, double* ws, cudaStream_t st, int* launches);
+cudaError_t op_ray_dirs(const double* pts, int64_t n, const double* o, double eps, double* out, cudaStream_t st, int* launches);
+cudaError_t op_soft_assign(const double* dirs, int64_t n, const double* bins, int B, double tau, double eps, double* resp,
+                           double* scalars, double* ws, cudaStream_t st, int* launches);
+cudaError_t op_kappa(const double* R, int64_t n, double eps_r, int d, double r0, double tau, double* out, cudaStream_t st, int* launches);
+cudaError_t op_atlas(int B, double eps, double* out, cudaStream_t st, int* launches);
+cudaError_t op_pack(const double* pts, const double* ts, const double* w, int64_t n, double t0, void* xyzt, float* wf,
+                    cudaStream_t st, int* launches);
+
+// offsets inside a stats record
+struct StatsLayout {
+  int B;
+  __host__ __device__ explicit StatsLayout(int b) : B(b) {}
+  __host__ __device__ int N() const { return 0; }
+  __host__ __device__ int s_dir() const { return B; }
+  __host__ __device__ int S_scatter() const { return 4 * B; }
+  __host__ __device__ int p_bar() const { return 13 * B; }
+  __host__ __device__ int Sigma_p() const { return 16 * B; }
+  __host__ __device__ int kappa() const { return 25 * B; }
+  __host__ __device__ int sum_p() const { return 26 * B; }
+  __host__ __device__ int sum_ppT() const { return 29 * B; }
+  __host__ __device__ int scalars() const { return 38 * B; }
+  __host__ __device__ int total() const { return 38 * B + GCL_STATS_SCALARS; }
+};
+
+}  // namespace gcl

@@ -1,0 +1,315 @@
+"""The fused per-scan LiDAR evidence path: PointBudgetResample -> DeskewConstantTwist -> ray directions ->
+BinSoftAssign -> ScanBinMomentMatch (+Kappa) -> MatrixFisherRotation -> PlanarTranslationEvidence -> 22-D evidence
+(README.md:105-120 of the reference; call sites pkg/backend/pipeline.py:400,569,587-593).
+
+Four launches per scan (batch): scan_moments (the only O(N) kernel), reduce_finalize, map_derived_stats,
+pose_evidence.  Nothing synchronises with the host until the caller asks for certificates.  Everything runs in
+libgcl_b200.so; without it this module cannot be imported.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi, constants
+from .certificates import CertBundle, ExpectedEffect, InfluenceCert, SupportCert
+from . import operators as ops
+
+_lib = _abi.lib
+PRECISIONS = {"fp64": _abi.GCL_F64, "fp32c": _abi.GCL_F32C}
+
+
+@dataclass
+class ResidentScan:
+    """A raw scan resident in HBM, in one of the two layouts of include/gcl_b200.h."""
+    points: torch.Tensor                 # (n,3) f64  |  (n,4) f32 {x,y,z,t - scan_start}
+    timestamps: Optional[torch.Tensor]   # (n,) f64   |  None
+    weights: torch.Tensor                # (n,) f64   |  (n,) f32
+    n_raw: int
+    layout: int
+    scan_start_time: float
+    scan_end_time: float
+    row_offset: int = 0                  # raw index of row 0 of these tensors (point sharding: a rank holds a slice)
+
+    @property
+    def bytes_per_point(self) -> int:
+        return 40 if self.layout == _abi.GCL_LAYOUT_REF_F64 else 20
+
+
+@dataclass
+class LidarScanEvidence:
+    """Everything the chain produces for one scan under H hypotheses.  Tensors stay on the device."""
+    n_bins: int
+    n_hyp: int
+    stats: torch.Tensor        # (H, stats record)
+    evidence: torch.Tensor     # (H, GCL_EVID_DOUBLES)
+    stats_host: Optional[np.ndarray] = None
+    evidence_host: Optional[np.ndarray] = None
+    chart_id: str = constants.GC_CHART_ID
+    anchor_id: str = "initial"
+    n_input: int = 0
+    n_points_cap: int = 0
+    ess_imu: float = 0.0
+
+    # -- typed views ------------------------------------------------------------------------------------------
+    def scan_bins(self, h: int = 0) -> ops.ScanBinStats:
+        return ops.stats_views(self.stats[h], self.n_bins)
+
+    def L_lidar(self, h: int = 0) -> torch.Tensor:
+        o = _abi.EV["L22"]
+        return self.evidence[h, o:o + 484].view(22, 22)
+
+    def h_lidar(self, h: int = 0) -> torch.Tensor:
+        o = _abi.EV["H22"]
+        return self.evidence[h, o:o + 22]
+
+    def _sync(self):
+        if self.stats_host is None:
+            self.stats_host = self.stats.detach().cpu().numpy()
+            self.evidence_host = self.evidence.detach().cpu().numpy()
+
+    def scalars(self, h: int = 0) -> Dict[str, float]:
+        self._sync()
+        tail = self.stats_host[h, 38 * self.n_bins:]
+        return {k: float(tail[i]) for k, i in _abi.SS.items()}
+
+    # -- certificates in pipeline order --------------------------------------------------------------------------
+    def certificates(self, h: int = 0) -> List[Tuple[str, Any, CertBundle, ExpectedEffect]]:
+        """[(operator name, result, CertBundle, ExpectedEffect)] in the order the reference pipeline emits them."""
+        self._sync()
+        s = self.scalars(h)
+        eps = constants.GC_EPS_MASS
+        out = []
+        ess = s["PB_ESS"]
+        pb_cert = CertBundle.create_approx(
+            chart_id=self.chart_id, anchor_id=self.anchor_id, triggers=["PointBudgetResample"],
+            support=SupportCert(ess_total=ess, support_frac=float(min(1.0, self.n_points_cap / (self.n_input + eps)))),
+            influence=InfluenceCert.identity().with_overrides(mass_epsilon_ratio=eps / (s["TOTAL_MASS_IN"] + eps)))
+        out.append(("PointBudgetResample", {"n_input": self.n_input, "n_output": int(s["N_SELECTED"]), "stride": int(s["STRIDE"]),
+                                            "total_mass_in": s["TOTAL_MASS_IN"], "total_mass_out": s["TOTAL_MASS_IN"]},
+                    pb_cert, ExpectedEffect("predicted_ess", ess)))
+        dk_cert = CertBundle.create_exact(chart_id=self.chart_id, anchor_id=self.anchor_id,
+                                          support=SupportCert(ess_total=float(self.ess_imu), support_frac=s["DESKEW_RETAINED"]),
+                                          influence=InfluenceCert.identity())
+        out.append(("DeskewConstantTwist", {"sum_w_out": s["SUM_W_OUT"]}, dk_cert,
+                    ExpectedEffect("deskew_variance_reduction_proxy", 0.0)))
+        sa_cert = CertBundle.create_exact(chart_id=self.chart_id, anchor_id=self.anchor_id,
+                                          support=SupportCert(ess_total=float(math.exp(s["AVG_ENTROPY"])), support_frac=s["MAX_RESP"]))
+        out.append(("BinSoftAssign", {"avg_entropy_valid_rows": s["ENTROPY_VALID_ROWS"], "max_resp_valid_rows": s["MAX_RESP_VALID_ROWS"]},
+                    sa_cert, ExpectedEffect("predicted_assignment_entropy", s["AVG_ENTROPY"])))
+        mm_cert, mm_eff = ops._moment_match_cert(self.stats_host[h, 38 * self.n_bins:], self.chart_id, self.anchor_id)
+        out.append(("ScanBinMomentMatch", self.scan_bins(h), mm_cert, mm_eff))
+        mf, mf_cert, mf_eff = ops.mf_result_from_record(self.evidence[h], self.evidence_host[h], self.chart_id, self.anchor_id)
+        out.append(("MatrixFisherRotationEvidence", mf, mf_cert, mf_eff))
+        pt, pt_cert, pt_eff = ops.pt_result_from_record(self.evidence[h], self.evidence_host[h], self.chart_id, self.anchor_id)
+        out.append(("PlanarTranslationEvidence", pt, pt_cert, pt_eff))
+        return out
+
+
+class LidarEvidencePipeline:
+    """Owns the atlas and the work buffers for one (n_bins, tau, precision) configuration on one GPU."""
+
+    def __init__(self, n_bins: int = constants.GC_B_BINS, tau: float = None, precision: str = "fp64",
+                 n_points_cap: int = constants.GC_N_POINTS_CAP, lidar_origin: Sequence[float] = (0.0, 0.0, 0.0),
+                 eps_psd: float = constants.GC_EPS_PSD, eps_mass: float = constants.GC_EPS_MASS, bin_directions=None,
+                 device: Optional[int] = None):
+        if tau is None:
+            raise ValueError("tau is required: the reference ships no GC_TAU_SOFT_ASSIGN (SURVEY.md 0.4)")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if not torch.cuda.is_available():
+            raise _abi.GclError("no CUDA device: fl_slam_b200 has no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.n_bins, self.tau, self.precision = int(n_bins), float(tau), precision
+        self.n_points_cap = int(n_points_cap)
+        self.origin = np.asarray(lidar_origin, dtype=np.float64).reshape(3)
+        self.eps_psd, self.eps_mass = float(eps_psd), float(eps_mass)
+        with torch.cuda.device(self.device):
+            self.handle = _abi.handle(self.device_index)
+            if bin_directions is None:
+                self.bin_dirs = ops.create_fibonacci_atlas(self.n_bins).dirs
+            else:
+                self.bin_dirs = ops._dev(bin_directions).reshape(self.n_bins, 3)
+        self.rec = int(_lib.gcl_partial_record_doubles(self.n_bins))
+        self.srec = int(_lib.gcl_stats_record_doubles(self.n_bins))
+        self._bufs: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        self._origin_c = _abi.dvec(self.origin)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def manifest_entries(self, n_gpus: int = 1, shard_mode: str = "none") -> Dict[str, Any]:
+        from .manifest import runtime_manifest_entries
+        return runtime_manifest_entries(self, n_gpus=n_gpus, shard_mode=shard_mode)
+
+    def upload_scan(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float,
+                    packed: Optional[bool] = None, row_offset: int = 0) -> ResidentScan:
+        """Host (or device) arrays -> a scan resident in HBM.  packed=True converts to the 20 B/point layout on the
+        device (fp32c mode only); default: packed iff precision == 'fp32c'."""
+        packed = (self.precision == "fp32c") if packed is None else bool(packed)
+        if packed and self.precision != "fp32c":
+            raise ValueError("the packed fp32 layout needs precision='fp32c'")
+        with torch.cuda.device(self.device):
+            pts, ts, w = ops._dev(points).reshape(-1, 3), ops._dev(timestamps).reshape(-1), ops._dev(weights).reshape(-1)
+            n = pts.shape[0]
+            if not packed:
+                return ResidentScan(pts, ts, w, n, _abi.GCL_LAYOUT_REF_F64, float(scan_start_time), float(scan_end_time), row_offset)
+            xyzt = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+            wf = torch.empty((n,), dtype=torch.float32, device=self.device)
+            _abi.check(_lib.gcl_pack_points_f32(self.handle, ops._stream(), ops._ptr(pts), ops._ptr(ts), ops._ptr(w), n,
+                                                float(scan_start_time), ops._ptr(xyzt), ops._ptr(wf)), self.handle)
+            return ResidentScan(xyzt, None, wf, n, _abi.GCL_LAYOUT_PACKED_F32, float(scan_start_time), float(scan_end_time), row_offset)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def make_job(self, scan: ResidentScan, xi_body, n_raw_total: Optional[int] = None, sel_range: Tuple[int, int] = (0, -1),
+                 point_lambda: Optional[torch.Tensor] = None, n_points_cap: Optional[int] = None) -> _abi.GclJob:
+        """A gcl_job for `scan`.  When the scan tensor holds only raw rows [row_offset, row_offset + len) of a larger
+        cloud (point sharding) the job carries virtual base pointers so that global raw indices address it."""
+        j = _abi.GclJob()
+        rowb = 24 if scan.layout == _abi.GCL_LAYOUT_REF_F64 else 16
+        wb = 8 if scan.layout == _abi.GCL_LAYOUT_REF_F64 else 4
+        off = int(scan.row_offset)
+        j.points = scan.points.data_ptr() - off * rowb
+        j.timestamps = (scan.timestamps.data_ptr() - off * 8) if scan.timestamps is not None else None
+        j.weights = scan.weights.data_ptr() - off * wb
+        j.point_lambda = None if point_lambda is None else point_lambda.data_ptr()
+        j.n_raw = int(scan.n_raw if n_raw_total is None else n_raw_total)
+        j.n_points_cap = int(self.n_points_cap if n_points_cap is None else n_points_cap)
+        j.sel_begin, j.sel_end = int(sel_range[0]), int(sel_range[1])
+        j.scan_start_time, j.scan_end_time = scan.scan_start_time, scan.scan_end_time
+        xi = np.asarray(xi_body, dtype=np.float64).reshape(6)
+        for k in range(6):
+            j.xi_body[k] = float(xi[k])
+        return j
+
+    def jobs_to_device(self, jobs: Sequence[_abi.GclJob]) -> torch.Tensor:
+        arr = (_abi.GclJob * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host.to(self.device, non_blocking=False)
+
+    @staticmethod
+    def selected_rows(n_raw: int, cap: int) -> Tuple[int, int]:
+        """(stride, n_selected) of point_budget.py:160,:70-71."""
+        stride = max(1, int(math.ceil(n_raw / cap))) if n_raw > 0 else 1
+        return stride, (n_raw + stride - 1) // stride
+
+    def _buffers(self, n_jobs: int, ctas: int) -> Dict[str, torch.Tensor]:
+        key = (n_jobs, ctas)
+        b = self._bufs.get(key)
+        if b is None:
+            z = lambda *s: torch.empty(s, dtype=torch.float64, device=self.device)
+            b = {"partials": z(n_jobs, ctas, self.rec), "reduced": z(n_jobs, self.rec), "stats": z(n_jobs, self.srec),
+                 "evidence": z(n_jobs, _abi.GCL_EVID_DOUBLES), "map_derived": z(16 * self.n_bins)}
+            self._bufs[key] = b
+        return b
+
+    def plan_ctas(self, n_jobs: int, max_sel_rows: int) -> int:
+        return int(_lib.gcl_plan_ctas_per_job(self.handle, int(n_jobs), int(max_sel_rows), self.n_bins, PRECISIONS[self.precision]))
+
+    # ---- the launches (all asynchronous on the current stream) ------------------------------------------------------
+    def launch_moments(self, jobs_dev: Optional[torch.Tensor], job: Optional[_abi.GclJob], n_jobs: int, ctas: int, layout: int,
+                       partials: torch.Tensor) -> None:
+        _abi.check(_lib.gcl_scan_moments(self.handle, ops._stream(), None if jobs_dev is None else C.c_void_p(jobs_dev.data_ptr()),
+                                         None if job is None else C.byref(job), n_jobs, ctas, layout, PRECISIONS[self.precision],
+                                         ops._ptr(self.bin_dirs), self.n_bins, self.tau, self._origin_c, self.eps_mass,
+                                         ops._ptr(partials)), self.handle)
+
+    def launch_finalize(self, parts: torch.Tensor, n_parts: int, part_stride: int, job_stride: int,
+                        jobs_dev: Optional[torch.Tensor], job: Optional[_abi.GclJob], n_jobs: int, finalize: bool,
+                        reduced: torch.Tensor, stats: Optional[torch.Tensor]) -> None:
+        _abi.check(_lib.gcl_reduce_finalize(self.handle, ops._stream(), ops._ptr(parts), n_parts, part_stride, job_stride,
+                                            None if jobs_dev is None else C.c_void_p(jobs_dev.data_ptr()),
+                                            None if job is None else C.byref(job), n_jobs, self.n_bins, ops._ptr(self.bin_dirs),
+                                            self.tau, self._origin_c, self.eps_psd, self.eps_mass, 1 if finalize else 0,
+                                            ops._ptr(reduced), ops._ptr(stats)), self.handle)
+
+    def launch_map_derived(self, m: ops.MapBinStats, out: torch.Tensor) -> None:
+        _abi.check(_lib.gcl_map_derived_stats(self.handle, ops._stream(), ops._ptr(m.S_dir), ops._ptr(m.N_dir), ops._ptr(m.N_pos),
+                                              ops._ptr(m.sum_p), ops._ptr(m.sum_ppT), self.n_bins, self.eps_mass, self.eps_psd,
+                                              ops._ptr(out)), self.handle)
+
+    def launch_evidence(self, stats: torch.Tensor, stats_stride: int, m: ops.MapBinStats, map_derived: torch.Tensor,
+                        poses: torch.Tensor, n_jobs: int, evidence: torch.Tensor) -> None:
+        _abi.check(_lib.gcl_pose_evidence(self.handle, ops._stream(), ops._ptr(stats), stats_stride, ops._ptr(m.S_dir),
+                                          ops._ptr(m.S_dir_scatter), ops._ptr(m.N_dir), ops._ptr(m.N_pos), ops._ptr(map_derived),
+                                          ops._ptr(poses), None, n_jobs, self.n_bins, self.eps_psd, self.eps_mass, 1, 1,
+                                          ops._ptr(evidence)), self.handle)
+
+    # ---- one scan, H hypotheses, data already in HBM -------------------------------------------------------------------
+    def run_resident(self, scan: ResidentScan, xi_bodies, poses_dev: torch.Tensor, map_stats: ops.MapBinStats,
+                     point_lambda: Optional[torch.Tensor] = None, jobs_dev: Optional[torch.Tensor] = None,
+                     ctas: Optional[int] = None) -> LidarScanEvidence:
+        """Device-resident pass (no host synchronisation).  xi_bodies: (H,6) host array; poses_dev: (H,6) device."""
+        xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
+        H = xi.shape[0]
+        _, n_sel = self.selected_rows(scan.n_raw, self.n_points_cap)
+        ctas = self.plan_ctas(H, n_sel) if ctas is None else ctas
+        b = self._buffers(H, ctas)
+        job = None
+        if H == 1 and jobs_dev is None:
+            job = self.make_job(scan, xi[0], point_lambda=point_lambda)
+        elif jobs_dev is None:
+            jobs_dev = self.jobs_to_device([self.make_job(scan, xi[h], point_lambda=point_lambda) for h in range(H)])
+        self.launch_moments(jobs_dev, job, H, ctas, scan.layout, b["partials"])
+        self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, job, H, True, b["reduced"], b["stats"])
+        self.launch_map_derived(map_stats, b["map_derived"])
+        self.launch_evidence(b["stats"], self.srec, map_stats, b["map_derived"], poses_dev, H, b["evidence"])
+        return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=b["stats"], evidence=b["evidence"], n_input=scan.n_raw,
+                                 n_points_cap=self.n_points_cap)
+
+    # ---- the reference-facing call: host arrays in, certificates out ------------------------------------------------------
+    def process_scan_host(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body, pose_pred,
+                          map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0, chart_id: str = constants.GC_CHART_ID,
+                          anchor_id: str = "initial") -> LidarScanEvidence:
+        """One call of gcl_lidar_scan_evidence_host: H2D of the scan, the four kernels, D2H of stats + evidence."""
+        f = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
+        pts, ts, w = f(points, (-1, 3)), f(timestamps, (-1,)), f(weights, (-1,))
+        n = pts.shape[0]
+        if ts.shape[0] != n or w.shape[0] != n:
+            raise ValueError("points / timestamps / weights disagree on N")
+        xi, poses = f(xi_body, (-1, 6)), f(pose_pred, (-1, 6))
+        H = xi.shape[0]
+        if poses.shape[0] != H:
+            raise ValueError("xi_body and pose_pred must have one row per hypothesis")
+        B = self.n_bins
+        m = {k: f(map_stats_host[k], s) for k, s in (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)),
+                                                    ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))}
+        bins_host = getattr(self, "_bins_host", None)
+        if bins_host is None:
+            bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
+        stats = np.empty((H, self.srec), dtype=np.float64)
+        evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _abi.check(_lib.gcl_lidar_scan_evidence_host(
+            self.handle, p(pts), p(ts), p(w), n, self.n_points_cap, float(scan_start_time), float(scan_end_time), p(xi), p(poses),
+            H, p(self.origin), p(bins_host), B, self.tau, PRECISIONS[self.precision], p(m["S_dir"]), p(m["S_dir_scatter"]),
+            p(m["N_dir"]), p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), self.eps_psd, self.eps_mass, p(stats), p(evid)),
+            self.handle)
+        return LidarScanEvidence(n_bins=B, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
+                                 stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
+                                 n_points_cap=self.n_points_cap, ess_imu=ess_imu)
+
+
+def lidar_scan_evidence(points, timestamps, weights, *, scan_start_time: float, scan_end_time: float, xi_body, belief_pred,
+                        map_stats, lidar_origin, tau: float, n_bins: int = constants.GC_B_BINS,
+                        n_points_cap: int = constants.GC_N_POINTS_CAP, precision: str = "fp64", ess_imu: float = 0.0,
+                        pipeline: Optional[LidarEvidencePipeline] = None) -> LidarScanEvidence:
+    """Fused drop-in for the operator sequence of the bin-era pipeline (README.md:110-115): one call, all certificates
+    (``.certificates()``) in pipeline order, 22-D evidence in ``.L_lidar()`` / ``.h_lidar()``."""
+    pl = pipeline or LidarEvidencePipeline(n_bins=n_bins, tau=tau, precision=precision, n_points_cap=n_points_cap,
+                                           lidar_origin=lidar_origin)
+    beliefs = belief_pred if isinstance(belief_pred, (list, tuple)) else [belief_pred]
+    poses = np.stack([ops._pose6(b, constants.GC_EPS_LIFT) for b in beliefs])
+    xi = np.asarray(xi_body, dtype=np.float64).reshape(-1, 6)
+    if xi.shape[0] == 1 and len(beliefs) > 1:
+        xi = np.repeat(xi, len(beliefs), axis=0)
+    if isinstance(map_stats, ops.MapBinStats):
+        msh = {k: getattr(map_stats, k).detach().cpu().numpy() for k in ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT")}
+    else:
+        msh = map_stats
+    return pl.process_scan_host(points, timestamps, weights, scan_start_time, scan_end_time, xi, poses, msh, ess_imu=ess_imu,
+                                chart_id=beliefs[0].chart_id, anchor_id=beliefs[0].anchor_id)

@@ -1,0 +1,243 @@
+/*
+ * gcl_b200.h -- C ABI of the B200-native GC-SLAM v2 LiDAR evidence hot path.
+ *
+ * The reference (whabacivch/FL-SLAM) has no FFI for this path: its operators are Python functions over JAX
+ * arrays (docs/OPERATOR_CONTRACTS.md:3).  Each entry point below therefore cites the reference *function*
+ * it replaces (file:line; pkg/ = fl_ws/src/fl_slam_poc/fl_slam_poc/).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to call them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gcl_status otherwise; gcl_last_error(h) has the text.
+ *     No CPU fallback exists anywhere behind this ABI (docs/GC_SLAM.md:128-132 "no GPU-else-CPU").
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; all device-pointer entry points are asynchronous on it and
+ *     perform no host synchronisation.  *_host entry points synchronise before returning.
+ *   - all floating point results are IEEE binary64 unless stated; integer/byte outputs are bit-exact.
+ *   - a handle is not thread-safe (the reference calls this path from one LiDAR worker thread,
+ *     pkg/backend/backend_node.py:1367); use one handle per (device, thread).
+ */
+#ifndef GCL_B200_H_
+#define GCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCL_ABI_VERSION 1
+#define GCL_MAX_BINS 1024
+#define GCL_NM 19            /* moments per bin: 1 + d(3) + ddT(6) + p(3) + ppT(6) */
+#define GCL_NCERT 8          /* per-partial certificate scalars (see GCL_CS_*) */
+#define GCL_STATS_SCALARS 24 /* per-job scalar block written by gcl_reduce_finalize (see GCL_SS_*) */
+#define GCL_EVID_DOUBLES 640 /* per-job evidence record written by gcl_pose_evidence (see GCL_EV_*) */
+
+typedef struct gcl_handle_s* gcl_handle;
+
+enum gcl_status {
+  GCL_OK = 0,
+  GCL_ERR_ARG = -1,      /* shape / contract violation (reference: ValueError, binning.py:253-264) */
+  GCL_ERR_CUDA = -2,     /* CUDA runtime error */
+  GCL_ERR_NO_DEVICE = -3,
+  GCL_ERR_UNSUPPORTED = -4
+};
+
+enum gcl_precision {
+  GCL_F64 = 0,  /* all arithmetic binary64: parity mode (moments <= 1e-9 rel of the reference) */
+  GCL_F32C = 1  /* binary32 per-point math + packed-fp32 tile accumulation carried in binary64 (<= 1e-5 rel) */
+};
+
+enum gcl_layout {
+  GCL_LAYOUT_REF_F64 = 0, /* the reference's arrays: points (n,3) f64 row-major, timestamps (n,) f64, weights (n,) f64 */
+  GCL_LAYOUT_PACKED_F32 = 1 /* float4 {x,y,z,t - scan_start} per point + float weight: 20 B/point */
+};
+
+/* One unit of work for the fused kernel: one scan under one hypothesis (twist).  Lives in device memory when a
+ * batch is launched (scan stream, hypothesis batch), or is passed by value for a single scan. */
+typedef struct gcl_job {
+  const void* points;      /* layout-dependent, raw (pre-resample) */
+  const void* timestamps;  /* f64 (n,) for REF_F64; unused for PACKED_F32 */
+  const void* weights;     /* f64 (n,) or f32 (n,) */
+  const double* point_lambda; /* optional (cap,) per-selected-row multiplier (binning.py:157), or NULL */
+  int64_t n_raw;           /* raw points in this scan */
+  int32_t n_points_cap;    /* PointBudget cap; stride = max(1, ceil(n_raw / cap)) (point_budget.py:160) */
+  int32_t sel_begin;       /* this rank's slice of the selected-row index space [sel_begin, sel_end) ... */
+  int32_t sel_end;         /* ... (0, n_sel) on one GPU; a contiguous sub-range when points are sharded */
+  int32_t reserved;
+  double scan_start_time;
+  double scan_end_time;
+  double xi_body[6];       /* constant twist over the sweep, [rho, phi] (deskew_constant_twist.py:31-69) */
+} gcl_job;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+int gcl_abi_version(void);
+int gcl_create(int device, gcl_handle* out);
+void gcl_destroy(gcl_handle h);
+const char* gcl_last_error(gcl_handle h); /* h may be NULL: error of the last failed gcl_create */
+int gcl_device_sm_count(gcl_handle h);
+/* number of kernels this handle has launched so far (bench.py reports it as gpu_launches) */
+int64_t gcl_launch_count(gcl_handle h);
+
+/* ---- fused hot path ------------------------------------------------------------------------------------- */
+/* Layout of one partial record: GCL_NM * n_bins moments (moment-major: [k][bin]) then GCL_NCERT scalars. */
+size_t gcl_partial_record_doubles(int n_bins);
+/* CTAs per job the launcher will use for (n_jobs, largest job) -- size the partials buffer with it. */
+int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_bins, int precision);
+
+/* Replaces, in one pass over the points and without materialising (N,B) or (N,3,3):
+ *   point_budget_resample gather   pkg/backend/operators/point_budget.py:50-109
+ *   deskew_constant_twist          pkg/backend/operators/deskew_constant_twist.py:31-69 (+ imu_preintegration.py:19-43)
+ *   ray directions                 pkg/backend/pipeline.py:591-593
+ *   bin_soft_assign                archive/legacy_operators/binning.py:56-76
+ *   scan_bin_moment_match (sums)   archive/legacy_operators/binning.py:157-173
+ * Writes partials[job][cta] records (fixed order => deterministic).  Exactly one of jobs_dev / job_by_value_host
+ * is used: jobs_dev != NULL launches n_jobs jobs read from device memory; otherwise the single job is passed by
+ * value from host memory. */
+int gcl_scan_moments(gcl_handle h, void* stream, const gcl_job* jobs_dev, const gcl_job* job_by_value_host,
+                     int n_jobs, int ctas_per_job, int layout, int precision, const double* bin_dirs /* (B,3) */,
+                     int n_bins, double tau, const double* lidar_origin_host /* (3,) */, double eps_mass,
+                     double* partials);
+
+enum { /* indices into the GCL_NCERT tail of a partial record */
+  GCL_CS_SUM_W_RAW = 0,   /* sum of all raw weights in this CTA's raw range           (point_budget.py:69) */
+  GCL_CS_SUM_W_SEL = 1,   /* sum of selected raw weights                               (point_budget.py:79) */
+  GCL_CS_SUM_W_SEL_SQ = 2,
+  GCL_CS_SUM_W_DESKEW = 3,/* sum of w_sel * w_time                                     (deskew_constant_twist.py:102) */
+  GCL_CS_SUM_ENTROPY = 4, /* sum of per-point assignment entropies                     (binning.py:70-74) */
+  GCL_CS_MAX_RESP = 5,    /* max responsibility (reduced with max, not +)              (binning.py:69) */
+  GCL_CS_ROWS = 6,        /* selected rows processed */
+  GCL_CS_SPARE = 7
+};
+
+/* Fixed-order sum of `n_parts` partial records per job, then (if finalize != 0) the non-linear per-bin part:
+ *   mass rescale                   point_budget.py:80-85
+ *   inv mass, centroid, scatter    binning.py:175-182, pkg/common/primitives.py:195-212
+ *   PSD projection per bin         pkg/common/primitives.py:80-123
+ *   kappa                          pkg/backend/operators/kappa.py:130-169
+ *   certificate scalars            point_budget.py:95-96,:202-213; deskew_constant_twist.py:102-109;
+ *                                  binning.py:70-75,:118-125 (incl. the padded rows); binning.py:201-204
+ * With finalize == 0 it only writes the reduced record to reduced[job] (the buffer that is exchanged between
+ * GPUs when points are sharded); a second call with parts = gathered records and finalize = 1 completes it.
+ * stats layout per job (doubles): N[B] s_dir[3B] S_dir_scatter[9B] p_bar[3B] Sigma_p[9B] kappa[B] sum_p[3B]
+ * sum_ppT[9B] then GCL_STATS_SCALARS scalars. */
+size_t gcl_stats_record_doubles(int n_bins);
+int gcl_reduce_finalize(gcl_handle h, void* stream, const double* parts, int n_parts, int64_t part_stride_doubles,
+                        int64_t job_stride_doubles, const gcl_job* jobs_dev, const gcl_job* job_by_value_host,
+                        int n_jobs, int n_bins, const double* bin_dirs, double tau,
+                        const double* lidar_origin_host, double eps_psd, double eps_mass, int finalize,
+                        double* reduced /* [n_jobs][record] or NULL */, double* stats /* [n_jobs][stats record] */);
+
+enum { /* indices into the scalar tail of a stats record */
+  GCL_SS_TOTAL_MASS_IN = 0, GCL_SS_TOTAL_MASS_SEL = 1, GCL_SS_MASS_SCALE = 2, GCL_SS_PB_ESS = 3,
+  GCL_SS_N_SELECTED = 4, GCL_SS_STRIDE = 5, GCL_SS_DESKEW_RETAINED = 6, GCL_SS_AVG_ENTROPY = 7,
+  GCL_SS_MAX_RESP = 8, GCL_SS_MM_ESS = 9, GCL_SS_MM_SUPPORT_FRAC = 10, GCL_SS_MM_PSD_DELTA = 11,
+  GCL_SS_MM_MAX_EPS_RATIO = 12, GCL_SS_ENTROPY_VALID_ROWS = 13, GCL_SS_MAX_RESP_VALID_ROWS = 14,
+  GCL_SS_SUM_W_OUT = 15
+};
+
+/* Map-side derived statistics.  Replaces compute_map_derived_stats, archive/bin_atlas.py:166-224.
+ * out layout: mu_dir[3B] kappa[B] centroid[3B] Sigma_c[9B]. */
+int gcl_map_derived_stats(gcl_handle h, void* stream, const double* S_dir, const double* N_dir, const double* N_pos,
+                          const double* sum_p, const double* sum_ppT, int n_bins, double eps_mass, double eps_psd,
+                          double* out);
+
+/* Matrix Fisher rotation + planar translation evidence + 22-D embedding, batched over hypotheses (one warp each).
+ * Replaces matrix_fisher_rotation_evidence / planar_translation_evidence / build_combined_lidar_evidence_22d,
+ * archive/legacy_operators/matrix_fisher_evidence.py:155-394, :413-671, :729-756.
+ * scan stats: one stats record per job (stride stats_stride_doubles; 0 = all hypotheses share record 0).
+ * pose_pred: (n_jobs,6) [t, rotvec] = belief_pred.mean_world_pose() (pkg/common/belief.py:408-434).
+ * If R_hat_override != NULL (n_jobs,9) it is used as R_hat for the translation step instead of R_mf.
+ * evidence: n_jobs records of GCL_EVID_DOUBLES doubles (see GCL_EV_*). */
+int gcl_pose_evidence(gcl_handle h, void* stream, const double* stats, int64_t stats_stride_doubles,
+                      const double* map_S_dir, const double* map_S_dir_scatter, const double* map_N_dir,
+                      const double* map_N_pos, const double* map_derived, const double* pose_pred,
+                      const double* R_hat_override, int n_jobs, int n_bins, double eps_psd, double eps_mass,
+                      int do_rotation, int do_translation, double* evidence);
+
+enum { /* offsets (doubles) into an evidence record */
+  GCL_EV_R_MF = 0, GCL_EV_L_ROT = 9, GCL_EV_H_ROT = 18, GCL_EV_DELTA_ROT = 21, GCL_EV_SVD_S = 24,
+  GCL_EV_ROT_CERT = 27,      /* [eig_min, eig_max, cond, near_null, nll_per_ess, directional_score, psd_delta,
+                                 mass_eps_ratio, rot_nll, N_eff] */
+  GCL_EV_SCAN_METRICS = 37,  /* [l1,l2,l3, linearity, planarity, sphericity, anisotropy, effective_rank] */
+  GCL_EV_MAP_METRICS = 45,
+  GCL_EV_SCAN_EIGVECS = 53, GCL_EV_MAP_EIGVECS = 62,
+  GCL_EV_T_WLS = 71, GCL_EV_L_TRANS = 74, GCL_EV_H_TRANS = 83, GCL_EV_DELTA_TRANS = 86,
+  GCL_EV_TRANS_CERT = 89,    /* [eig_min, eig_max, cond, near_null, nll_per_ess, psd_delta, mass_eps_ratio,
+                                 trans_nll, N_eff, xy_info, z_info, z_precision_scale] */
+  GCL_EV_H22 = 101, GCL_EV_L22 = 123 /* 22 + 484 doubles; ends at 607 <= GCL_EVID_DOUBLES */
+};
+
+/* ---- reference operators one by one (device pointers; used by the drop-in Python operators) --------------- */
+/* point_budget_resample, pkg/backend/operators/point_budget.py:117-221.  Outputs are cap-sized and zero padded.
+ * scalars_out (8 doubles): [n_input, n_selected, stride, total_mass_in, total_mass_selected, mass_scale, ess, 0]. */
+int gcl_point_budget_resample(gcl_handle h, void* stream, const double* points, const double* timestamps,
+                              const double* weights, const uint8_t* ring, const uint8_t* tag, int64_t n_input,
+                              int32_t n_points_cap, double eps_mass, double* points_out, double* timestamps_out,
+                              double* weights_out, uint8_t* ring_out, uint8_t* tag_out, double* scalars_out,
+                              double* workspace /* >= 4096 doubles */);
+
+/* deskew_constant_twist, pkg/backend/operators/deskew_constant_twist.py:72-117.
+ * scalars_out (4 doubles): [sum_w_out, sum_w_in, retained_fraction, 0]. */
+int gcl_deskew_constant_twist(gcl_handle h, void* stream, const double* points, const double* timestamps,
+                              const double* weights, int64_t n, double scan_start_time, double scan_end_time,
+                              const double* xi_body_host, double eps_mass, double* points_out, double* weights_out,
+                              double* scalars_out, double* workspace /* >= 4096 doubles */);
+
+/* ray directions, pkg/backend/pipeline.py:591-593. */
+int gcl_ray_directions(gcl_handle h, void* stream, const double* points, int64_t n, const double* origin_host,
+                       double eps_mass, double* dirs_out);
+
+/* bin_soft_assign, archive/legacy_operators/binning.py:79-131.  responsibilities (N,B) row-major.
+ * scalars_out (4 doubles): [avg_entropy, max_resp, exp(avg_entropy), 0]. */
+int gcl_bin_soft_assign(gcl_handle h, void* stream, const double* point_dirs, int64_t n, const double* bin_dirs,
+                        int n_bins, double tau, double eps_mass, double* responsibilities, double* scalars_out,
+                        double* workspace /* >= 4096 doubles */);
+
+/* scan_bin_moment_match with materialised responsibilities and optional per-point covariances,
+ * archive/legacy_operators/binning.py:212-324.  stats: one stats record (gcl_stats_record_doubles). */
+size_t gcl_moment_match_workspace_doubles(gcl_handle h, int64_t n, int n_bins);
+int gcl_scan_bin_moment_match(gcl_handle h, void* stream, const double* points, const double* point_covariances,
+                              const double* weights, const double* responsibilities, const double* point_lambda,
+                              const double* origin_host, int64_t n, int n_bins, double eps_psd, double eps_mass,
+                              double* stats, double* workspace);
+
+/* kappa_from_resultant_batch, pkg/backend/operators/kappa.py:130-169. */
+int gcl_kappa_from_resultant(gcl_handle h, void* stream, const double* R_bar, int64_t n, double eps_r, int d,
+                             double r0, double tau, double* kappa_out);
+
+/* create_fibonacci_atlas, archive/bin_atlas.py:40-75. */
+int gcl_fibonacci_atlas(gcl_handle h, void* stream, int n_bins, double eps_mass, double* dirs_out);
+
+/* Map maintenance ("next" row): world-frame increments of one scan's bin sums under pose (R, t) with t_z forced
+ * to 0, forgetting and additive update in one kernel.  archive/bin_atlas.py:137-163, :232-257; the pushforward rule
+ * itself is not in the reference tree -- declared in DESIGN.md.  Map arrays are updated in place. */
+int gcl_map_update(gcl_handle h, void* stream, const double* stats /* one stats record */, const double* R_world,
+                   const double* t_world, int n_bins, double forgetting, double* S_dir, double* S_dir_scatter,
+                   double* N_dir, double* N_pos, double* sum_p, double* sum_ppT);
+
+/* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
+int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,
+                        const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,
+                        float* packed_w);
+
+/* ---- reference-facing call with HOST buffers ------------------------------------------------------------- */
+/* The whole chain for one scan and n_hyp hypotheses: H2D of the scan, fused moments, finalize, pose evidence, D2H
+ * of the stats and evidence records; synchronises.  This is the entry a maintainer binds in place of the operator
+ * sequence at pkg/backend/pipeline.py:400-593 + README.md:110-115.  map_*_host are the six MapBinStats arrays
+ * (archive/bin_atlas.py:83-101); xi_body_host and pose_pred_host are (n_hyp,6). */
+int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
+                                 const double* weights_host, int64_t n_raw, int32_t n_points_cap,
+                                 double scan_start_time, double scan_end_time, const double* xi_body_host,
+                                 const double* pose_pred_host, int n_hyp, const double* lidar_origin_host,
+                                 const double* bin_dirs_host, int n_bins, double tau, int precision,
+                                 const double* map_S_dir_host, const double* map_S_dir_scatter_host,
+                                 const double* map_N_dir_host, const double* map_N_pos_host,
+                                 const double* map_sum_p_host, const double* map_sum_ppT_host, double eps_psd,
+                                 double eps_mass, double* stats_host /* n_hyp stats records */,
+                                 double* evidence_host /* n_hyp evidence records */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCL_B200_H_ */
