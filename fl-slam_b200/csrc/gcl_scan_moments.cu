@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_moments_kernel(const __grid_
   size_t off = (size_t)3 * Btot * sizeof(T);
   off = (off + 15) & ~(size_t)15;
   V* s_tile = reinterpret_cast<V*>(smem_raw + off);                 // [kTilePoints / W][STRIDE]
-  double* s_stage = reinterpret_cast<double*>(smem_raw + off);      // aliases the tile during a flush
+  off += (size_t)(kTilePoints / W) * STRIDE * sizeof(V);
+  off = (off + 15) & ~(size_t)15;
+  double* s_stage = reinterpret_cast<double*>(smem_raw + off);      // [PS][kKC][Bp] flush staging (not aliased: with
+                                                                    // several bin chunks the tile outlives a flush)
   __shared__ double s_red[kThreads / 32][GCL_NCERT];
 
   const int tid = threadIdx.x;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_moments_kernel(const __grid_
   for (int i = tid; i < NMOM * B + GCL_NCERT; i += kThreads) part[i] = 0.0;
   for (int i = tid; i < 3 * Btot; i += kThreads) {
     const int c = i / Btot, b = i - c * Btot;
-    s_bins[i] = (b < B) ? (T)P.bin_dirs[b * 3 + c] : (T)0;
+    s_bins[i] = (!FROM_RESP && b < B) ? (T)P.bin_dirs[b * 3 + c] : (T)0;  // no atlas on the materialised-r path
   }
   const int binlane = tid & (L - 1);
   const int slice = tid / L;
@@ -501,9 +504,10 @@ size_t scan_moments_smem_bytes(int precision, int G, int L, int n_chunks, int nm
   const int stride = (nmom == 19) ? (precision == GCL_F64 ? 25 : 26) : 33;
   size_t off = (size_t)3 * G * L * n_chunks * tsz;
   off = (off + 15) & ~(size_t)15;
-  const size_t tile = (size_t)(kTilePoints / W) * stride * tsz * W;
+  size_t tile = (size_t)(kTilePoints / W) * stride * tsz * W;
+  tile = (tile + 15) & ~(size_t)15;
   const size_t stage = (size_t)(kThreads / L) * kKC * G * L * sizeof(double);
-  return off + (tile > stage ? tile : stage);
+  return off + tile + stage;
 }
 
 cudaError_t launch_scan_moments(const ScanParams& P, int n_jobs, int ctas_per_job, int precision, int G, int nmom,

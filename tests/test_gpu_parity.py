@@ -153,7 +153,11 @@ def test_operators_against_reference_goldens(g, O, ref_certs, name):
 
 def test_kappa_and_atlas_against_reference(g):
     p = np.load(os.path.join(GOLDEN, "ref_pieces.npz"))
-    np.testing.assert_allclose(H(g.kappa_from_resultant_batch(p["kappa_in"])), p["kappa_out"], rtol=1e-12)
+    k = H(g.kappa_from_resultant_batch(p["kappa_in"]))
+    lowR = p["kappa_in"] < 0.99
+    np.testing.assert_allclose(k[lowR], p["kappa_out"][lowR], rtol=1e-13)
+    # near R = 1 the formula divides by 1 - R^2 + eps ~ 2e-6: one ulp of R^2 is amplified ~1e5 times
+    np.testing.assert_allclose(k, p["kappa_out"], rtol=1e-10)
     for B in (16, 48, 256, 1024):
         assert np.max(np.abs(H(g.create_fibonacci_atlas(B).dirs) - p[f"atlas_{B}"])) < 1e-14
 
