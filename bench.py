@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the LiDAR evidence hot path on B200 (contract in the task brief, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Default workload = BASELINE.json configs[1]: a Kimera-jackal-shaped synthetic scan stream (200 scans of ~30k points,
+cap 8192 => stride 4 / 7500 selected rows, 48 bins, 1 hypothesis) with the map bin statistics carried from scan to scan
+(forgetting 0.99).  One "step" = one pass over the whole stream.  `value` = raw points per second with the scans
+resident in HBM (one CUDA graph per stream pass); `e2e` = the same stream through the reference-facing host call
+(pinned host buffers, H2D + kernels + D2H per scan).  `roofline` is for the dominant kernel, scan_moments.
+`extra` carries the 1M-point x 256-bin cloud (configs[3]) -- the configuration the HBM target is quoted on -- and
+the 64-hypothesis batch (configs[2]).  At N > 1 the stream workload runs as N independent replicas (scan k+1 depends on
+scan k's map: it does not shard); configs[3] shards by points with one all-gather of the per-bin moment
+buffer, configs[2] shards by hypothesis.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_stream(n_scans, seed0=1234 + 2):
+    """configs[1]: n = 30000 +- 2 % per scan, 10 Hz sweeps, a slow known trajectory for the map update."""
+    from fl_slam_b200 import synth
+    rng = np.random.default_rng(seed0)
+    scans, poses = [], []
+    for k in range(n_scans):
+        n = int(round(PTS_PER_SCAN * (1 + 0.02 * rng.uniform(-1, 1))))
+        scans.append(synth.make_scan(n, seed=seed0 + 1 + k, t0=synth.T0_EPOCH + 0.1 * k))
+        poses.append(np.array([0.05 * k, 0.01 * k, 0.0, 0.0, 0.0, 0.008 * k]))
+    return scans, np.stack(poses)
+
+
+def oracle_scan(O, sc, cap, bins, tau, ms, pose):
+    return O.lidar_scan_evidence(sc.points, sc.timestamps, sc.weights, sc.ring, sc.tag, n_points_cap=cap,
+                                 scan_start_time=sc.scan_start_time, scan_end_time=sc.scan_end_time, xi_body=sc.xi_body,
+                                 lidar_origin=sc.lidar_origin, bin_directions=bins, tau=tau, map_stats=ms, pose_pred=pose,
+                                 materialize=True)
+
+
+def oracle_map_update(O, ms, mm, pose, gamma=0.99):
+    """Same rule as gcl_map_update: forget, then add the scan sums pushed by (R, t) with t_z = 0."""
+    R = O.so3_exp(pose[3:6]); t = np.array([pose[0], pose[1], 0.0])
+    raw = mm["raw"]; N = raw["N"]
+    Rp = np.einsum("ij,bj->bi", R, raw["sum_p"])
+    out = {k: gamma * v for k, v in ms.items()}
+    out["S_dir"] += np.einsum("ij,bj->bi", R, raw["s_dir"])
+    out["S_dir_scatter"] += np.einsum("ij,bjk,lk->bil", R, raw["S_dir_scatter"], R)
+    out["N_dir"] += N; out["N_pos"] += N
+    out["sum_p"] += Rp + N[:, None] * t[None]
+    out["sum_ppT"] += (np.einsum("ij,bjk,lk->bil", R, raw["sum_ppT"], R) + Rp[:, :, None] * t[None, None, :]
+                       + t[None, :, None] * Rp[:, None, :] + N[:, None, None] * np.outer(t, t)[None])
+    return out
+
+
+def cpu_stream_rate(n_sample, tau):
+    """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the stream workload."""
+    from oracle import gc_oracle as O
+    scans, poses = make_stream(n_sample)
+    bins = O.create_fibonacci_atlas(N_BINS)
+    ms = {"S_dir": np.zeros((N_BINS, 3)), "S_dir_scatter": np.zeros((N_BINS, 3, 3)), "N_dir": np.zeros(N_BINS),
+          "N_pos": np.zeros(N_BINS), "sum_p": np.zeros((N_BINS, 3)), "sum_ppT": np.zeros((N_BINS, 3, 3))}
+    t0 = time.perf_counter()
+    pts = 0
+    for sc, pose in zip(scans, poses):
+        out = oracle_scan(O, sc, CAP, bins, tau, ms, pose)
+        ms = oracle_map_update(O, ms, out["scan_bins"], pose)
+        pts += sc.points.shape[0]
+    dt = time.perf_counter() - t0
+    return pts / dt, n_sample / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i.get("num_threads", 1)) for i in threadpool_info()] + [1])
+    except Exception:
+        return 1
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path = the NumPy restatement (the JAX
+    implementation cannot run here), all host threads NumPy/BLAS will use, bounded sample per step."""
+    if rank != 0:
+        return
+    from fl_slam_b200 import synth
+    tau = synth.DEFAULT_TAU
+    n_sample = 6
+    for _ in range(args.warmup):
+        cpu_stream_rate(2, tau)
+    t_all, pts_all, scans_all = 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        pps, sps, dt = cpu_stream_rate(n_sample, tau)
+        t_all += dt; pts_all += pps * dt; scans_all += n_sample
+    value = pts_all / t_all
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value,
+            "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[1] scan stream, bounded sample of {n_sample} scans per step (~30k points, cap {CAP}, "
+                                   f"{N_BINS} bins, 1 hypothesis, map carried)", "tau": tau},
+            "scans_per_sec": scans_all / t_all,
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} scans/step x {args.steps} steps of the configs[1] stream; NumPy float64 "
+                                       f"restatement of the reference (JAX unavailable); os.cpu_count()={os.cpu_count()}"},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2]/[3] side measurements")
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fl_slam_b200 as g
+    from fl_slam_b200 import synth
+    from fl_slam_b200 import sharding
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tau = synth.DEFAULT_TAU
+    peak_gbs, peak_src = load_peaks()
+
+    # ---------------------------------------------------------------- workload: configs[1] scan stream (replica per rank)
+    scans, poses = make_stream(N_SCANS, seed0=1234 + 2 + 1000 * rank)
+    pl = g.LidarEvidencePipeline(n_bins=N_BINS, tau=tau, precision=args.precision, n_points_cap=CAP,
+                                 lidar_origin=scans[0].lidar_origin)
+    res = [pl.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
+    poses_dev = torch.from_numpy(poses).to(dev)
+    from oracle import gc_oracle as O  # only for so3_exp of the synthetic trajectory (host set-up, not timed)
+    R_dev = torch.from_numpy(np.stack([O.so3_exp(p[3:6]) for p in poses])).to(dev).contiguous()
+    t_dev = torch.from_numpy(poses[:, :3].copy()).to(dev)
+    ms = g.create_empty_map_stats(N_BINS)
+    total_points = sum(s.points.shape[0] for s in scans)
+    bpp = res[0].bytes_per_point
+    # algorithmic bytes of one scan_moments launch: 5 scalars per SELECTED row + every raw weight (stride > 1)
+    def _alg_bytes(n):
+        stride, n_sel = pl.selected_rows(n, CAP)
+        return n_sel * bpp + (n * (bpp // 5) if stride > 1 else 0)
+    bytes_per_launch = float(np.mean([_alg_bytes(s.points.shape[0]) for s in scans]))
+
+    def stream_pass():
+        for k in range(N_SCANS):
+            ev = pl.run_resident(res[k], scans[k].xi_body[None], poses_dev[k:k + 1], ms)
+            g.map_update_inplace(ms, ev.stats[0], R_dev[k], t_dev[k], 0.99)
+
+    launches0 = g._abi.launch_count(local_rank)
+    stream_pass()                                   # eager warm-up (allocates work buffers, sets kernel attributes)
+    torch.cuda.synchronize()
+    launches_per_step = g._abi.launch_count(local_rank) - launches0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        stream_pass()
+    for _ in range(args.warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * total_points / (ms_per_step * 1e-3)
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (scan_moments alone)
+    def moments_only():
+        for k in range(N_SCANS):
+            job = pl.make_job(res[k], scans[k].xi_body)
+            b = pl._buffers(1, pl.plan_ctas(1, CAP))
+            pl.launch_moments(None, job, 1, pl.plan_ctas(1, CAP), res[k].layout, b["partials"])
+    moments_only(); torch.cuda.synchronize()
+    gk = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gk):
+        moments_only()
+    gk.replay(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        gk.replay()
+    ev1.record(); torch.cuda.synchronize()
+    k1_us = 1e3 * ev0.elapsed_time(ev1) / (args.steps * N_SCANS)
+    achieved = bytes_per_launch / (k1_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "scan_moments_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src, "us_per_launch": k1_us,
+                "algorithmic_bytes_per_launch": float(bytes_per_launch),
+                "note": "latency-bound at this size (7500 rows x 48 bins per launch); see extra.cfg4 and DESIGN.md"}
+    clocks = sampler.stop()
+
+    # ---------------------------------------------------------------- e2e: the reference-facing host call, pinned buffers
+    n_e2e = min(N_SCANS, 50)
+    pinned = []
+    for s in scans[:n_e2e]:
+        p, t_, w_ = (torch.from_numpy(a).pin_memory() for a in (s.points, s.timestamps, s.weights))
+        pinned.append((p, t_, w_))
+    ms_host = {k: np.zeros(v) for k, v in (("S_dir", (N_BINS, 3)), ("S_dir_scatter", (N_BINS, 3, 3)), ("N_dir", (N_BINS,)),
+                                                ("N_pos", (N_BINS,)), ("sum_p", (N_BINS, 3)), ("sum_ppT", (N_BINS, 3, 3)))}
+
+    def e2e_pass():
+        m = ms_host
+        for k in range(n_e2e):
+            p, t_, w_ = pinned[k]
+            out = pl.process_scan_host(p.numpy(), t_.numpy(), w_.numpy(), scans[k].scan_start_time, scans[k].scan_end_time,
+                                       scans[k].xi_body[None], poses[k][None], m)
+            sb = out.stats_host[0]
+            raw = {"N": sb[:N_BINS], "s_dir": sb[N_BINS:4 * N_BINS].reshape(N_BINS, 3),
+                   "S_dir_scatter": sb[4 * N_BINS:13 * N_BINS].reshape(N_BINS, 3, 3),
+                   "sum_p": sb[26 * N_BINS:29 * N_BINS].reshape(N_BINS, 3), "sum_ppT": sb[29 * N_BINS:38 * N_BINS].reshape(N_BINS, 3, 3)}
+            m = oracle_map_update(O, m, {"raw": raw}, poses[k])   # O(B) host bookkeeping between calls
+        return m
+    e2e_pass()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_rep = max(1, args.steps // 2)
+    for _ in range(n_rep):
+        e2e_pass()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_points = sum(s.points.shape[0] for s in scans[:n_e2e])
+    rec_bytes = (38 * N_BINS + 24 + 640) * 8
+    e2e = {"value": world * n_rep * e2e_points / e2e_s, "unit": "points/s",
+           "h2d_bytes_per_step": int(e2e_points * 40 + n_e2e * (N_BINS * 26 * 8 + N_BINS * 24 + 48 + 128)),
+           "d2h_bytes_per_step": int(n_e2e * rec_bytes), "scans_per_sec": world * n_rep * n_e2e / e2e_s,
+           "note": f"{n_e2e} scans per pass through gcl_lidar_scan_evidence_host (pinned host arrays; H2D + 4 kernels + D2H + sync per scan)"}
+
+    # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
+    extra = {}
+    if not args.no_extra:
+        extra["cfg4_1Mx256"] = sharding.bench_points_sharded(g, n_points=1 << 20, n_bins=256, tau=tau, steps=max(args.steps, 10),
+                                                            warmup=args.warmup, rank=rank, world=world, peak_gbs=peak_gbs)
+        extra["cfg3_64hyp"] = sharding.bench_hypothesis_sharded(g, n_points=30000, cap=32768, n_bins=48, n_hyp=64, tau=tau,
+                                                               steps=max(args.steps, 10), warmup=args.warmup, rank=rank, world=world)
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1:
+        pps, sps, dt = cpu_stream_rate(args.cpu_sample, tau)
+        cpu = {"value": pps, "unit": "points/s", "cores": blas_threads(), "kind": "port", "scans_per_sec": sps,
+               "sample": f"first {args.cpu_sample} scans of the same stream ({dt:.1f} s); NumPy float64 restatement of the "
+                         f"reference operators (JAX unavailable); os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {"metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value, "unit": "points/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32 (fp64 carry)",
+                "data": "synthetic",
+                "config": {"workload": f"configs[1]: scan stream, {N_SCANS} scans x ~{PTS_PER_SCAN} points, cap {CAP} (stride 4, "
+                                       f"7500 rows), {N_BINS} bins, 1 hypothesis, map statistics carried (forgetting 0.99)",
+                           "tau": tau, "precision": args.precision, "layout": "ref_f64 (40 B/point)" if args.precision == "fp64" else "packed_f32 (20 B/point)",
+                           "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (stream does not shard)",
+                           "l2": "inputs total 240 MB > 126 MB L2; each scan is read once per step"},
+                "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "gpu_launches": int(launches_per_step * args.steps),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "extra": extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

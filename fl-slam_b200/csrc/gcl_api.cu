@@ -358,6 +358,12 @@ static int ensure_buffers(gcl_handle h, size_t dbytes, size_t hbytes) {
 
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
                                  const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1,
                                  const double* xi_host, const double* pose_host, int n_hyp, const double* origin_host,
@@ -391,9 +397,14 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
   unsigned char* db = static_cast<unsigned char*>(h->d_buf);
   cudaStream_t st = h->stream;
-  memcpy(hb + o_pts, points_host, n * 24);
-  memcpy(hb + o_ts, timestamps_host, n * 8);
-  memcpy(hb + o_w, weights_host, n * 8);
+  // Scan arrays that already live in page-locked memory are copied straight from the caller's buffers; pageable
+  // arrays go through the pinned staging block (the memcpy is the price of pageable inputs).
+  const bool direct = n > 0 && is_pinned(points_host) && is_pinned(timestamps_host) && is_pinned(weights_host);
+  if (!direct) {
+    memcpy(hb + o_pts, points_host, n * 24);
+    memcpy(hb + o_ts, timestamps_host, n * 8);
+    memcpy(hb + o_w, weights_host, n * 8);
+  }
   memcpy(hb + o_bins, bins_host, B * 24);
   double* hm = reinterpret_cast<double*>(hb + o_map);
   memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
@@ -408,7 +419,14 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
     j.scan_start_time = t0; j.scan_end_time = t1;
     for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host[i * 6 + k];
   }
-  GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, st));
+  if (direct) {
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_pts, points_host, n * 24, cudaMemcpyHostToDevice, st));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_ts, timestamps_host, n * 8, cudaMemcpyHostToDevice, st));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_w, weights_host, n * 8, cudaMemcpyHostToDevice, st));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, in_end - o_bins, cudaMemcpyHostToDevice, st));
+  } else {
+    GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, st));
+  }
   const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
   const double* dm = reinterpret_cast<const double*>(db + o_map);
   const gcl_job* d_jobs = reinterpret_cast<const gcl_job*>(db + o_jobs);
