@@ -1,5 +1,6 @@
 // gcl_api.cu -- the C ABI declared in include/gcl_b200.h: argument checks, launch planning, error text.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -125,6 +126,7 @@ int gcl_scan_moments(gcl_handle h, void* stream, const gcl_job* jobs_dev, const 
   P.lanes = L; P.n_chunks = chunks;
   P.layout = layout;
   P.fixed_shift = fixed_shift_ok(tau, precision) ? 1 : 0;
+  if (const char* dbg = getenv("GCL_DEBUG_SKIP")) P.fixed_shift |= (atoi(dbg) << 1);  // profiling only: 1 = skip phase B, 2 = skip phase A bin loop
   cudaSetDevice(h->device);
   GCL_CUDA(h, launch_scan_moments(P, n_jobs, ctas_per_job, precision, G, GCL_NM, false, (cudaStream_t)stream));
   h->launches += 1;

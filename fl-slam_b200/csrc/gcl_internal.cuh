@@ -8,6 +8,12 @@
 #include "../../include/gcl_b200.h"
 #include "gcl_math.cuh"
 
+#ifndef GCL_NT_F32
+#define GCL_NT_F32 256  // threads per CTA of the fp32 scan_moments kernel
+#endif
+#ifndef GCL_GMAX_F32
+#define GCL_GMAX_F32 4   // bins per thread (register tile) of the fp32 scan_moments kernel
+#endif
 #ifndef GCL_USE_FFMA2
 #define GCL_USE_FFMA2 1  // packed fp32 FMA (fma.rn.f32x2, sm_100+); 0 = two scalar FFMAs (for A/B timing)
 #endif
@@ -49,6 +55,7 @@ struct ScanParams {
 };
 
 void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_out);
+int scan_moments_threads(int precision);
 size_t scan_moments_smem_bytes(int precision, int G, int L, int n_chunks, int nmom);
 cudaError_t launch_scan_moments(const ScanParams& P, int n_jobs, int ctas_per_job, int precision, int G, int nmom,
                                 bool from_resp, cudaStream_t stream);
