@@ -54,7 +54,7 @@ def run_chain(ref, synth, name, *, n_raw, cap, n_bins, tau, seed, with_times=Tru
 
     pb, c, e = ref["point_budget"].point_budget_resample(sc.points, sc.timestamps, sc.weights, sc.ring, sc.tag,
                                                          n_points_cap=cap)
-    certs["point_budget"] = {"cert": _cert_numbers(c), "effect": e.to_dict()}
+    certs["point_budget"] = {"cert": _cert_numbers(c), "effect": e.to_dict(), "full_to_dict": c.to_dict()}
     for k in ("points", "timestamps", "weights", "ring", "tag"):
         out["pb_" + k] = np.asarray(getattr(pb, k))
     out["pb_scalars"] = np.array([pb.n_input, pb.n_output, pb.total_mass_in, pb.total_mass_out], dtype=np.float64)

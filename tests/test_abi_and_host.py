@@ -1,0 +1,122 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/gcl_b200.h declares (no compute calls),
+the host-side mirror of the reference interface (certificates, constants, manifest, planning helpers) behaves as the
+reference does, and the product never routes through the oracle."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def g():
+    import fl_slam_b200
+    return fl_slam_b200
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gcl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(g):
+    lib = ctypes.CDLL(g._abi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libgcl_b200.so does not export {n}"
+    assert set(g._abi.EXPORTED) == set(names), "the ctypes table and the header disagree"
+    assert lib.gcl_abi_version() == 1
+
+
+def test_record_sizes_match_header_constants(g):
+    lib = g._abi.lib
+    for B in (1, 7, 48, 256, 1024):
+        assert lib.gcl_partial_record_doubles(B) == 19 * B + 8
+        assert lib.gcl_stats_record_doubles(B) == 38 * B + 24
+    assert g._abi.EV["L22"] + 484 <= g._abi.GCL_EVID_DOUBLES
+    assert ctypes.sizeof(g._abi.GclJob) == 120
+
+
+def test_fails_loudly_without_a_gpu(g):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(g._abi.GclError):
+        g._abi.handle(0)
+    with pytest.raises(g._abi.GclError):
+        g.LidarEvidencePipeline(n_bins=48, tau=0.1)
+    with pytest.raises(g._abi.GclError):
+        g.point_budget_resample(np.zeros((4, 3)), np.zeros(4), np.ones(4))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "fl-slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "gc_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_constants_match_reference_values(g):
+    C = g.constants   # values asserted by the reference's own tests: test_geometric_compositional_invariants.py:117-143
+    assert C.GC_N_POINTS_CAP == 8192 and C.GC_CHART_ID == "GC-RIGHT-01" and C.GC_K_HYP == 4
+    assert 1e-15 < C.GC_EPS_PSD < 1e-6 and 1e-15 < C.GC_EPS_MASS < 1e-6 and 1e-12 < C.GC_EPS_LIFT < 1e-6
+    assert (C.GC_EPS_R, C.GC_KAPPA_BLEND_R0, C.GC_KAPPA_BLEND_TAU) == (1e-6, 0.8, 0.03)
+    assert (C.GC_TIME_WARP_SIGMA_FRAC, C.GC_WEIGHT_FLOOR) == (0.1, 1e-12)
+
+
+def test_certificates_serialise_like_the_reference(g):
+    """to_dict() of our CertBundle has exactly the keys of the reference's (golden written by the reference's own
+    certificates.py through generate_goldens.py), and reproduces its numbers when fed the same fields."""
+    ref = json.load(open(os.path.join(GOLDEN, "ref_certs.json")))["stride3_pad"]["point_budget"]["full_to_dict"]
+    cert = g.CertBundle.create_approx(
+        chart_id=ref["chart_id"], anchor_id=ref["anchor_id"], triggers=list(ref["approximation_triggers"]),
+        support=g.SupportCert(**ref["support"]),
+        influence=g.InfluenceCert.identity().with_overrides(mass_epsilon_ratio=ref["influence"]["mass_epsilon_ratio"]))
+    ours = cert.to_dict()
+    assert set(ours) == set(ref)
+    for k in ("conditioning", "support", "mismatch", "excitation", "influence", "overconfidence", "compute"):
+        assert set(ours[k]) == set(ref[k]), k
+    assert ours["support"] == ref["support"] and ours["influence"] == ref["influence"]
+    assert ours["total_trigger_magnitude"] == ref["total_trigger_magnitude"]
+    assert ours["exact"] is False and ours["frobenius_applied"] is False
+    ex = g.CertBundle.create_exact(chart_id="GC-RIGHT-01", anchor_id="a")
+    assert ex.exact and ex.approximation_triggers == [] and ex.total_trigger_magnitude() == 0.0
+    eff = g.ExpectedEffect("predicted_ess", 3.0).to_dict()
+    assert eff == {"objective_name": "predicted_ess", "predicted": 3.0, "realized": None}
+
+
+def test_selected_rows_follow_point_budget_rule(g):
+    f = g.LidarEvidencePipeline.selected_rows   # point_budget.py:160,:70-71
+    assert f(100, 8192) == (1, 100) and f(10000, 8192) == (2, 5000) and f(30000, 8192) == (4, 7500)
+    assert f(30000, 32768) == (1, 30000) and f(1048576, 8192) == (128, 8192) and f(0, 8192) == (1, 0)
+    for n in (1, 8191, 8192, 8193, 16384, 16385, 99999):
+        s, k = f(n, 8192)
+        assert k == len(range(0, n, s)) and k <= 8192
+
+
+def test_synthetic_scans_are_deterministic(g):
+    a, b = g.synth.make_scan(5000, seed=1234), g.synth.make_scan(5000, seed=1234)
+    assert np.array_equal(a.points, b.points) and np.array_equal(a.weights, b.weights)
+    assert a.points.dtype == np.float64 and a.ring.dtype == np.uint8 and a.timestamps.min() >= a.scan_start_time
+    assert np.all(a.weights > 0) and np.all(np.isfinite(a.points))
+    R, t = g.synth.known_map_transform(3)
+    assert abs(np.linalg.det(R) - 1) < 1e-12 and abs(np.arccos((np.trace(R) - 1) / 2) - 0.05) < 1e-12
+
+
+def test_manifest_entries(g):
+    class P:  # the manifest only reads these attributes
+        precision, n_points_cap, n_bins, tau, eps_psd, eps_mass = "fp64", 8192, 48, 0.1, 1e-12, 1e-12
+    m = g.runtime_manifest_entries(P(), n_gpus=8, shard_mode="points")
+    for k in ("point_budget", "deskew", "bin_soft_assign", "scan_bin_moment_match", "lidar_evidence", "domain_projection_psd", "se3"):
+        assert "sm_100a" in m["backends"][k]
+    assert m["B_BINS"] == 48 and m["tau_soft_assign"] == 0.1 and m["precision_mode"] == "fp64"
+    assert m["n_gpus"] == 8 and m["shard_mode"] == "points" and m["pose_evidence_backend"] == "bins"
