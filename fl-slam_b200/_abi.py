@@ -70,6 +70,8 @@ def _load():
         "gcl_kappa_from_resultant": (i32, [vp, vp, vp, i64, f64, i32, f64, f64, vp]),
         "gcl_fibonacci_atlas": (i32, [vp, vp, i32, f64, vp]),
         "gcl_map_update": (i32, [vp, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, vp, vp]),
+        "gcl_scan_chain": (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, f64,
+                                 f64, f64, vp]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
         "gcl_lidar_scan_evidence_host": (i32, [vp, vp, vp, vp, i64, C.c_int32, f64, f64, vp, vp, i32, vp, vp, i32, f64, i32,
                                                vp, vp, vp, vp, vp, vp, f64, f64, vp, vp]),

@@ -20,6 +20,10 @@ GC_NONFINITE_SENTINEL = 1e6      # :257
 GC_RANGE_WEIGHT_SIGMA = 0.25     # :260
 GC_RANGE_WEIGHT_MIN_R = 0.5      # :261
 GC_RANGE_WEIGHT_MAX_R = 50.0     # :262
+GC_IW_NU_WEAK_ADD = 0.5          # :164
+GC_LIDAR_SIGMA_MEAS = 0.01       # :210 (Kimera YAML overrides to 1e-3, config/gc_unified.yaml:16)
+GC_IW_RHO_MEAS_LIDAR = 0.99      # :281
+GC_IW_NU_MAX = 1000.0            # measurement_noise_iw_jax.py:66 default
 GC_D_Z = 22
 GC_B_BINS = 48                   # recovered, see module docstring
 GC_TAU_SOFT_ASSIGN = 0.1         # DECLARED by this build, see module docstring

@@ -329,6 +329,30 @@ int gcl_map_update(gcl_handle h, void* stream, const double* stats, const double
   return GCL_OK;
 }
 
+int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stride, int n_scans, int n_hyp, int n_bins,
+                   double* mS_dir, double* mS_sc, double* mN_dir, double* mN_pos, double* msum_p, double* msum_ppT,
+                   double* map_derived, const double* pose_pred, const double* pose_update, double forgetting, double* iw_state,
+                   int use_sigma_meas, double iw_rho, double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass,
+                   double* evidence) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_scans >= 1 && n_hyp >= 1 && n_bins >= 1, "n_scans, n_hyp, n_bins must be >= 1");
+  GCL_REQUIRE(h, stats && mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT && map_derived && pose_pred && evidence,
+              "NULL pointer");
+  GCL_REQUIRE(h, !pose_update || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
+  GCL_REQUIRE(h, !use_sigma_meas || iw_state, "use_sigma_meas needs iw_state");
+  ChainParams P;
+  P.stats = stats; P.stats_stride = stats_stride;
+  P.map_S_dir = mS_dir; P.map_S_dir_scatter = mS_sc; P.map_N_dir = mN_dir; P.map_N_pos = mN_pos; P.map_sum_p = msum_p;
+  P.map_sum_ppT = msum_ppT; P.map_derived = map_derived; P.pose_pred = pose_pred; P.pose_update = pose_update;
+  P.iw_state = iw_state; P.evidence = evidence; P.n_scans = n_scans; P.n_hyp = n_hyp; P.n_bins = n_bins;
+  P.use_sigma_meas = use_sigma_meas; P.forgetting = forgetting; P.iw_rho = iw_rho; P.iw_nu_weak_add = iw_nu_weak_add;
+  P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_chain(P, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps, const double* weights,
                         int64_t n, double t0, void* packed_xyzt, float* packed_w) {
   if (!h) return GCL_ERR_ARG;

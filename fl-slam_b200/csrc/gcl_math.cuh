@@ -106,9 +106,7 @@ __host__ __device__ inline void sym_eig3(const double* Ain, double* val, double*
   for (int sweep = 0; sweep < 12; ++sweep) {
     const double off = fabs(a01) + fabs(a02) + fabs(a12);
     const double dg = fabs(a00) + fabs(a11) + fabs(a22);
-    if (off <= 1e-300 || off <= 1e-22 * dg) {
-      if (off + dg == dg) break;
-    }
+    if (off == 0.0 || off + dg == dg) break;  // off-diagonal below one ulp of the diagonal
     GCL_JROT(a00, a11, a01, a02, a12, 0, 1)
     GCL_JROT(a00, a22, a02, a01, a12, 0, 2)
     GCL_JROT(a11, a22, a12, a01, a02, 1, 2)
@@ -128,7 +126,7 @@ __host__ __device__ inline void sym_eig3(const double* Ain, double* val, double*
 
 // domain_projection_psd_core, pkg/common/primitives.py:80-123.
 // cert = [projection_delta, sym_delta, eig_min, eig_max, cond, near_null_count]
-__host__ __device__ inline void psd_project3(const double* M, double eps_psd, double* Mpsd, double* cert) {
+__host__ __device__ inline void psd_project3(const double* M, double eps_psd, double* Mpsd, double* cert, double* vals_floored = nullptr) {
   double Ms[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) Ms[i * 3 + j] = 0.5 * (M[i * 3 + j] + M[j * 3 + i]);
@@ -138,6 +136,7 @@ __host__ __device__ inline void psd_project3(const double* M, double eps_psd, do
   sym_eig3(Ms, val, V);
   double vc[3];
   for (int k = 0; k < 3; ++k) vc[k] = fmax(val[k], eps_psd);
+  if (vals_floored) { vals_floored[0] = vc[0]; vals_floored[1] = vc[1]; vals_floored[2] = vc[2]; }
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
       Mpsd[i * 3 + j] = V[i * 3 + 0] * vc[0] * V[j * 3 + 0] + V[i * 3 + 1] * vc[1] * V[j * 3 + 1] + V[i * 3 + 2] * vc[2] * V[j * 3 + 2];
@@ -169,7 +168,7 @@ __host__ __device__ inline void svd3(const double* H, double* U, double* s, doub
           be += a[k * 3 + q] * a[k * 3 + q];
           ga += a[k * 3 + p] * a[k * 3 + q];
         }
-        if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        if (ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be)) continue;  // columns orthogonal to working precision
         rotated = 1;
         const double zeta = (be - al) / (2.0 * ga);
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

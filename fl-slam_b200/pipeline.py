@@ -239,11 +239,52 @@ class LidarEvidencePipeline:
                                           ops._ptr(poses), None, n_jobs, self.n_bins, self.eps_psd, self.eps_mass, 1, 1,
                                           ops._ptr(evidence)), self.handle)
 
+    def launch_chain(self, stats: torch.Tensor, n_scans: int, n_hyp: int, m: ops.MapBinStats, map_derived: torch.Tensor,
+                     poses_pred: torch.Tensor, poses_update: Optional[torch.Tensor], evidence: torch.Tensor,
+                     iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False, forgetting: float = 0.99) -> None:
+        """The sequential part of a stream in one launch (gcl_scan_chain): map + IW state stay on the device."""
+        _abi.check(_lib.gcl_scan_chain(self.handle, ops._stream(), ops._ptr(stats), self.srec, n_scans, n_hyp, self.n_bins,
+                                       ops._ptr(m.S_dir), ops._ptr(m.S_dir_scatter), ops._ptr(m.N_dir), ops._ptr(m.N_pos),
+                                       ops._ptr(m.sum_p), ops._ptr(m.sum_ppT), ops._ptr(map_derived), ops._ptr(poses_pred),
+                                       ops._ptr(poses_update), float(forgetting), ops._ptr(iw_state), 1 if use_sigma_meas else 0,
+                                       constants.GC_IW_RHO_MEAS_LIDAR, constants.GC_IW_NU_WEAK_ADD, constants.GC_IW_NU_MAX,
+                                       self.eps_psd, self.eps_mass, ops._ptr(evidence)), self.handle)
+
+    def create_lidar_iw_state(self, sigma_meas: float = constants.GC_LIDAR_SIGMA_MEAS) -> torch.Tensor:
+        """[nu, Psi(3x3)] of the LiDAR measurement-noise block: nu = p + 1 + nu_extra, Psi = sigma I nu_extra
+        (pkg/backend/structures/measurement_noise_iw_jax.py:36-68)."""
+        v = np.concatenate([[3.0 + 1.0 + constants.GC_IW_NU_WEAK_ADD], (sigma_meas * constants.GC_IW_NU_WEAK_ADD * np.eye(3)).reshape(-1)])
+        return torch.from_numpy(v).to(self.device)
+
+    # ---- a stream of scans resident in HBM: three launches for the whole stream -------------------------------------------
+    def run_stream(self, scans: Sequence[ResidentScan], xi_bodies, poses_pred: torch.Tensor, poses_update: Optional[torch.Tensor],
+                   map_stats: ops.MapBinStats, iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False,
+                   forgetting: float = 0.99, jobs_dev: Optional[torch.Tensor] = None, ctas: Optional[int] = None) -> LidarScanEvidence:
+        """scan_moments and reduce_finalize run for ALL scans at once (they do not depend on the map); one chain launch
+        then walks the scans in order.  Returns per-scan stats / evidence records (n_hyp = number of scans here)."""
+        S = len(scans)
+        xi = np.asarray(xi_bodies, dtype=np.float64).reshape(S, 6)
+        max_sel = max(self.selected_rows(s.n_raw, self.n_points_cap)[1] for s in scans)
+        ctas = self.plan_ctas(S, max_sel) if ctas is None else ctas
+        b = self._buffers(S, ctas)
+        if jobs_dev is None:
+            jobs_dev = self.jobs_to_device([self.make_job(scans[k], xi[k]) for k in range(S)])
+        self.launch_moments(jobs_dev, None, S, ctas, scans[0].layout, b["partials"])
+        self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, None, S, True, b["reduced"], b["stats"])
+        self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
+                          use_sigma_meas, forgetting)
+        return LidarScanEvidence(n_bins=self.n_bins, n_hyp=S, stats=b["stats"], evidence=b["evidence"], n_input=scans[0].n_raw,
+                                 n_points_cap=self.n_points_cap)
+
     # ---- one scan, H hypotheses, data already in HBM -------------------------------------------------------------------
     def run_resident(self, scan: ResidentScan, xi_bodies, poses_dev: torch.Tensor, map_stats: ops.MapBinStats,
                      point_lambda: Optional[torch.Tensor] = None, jobs_dev: Optional[torch.Tensor] = None,
-                     ctas: Optional[int] = None) -> LidarScanEvidence:
-        """Device-resident pass (no host synchronisation).  xi_bodies: (H,6) host array; poses_dev: (H,6) device."""
+                     ctas: Optional[int] = None, pose_update: Optional[torch.Tensor] = None,
+                     iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False, forgetting: float = 0.99
+                     ) -> LidarScanEvidence:
+        """Device-resident pass, three launches, no host synchronisation.  xi_bodies: (H,6) host array; poses_dev: (H,6)
+        device.  pose_update (1,6): if given, the map statistics are updated in place after the evidence (hypothesis 0);
+        iw_state: LiDAR measurement-noise IW block updated in place."""
         xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
         H = xi.shape[0]
         _, n_sel = self.selected_rows(scan.n_raw, self.n_points_cap)
@@ -256,8 +297,8 @@ class LidarEvidencePipeline:
             jobs_dev = self.jobs_to_device([self.make_job(scan, xi[h], point_lambda=point_lambda) for h in range(H)])
         self.launch_moments(jobs_dev, job, H, ctas, scan.layout, b["partials"])
         self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, job, H, True, b["reduced"], b["stats"])
-        self.launch_map_derived(map_stats, b["map_derived"])
-        self.launch_evidence(b["stats"], self.srec, map_stats, b["map_derived"], poses_dev, H, b["evidence"])
+        self.launch_chain(b["stats"], 1, H, map_stats, b["map_derived"], poses_dev, pose_update, b["evidence"], iw_state,
+                          use_sigma_meas, forgetting)
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=b["stats"], evidence=b["evidence"], n_input=scan.n_raw,
                                  n_points_cap=self.n_points_cap)
 

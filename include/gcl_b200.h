@@ -216,6 +216,22 @@ int gcl_map_update(gcl_handle h, void* stream, const double* stats /* one stats 
                    const double* t_world, int n_bins, double forgetting, double* S_dir, double* S_dir_scatter,
                    double* N_dir, double* N_pos, double* sum_p, double* sum_ppT);
 
+/* The sequential part of a scan stream in ONE launch: a single CTA walks n_scans scans in order and carries the map bin
+ * statistics and the LiDAR measurement-noise inverse-Wishart block on the device.  Per scan: [bin covariances +=
+ * Sigma_meas] -> map-derived statistics -> pose evidence (n_hyp hypotheses) -> IW update -> map update.
+ * Replaces the per-scan host loop pkg/backend/backend_node.py:2036-2119 for this path; the IW rules are
+ * pkg/backend/operators/measurement_noise_iw_jax.py:37-127 (mode, residual sufficient statistics, forgetful update
+ * with the softplus nu projection), GC_IW_RHO_MEAS_LIDAR / GC_IW_NU_WEAK_ADD from pkg/common/constants.py:281,:164.
+ * stats: n_scans*n_hyp records from gcl_reduce_finalize (scan-major); Sigma_p is rewritten in place when
+ * use_sigma_meas != 0.  pose_update: (n_scans,6) pose applied by the map update (NULL = map is read-only).
+ * iw_state: 10 doubles [nu, Psi (3x3)] updated in place (NULL = no measurement-noise adaptation).
+ * map_derived_scratch: 16*n_bins doubles. */
+int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stride_doubles, int n_scans, int n_hyp,
+                   int n_bins, double* map_S_dir, double* map_S_dir_scatter, double* map_N_dir, double* map_N_pos,
+                   double* map_sum_p, double* map_sum_ppT, double* map_derived_scratch, const double* pose_pred,
+                   const double* pose_update, double forgetting, double* iw_state, int use_sigma_meas, double iw_rho,
+                   double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass, double* evidence);
+
 /* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,
                         const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,

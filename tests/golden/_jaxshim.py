@@ -284,7 +284,9 @@ def load_reference(reference_root="/root/reference", n_bins=48, tau=0.1):
                         ("kappa", "fl_slam_poc.backend.operators.kappa"),
                         ("imu_preintegration", "fl_slam_poc.backend.operators.imu_preintegration"),
                         ("point_budget", "fl_slam_poc.backend.operators.point_budget"),
-                        ("deskew_constant_twist", "fl_slam_poc.backend.operators.deskew_constant_twist")]:
+                        ("deskew_constant_twist", "fl_slam_poc.backend.operators.deskew_constant_twist"),
+                        ("mn_iw_struct", "fl_slam_poc.backend.structures.measurement_noise_iw_jax"),
+                        ("mn_iw", "fl_slam_poc.backend.operators.measurement_noise_iw_jax")]:
         mods[short] = importlib.import_module(full)
         parent, leaf = full.rsplit(".", 1)
         setattr(sys.modules[parent], leaf, mods[short])

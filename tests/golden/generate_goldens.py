@@ -186,6 +186,20 @@ def run_pieces(ref):
     t = np.linspace(-0.05, 0.15, 33) + 1.7e9
     out["sww_t"] = t
     out["sww_w"] = np.asarray(ref["imu_preintegration"].smooth_window_weights(t, 1.7e9, 1.7e9 + 0.1, 0.01))
+    # LiDAR measurement-noise inverse-Wishart block: three successive updates from random per-bin residuals
+    jnp = sys.modules["jax.numpy"]
+    st = ref["mn_iw_struct"].create_datasheet_measurement_noise_state(lidar_sigma_meas=1e-3)
+    out["iw_nu0"], out["iw_Psi0"] = np.asarray(st.nu), np.asarray(st.Psi_blocks)
+    res_all, w_all, nus, Psis, Sigs = [], [], [], [], []
+    for k in range(3):
+        res = rng.normal(size=(48, 3)) * np.array([0.02, 0.03, 0.005]) * (1 + k)
+        w = rng.uniform(0.0, 2.0, 48)
+        dPsi, dnu = ref["mn_iw"].lidar_meas_iw_suffstats_from_translation_residuals_jax(res, w)
+        st, _ = ref["mn_iw"].measurement_noise_apply_suffstats_jax(st, dPsi, dnu)
+        res_all.append(res); w_all.append(w); nus.append(np.asarray(st.nu)); Psis.append(np.asarray(st.Psi_blocks))
+        Sigs.append(np.asarray(ref["mn_iw"].measurement_noise_mean_jax(st, 2)))
+    out["iw_res"], out["iw_w"] = np.stack(res_all), np.stack(w_all)
+    out["iw_nu"], out["iw_Psi"], out["iw_Sigma_lidar"] = np.stack(nus), np.stack(Psis), np.stack(Sigs)
     np.savez_compressed(os.path.join(HERE, "ref_pieces.npz"), **out)
 
 

@@ -370,3 +370,34 @@ def test_moment_match_with_point_covariances(g, O):
     for k in ("N", "s_dir", "S_dir_scatter", "p_bar", "Sigma_p", "kappa_scan"):
         assert rel_err(H(getattr(mm, k)), ref[k]) < 1e-9, k
     assert abs(cert.support.ess_total / ref["ess"] - 1) < 1e-10
+
+
+def test_stream_chain_with_map_and_iw_state(g, O):
+    """configs[1] in miniature: a short scan stream, map statistics and the LiDAR measurement-noise IW block carried
+    on the device by one chain launch, against the sequential oracle loop."""
+    S, B, cap, tau = 6, 48, 2048, 0.1
+    scans = [g.synth.make_scan(5000 + 37 * k, seed=300 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
+    poses = np.stack([np.array([0.05 * k, 0.01 * k, 0.0, 0.0, 0.0, 0.01 * k]) for k in range(S)])
+    bins = O.create_fibonacci_atlas(B)
+    for use_sigma in (False, True):
+        ref, ref_map, ref_iw = O.scan_stream(scans, poses, poses, n_points_cap=cap, bin_directions=bins, tau=tau,
+                                             lidar_origin=scans[0].lidar_origin, iw_state=O.iw_lidar_init(1e-3), use_sigma_meas=use_sigma)
+        pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=scans[0].lidar_origin, bin_directions=bins)
+        res = [pl.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
+        ms = g.create_empty_map_stats(B)
+        iw = pl.create_lidar_iw_state(1e-3)
+        pd = torch.from_numpy(poses).cuda()
+        ev = pl.run_stream(res, np.stack([s.xi_body for s in scans]), pd, pd, ms, iw_state=iw, use_sigma_meas=use_sigma)
+        st, evd = H(ev.stats), H(ev.evidence)
+        for k in range(S):
+            assert rel_err(st[k, :B], ref[k]["scan_bins"]["N"]) < 1e-9
+            assert rel_err(st[k, 16 * B:25 * B].reshape(B, 3, 3), ref[k]["scan_bins"]["Sigma_p"]) < 1e-8
+            if k > 0:   # scan 0 sees an empty map: H = 0, rotation undefined (SVD of the zero matrix)
+                assert geodesic(evd[k, 0:9].reshape(3, 3), ref[k]["matrix_fisher"]["R_mf"]) < 1e-8
+                assert rel_err(evd[k, 71:74], ref[k]["planar_translation"]["t_wls"]) < 1e-7
+                assert rel_err(evd[k, 123:123 + 484].reshape(22, 22), ref[k]["L_lidar"]) < 1e-7
+        for name in ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT"):
+            assert rel_err(H(getattr(ms, name)), ref_map[name]) < 1e-9, name
+        iwh = H(iw)
+        assert abs(iwh[0] / ref_iw["nu"] - 1) < 1e-12
+        assert rel_err(iwh[1:].reshape(3, 3), ref_iw["Psi"]) < 1e-6
