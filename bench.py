@@ -95,42 +95,17 @@ def make_stream(n_scans, seed0=1234 + 2):
     return scans, np.stack(poses)
 
 
-def oracle_scan(O, sc, cap, bins, tau, ms, pose):
-    return O.lidar_scan_evidence(sc.points, sc.timestamps, sc.weights, sc.ring, sc.tag, n_points_cap=cap,
-                                 scan_start_time=sc.scan_start_time, scan_end_time=sc.scan_end_time, xi_body=sc.xi_body,
-                                 lidar_origin=sc.lidar_origin, bin_directions=bins, tau=tau, map_stats=ms, pose_pred=pose,
-                                 materialize=True)
-
-
-def oracle_map_update(O, ms, mm, pose, gamma=0.99):
-    """Same rule as gcl_map_update: forget, then add the scan sums pushed by (R, t) with t_z = 0."""
-    R = O.so3_exp(pose[3:6]); t = np.array([pose[0], pose[1], 0.0])
-    raw = mm["raw"]; N = raw["N"]
-    Rp = np.einsum("ij,bj->bi", R, raw["sum_p"])
-    out = {k: gamma * v for k, v in ms.items()}
-    out["S_dir"] += np.einsum("ij,bj->bi", R, raw["s_dir"])
-    out["S_dir_scatter"] += np.einsum("ij,bjk,lk->bil", R, raw["S_dir_scatter"], R)
-    out["N_dir"] += N; out["N_pos"] += N
-    out["sum_p"] += Rp + N[:, None] * t[None]
-    out["sum_ppT"] += (np.einsum("ij,bjk,lk->bil", R, raw["sum_ppT"], R) + Rp[:, :, None] * t[None, None, :]
-                       + t[None, :, None] * Rp[:, None, :] + N[:, None, None] * np.outer(t, t)[None])
-    return out
-
-
 def cpu_stream_rate(n_sample, tau):
-    """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the stream workload."""
+    """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the SAME stream workload:
+    resample, deskew, soft assign, moment match, Matrix Fisher, planar translation, IW update, map update per scan."""
     from oracle import gc_oracle as O
     scans, poses = make_stream(n_sample)
     bins = O.create_fibonacci_atlas(N_BINS)
-    ms = {"S_dir": np.zeros((N_BINS, 3)), "S_dir_scatter": np.zeros((N_BINS, 3, 3)), "N_dir": np.zeros(N_BINS),
-          "N_pos": np.zeros(N_BINS), "sum_p": np.zeros((N_BINS, 3)), "sum_ppT": np.zeros((N_BINS, 3, 3))}
     t0 = time.perf_counter()
-    pts = 0
-    for sc, pose in zip(scans, poses):
-        out = oracle_scan(O, sc, CAP, bins, tau, ms, pose)
-        ms = oracle_map_update(O, ms, out["scan_bins"], pose)
-        pts += sc.points.shape[0]
+    O.scan_stream(scans, poses, poses, n_points_cap=CAP, bin_directions=bins, tau=tau, lidar_origin=scans[0].lidar_origin,
+                  iw_state=O.iw_lidar_init(1e-3), use_sigma_meas=True)
     dt = time.perf_counter() - t0
+    pts = sum(s.points.shape[0] for s in scans)
     return pts / dt, n_sample / dt, dt
 
 
@@ -211,32 +186,31 @@ def main():
                                  lidar_origin=scans[0].lidar_origin)
     res = [pl.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
     poses_dev = torch.from_numpy(poses).to(dev)
-    from oracle import gc_oracle as O  # only for so3_exp of the synthetic trajectory (host set-up, not timed)
-    R_dev = torch.from_numpy(np.stack([O.so3_exp(p[3:6]) for p in poses])).to(dev).contiguous()
-    t_dev = torch.from_numpy(poses[:, :3].copy()).to(dev)
+    xis = np.stack([s.xi_body for s in scans])
+    jobs_dev = pl.jobs_to_device([pl.make_job(res[k], xis[k]) for k in range(N_SCANS)])
     ms = g.create_empty_map_stats(N_BINS)
+    iw = pl.create_lidar_iw_state(1e-3)        # Kimera value of GC_LIDAR_SIGMA_MEAS (config/gc_unified.yaml:16)
     total_points = sum(s.points.shape[0] for s in scans)
     bpp = res[0].bytes_per_point
-    # algorithmic bytes of one scan_moments launch: 5 scalars per SELECTED row + every raw weight (stride > 1)
+    # algorithmic bytes of scan_moments: 5 scalars per SELECTED row + every raw weight when stride > 1
     def _alg_bytes(n):
         stride, n_sel = pl.selected_rows(n, CAP)
         return n_sel * bpp + (n * (bpp // 5) if stride > 1 else 0)
-    bytes_per_launch = float(np.mean([_alg_bytes(s.points.shape[0]) for s in scans]))
+    bytes_per_launch = float(sum(_alg_bytes(s.points.shape[0]) for s in scans))
+    max_sel = max(pl.selected_rows(s.points.shape[0], CAP)[1] for s in scans)
+    ctas = pl.plan_ctas(N_SCANS, max_sel)
 
     def stream_pass():
-        for k in range(N_SCANS):
-            ev = pl.run_resident(res[k], scans[k].xi_body[None], poses_dev[k:k + 1], ms)
-            g.map_update_inplace(ms, ev.stats[0], R_dev[k], t_dev[k], 0.99)
+        # scan_moments + reduce_finalize for all 200 scans (independent of the map), then ONE chain launch that walks the
+        # scans in order carrying map statistics (forgetting 0.99) and the LiDAR measurement-noise IW state on the device
+        pl.run_stream(res, xis, poses_dev, poses_dev, ms, iw_state=iw, use_sigma_meas=True, jobs_dev=jobs_dev, ctas=ctas)
 
     launches0 = g._abi.launch_count(local_rank)
-    stream_pass()                                   # eager warm-up (allocates work buffers, sets kernel attributes)
+    stream_pass()                                   # warm-up (allocates work buffers, sets kernel attributes)
     torch.cuda.synchronize()
     launches_per_step = g._abi.launch_count(local_rank) - launches0
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        stream_pass()
     for _ in range(args.warmup):
-        graph.replay()
+        stream_pass()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -246,7 +220,7 @@ def main():
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(args.steps):
-        graph.replay()
+        stream_pass()
     ev1.record()
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
@@ -258,26 +232,30 @@ def main():
     value = world * total_points / (ms_per_step * 1e-3)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (scan_moments alone)
+    b = pl._buffers(N_SCANS, ctas)
     def moments_only():
-        for k in range(N_SCANS):
-            job = pl.make_job(res[k], scans[k].xi_body)
-            b = pl._buffers(1, pl.plan_ctas(1, CAP))
-            pl.launch_moments(None, job, 1, pl.plan_ctas(1, CAP), res[k].layout, b["partials"])
-    moments_only(); torch.cuda.synchronize()
-    gk = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gk):
-        moments_only()
-    gk.replay(); torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        gk.replay()
-    ev1.record(); torch.cuda.synchronize()
-    k1_us = 1e3 * ev0.elapsed_time(ev1) / (args.steps * N_SCANS)
-    achieved = bytes_per_launch / (k1_us * 1e-6) / 1e9
+        pl.launch_moments(jobs_dev, None, N_SCANS, ctas, res[0].layout, b["partials"])
+    def rest_only():
+        pl.launch_finalize(b["partials"], ctas, pl.rec, pl.rec * ctas, jobs_dev, None, N_SCANS, True, b["reduced"], b["stats"])
+        pl.launch_chain(b["stats"], N_SCANS, 1, ms, b["map_derived"], poses_dev, poses_dev, b["evidence"], iw, True, 0.99)
+    def _time(fn):
+        fn(); torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            fn()
+        ev1.record(); torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / args.steps
+    k1_ms = _time(moments_only)
+    rest_ms = _time(rest_only)
+    achieved = bytes_per_launch / (k1_ms * 1e-3) / 1e9
+    pairs = float(sum(pl.selected_rows(s.points.shape[0], CAP)[1] for s in scans)) * N_BINS
     roofline = {"bound": "hbm", "kernel": "scan_moments_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src, "us_per_launch": k1_us,
-                "algorithmic_bytes_per_launch": float(bytes_per_launch),
-                "note": "latency-bound at this size (7500 rows x 48 bins per launch); see extra.cfg4 and DESIGN.md"}
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src, "ms_per_launch": k1_ms,
+                "launches_per_step": 1, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "share_of_step": k1_ms / ms_per_step, "rest_of_step_ms": rest_ms,
+                "pairs_per_sec": pairs / (k1_ms * 1e-3),
+                "note": "one launch covers all 200 scans (7500 rows x 48 bins each); the kernel is bound by FP64 FMA/exp issue, "
+                        "not by HBM (DESIGN.md); the sequential chain launch dominates the step"}
     clocks = sampler.stop()
 
     # ---------------------------------------------------------------- e2e: the reference-facing host call, pinned buffers
@@ -285,21 +263,15 @@ def main():
     pinned = []
     for s in scans[:n_e2e]:
         p, t_, w_ = (torch.from_numpy(a).pin_memory() for a in (s.points, s.timestamps, s.weights))
-        pinned.append((p, t_, w_))
-    ms_host = {k: np.zeros(v) for k, v in (("S_dir", (N_BINS, 3)), ("S_dir_scatter", (N_BINS, 3, 3)), ("N_dir", (N_BINS,)),
-                                                ("N_pos", (N_BINS,)), ("sum_p", (N_BINS, 3)), ("sum_ppT", (N_BINS, 3, 3)))}
+        pinned.append((p.numpy(), t_.numpy(), w_.numpy(), p, t_, w_))
 
     def e2e_pass():
-        m = ms_host
+        m = {k: np.zeros(v) for k, v in (("S_dir", (N_BINS, 3)), ("S_dir_scatter", (N_BINS, 3, 3)), ("N_dir", (N_BINS,)),
+                                         ("N_pos", (N_BINS,)), ("sum_p", (N_BINS, 3)), ("sum_ppT", (N_BINS, 3, 3)))}
+        iw_h = np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
         for k in range(n_e2e):
-            p, t_, w_ = pinned[k]
-            out = pl.process_scan_host(p.numpy(), t_.numpy(), w_.numpy(), scans[k].scan_start_time, scans[k].scan_end_time,
-                                       scans[k].xi_body[None], poses[k][None], m)
-            sb = out.stats_host[0]
-            raw = {"N": sb[:N_BINS], "s_dir": sb[N_BINS:4 * N_BINS].reshape(N_BINS, 3),
-                   "S_dir_scatter": sb[4 * N_BINS:13 * N_BINS].reshape(N_BINS, 3, 3),
-                   "sum_p": sb[26 * N_BINS:29 * N_BINS].reshape(N_BINS, 3), "sum_ppT": sb[29 * N_BINS:38 * N_BINS].reshape(N_BINS, 3, 3)}
-            m = oracle_map_update(O, m, {"raw": raw}, poses[k])   # O(B) host bookkeeping between calls
+            pl.process_scan_host(pinned[k][0], pinned[k][1], pinned[k][2], scans[k].scan_start_time, scans[k].scan_end_time,
+                                 xis[k][None], poses[k][None], m, pose_update=poses[k], iw_state_host=iw_h, use_sigma_meas=True)
         return m
     e2e_pass()
     if world > 1:
@@ -315,11 +287,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_points = sum(s.points.shape[0] for s in scans[:n_e2e])
-    rec_bytes = (38 * N_BINS + 24 + 640) * 8
+    rec_bytes = (38 * N_BINS + 24 + 640 + 26 * N_BINS + 10) * 8
     e2e = {"value": world * n_rep * e2e_points / e2e_s, "unit": "points/s",
-           "h2d_bytes_per_step": int(e2e_points * 40 + n_e2e * (N_BINS * 26 * 8 + N_BINS * 24 + 48 + 128)),
+           "h2d_bytes_per_step": int(e2e_points * 40 + n_e2e * (N_BINS * 26 * 8 + N_BINS * 24 + 48 + 48 + 80 + 120)),
            "d2h_bytes_per_step": int(n_e2e * rec_bytes), "scans_per_sec": world * n_rep * n_e2e / e2e_s,
-           "note": f"{n_e2e} scans per pass through gcl_lidar_scan_evidence_host (pinned host arrays; H2D + 4 kernels + D2H + sync per scan)"}
+           "us_per_scan": 1e6 * e2e_s / (n_rep * n_e2e),
+           "note": f"{n_e2e} scans per pass, one gcl_lidar_scan_evidence_host call per scan (pinned host arrays; H2D of the scan + "
+                   "map, 3 kernels incl. IW + map update, D2H of stats/evidence/map, sync)"}
 
     # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
     extra = {}
@@ -346,7 +320,8 @@ def main():
                                        f"7500 rows), {N_BINS} bins, 1 hypothesis, map statistics carried (forgetting 0.99)",
                            "tau": tau, "precision": args.precision, "layout": "ref_f64 (40 B/point)" if args.precision == "fp64" else "packed_f32 (20 B/point)",
                            "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (stream does not shard)",
-                           "l2": "inputs total 240 MB > 126 MB L2; each scan is read once per step"},
+                           "l2": "inputs total 240 MB > 126 MB L2; each scan is read once per step",
+                           "launches_per_step": int(launches_per_step), "iw": "LiDAR measurement-noise IW block adapted every scan (Sigma_meas into bin covariances)"},
                 "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "extra": extra}
         print(json.dumps(line))

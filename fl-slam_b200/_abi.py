@@ -74,7 +74,7 @@ def _load():
                                  f64, f64, vp]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
         "gcl_lidar_scan_evidence_host": (i32, [vp, vp, vp, vp, i64, C.c_int32, f64, f64, vp, vp, i32, vp, vp, i32, f64, i32,
-                                               vp, vp, vp, vp, vp, vp, f64, f64, vp, vp]),
+                                               vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = the .so does not export what the header declares

@@ -81,14 +81,18 @@ size_t gcl_stats_record_doubles(int n_bins) { return (size_t)StatsLayout(n_bins)
 
 int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_bins, int precision) {
   (void)n_bins; (void)precision;
-  const int sms = h ? h->sm_count : 148;
+  const int64_t sms = h ? h->sm_count : 148;
   if (n_jobs < 1) n_jobs = 1;
-  // enough CTAs to cover the SMs once, never less than one tile (256 rows) of work per CTA
+  if (max_sel_rows < 1) max_sel_rows = 1;
+  // at least one 256-row tile of work per CTA; when that would leave SMs idle (one small scan: the latency case),
+  // go down to 64 rows per CTA so that phase B of every CTA is short
   int64_t by_rows = (max_sel_rows + 255) / 256;
-  if (by_rows < 1) by_rows = 1;
-  int64_t want = (sms + n_jobs - 1) / n_jobs;
+  if ((int64_t)n_jobs * by_rows < sms) by_rows = (max_sel_rows + 63) / 64;
+  // one job: one CTA per SM (equal slices, no tail).  several jobs: about four waves of CTAs in total
+  int64_t want = (n_jobs == 1) ? sms : (4 * sms + n_jobs - 1) / n_jobs;
   if (want < 1) want = 1;
   int64_t c = want < by_rows ? want : by_rows;
+  if (c > 65535) c = 65535;
   return (int)c;
 }
 
@@ -393,10 +397,10 @@ static bool is_pinned(const void* p) {
 int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
                                  const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1,
                                  const double* xi_host, const double* pose_host, int n_hyp, const double* origin_host,
-                                 const double* bins_host, int n_bins, double tau, int precision, const double* mS_dir,
-                                 const double* mS_sc, const double* mN_dir, const double* mN_pos, const double* msum_p,
-                                 const double* msum_ppT, double eps_psd, double eps_mass, double* stats_host,
-                                 double* evidence_host) {
+                                 const double* bins_host, int n_bins, double tau, int precision, double* mS_dir, double* mS_sc,
+                                 double* mN_dir, double* mN_pos, double* msum_p, double* msum_ppT, const double* pose_update_host,
+                                 double forgetting, double* iw_state_host, int use_sigma_meas, double eps_psd, double eps_mass,
+                                 double* stats_host, double* evidence_host) {
   if (!h) return GCL_ERR_ARG;
   GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
   GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
@@ -404,6 +408,8 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   GCL_REQUIRE(h, xi_host && pose_host && origin_host && bins_host && stats_host && evidence_host, "NULL pointer");
   GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
   GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
+  GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
   cudaSetDevice(h->device);
   const size_t B = n_bins, H = n_hyp, n = (size_t)n_raw;
   int64_t stride = (n_raw + cap - 1) / cap; if (stride < 1) stride = 1;
@@ -413,12 +419,13 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   // one pinned staging block (inputs) and one device block, carved identically
   const size_t o_pts = 0, o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), o_bins = al(o_w + n * 8);
   const size_t o_map = al(o_bins + B * 24);                    // S_dir 3B, S_sc 9B, N_dir B, N_pos B, sum_p 3B, sum_ppT 9B
-  const size_t o_pose = al(o_map + B * 26 * 8), o_jobs = al(o_pose + H * 48), in_end = al(o_jobs + H * sizeof(gcl_job));
+  const size_t o_pose = al(o_map + B * 26 * 8), o_pupd = al(o_pose + H * 48), o_iw = al(o_pupd + 48);
+  const size_t o_jobs = al(o_iw + 80), in_end = al(o_jobs + H * sizeof(gcl_job));
   const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
   const size_t o_evid = al(o_stats + H * srec * 8), o_mder = al(o_evid + H * GCL_EVID_DOUBLES * 8);
   const size_t d_end = al(o_mder + B * 16 * 8);
-  const size_t out_bytes = H * srec * 8 + H * GCL_EVID_DOUBLES * 8;
-  int rc = ensure_buffers(h, d_end, in_end + al(out_bytes));
+  const size_t out_bytes = al(H * srec * 8) + al(H * GCL_EVID_DOUBLES * 8) + al(B * 26 * 8) + 256;
+  int rc = ensure_buffers(h, d_end, in_end + out_bytes);
   if (rc != GCL_OK) return rc;
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
   unsigned char* db = static_cast<unsigned char*>(h->d_buf);
@@ -436,6 +443,8 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
   memcpy(hm + 13 * B, mN_pos, B * 8); memcpy(hm + 14 * B, msum_p, B * 24); memcpy(hm + 17 * B, msum_ppT, B * 72);
   memcpy(hb + o_pose, pose_host, H * 48);
+  if (pose_update_host) memcpy(hb + o_pupd, pose_update_host, 48);
+  if (iw_state_host) memcpy(hb + o_iw, iw_state_host, 80);
   gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
   for (int i = 0; i < n_hyp; ++i) {
     gcl_job& j = hj[i];
@@ -454,31 +463,41 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
     GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, st));
   }
   const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
-  const double* dm = reinterpret_cast<const double*>(db + o_map);
+  double* dm = reinterpret_cast<double*>(db + o_map);
   const gcl_job* d_jobs = reinterpret_cast<const gcl_job*>(db + o_jobs);
   double* d_parts = reinterpret_cast<double*>(db + o_parts);
   double* d_red = reinterpret_cast<double*>(db + o_red);
   double* d_stats = reinterpret_cast<double*>(db + o_stats);
   double* d_evid = reinterpret_cast<double*>(db + o_evid);
   double* d_mder = reinterpret_cast<double*>(db + o_mder);
+  double* d_iw = iw_state_host ? reinterpret_cast<double*>(db + o_iw) : nullptr;
   rc = gcl_scan_moments(h, st, d_jobs, nullptr, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host,
                         eps_mass, d_parts);
   if (rc != GCL_OK) return rc;
   rc = gcl_reduce_finalize(h, st, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
                            origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
   if (rc != GCL_OK) return rc;
-  rc = gcl_map_derived_stats(h, st, dm, dm + 12 * B, dm + 13 * B, dm + 14 * B, dm + 17 * B, n_bins, eps_mass, eps_psd, d_mder);
+  rc = gcl_scan_chain(h, st, d_stats, (int64_t)srec, 1, n_hyp, n_bins, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, dm + 14 * B,
+                      dm + 17 * B, d_mder, reinterpret_cast<const double*>(db + o_pose),
+                      pose_update_host ? reinterpret_cast<const double*>(db + o_pupd) : nullptr, forgetting, d_iw, use_sigma_meas,
+                      0.99 /* GC_IW_RHO_MEAS_LIDAR, constants.py:281 */, 0.5 /* GC_IW_NU_WEAK_ADD, :164 */, 1000.0, eps_psd,
+                      eps_mass, d_evid);
   if (rc != GCL_OK) return rc;
-  rc = gcl_pose_evidence(h, st, d_stats, (int64_t)srec, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, d_mder,
-                         reinterpret_cast<const double*>(db + o_pose), nullptr, n_hyp, n_bins, eps_psd, eps_mass, 1, 1, d_evid);
-  if (rc != GCL_OK) return rc;
-  // stats and evidence are adjacent on the device only up to alignment: two copies into the pinned out block
   unsigned char* hout = hb + in_end;
+  const size_t oo_ev = al(H * srec * 8), oo_map = oo_ev + al(H * GCL_EVID_DOUBLES * 8), oo_iw = oo_map + al(B * 26 * 8);
   GCL_CUDA(h, cudaMemcpyAsync(hout, d_stats, H * srec * 8, cudaMemcpyDeviceToHost, st));
-  GCL_CUDA(h, cudaMemcpyAsync(hout + H * srec * 8, d_evid, H * GCL_EVID_DOUBLES * 8, cudaMemcpyDeviceToHost, st));
+  GCL_CUDA(h, cudaMemcpyAsync(hout + oo_ev, d_evid, H * GCL_EVID_DOUBLES * 8, cudaMemcpyDeviceToHost, st));
+  if (pose_update_host) GCL_CUDA(h, cudaMemcpyAsync(hout + oo_map, dm, B * 26 * 8, cudaMemcpyDeviceToHost, st));
+  if (iw_state_host) GCL_CUDA(h, cudaMemcpyAsync(hout + oo_iw, d_iw, 80, cudaMemcpyDeviceToHost, st));
   GCL_CUDA(h, cudaStreamSynchronize(st));
   memcpy(stats_host, hout, H * srec * 8);
-  memcpy(evidence_host, hout + H * srec * 8, H * GCL_EVID_DOUBLES * 8);
+  memcpy(evidence_host, hout + oo_ev, H * GCL_EVID_DOUBLES * 8);
+  if (pose_update_host) {
+    const double* om = reinterpret_cast<const double*>(hout + oo_map);
+    memcpy(mS_dir, om, B * 24); memcpy(mS_sc, om + 3 * B, B * 72); memcpy(mN_dir, om + 12 * B, B * 8);
+    memcpy(mN_pos, om + 13 * B, B * 8); memcpy(msum_p, om + 14 * B, B * 24); memcpy(msum_ppT, om + 17 * B, B * 72);
+  }
+  if (iw_state_host) memcpy(iw_state_host, hout + oo_iw, 80);
   return GCL_OK;
 }
 

@@ -26,10 +26,10 @@ __device__ __forceinline__ void map_derived_bin(const double* S_dir, const doubl
   kap[b] = kappa_from_resultant(n * invNd, 1e-6, 3.0, 0.8, 0.03);
   const double invNp = 1.0 / (N_pos[b] + eps_mass + kF64Eps);
   const double c[3] = {sum_p[b * 3] * invNp, sum_p[b * 3 + 1] * invNp, sum_p[b * 3 + 2] * invNp};
-  double Sraw[9], Spsd[9], pc[6];
+  double Sraw[9], Spsd[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) Sraw[i * 3 + j] = sum_ppT[b * 9 + i * 3 + j] * invNp - c[i] * c[j];
-  psd_project3(Sraw, eps_psd, Spsd, pc);
+  psd_project3_fast(Sraw, eps_psd, Spsd);
   for (int i = 0; i < 3; ++i) cen[b * 3 + i] = c[i];
   for (int i = 0; i < 9; ++i) Sig[b * 9 + i] = Spsd[i];
 }
@@ -149,7 +149,7 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
       mat3_mul_tn(Rp, Rmf, Rerr);
       so3_log(Rerr, delta);
       double Lpsd[9], pc[6];
-      psd_project3(Lraw, eps_psd, Lpsd, pc);
+      pc[0] = psd_project3_fast(Lraw, eps_psd, Lpsd);
       double h[3];
       for (int i = 0; i < 3; ++i) h[i] = Lpsd[i * 3] * delta[0] + Lpsd[i * 3 + 1] * delta[1] + Lpsd[i * 3 + 2] * delta[2];
       const double nll = 0.5 * (delta[0] * h[0] + delta[1] * h[1] + delta[2] * h[2]);
@@ -314,23 +314,23 @@ __device__ __forceinline__ double softplus64(double x) { return (x > 0.0 ? x : 0
 
 // IW mode Sigma = PSD(Psi / (nu + p + 1)), p = 3   (measurement_noise_iw_jax.py:37-57)
 __device__ inline void iw_sigma_mode(const double* iw /* [nu, Psi(9)] */, double eps_psd, double* Sigma) {
-  double S[9], pc[6];
+  double S[9];
   const double den = iw[0] + 3.0 + 1.0;
   for (int i = 0; i < 9; ++i) S[i] = iw[1 + i] / den;
-  psd_project3(S, eps_psd, Sigma, pc);
+  psd_project3_fast(S, eps_psd, Sigma);
 }
 
 // suffstats from residuals (:104-127) then the forgetful update with the smooth nu projection (:60-100)
 __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T (9), sum w] */, double rho, double nu_weak_add,
                                  double nu_max, double eps_mass, double eps_psd) {
-  double rrT[9], dPsi[9], pc[6];
+  double rrT[9], dPsi[9];
   const double wsum = rr_w[9] + eps_mass;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) rrT[i * 3 + j] = 0.5 * (rr_w[i * 3 + j] + rr_w[j * 3 + i]) / wsum;
-  psd_project3(rrT, eps_psd, dPsi, pc);
+  psd_project3_fast(rrT, eps_psd, dPsi);
   double Praw[9], Ppsd[9];
   for (int i = 0; i < 9; ++i) Praw[i] = rho * iw[1 + i] + dPsi[i];
-  psd_project3(Praw, eps_psd, Ppsd, pc);  // symmetrises first
+  psd_project3_fast(Praw, eps_psd, Ppsd);  // symmetrises first
   const double nu_raw = rho * iw[0] + 1.0;
   const double nu_min = 3.0 + 1.0 + nu_weak_add;
   const double nu_floor = nu_min + softplus64(nu_raw - nu_min);
@@ -362,10 +362,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
         const double invN = 1.0 / (N + P.eps_mass + kF64Eps);
         const double* pb = st + SL.p_bar() + b * 3;
         const double* spp = st + SL.sum_ppT() + b * 9;
-        double Sraw[9], Spsd[9], pc[6];
+        double Sraw[9], Spsd[9];
         for (int i = 0; i < 3; ++i)
           for (int j = 0; j < 3; ++j) Sraw[i * 3 + j] = spp[i * 3 + j] * invN - pb[i] * pb[j] + s_sigma[i * 3 + j] * (N * invN);
-        psd_project3(Sraw, P.eps_psd, Spsd, pc);
+        psd_project3_fast(Sraw, P.eps_psd, Spsd);
         for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Spsd[i];
       }
     }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __gr
         Sraw[i * 3 + j] = v;
       }
     double Spsd[9], pc[6];
-    psd_project3(Sraw, P.eps_psd, Spsd, pc);
+    pc[0] = psd_project3_fast(Sraw, P.eps_psd, Spsd);
     const double sn = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
     const double kap = kappa_from_resultant(sn * invN, 1e-6, 3.0, 0.8, 0.03);  // GC_EPS_R, blend r0/tau: constants.py:73,:95-96
     st[SL.N() + b] = N;

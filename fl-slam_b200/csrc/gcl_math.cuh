@@ -88,9 +88,10 @@ __host__ __device__ inline void sym_eig3(const double* Ain, double* val, double*
   double v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 #define GCL_JROT(app, aqq, apq, arp, arq, P, Q)                                        \
   if (apq != 0.0) {                                                                     \
-    const double theta = (aqq - app) / (2.0 * apq);                                    \
-    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
-    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;                            \
+    /* t = tan(phi) of the annihilating rotation: t = 2b sgn(d) / (|d| + sqrt(d^2 + 4b^2)), d = aqq - app */ \
+    const double dd = aqq - app, b2 = 2.0 * apq;                                        \
+    const double t = (dd >= 0.0 ? b2 : -b2) / (fabs(dd) + sqrt(dd * dd + b2 * b2));     \
+    const double cs = rsqrt(t * t + 1.0), sn = t * cs;                                  \
     app -= t * apq;                                                                     \
     aqq += t * apq;                                                                     \
     apq = 0.0;                                                                          \
@@ -149,6 +150,25 @@ __host__ __device__ inline void psd_project3(const double* M, double eps_psd, do
   cert[3] = emax;
   cert[4] = emax / emin;
   cert[5] = (double)((vc[0] < 10.0 * eps_psd) + (vc[1] < 10.0 * eps_psd) + (vc[2] < 10.0 * eps_psd));
+}
+
+// PSD projection with a shortcut: when the symmetrised matrix is positive definite with every eigenvalue provably above
+// eps_psd (Sylvester minors > 0 and lambda_min >= 4 det / tr^2 > 2 eps_psd), flooring changes nothing and
+// V diag(lambda) V^T == M_sym up to round-off, so the eigen decomposition is skipped.  Returns the projection delta
+// (0 on the shortcut).  Used where only M_psd and the delta are consumed.
+__host__ __device__ inline double psd_project3_fast(const double* M, double eps_psd, double* Mpsd) {
+  const double a = M[0], d = M[4], f = M[8];
+  const double b = 0.5 * (M[1] + M[3]), c = 0.5 * (M[2] + M[6]), e = 0.5 * (M[5] + M[7]);
+  const double m2 = a * d - b * b;
+  const double det = a * (d * f - e * e) - b * (b * f - e * c) + c * (b * e - d * c);
+  const double tr = a + d + f;
+  if (a > 0.0 && m2 > 0.0 && det > 0.0 && 4.0 * det > 2.0 * eps_psd * tr * tr) {
+    Mpsd[0] = a; Mpsd[1] = b; Mpsd[2] = c; Mpsd[3] = b; Mpsd[4] = d; Mpsd[5] = e; Mpsd[6] = c; Mpsd[7] = e; Mpsd[8] = f;
+    return 0.0;
+  }
+  double pc[6];
+  psd_project3(M, eps_psd, Mpsd, pc);
+  return pc[0];
 }
 
 // ---- 3x3 SVD: one-sided (Hestenes) Jacobi ------------------------------------------------------------------

@@ -2,8 +2,8 @@
 BinSoftAssign -> ScanBinMomentMatch (+Kappa) -> MatrixFisherRotation -> PlanarTranslationEvidence -> 22-D evidence
 (README.md:105-120 of the reference; call sites pkg/backend/pipeline.py:400,569,587-593).
 
-Four launches per scan (batch): scan_moments (the only O(N) kernel), reduce_finalize, map_derived_stats,
-pose_evidence.  Nothing synchronises with the host until the caller asks for certificates.  Everything runs in
+Three launches per scan (or per whole scan stream): scan_moments (the only O(N) kernel), reduce_finalize, and the
+chain step (map-derived statistics, pose evidence, measurement-noise IW update, map update).  Nothing synchronises with the host until the caller asks for certificates.  Everything runs in
 libgcl_b200.so; without it this module cannot be imported.
 """
 from __future__ import annotations
@@ -305,8 +305,12 @@ class LidarEvidencePipeline:
     # ---- the reference-facing call: host arrays in, certificates out ------------------------------------------------------
     def process_scan_host(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body, pose_pred,
                           map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0, chart_id: str = constants.GC_CHART_ID,
-                          anchor_id: str = "initial") -> LidarScanEvidence:
-        """One call of gcl_lidar_scan_evidence_host: H2D of the scan, the four kernels, D2H of stats + evidence."""
+                          anchor_id: str = "initial", pose_update=None, forgetting: float = 0.99,
+                          iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> LidarScanEvidence:
+        """One call of gcl_lidar_scan_evidence_host: H2D of the scan, three kernels, D2H of stats + evidence.
+
+        With ``pose_update`` (6,) the six arrays of ``map_stats_host`` (float64, C-contiguous) are updated IN PLACE
+        (forgetting + this scan's bin sums in the world frame); ``iw_state_host`` (10,) likewise."""
         f = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
         pts, ts, w = f(points, (-1, 3)), f(timestamps, (-1,)), f(weights, (-1,))
         n = pts.shape[0]
@@ -317,19 +321,30 @@ class LidarEvidencePipeline:
         if poses.shape[0] != H:
             raise ValueError("xi_body and pose_pred must have one row per hypothesis")
         B = self.n_bins
-        m = {k: f(map_stats_host[k], s) for k, s in (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)),
-                                                    ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))}
+        shapes = (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))
+        if pose_update is not None:
+            for k, sh in shapes:   # in/out: the caller's arrays are written, so they must be usable as they are
+                a = map_stats_host[k]
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == sh):
+                    raise ValueError(f"map_stats_host[{k!r}] must be a C-contiguous float64 array of shape {sh} for an in-place update")
+            m = map_stats_host
+        else:
+            m = {k: f(map_stats_host[k], sh) for k, sh in shapes}
         bins_host = getattr(self, "_bins_host", None)
         if bins_host is None:
             bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
         stats = np.empty((H, self.srec), dtype=np.float64)
         evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
-        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        pu = None if pose_update is None else f(pose_update, (6,))
+        if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
+                                              and iw_state_host.shape == (10,) and iw_state_host.flags.c_contiguous):
+            raise ValueError("iw_state_host must be a C-contiguous float64 array of shape (10,)")
         _abi.check(_lib.gcl_lidar_scan_evidence_host(
             self.handle, p(pts), p(ts), p(w), n, self.n_points_cap, float(scan_start_time), float(scan_end_time), p(xi), p(poses),
             H, p(self.origin), p(bins_host), B, self.tau, PRECISIONS[self.precision], p(m["S_dir"]), p(m["S_dir_scatter"]),
-            p(m["N_dir"]), p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), self.eps_psd, self.eps_mass, p(stats), p(evid)),
-            self.handle)
+            p(m["N_dir"]), p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting), p(iw_state_host),
+            1 if use_sigma_meas else 0, self.eps_psd, self.eps_mass, p(stats), p(evid)), self.handle)
         return LidarScanEvidence(n_bins=B, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
                                  stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
                                  n_points_cap=self.n_points_cap, ess_imu=ess_imu)

@@ -238,19 +238,26 @@ int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const 
                         float* packed_w);
 
 /* ---- reference-facing call with HOST buffers ------------------------------------------------------------- */
-/* The whole chain for one scan and n_hyp hypotheses: H2D of the scan, fused moments, finalize, pose evidence, D2H
- * of the stats and evidence records; synchronises.  This is the entry a maintainer binds in place of the operator
- * sequence at pkg/backend/pipeline.py:400-593 + README.md:110-115.  map_*_host are the six MapBinStats arrays
- * (archive/bin_atlas.py:83-101); xi_body_host and pose_pred_host are (n_hyp,6). */
+/* The whole chain for one scan and n_hyp hypotheses: H2D of the scan, fused moments, finalize, the chain step (map
+ * derived statistics, pose evidence, optional IW + map update), D2H of the stats and evidence records; synchronises.
+ * This is the entry a maintainer binds in place of the operator sequence at pkg/backend/pipeline.py:400-593 +
+ * README.md:110-115 (and, with pose_update_host, the per-scan map / noise bookkeeping of
+ * pkg/backend/backend_node.py:2106-2119).  map_*_host are the six MapBinStats arrays (archive/bin_atlas.py:83-101);
+ * xi_body_host and pose_pred_host are (n_hyp,6).  Scan arrays that live in page-locked memory are copied directly.
+ *   pose_update_host  (6,) or NULL: if given, the map arrays are updated IN PLACE (forgetting, then this scan's bin sums
+ *                     pushed to the world frame) and written back to the caller's host arrays.
+ *   iw_state_host     (10,) [nu, Psi(3x3)] or NULL: LiDAR measurement-noise IW block, updated in place.
+ *   use_sigma_meas    add the IW mode to every bin covariance before the translation evidence. */
 int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
                                  const double* weights_host, int64_t n_raw, int32_t n_points_cap,
                                  double scan_start_time, double scan_end_time, const double* xi_body_host,
                                  const double* pose_pred_host, int n_hyp, const double* lidar_origin_host,
                                  const double* bin_dirs_host, int n_bins, double tau, int precision,
-                                 const double* map_S_dir_host, const double* map_S_dir_scatter_host,
-                                 const double* map_N_dir_host, const double* map_N_pos_host,
-                                 const double* map_sum_p_host, const double* map_sum_ppT_host, double eps_psd,
-                                 double eps_mass, double* stats_host /* n_hyp stats records */,
+                                 double* map_S_dir_host, double* map_S_dir_scatter_host, double* map_N_dir_host,
+                                 double* map_N_pos_host, double* map_sum_p_host, double* map_sum_ppT_host,
+                                 const double* pose_update_host, double forgetting, double* iw_state_host,
+                                 int use_sigma_meas, double eps_psd, double eps_mass,
+                                 double* stats_host /* n_hyp stats records */,
                                  double* evidence_host /* n_hyp evidence records */);
 
 #ifdef __cplusplus
