@@ -333,6 +333,10 @@ int gcl_map_update(gcl_handle h, void* stream, const double* stats, const double
   return GCL_OK;
 }
 
+size_t gcl_scan_chain_workspace_doubles(int n_scans, int n_hyp, int n_bins) {
+  return chain_workspace_doubles(n_scans < 1 ? 1 : n_scans, n_hyp < 1 ? 1 : n_hyp, n_bins < 1 ? 1 : n_bins);
+}
+
 int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stride, int n_scans, int n_hyp, int n_bins,
                    double* mS_dir, double* mS_sc, double* mN_dir, double* mN_pos, double* msum_p, double* msum_ppT,
                    double* map_derived, const double* pose_pred, const double* pose_update, double forgetting, double* iw_state,
@@ -347,13 +351,14 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
   ChainParams P;
   P.stats = stats; P.stats_stride = stats_stride;
   P.map_S_dir = mS_dir; P.map_S_dir_scatter = mS_sc; P.map_N_dir = mN_dir; P.map_N_pos = mN_pos; P.map_sum_p = msum_p;
-  P.map_sum_ppT = msum_ppT; P.map_derived = map_derived; P.pose_pred = pose_pred; P.pose_update = pose_update;
+  P.map_sum_ppT = msum_ppT; P.workspace = map_derived; P.pose_pred = pose_pred; P.pose_update = pose_update;
   P.iw_state = iw_state; P.evidence = evidence; P.n_scans = n_scans; P.n_hyp = n_hyp; P.n_bins = n_bins;
   P.use_sigma_meas = use_sigma_meas; P.forgetting = forgetting; P.iw_rho = iw_rho; P.iw_nu_weak_add = iw_nu_weak_add;
   P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass;
   cudaSetDevice(h->device);
-  GCL_CUDA(h, launch_chain(P, (cudaStream_t)stream));
-  h->launches += 1;
+  int l = 0;
+  GCL_CUDA(h, launch_chain(P, (cudaStream_t)stream, &l));
+  h->launches += l;
   return GCL_OK;
 }
 

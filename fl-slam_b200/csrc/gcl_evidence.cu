@@ -74,6 +74,94 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- planar translation evidence, in pieces (matrix_fisher_evidence.py:413-499) -------------------------------------
+// pass over bins (lane-strided) + warp sums: L_full = sum W_b, h_full = sum W_b t_b, N_eff = sum w_b; every lane gets the sums
+__device__ __forceinline__ void translation_sums_warp(int lane, int B, const double* R_hat, const double* p_bar,
+                                                      const double* Sig_p, const double* sN, const double* m_cen,
+                                                      const double* m_Sig, const double* map_N_pos, double eps, double* Lf,
+                                                      double* hf, double& NeffT) {
+  for (int i = 0; i < 9; ++i) Lf[i] = 0.0;
+  hf[0] = hf[1] = hf[2] = 0.0;
+  NeffT = 0.0;
+  for (int b = lane; b < B; b += 32) {
+    double tb[3];
+    for (int i = 0; i < 3; ++i)
+      tb[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]);
+    double RS[9], RSR[9], Sg[9], Si[9];
+    mat3_mul(R_hat, Sig_p + b * 9, RS);
+    mat3_mul_nt(RS, R_hat, RSR);
+    for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? eps : 0.0);
+    mat3_inv_lu(Sg, Si);  // plain inverse, matrix_fisher_evidence.py:462-466
+    const double wb = sqrt(sN[b] * map_N_pos[b] + eps);
+    for (int i = 0; i < 9; ++i) Si[i] *= wb;
+    for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
+    for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * tb[0] + Si[i * 3 + 1] * tb[1] + Si[i * 3 + 2] * tb[2];
+    NeffT += wb;
+  }
+  for (int i = 0; i < 9; ++i) Lf[i] = warp_sum(Lf[i]);
+  for (int i = 0; i < 3; ++i) hf[i] = warp_sum(hf[i]);
+  NeffT = warp_sum(NeffT);
+}
+
+// t_wls = solve(L_full + eps I, h_full)  (jnp.linalg.solve, :479); evaluated identically on every lane
+__device__ __forceinline__ void translation_solve(const double* Lf, const double* hf, double eps, double* tw) {
+  double Lreg[9];
+  for (int i = 0; i < 9; ++i) Lreg[i] = Lf[i] + ((i % 4 == 0) ? eps : 0.0);
+  int piv[3];
+  lu3(Lreg, piv);
+  tw[0] = hf[0]; tw[1] = hf[1]; tw[2] = hf[2];
+  lu3_solve(Lreg, piv, tw);
+}
+
+// planar mask, PSD projection, information vector, certificate and the 22-D blocks (one thread)
+__device__ inline void translation_finish(const double* Lf, const double* tw, double NeffT, double l1m, double l3m,
+                                          const double* pose, double eps_psd, double eps, double* ev) {
+  // self-adaptive z precision from the map scatter, :572-587.  scatter_metrics clamps eigenvalues at 0, which is what
+  // the rule does to lambda3; lambda1 is additionally floored at eps.
+  const double zs = fmax(l3m, 0.0) / fmax(l1m, eps);
+  const double mask[3] = {1.0, 1.0, zs};
+  double Lraw[9], Lpsd[9], pc[6], lv[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Lraw[i * 3 + j] = Lf[i * 3 + j] * mask[i] * mask[j];
+  double dt[3] = {tw[0] - pose[0], tw[1] - pose[1], tw[2] - pose[2]};
+  psd_project3(Lraw, eps_psd, Lpsd, pc, lv);
+  double h[3];
+  for (int i = 0; i < 3; ++i) h[i] = Lpsd[i * 3] * dt[0] + Lpsd[i * 3 + 1] * dt[1] + Lpsd[i * 3 + 2] * dt[2];
+  const double nll = 0.5 * (dt[0] * h[0] + dt[1] * h[1] + dt[2] * h[2]);
+  for (int i = 0; i < 3; ++i) { ev[GCL_EV_T_WLS + i] = tw[i]; ev[GCL_EV_H_TRANS + i] = h[i]; ev[GCL_EV_DELTA_TRANS + i] = dt[i]; }
+  for (int i = 0; i < 9; ++i) ev[GCL_EV_L_TRANS + i] = Lpsd[i];
+  double* c = ev + GCL_EV_TRANS_CERT;
+  // eigvalsh(L_trans_psd) = the floored eigenvalues the projection just produced (pc[2] = min, pc[3] = max)
+  c[0] = pc[2]; c[1] = pc[3]; c[2] = pc[3] / (pc[2] + eps);
+  c[3] = (double)((lv[0] < eps) + (lv[1] < eps) + (lv[2] < eps));
+  c[4] = nll / (NeffT + eps); c[5] = pc[0]; c[6] = eps / (NeffT + eps); c[7] = nll; c[8] = NeffT;
+  c[9] = 0.5 * (Lpsd[0] + Lpsd[4]); c[10] = Lpsd[8]; c[11] = zs;
+  for (int i = 0; i < 3; ++i) {
+    ev[GCL_EV_H22 + i] = h[i];
+    for (int j = 0; j < 3; ++j) ev[GCL_EV_L22 + i * 22 + j] = Lpsd[i * 3 + j];
+  }
+}
+
+// sum_b w_b r_b r_b^T and sum_b w_b with r_b = t_b - t_wls: the sufficient statistics of
+// lidar_meas_iw_suffstats_from_translation_residuals_jax (measurement_noise_iw_jax.py:104-127); every lane gets the sums
+__device__ __forceinline__ void residual_sums_warp(int lane, int B, const double* R_hat, const double* p_bar, const double* sN,
+                                                   const double* m_cen, const double* map_N_pos, const double* tw, double eps,
+                                                   double* rr, double& ws) {
+  for (int i = 0; i < 9; ++i) rr[i] = 0.0;
+  ws = 0.0;
+  for (int b = lane; b < B; b += 32) {
+    double r[3];
+    for (int i = 0; i < 3; ++i)
+      r[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]) - tw[i];
+    const double wb = sqrt(sN[b] * map_N_pos[b] + eps);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) rr[i * 3 + j] += wb * r[i] * r[j];
+    ws += wb;
+  }
+  for (int i = 0; i < 9; ++i) rr[i] = warp_sum(rr[i]);
+  ws = warp_sum(ws);
+}
+
 // ---- one hypothesis, one warp ---------------------------------------------------------------------------------------
 // iw_out (may be null): [sum_b w_b r_b r_b^T (9), sum_b w_b] with r_b = t_b - t_wls, the sufficient statistics of
 // lidar_meas_iw_suffstats_from_translation_residuals_jax (measurement_noise_iw_jax.py:104-127).
@@ -173,72 +261,13 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
     for (int i = 0; i < 9; ++i) R_hat[i] = R_hat_override[i];
   if (!do_translation) return;
 
-  // ---- pass 2 over bins: per-bin WLS terms ----------------------------------------------------------------------
-  double Lf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hf[3] = {0, 0, 0}, NeffT = 0;
-  for (int b = lane; b < B; b += 32) {
-    double tb[3];
-    for (int i = 0; i < 3; ++i)
-      tb[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]);
-    double RS[9], RSR[9], Sg[9], Si[9];
-    mat3_mul(R_hat, Sig_p + b * 9, RS);
-    mat3_mul_nt(RS, R_hat, RSR);
-    for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? eps : 0.0);
-    mat3_inv_lu(Sg, Si);  // plain inverse, matrix_fisher_evidence.py:462-466
-    const double wb = sqrt(sN[b] * map_N_pos[b] + eps);
-    for (int i = 0; i < 9; ++i) Si[i] *= wb;
-    for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
-    for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * tb[0] + Si[i * 3 + 1] * tb[1] + Si[i * 3 + 2] * tb[2];
-    NeffT += wb;
-  }
-  for (int i = 0; i < 9; ++i) Lf[i] = warp_sum(Lf[i]);
-  for (int i = 0; i < 3; ++i) hf[i] = warp_sum(hf[i]);
-  NeffT = warp_sum(NeffT);
-  double tw[3] = {hf[0], hf[1], hf[2]};
-  if (lane == 0) {
-    // self-adaptive z precision from the map scatter, :572-587.  scatter_metrics clamps eigenvalues at 0, which is what
-    // the rule does to lambda3; lambda1 is additionally floored at eps.
-    const double zs = fmax(l3m, 0.0) / fmax(l1m, eps);
-    double Lreg[9];
-    for (int i = 0; i < 9; ++i) Lreg[i] = Lf[i] + ((i % 4 == 0) ? eps : 0.0);
-    int piv[3];
-    lu3(Lreg, piv);
-    lu3_solve(Lreg, piv, tw);  // jnp.linalg.solve, :479
-    const double mask[3] = {1.0, 1.0, zs};
-    double Lraw[9], Lpsd[9], pc[6], lv[3];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Lraw[i * 3 + j] = Lf[i * 3 + j] * mask[i] * mask[j];
-    double dt[3] = {tw[0] - pose[0], tw[1] - pose[1], tw[2] - pose[2]};
-    psd_project3(Lraw, eps_psd, Lpsd, pc, lv);
-    double h[3];
-    for (int i = 0; i < 3; ++i) h[i] = Lpsd[i * 3] * dt[0] + Lpsd[i * 3 + 1] * dt[1] + Lpsd[i * 3 + 2] * dt[2];
-    const double nll = 0.5 * (dt[0] * h[0] + dt[1] * h[1] + dt[2] * h[2]);
-    for (int i = 0; i < 3; ++i) { ev[GCL_EV_T_WLS + i] = tw[i]; ev[GCL_EV_H_TRANS + i] = h[i]; ev[GCL_EV_DELTA_TRANS + i] = dt[i]; }
-    for (int i = 0; i < 9; ++i) ev[GCL_EV_L_TRANS + i] = Lpsd[i];
-    double* c = ev + GCL_EV_TRANS_CERT;
-    // eigvalsh(L_trans_psd) = the floored eigenvalues the projection just produced (pc[2] = min, pc[3] = max)
-    c[0] = pc[2]; c[1] = pc[3]; c[2] = pc[3] / (pc[2] + eps);
-    c[3] = (double)((lv[0] < eps) + (lv[1] < eps) + (lv[2] < eps));
-    c[4] = nll / (NeffT + eps); c[5] = pc[0]; c[6] = eps / (NeffT + eps); c[7] = nll; c[8] = NeffT;
-    c[9] = 0.5 * (Lpsd[0] + Lpsd[4]); c[10] = Lpsd[8]; c[11] = zs;
-    for (int i = 0; i < 3; ++i) {
-      ev[GCL_EV_H22 + i] = h[i];
-      for (int j = 0; j < 3; ++j) ev[GCL_EV_L22 + i * 22 + j] = Lpsd[i * 3 + j];
-    }
-  }
+  double Lf[9], hf[3], NeffT, tw[3];
+  translation_sums_warp(lane, B, R_hat, p_bar, Sig_p, sN, m_cen, m_Sig, map_N_pos, eps, Lf, hf, NeffT);
+  translation_solve(Lf, hf, eps, tw);
+  if (lane == 0) translation_finish(Lf, tw, NeffT, l1m, l3m, pose, eps_psd, eps, ev);
   if (iw_out) {  // residual sufficient statistics for the measurement-noise IW update (uniform branch)
-    for (int i = 0; i < 3; ++i) tw[i] = __shfl_sync(0xffffffffu, tw[i], 0);
-    double rr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ws = 0;
-    for (int b = lane; b < B; b += 32) {
-      double r[3];
-      for (int i = 0; i < 3; ++i)
-        r[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]) - tw[i];
-      const double wb = sqrt(sN[b] * map_N_pos[b] + eps);
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) rr[i * 3 + j] += wb * r[i] * r[j];
-      ws += wb;
-    }
-    for (int i = 0; i < 9; ++i) rr[i] = warp_sum(rr[i]);
-    ws = warp_sum(ws);
+    double rr[9], ws;
+    residual_sums_warp(lane, B, R_hat, p_bar, sN, m_cen, map_N_pos, tw, eps, rr, ws);
     if (lane == 0) {
       for (int i = 0; i < 9; ++i) iw_out[i] = rr[i];
       iw_out[9] = ws;
@@ -338,10 +367,33 @@ __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T 
   for (int i = 0; i < 9; ++i) iw[1 + i] = Ppsd[i];
 }
 
-// ---- the sequential chain: one CTA walks a stream of scans, carrying map and IW state on the device -------------------
+// ---- the chain over a stream of scans ---------------------------------------------------------------------------------
 // per scan s:  [Sigma_p += Sigma_meas]  ->  map-derived stats  ->  pose evidence (H hypotheses, one warp each)
 //              ->  measurement-noise IW update  ->  map update with pose_update[s]
+// (a) chain_kernel: one CTA walks the scans in order -- used for a single scan (the per-scan host call).
+// (b) staged stream (n_scans >= kStagedMinScans): only what truly depends on the previous scan stays sequential.
+//     The map recurrence m <- gamma m + inc(s) does not depend on the evidence (the update poses are inputs), so the
+//     increments are computed in parallel and the recurrence runs elementwise; map-derived statistics and the rotation
+//     evidence then run in parallel over scans.  With use_sigma_meas the IW state feeds every bin covariance of the next
+//     scan, so ONE warp walks the scans doing just  Sigma_meas -> bin covariances -> t_wls -> residuals -> IW update
+//     (inputs of scan s+1 are staged into shared memory by a helper warp meanwhile); the planar mask / PSD projection /
+//     certificates of the translation evidence are finished in parallel afterwards.  Same arithmetic, same order within
+//     a scan as (a): results are bit-identical.
 constexpr int kChainThreads = 128;
+constexpr int kStagedMinScans = 4;
+
+__device__ __forceinline__ void sigma_p_with_meas(const double* st, const StatsLayout& SL, int b, const double* sigma,
+                                                  double eps_mass, double eps_psd, double* Spsd) {
+  // C_i = Sigma_meas for every point  =>  sum_C / N = Sigma_meas N/(N+eps)   (binning.py:173-182)
+  const double N = st[SL.N() + b];
+  const double invN = 1.0 / (N + eps_mass + kF64Eps);
+  const double* pb = st + SL.p_bar() + b * 3;
+  const double* spp = st + SL.sum_ppT() + b * 9;
+  double Sraw[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Sraw[i * 3 + j] = spp[i * 3 + j] * invN - pb[i] * pb[j] + sigma[i * 3 + j] * (N * invN);
+  psd_project3_fast(Sraw, eps_psd, Spsd);
+}
 
 __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_constant__ ChainParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,32 +403,26 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
   __shared__ double s_sigma[9];
   for (int s = 0; s < P.n_scans; ++s) {
     double* st0 = P.stats + (size_t)s * H * P.stats_stride;
-    // 1. measurement noise enters every bin covariance: C_i = Sigma_meas  =>  sum_C / N = Sigma_meas N/(N+eps)
+    // 1. measurement noise enters every bin covariance
     if (P.iw_state && P.use_sigma_meas) {
       if (tid == 0) iw_sigma_mode(P.iw_state, P.eps_psd, s_sigma);
       __syncthreads();
       for (int idx = tid; idx < B * H; idx += kChainThreads) {
         const int h = idx / B, b = idx - h * B;
         double* st = st0 + (size_t)h * P.stats_stride;
-        const double N = st[SL.N() + b];
-        const double invN = 1.0 / (N + P.eps_mass + kF64Eps);
-        const double* pb = st + SL.p_bar() + b * 3;
-        const double* spp = st + SL.sum_ppT() + b * 9;
-        double Sraw[9], Spsd[9];
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) Sraw[i * 3 + j] = spp[i * 3 + j] * invN - pb[i] * pb[j] + s_sigma[i * 3 + j] * (N * invN);
-        psd_project3_fast(Sraw, P.eps_psd, Spsd);
+        double Spsd[9];
+        sigma_p_with_meas(st, SL, b, s_sigma, P.eps_mass, P.eps_psd, Spsd);
         for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Spsd[i];
       }
     }
     // 2. map-derived statistics
     for (int b = tid; b < B; b += kChainThreads)
-      map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, P.map_derived);
+      map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, P.workspace);
     __syncthreads();
     // 3. pose evidence, one warp per hypothesis
     for (int h = warp; h < H; h += kChainThreads / 32)
       pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
-                         P.map_derived, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                         P.workspace, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
                          P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr);
     __syncthreads();
     // 4. IW update from hypothesis 0's translation residuals
@@ -393,8 +439,274 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
   }
 }
 
-cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream) {
-  chain_kernel<<<1, kChainThreads, 0, stream>>>(P);
+// ---- staged stream ----------------------------------------------------------------------------------------------------
+// workspace carve (doubles): [single-scan map-derived 16B][map_pre: S x 26B][mder: S x 16B][sigma: S x 16][tpart: S*H x 32]
+struct StreamWs {
+  double *map_pre, *mder, *sigma, *tpart;
+  __host__ __device__ StreamWs(double* ws, int S, int B) {
+    map_pre = ws + 16 * (size_t)B;
+    mder = map_pre + (size_t)S * 26 * B;
+    sigma = mder + (size_t)S * 16 * B;
+    tpart = sigma + (size_t)S * 16;
+  }
+};
+size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins) {
+  return 16 * (size_t)n_bins + (size_t)n_scans * (26 * (size_t)n_bins + 16 * (size_t)n_bins + 16) + (size_t)n_scans * n_hyp * 32;
+}
+// tpart record: Lf[0..9) tw[9..12) NeffT[12] rr[13..22) ws[22]
+
+// S1: world-frame increments of every scan's bin sums (same expressions as map_update_bin, without the recurrence);
+//     layout of one scan's block = the six map arrays back to back [S_dir 3B | S_sc 9B | N_dir B | N_pos B | sum_p 3B | sum_ppT 9B]
+__global__ void stream_increments_kernel(const __grid_constant__ ChainParams P) {
+  const int s = blockIdx.x, B = P.n_bins;
+  const StatsLayout SL(B);
+  const StreamWs W(P.workspace, P.n_scans, B);
+  const double* stats = P.stats + (size_t)s * P.n_hyp * P.stats_stride;
+  const double* pu = P.pose_update + (size_t)s * 6;
+  double R[9];
+  so3_exp(pu + 3, R);
+  const double t[3] = {pu[0], pu[1], 0.0};
+  double* o = W.map_pre + (size_t)s * 26 * B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double N = stats[SL.N() + b];
+    const double* sd = stats + SL.s_dir() + b * 3;
+    const double* S = stats + SL.S_scatter() + b * 9;
+    const double* sp = stats + SL.sum_p() + b * 3;
+    const double* spp = stats + SL.sum_ppT() + b * 9;
+    double Rs[3], Rp[3], T1[9], RSR[9], RPR[9];
+    for (int i = 0; i < 3; ++i) {
+      Rs[i] = R[i * 3] * sd[0] + R[i * 3 + 1] * sd[1] + R[i * 3 + 2] * sd[2];
+      Rp[i] = R[i * 3] * sp[0] + R[i * 3 + 1] * sp[1] + R[i * 3 + 2] * sp[2];
+    }
+    mat3_mul(R, S, T1); mat3_mul_nt(T1, R, RSR);
+    mat3_mul(R, spp, T1); mat3_mul_nt(T1, R, RPR);
+    for (int i = 0; i < 3; ++i) {
+      o[b * 3 + i] = Rs[i];
+      o[14 * B + b * 3 + i] = Rp[i] + N * t[i];
+      for (int j = 0; j < 3; ++j) {
+        o[3 * B + b * 9 + i * 3 + j] = RSR[i * 3 + j];
+        o[17 * B + b * 9 + i * 3 + j] = RPR[i * 3 + j] + Rp[i] * t[j] + t[i] * Rp[j] + N * t[i] * t[j];
+      }
+    }
+    o[12 * B + b] = N;
+    o[13 * B + b] = N;
+  }
+}
+
+// S2: m <- gamma m + inc(s), elementwise; the slot of scan s is overwritten with the map state that scan s SEES
+__global__ void stream_map_recurrence_kernel(const __grid_constant__ ChainParams P) {
+  const int B = P.n_bins, e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 26 * B) return;
+  const StreamWs W(P.workspace, P.n_scans, B);
+  double* arr = e < 3 * B ? P.map_S_dir + e : e < 12 * B ? P.map_S_dir_scatter + (e - 3 * B) : e < 13 * B ? P.map_N_dir + (e - 12 * B)
+              : e < 14 * B ? P.map_N_pos + (e - 13 * B) : e < 17 * B ? P.map_sum_p + (e - 14 * B) : P.map_sum_ppT + (e - 17 * B);
+  double m = *arr;
+  const double g = P.forgetting;
+  double* slot = W.map_pre + e;
+  const size_t pitch = 26 * (size_t)B;
+#pragma unroll 8
+  for (int s = 0; s < P.n_scans; ++s) {
+    const double inc = slot[s * pitch];
+    slot[s * pitch] = m;
+    m = g * m + inc;
+  }
+  *arr = m;
+}
+
+struct MapView { const double *S_dir, *S_sc, *N_dir, *N_pos, *sum_p, *sum_ppT; };
+__device__ __forceinline__ MapView map_view(const ChainParams& P, const StreamWs& W, int s) {
+  MapView v;
+  if (P.pose_update) {
+    const double* m = W.map_pre + (size_t)s * 26 * P.n_bins;
+    const int B = P.n_bins;
+    v.S_dir = m; v.S_sc = m + 3 * B; v.N_dir = m + 12 * B; v.N_pos = m + 13 * B; v.sum_p = m + 14 * B; v.sum_ppT = m + 17 * B;
+  } else {
+    v.S_dir = P.map_S_dir; v.S_sc = P.map_S_dir_scatter; v.N_dir = P.map_N_dir; v.N_pos = P.map_N_pos; v.sum_p = P.map_sum_p;
+    v.sum_ppT = P.map_sum_ppT;
+  }
+  return v;
+}
+
+// S3: one CTA per scan: map-derived statistics of the map state that scan sees, then one warp per hypothesis.
+//     With use_sigma_meas only the rotation part can run here (the bin covariances are not known yet).
+__global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __grid_constant__ ChainParams P) {
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = P.n_bins, H = P.n_hyp;
+  const StreamWs W(P.workspace, P.n_scans, B);
+  const MapView mv = map_view(P, W, s);
+  double* mder = W.mder + (size_t)s * 16 * B;
+  for (int b = tid; b < B; b += kChainThreads)
+    map_derived_bin(mv.S_dir, mv.N_dir, mv.N_pos, mv.sum_p, mv.sum_ppT, B, b, P.eps_mass, P.eps_psd, mder);
+  __syncthreads();
+  const bool sig = P.iw_state && P.use_sigma_meas;
+  for (int h = warp; h < H; h += kChainThreads / 32)
+    pose_evidence_warp(lane, P.stats + ((size_t)s * H + h) * P.stats_stride, mv.S_dir, mv.S_sc, mv.N_dir, mv.N_pos, mder,
+                       P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, sig ? 0 : 1,
+                       P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES,
+                       (h == 0 && P.iw_state && !sig) ? W.tpart + ((size_t)s * H) * 32 + 13 : nullptr);
+}
+
+// S4a: IW recurrence alone (the residual statistics do not depend on the IW state when Sigma_meas is not fed back)
+__global__ void stream_iw_recurrence_kernel(const __grid_constant__ ChainParams P) {
+  if (threadIdx.x != 0) return;
+  const StreamWs W(P.workspace, P.n_scans, P.n_bins);
+  double iw[10];
+  for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
+  for (int s = 0; s < P.n_scans; ++s)
+    iw_update(iw, W.tpart + ((size_t)s * P.n_hyp) * 32 + 13, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
+  for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
+}
+
+// S4b: the sequential core with Sigma_meas fed back.  Warp 0 computes, warp 1 stages the next scan's inputs in shared memory.
+//      staged block per scan (doubles): N[B] p_bar[3B] sum_ppT[9B] | cen[3B] Sig_c[9B] | N_pos[B] | R_hat[9]
+__device__ __forceinline__ size_t seq_block_doubles(int B) { return 26 * (size_t)B + 9; }
+__global__ void __launch_bounds__(64) stream_sigma_chain_kernel(const __grid_constant__ ChainParams P, int use_smem) {
+  extern __shared__ __align__(16) double s_stage[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = P.n_bins, H = P.n_hyp, S = P.n_scans;
+  const StatsLayout SL(B);
+  const StreamWs W(P.workspace, S, B);
+  const size_t blk = seq_block_doubles(B);
+  auto stage = [&](int s, double* dst) {  // all 32 lanes of the calling warp
+    const double* st = P.stats + (size_t)s * H * P.stats_stride;
+    const double* md = W.mder + (size_t)s * 16 * B;
+    const MapView mv = map_view(P, W, s);
+    const double* ev = P.evidence + (size_t)s * H * GCL_EVID_DOUBLES;
+    for (int i = lane; i < B; i += 32) { dst[i] = st[SL.N() + i]; dst[25 * B + i] = mv.N_pos[i]; }
+    for (int i = lane; i < 3 * B; i += 32) { dst[B + i] = st[SL.p_bar() + i]; dst[13 * B + i] = md[4 * B + i]; }
+    for (int i = lane; i < 9 * B; i += 32) { dst[4 * B + i] = st[SL.sum_ppT() + i]; dst[16 * B + i] = md[7 * B + i]; }
+    if (lane < 9) dst[26 * B + lane] = ev[GCL_EV_R_MF + lane];
+  };
+  if (use_smem) {
+    if (warp == 1) stage(0, s_stage);
+    __syncthreads();
+  }
+  double iw[10];
+  for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
+  for (int s = 0; s < S; ++s) {
+    if (warp == 1) {
+      if (use_smem && s + 1 < S) stage(s + 1, s_stage + ((s + 1) & 1) * blk);
+    } else {
+      double* st0 = P.stats + (size_t)s * H * P.stats_stride;
+      double sigma[9];
+      iw_sigma_mode(iw, P.eps_psd, sigma);
+      const double *sN, *p_bar, *spp, *m_cen, *m_Sig, *Npos;
+      double R_hat[9];
+      if (use_smem) {
+        const double* in = s_stage + (s & 1) * blk;
+        sN = in; p_bar = in + B; spp = in + 4 * B; m_cen = in + 13 * B; m_Sig = in + 16 * B; Npos = in + 25 * B;
+        for (int i = 0; i < 9; ++i) R_hat[i] = in[26 * B + i];
+      } else {
+        const double* md = W.mder + (size_t)s * 16 * B;
+        sN = st0 + SL.N(); p_bar = st0 + SL.p_bar(); spp = st0 + SL.sum_ppT(); m_cen = md + 4 * B; m_Sig = md + 7 * B;
+        Npos = map_view(P, W, s).N_pos;
+        for (int i = 0; i < 9; ++i) R_hat[i] = P.evidence[(size_t)s * H * GCL_EVID_DOUBLES + GCL_EV_R_MF + i];
+      }
+      // bin covariances with the measurement noise (written back: they are an output), then the WLS sums
+      double Lf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hf[3] = {0, 0, 0}, NeffT = 0;
+      for (int b = lane; b < B; b += 32) {
+        const double N = sN[b];
+        const double invN = 1.0 / (N + P.eps_mass + kF64Eps);
+        double Sraw[9], Sp[9];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j)
+            Sraw[i * 3 + j] = spp[b * 9 + i * 3 + j] * invN - p_bar[b * 3 + i] * p_bar[b * 3 + j] + sigma[i * 3 + j] * (N * invN);
+        psd_project3_fast(Sraw, P.eps_psd, Sp);
+        for (int i = 0; i < 9; ++i) st0[SL.Sigma_p() + b * 9 + i] = Sp[i];
+        double tb[3];
+        for (int i = 0; i < 3; ++i)
+          tb[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]);
+        double RS[9], RSR[9], Sg[9], Si[9];
+        mat3_mul(R_hat, Sp, RS);
+        mat3_mul_nt(RS, R_hat, RSR);
+        for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
+        mat3_inv_lu(Sg, Si);
+        const double wb = sqrt(N * Npos[b] + P.eps_mass);
+        for (int i = 0; i < 9; ++i) Si[i] *= wb;
+        for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
+        for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * tb[0] + Si[i * 3 + 1] * tb[1] + Si[i * 3 + 2] * tb[2];
+        NeffT += wb;
+      }
+      for (int i = 0; i < 9; ++i) Lf[i] = warp_sum(Lf[i]);
+      for (int i = 0; i < 3; ++i) hf[i] = warp_sum(hf[i]);
+      NeffT = warp_sum(NeffT);
+      double tw[3], rr_w[10];
+      translation_solve(Lf, hf, P.eps_mass, tw);
+      residual_sums_warp(lane, B, R_hat, p_bar, sN, m_cen, Npos, tw, P.eps_mass, rr_w, rr_w[9]);
+      double* tp = W.tpart + ((size_t)s * H) * 32;
+      if (lane < 9) { tp[lane] = Lf[lane]; W.sigma[(size_t)s * 16 + lane] = sigma[lane]; }
+      if (lane == 0) { tp[9] = tw[0]; tp[10] = tw[1]; tp[11] = tw[2]; tp[12] = NeffT; }
+      iw_update(iw, rr_w, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);  // identical on every lane
+    }
+    if (use_smem) __syncthreads();
+  }
+  if (tid == 0)
+    for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
+}
+
+// S5: finish the translation evidence in parallel: hypothesis 0 from the stored sums, the others from scratch with the
+//     stored Sigma_meas of their scan
+__global__ void __launch_bounds__(32) stream_translation_finish_kernel(const __grid_constant__ ChainParams P) {
+  const int job = blockIdx.x, lane = threadIdx.x, B = P.n_bins, H = P.n_hyp;
+  const int s = job / H, h = job - s * H;
+  const StatsLayout SL(B);
+  const StreamWs W(P.workspace, P.n_scans, B);
+  double* st = P.stats + (size_t)job * P.stats_stride;
+  double* ev = P.evidence + (size_t)job * GCL_EVID_DOUBLES;
+  const double* pose = P.pose_pred + (size_t)job * 6;
+  const double l1m = ev[GCL_EV_MAP_METRICS + 0], l3m = ev[GCL_EV_MAP_METRICS + 2];
+  double Lf[9], tw[3], NeffT;
+  if (h == 0) {
+    const double* tp = W.tpart + ((size_t)s * H) * 32;
+    for (int i = 0; i < 9; ++i) Lf[i] = tp[i];
+    tw[0] = tp[9]; tw[1] = tp[10]; tw[2] = tp[11]; NeffT = tp[12];
+  } else {
+    const double* sigma = W.sigma + (size_t)s * 16;
+    for (int b = lane; b < B; b += 32) {
+      double Sp[9];
+      sigma_p_with_meas(st, SL, b, sigma, P.eps_mass, P.eps_psd, Sp);
+      for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Sp[i];
+    }
+    __syncwarp();
+    const double* md = W.mder + (size_t)s * 16 * B;
+    double R_hat[9], hf[3];
+    for (int i = 0; i < 9; ++i) R_hat[i] = ev[GCL_EV_R_MF + i];
+    translation_sums_warp(lane, B, R_hat, st + SL.p_bar(), st + SL.Sigma_p(), st + SL.N(), md + 4 * B, md + 7 * B,
+                          map_view(P, W, s).N_pos, P.eps_mass, Lf, hf, NeffT);
+    translation_solve(Lf, hf, P.eps_mass, tw);
+  }
+  if (lane == 0) translation_finish(Lf, tw, NeffT, l1m, l3m, pose, P.eps_psd, P.eps_mass, ev);
+}
+
+cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches) {
+  *launches = 0;
+  if (P.n_scans < kStagedMinScans) {
+    chain_kernel<<<1, kChainThreads, 0, stream>>>(P);
+    *launches = 1;
+    return cudaGetLastError();
+  }
+  const int B = P.n_bins, S = P.n_scans;
+  if (P.pose_update) {
+    stream_increments_kernel<<<S, B < 128 ? ((B + 31) / 32) * 32 : 128, 0, stream>>>(P);
+    stream_map_recurrence_kernel<<<(26 * B + 127) / 128, 128, 0, stream>>>(P);
+    *launches += 2;
+  }
+  stream_evidence_kernel<<<S, kChainThreads, 0, stream>>>(P);
+  *launches += 1;
+  if (P.iw_state && P.use_sigma_meas) {
+    const size_t smem = 2 * (26 * (size_t)B + 9) * sizeof(double);
+    const int use_smem = smem <= 200 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(stream_sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_done = true;
+    }
+    stream_sigma_chain_kernel<<<1, 64, use_smem ? smem : 0, stream>>>(P, use_smem);
+    stream_translation_finish_kernel<<<S * P.n_hyp, 32, 0, stream>>>(P);
+    *launches += 2;
+  } else if (P.iw_state) {
+    stream_iw_recurrence_kernel<<<1, 32, 0, stream>>>(P);
+    *launches += 1;
+  }
   return cudaGetLastError();
 }
 

@@ -94,7 +94,7 @@ struct ChainParams {
   double* stats;            // n_scans * n_hyp stats records (Sigma_p is rewritten when use_sigma_meas)
   int64_t stats_stride;
   double *map_S_dir, *map_S_dir_scatter, *map_N_dir, *map_N_pos, *map_sum_p, *map_sum_ppT;  // updated in place
-  double* map_derived;      // scratch, 16 * n_bins
+  double* workspace;        // chain_workspace_doubles(n_scans, n_hyp, n_bins) doubles
   const double* pose_pred;  // (n_scans * n_hyp, 6)
   const double* pose_update;  // (n_scans, 6) pose used for the map update, or nullptr
   double* iw_state;         // [nu, Psi(9)] LiDAR measurement-noise block, or nullptr
@@ -102,7 +102,8 @@ struct ChainParams {
   int n_scans, n_hyp, n_bins, use_sigma_meas;
   double forgetting, iw_rho, iw_nu_weak_add, iw_nu_max, eps_psd, eps_mass;
 };
-cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream);
+cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches);
+size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins);
 cudaError_t launch_map_derived(const double* S_dir, const double* N_dir, const double* N_pos, const double* sum_p,
                                const double* sum_ppT, int n_bins, double eps_mass, double eps_psd, double* out,
                                cudaStream_t stream);

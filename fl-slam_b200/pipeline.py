@@ -203,7 +203,8 @@ class LidarEvidencePipeline:
         if b is None:
             z = lambda *s: torch.empty(s, dtype=torch.float64, device=self.device)
             b = {"partials": z(n_jobs, ctas, self.rec), "reduced": z(n_jobs, self.rec), "stats": z(n_jobs, self.srec),
-                 "evidence": z(n_jobs, _abi.GCL_EVID_DOUBLES), "map_derived": z(16 * self.n_bins)}
+                 "evidence": z(n_jobs, _abi.GCL_EVID_DOUBLES), "map_derived": z(max(int(_lib.gcl_scan_chain_workspace_doubles(n_jobs, 1, self.n_bins)),
+                                      int(_lib.gcl_scan_chain_workspace_doubles(1, n_jobs, self.n_bins))))}
             self._bufs[key] = b
         return b
 

@@ -225,10 +225,13 @@ int gcl_map_update(gcl_handle h, void* stream, const double* stats /* one stats 
  * stats: n_scans*n_hyp records from gcl_reduce_finalize (scan-major); Sigma_p is rewritten in place when
  * use_sigma_meas != 0.  pose_update: (n_scans,6) pose applied by the map update (NULL = map is read-only).
  * iw_state: 10 doubles [nu, Psi (3x3)] updated in place (NULL = no measurement-noise adaptation).
- * map_derived_scratch: 16*n_bins doubles. */
+ * workspace: gcl_scan_chain_workspace_doubles(n_scans, n_hyp, n_bins) doubles of scratch.
+ * A single scan runs as one launch; a stream (n_scans >= 4) runs staged: map recurrence, map-derived statistics and
+ * rotation evidence in parallel over scans, and only Sigma_meas -> t_wls -> residuals -> IW update sequentially. */
+size_t gcl_scan_chain_workspace_doubles(int n_scans, int n_hyp, int n_bins);
 int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stride_doubles, int n_scans, int n_hyp,
                    int n_bins, double* map_S_dir, double* map_S_dir_scatter, double* map_N_dir, double* map_N_pos,
-                   double* map_sum_p, double* map_sum_ppT, double* map_derived_scratch, const double* pose_pred,
+                   double* map_sum_p, double* map_sum_ppT, double* workspace, const double* pose_pred,
                    const double* pose_update, double forgetting, double* iw_state, int use_sigma_meas, double iw_rho,
                    double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass, double* evidence);
 

@@ -401,3 +401,50 @@ def test_stream_chain_with_map_and_iw_state(g, O):
         iwh = H(iw)
         assert abs(iwh[0] / ref_iw["nu"] - 1) < 1e-12
         assert rel_err(iwh[1:].reshape(3, 3), ref_iw["Psi"]) < 1e-6
+
+
+@pytest.mark.parametrize("variant", ["sigma", "iw_only", "plain", "read_only_map"])
+def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
+    """The staged stream chain (parallel map recurrence / rotation evidence, sequential IW core) must give exactly what
+    walking the scans one launch at a time gives, for several hypotheses per scan."""
+    S, Hh, B, cap, tau = 7, 3, 48, 2048, 0.1
+    rng = np.random.default_rng(5)
+    scans = [g.synth.make_scan(4000 + 53 * k, seed=500 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=scans[0].lidar_origin)
+    stats = torch.empty((S * Hh, pl.srec), dtype=torch.float64, device="cuda")
+    ms0 = g.create_empty_map_stats(B)
+    zero_pose = torch.zeros((Hh, 6), dtype=torch.float64, device="cuda")
+    for k, sc in enumerate(scans):
+        xis = sc.xi_body[None] * (1 + 0.02 * rng.standard_normal((Hh, 1)))
+        ev = pl.run_resident(pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time), xis, zero_pose, ms0)
+        stats[k * Hh:(k + 1) * Hh] = ev.stats
+    poses_upd = torch.from_numpy(np.stack([np.array([0.05 * k, 0.01 * k, 0.3, 0.001 * k, 0.0, 0.01 * k]) for k in range(S)])).cuda()
+    poses_pred = torch.from_numpy(np.repeat(poses_upd.cpu().numpy(), Hh, axis=0) + 1e-3 * rng.standard_normal((S * Hh, 6))).cuda()
+    # a non-empty starting map so that scan 0 already has evidence
+    Rs, ts = g.synth.known_map_transform(0)
+
+    def fresh_map():
+        m = g.create_empty_map_stats(B)
+        g.map_update_inplace(m, stats[0], Rs, ts, 1.0)
+        return m
+
+    use_iw, use_sigma, upd = variant in ("sigma", "iw_only"), variant == "sigma", variant != "read_only_map"
+    ws = torch.empty(int(g._abi.lib.gcl_scan_chain_workspace_doubles(S, Hh, B)), dtype=torch.float64, device="cuda")
+    # (a) staged: one call for the whole stream
+    st_a, ms_a, iw_a = stats.clone(), fresh_map(), (pl.create_lidar_iw_state(1e-3) if use_iw else None)
+    ev_a = torch.zeros((S * Hh, g._abi.GCL_EVID_DOUBLES), dtype=torch.float64, device="cuda")
+    pl.launch_chain(st_a, S, Hh, ms_a, ws, poses_pred, poses_upd if upd else None, ev_a, iw_a, use_sigma, 0.97)
+    # (b) one launch per scan
+    st_b, ms_b, iw_b = stats.clone(), fresh_map(), (pl.create_lidar_iw_state(1e-3) if use_iw else None)
+    ev_b = torch.zeros_like(ev_a)
+    for k in range(S):
+        pl.launch_chain(st_b[k * Hh:(k + 1) * Hh], 1, Hh, ms_b, ws, poses_pred[k * Hh:(k + 1) * Hh],
+                        poses_upd[k:k + 1] if upd else None, ev_b[k * Hh:(k + 1) * Hh], iw_b, use_sigma, 0.97)
+    torch.cuda.synchronize()
+    assert torch.equal(st_a, st_b)
+    assert torch.equal(ev_a, ev_b)
+    for name in ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT"):
+        assert torch.equal(getattr(ms_a, name), getattr(ms_b, name)), name
+    if use_iw:
+        assert torch.equal(iw_a, iw_b)
+    assert float(ev_a[:, g._abi.EV['T_WLS']:g._abi.EV['T_WLS'] + 3].abs().sum()) > 0
