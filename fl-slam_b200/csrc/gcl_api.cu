@@ -80,8 +80,8 @@ size_t gcl_partial_record_doubles(int n_bins) { return (size_t)GCL_NM * n_bins +
 size_t gcl_stats_record_doubles(int n_bins) { return (size_t)StatsLayout(n_bins).total(); }
 
 int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_bins, int precision) {
-  (void)n_bins; (void)precision;
-  const int64_t sms = h ? h->sm_count : 148;
+  // resident CTA slots: SMs x CTAs per SM of the kernel variant this (n_bins, precision) selects
+  const int64_t sms = (int64_t)(h ? h->sm_count : 148) * fused_ctas_per_sm(n_bins < 1 ? 1 : n_bins, precision);
   if (n_jobs < 1) n_jobs = 1;
   if (max_sel_rows < 1) max_sel_rows = 1;
   // at least one 256-row tile of work per CTA; when that would leave SMs idle (one small scan: the latency case),
@@ -125,14 +125,10 @@ int gcl_scan_moments(gcl_handle h, void* stream, const gcl_job* jobs_dev, const 
   P.rec_doubles = (int64_t)gcl_partial_record_doubles(n_bins);
   P.tau = tau;
   P.n_bins = n_bins;
-  int G, L, chunks;
-  plan_bins(n_bins, precision, &G, &L, &chunks);
-  P.lanes = L; P.n_chunks = chunks;
   P.layout = layout;
   P.fixed_shift = fixed_shift_ok(tau, precision) ? 1 : 0;
-  if (const char* dbg = getenv("GCL_DEBUG_SKIP")) P.fixed_shift |= (atoi(dbg) << 1);  // profiling only: 1 = skip phase B, 2 = skip phase A bin loop
   cudaSetDevice(h->device);
-  GCL_CUDA(h, launch_scan_moments(P, n_jobs, ctas_per_job, precision, G, GCL_NM, false, (cudaStream_t)stream));
+  GCL_CUDA(h, launch_scan_moments_fused(P, n_jobs, ctas_per_job, precision, (cudaStream_t)stream));
   h->launches += 1;
   return GCL_OK;
 }

@@ -1,0 +1,114 @@
+// gcl_point.cuh -- per-point device helpers shared by the O(N) kernels: packed fp32 arithmetic, cp.async staging and the
+// per-point front end (constant-twist deskew, time-window weight, ray direction).
+#pragma once
+#include "gcl_internal.cuh"
+
+namespace gcl {
+
+// ------------------------------------------------------------------------------------------------------------
+// packed arithmetic (sm_100: FFMA2 / FADD2)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if GCL_USE_FFMA2
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+#if GCL_USE_FFMA2
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// cp.async (LDGSTS): global -> shared without staging registers; used to prefetch the next tile's raw rows
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float expo(float x) { return fast_exp2(x); }
+__device__ __forceinline__ double expo(double x) { return exp(x); }
+
+// ------------------------------------------------------------------------------------------------------------
+// per-point front end (phase A, before the bin loop)
+// ------------------------------------------------------------------------------------------------------------
+struct PointOut64 { double p0[3], d[3], w_time; };
+
+// fp64: the reference formulas verbatim (gcl_math.cuh cites the lines)
+__device__ __forceinline__ void point_front64(const gcl_job& J, const ScanConst& C, double px, double py, double pz,
+                                              double t, PointOut64& o) {
+  const double denom = fmax(J.scan_end_time - J.scan_start_time, 1e-12);
+  const double alpha = (t - J.scan_start_time) / denom;
+  const double p[3] = {px, py, pz};
+  deskew_point64(J.xi_body, alpha, p, o.p0);
+  const double sigma = fmax(0.1 * denom, 1e-6);  // GC_TIME_WARP_SIGMA_FRAC, constants.py:143; floor imu_preintegration.py:32
+  o.w_time = window_weight64(t, J.scan_start_time, J.scan_end_time, sigma, 1e-12);
+  const double r0 = o.p0[0] - C.origin[0], r1 = o.p0[1] - C.origin[1], r2 = o.p0[2] - C.origin[2];
+  const double inv = 1.0 / (sqrt(r0 * r0 + r1 * r1 + r2 * r2) + C.eps_mass);
+  o.d[0] = r0 * inv; o.d[1] = r1 * inv; o.d[2] = r2 * inv;
+}
+
+struct PointOut32 { float p0[3], d[3], w_time; };
+
+// fp32: same maps; series for the Rodrigues coefficients below 0.5 rad (no cancellation), sincosf above
+__device__ __forceinline__ void point_front32(const gcl_job& J, const ScanConst& C, const float* xi32, float px, float py,
+                                              float pz, float trel /* t - scan_start */, PointOut32& o) {
+  const float D = (float)(J.scan_end_time - J.scan_start_time);
+  const float denom = fmaxf(D, 1e-12f);
+  const float alpha = trel / denom;
+  const float r0 = alpha * xi32[0], r1 = alpha * xi32[1], r2 = alpha * xi32[2];
+  const float f0 = alpha * xi32[3], f1 = alpha * xi32[4], f2 = alpha * xi32[5];
+  const float th2 = f0 * f0 + f1 * f1 + f2 * f2;
+  float sinc, Bc, Cc;
+  if (th2 < 0.25f) {
+    sinc = 1.f + th2 * (-1.f / 6.f + th2 * (1.f / 120.f + th2 * (-1.f / 5040.f + th2 * (1.f / 362880.f))));
+    Bc = 0.5f + th2 * (-1.f / 24.f + th2 * (1.f / 720.f + th2 * (-1.f / 40320.f + th2 * (1.f / 3628800.f))));
+    Cc = 1.f / 6.f + th2 * (-1.f / 120.f + th2 * (1.f / 5040.f + th2 * (-1.f / 362880.f + th2 * (1.f / 39916800.f))));
+  } else {
+    const float th = sqrtf(th2);
+    float sn, cs, sh, ch;
+    sincosf(th, &sn, &cs);
+    sincosf(0.5f * th, &sh, &ch);
+    sinc = sn / th;
+    Bc = 2.f * sh * sh / th2;
+    Cc = (th - sn) / (th2 * th);
+  }
+  const float c0 = f1 * r2 - f2 * r1, c1 = f2 * r0 - f0 * r2, c2 = f0 * r1 - f1 * r0;
+  const float d0 = f1 * c2 - f2 * c1, d1 = f2 * c0 - f0 * c2, d2 = f0 * c1 - f1 * c0;
+  const float u0 = px - (r0 + Bc * c0 + Cc * d0), u1 = py - (r1 + Bc * c1 + Cc * d1), u2 = pz - (r2 + Bc * c2 + Cc * d2);
+  const float g0 = f1 * u2 - f2 * u1, g1 = f2 * u0 - f0 * u2, g2 = f0 * u1 - f1 * u0;
+  const float h0 = f1 * g2 - f2 * g1, h1 = f2 * g0 - f0 * g2, h2 = f0 * g1 - f1 * g0;
+  o.p0[0] = u0 - sinc * g0 + Bc * h0;
+  o.p0[1] = u1 - sinc * g1 + Bc * h1;
+  o.p0[2] = u2 - sinc * g2 + Bc * h2;
+  const float sigma = fmaxf(0.1f * denom, 1e-6f);
+  const float a = trel / sigma, b = (D - trel) / sigma;
+  const float sa = 1.f / (1.f + __expf(-a)), sb = 1.f / (1.f + __expf(-b));
+  o.w_time = sa * sb * (1.f - 1e-12f) + 1e-12f;
+  const float q0 = o.p0[0] - (float)C.origin[0], q1 = o.p0[1] - (float)C.origin[1], q2 = o.p0[2] - (float)C.origin[2];
+  const float inv = 1.f / (sqrtf(q0 * q0 + q1 * q1 + q2 * q2) + (float)C.eps_mass);
+  o.d[0] = q0 * inv; o.d[1] = q1 * inv; o.d[2] = q2 * inv;
+}
+
+}  // namespace gcl

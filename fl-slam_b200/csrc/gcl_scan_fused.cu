@@ -1,0 +1,610 @@
+// gcl_scan_fused.cu -- K1: the one kernel that touches O(N) data.
+//
+// One pass over the raw points fuses: PointBudget gather (stride), constant-twist deskew + time-window weights,
+// ray directions, softmax responsibilities over the bin atlas and the per-bin weighted moment sums
+//   M_b[19] = sum_i w_i r_ib [1, d, ddT(6), p, ppT(6)]
+// without materialising the (N,B) responsibilities or the (N,3,3) outer products the reference builds
+// (archive/legacy_operators/binning.py:69,:171).
+//
+// Per CTA (256 threads, persistent over its slice of the selected rows), tile = TP points (TP = 256/TA, a power of two):
+//   front     threads [0,TP): cp.async-staged raw row -> deskew, window weight, direction d_i (kept in registers),
+//             {d_i, shift} to shared memory.
+//   phase A   TA threads per point, each over B/TA bins: e_ib = exp(d_i . b'_b + shift) with the atlas pre-scaled
+//             (fp32: log2(e)/tau and ex2.approx; fp64: 128 log2(e)/tau and a table-driven exp, below); e_ib goes to a
+//             shared-memory tile [point][bin] and is computed ONCE; partial Z, sum e x (entropy) and max per thread.
+//   scale     threads [0,TP): Z_i, certificate partials, row (w_i/Z_i) * phi_i to shared memory.
+//   phase B   "GEMM by hand" on CUDA cores: thread = (bin lane, point slice) owns G consecutive bins x 19 accumulators in
+//             registers; per point one vector LDS of its G exponentials and warp-broadcast LDS.128 of the row, then
+//             19 G multiply-adds (fp32: packed fma.rn.f32x2 over bin pairs; fp64: DFMA).
+//   flush     per-thread partials are combined across point slices in a FIXED order and carried in fp64 in this CTA's
+//             record (no atomics => bit-reproducible).  fp32 mode flushes at least every ~512 accumulated points per
+//             thread so that fp32 chains stay short ("fp32c").
+// The contraction depth of the similarity is 3, so tensor cores are not used (BASELINE.json north_star).
+#include "gcl_internal.cuh"
+#include "gcl_point.cuh"
+
+namespace gcl {
+
+constexpr int kNT = 256;       // threads per CTA
+constexpr int kRowPitch = 20;  // values per scaled row: 19 moments + 1 pad (16-byte aligned rows)
+constexpr int kKC = 5;         // moments per flush pass
+
+// ---- fp64 exp for arguments in units of 1/128 octave ---------------------------------------------------------------------
+// 2^(t/128) = 2^k * T[j] * exp(r ln2/128), n = rint(t) = 128 k + j, r = t - n in [-1/2, 1/2].  T[j] = 2^(j/128) lives in
+// shared memory; the degree-5 polynomial has a truncation error below 1e-18.  Relative error vs libm exp <= ~3e-16.
+// Arguments below 2^-1000 (never reached for tau >= 0.003) return 0.
+__device__ __forceinline__ double exp2_128(double t, const double* __restrict__ tab) {
+  const double magic = 6755399441055744.0;  // 2^52 + 2^51
+  const double tm = t + magic;
+  const int n = __double2loint(tm);
+  const double r = t - (tm - magic);
+  double p = 3.8805761567865385e-14;
+  p = fma(p, r, 3.583032305400251e-11);
+  p = fma(p, r, 2.6466421444330967e-08);
+  p = fma(p, r, 1.4662262387640423e-05);
+  p = fma(p, r, 0.0054152123481245725);
+  p = fma(p, r, 1.0);
+  const int k = n >> 7;
+  const double y = tab[n & 127] * p;
+  const double z = __hiloint2double(__double2hiint(y) + (k << 20), __double2loint(y));
+  return (t < -128000.0) ? 0.0 : z;  // also covers the -1e300 marker of bins past the atlas
+}
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr double kScale = 1.4426950408889634;          // logits in octaves
+  static constexpr double kToNat = 0.6931471805599453;          // octaves -> nats
+  static constexpr int kEpMod = 8, kEpRem = 4;                  // e-tile pitch = 4 (mod 8) floats
+  static constexpr int kVec = 4;                                // bins per phase-A step
+};
+template <> struct Num<double> {
+  static constexpr double kScale = 184.6649652337873;           // logits in 1/128 octaves
+  static constexpr double kToNat = 0.0054152123481245725;
+  static constexpr int kEpMod = 4, kEpRem = 2;                  // e-tile pitch = 2 (mod 4) doubles
+  static constexpr int kVec = 2;
+};
+
+__host__ __device__ inline int e_pitch(int cols, int mod, int rem) {
+  int p = cols + ((rem - cols % mod) + mod) % mod;
+  return p;
+}
+
+// ---- register tile of phase B ------------------------------------------------------------------------------------------
+template <typename T, int G> struct Tile;
+template <int G> struct Tile<float, G> {
+  static_assert(G % 2 == 0, "fp32 pairs bins");
+  float2 a[G / 2][19];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int gp = 0; gp < G / 2; ++gp)
+#pragma unroll
+      for (int k = 0; k < 19; ++k) a[gp][k] = make_float2(0.f, 0.f);
+  }
+  static constexpr int VB = (G % 4 == 0) ? 4 : 2;  // bins per vector load; thread owns bins q*VB*L + VB*binlane + [0,VB)
+  __device__ __forceinline__ void step(const float* erow /* + VB*binlane */, int L, const float* row) {
+    float2 e[G / 2];
+    if (VB == 4) {
+#pragma unroll
+      for (int q = 0; q < G / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(erow + q * 4 * L);
+        e[2 * q] = make_float2(v.x, v.y); e[2 * q + 1] = make_float2(v.z, v.w);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < G / 2; ++q) e[q] = *reinterpret_cast<const float2*>(erow + q * 2 * L);
+    }
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float4 f0 = r4[0], f1 = r4[1], f2 = r4[2], f3 = r4[3], f4 = r4[4];
+    const float f[19] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w, f4.x, f4.y, f4.z};
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+      const float2 fk = make_float2(f[k], f[k]);
+#pragma unroll
+      for (int gp = 0; gp < G / 2; ++gp) a[gp][k] = ffma2(e[gp], fk, a[gp][k]);
+    }
+  }
+  __device__ __forceinline__ float get(int g, int k) const { return (g & 1) ? a[g >> 1][k].y : a[g >> 1][k].x; }
+};
+template <int G> struct Tile<double, G> {
+  double a[G][19];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int k = 0; k < 19; ++k) a[g][k] = 0.0;
+  }
+  static constexpr int VB = (G % 2 == 0) ? 2 : 1;
+  __device__ __forceinline__ void step(const double* erow /* + VB*binlane */, int L, const double* row) {
+    double e[G];
+    if (VB == 2) {
+#pragma unroll
+      for (int q = 0; q < G / 2; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(erow + q * 2 * L);
+        e[2 * q] = v.x; e[2 * q + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) e[g] = erow[g * L];
+    }
+    const double2* r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const double2 f = r2[q];
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g][2 * q] = fma(e[g], f.x, a[g][2 * q]);
+      if (2 * q + 1 < 19) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) a[g][(2 * q + 1 < 19) ? 2 * q + 1 : 0] = fma(e[g], f.y, a[g][(2 * q + 1 < 19) ? 2 * q + 1 : 0]);
+      }
+    }
+  }
+  __device__ __forceinline__ double get(int g, int k) const { return a[g][k]; }
+};
+
+// ---- phase A: exponentials of one point over bins [b0, b1), stored to its e-tile row; partial Z, sum e x, max x -----------
+// fp32 atlas: per group of 4 bins three float4 {bx0..3} {by0..3} {bz0..3}; bins >= n_bins hold zeros and are masked to e = 0
+// NG groups of 4 bins at a time, written stage by stage (loads, similarity, exp, store/accumulate) so that the in-order
+// issue sees NG independent chains and the MUFU latency of one group hides behind the others
+template <int NG, bool TAIL>
+__device__ __forceinline__ void phase_a_groups(const float4* __restrict__ p, int b, int B, float2 dx, float2 dy, float2 dz, float2 o2,
+                                               float* __restrict__ erow, float2& Z2, float2& S2, float& m) {
+  float4 ax[NG], ay[NG], az[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { ax[g] = p[3 * g]; ay[g] = p[3 * g + 1]; az[g] = p[3 * g + 2]; }
+  float2 s0[NG], s1[NG], e0[NG], e1[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { s0[g] = ffma2(dz, make_float2(az[g].x, az[g].y), o2); s1[g] = ffma2(dz, make_float2(az[g].z, az[g].w), o2); }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { s0[g] = ffma2(dy, make_float2(ay[g].x, ay[g].y), s0[g]); s1[g] = ffma2(dy, make_float2(ay[g].z, ay[g].w), s1[g]); }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { s0[g] = ffma2(dx, make_float2(ax[g].x, ax[g].y), s0[g]); s1[g] = ffma2(dx, make_float2(ax[g].z, ax[g].w), s1[g]); }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    e0[g] = make_float2(fast_exp2(s0[g].x), fast_exp2(s0[g].y));
+    e1[g] = make_float2(fast_exp2(s1[g].x), fast_exp2(s1[g].y));
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (TAIL) {
+      const int bb = b + 4 * g;
+      if (bb + 0 >= B) { e0[g].x = 0.f; s0[g].x = -3.0e38f; }
+      if (bb + 1 >= B) { e0[g].y = 0.f; s0[g].y = -3.0e38f; }
+      if (bb + 2 >= B) { e1[g].x = 0.f; s1[g].x = -3.0e38f; }
+      if (bb + 3 >= B) { e1[g].y = 0.f; s1[g].y = -3.0e38f; }
+    }
+    *reinterpret_cast<float4*>(erow + b + 4 * g) = make_float4(e0[g].x, e0[g].y, e1[g].x, e1[g].y);
+    Z2 = fadd2(Z2, fadd2(e0[g], e1[g]));
+    S2 = ffma2(e0[g], s0[g], S2); S2 = ffma2(e1[g], s1[g], S2);   // masked bins: 0 * -3e38 = -0
+    m = fmaxf(fmaxf(m, fmaxf(s0[g].x, s0[g].y)), fmaxf(s1[g].x, s1[g].y));
+  }
+}
+__device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, const double*, int b0, int b1, int B, float d0,
+                                             float d1, float d2, float off, float* __restrict__ erow, float& Z, float& S1, float& xmax) {
+  const float2 dx = make_float2(d0, d0), dy = make_float2(d1, d1), dz = make_float2(d2, d2), o2 = make_float2(off, off);
+  float2 Z2 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
+  float m = -3.0e38f;
+  const float4* p = reinterpret_cast<const float4*>(atlas);
+  const int bmain = (b1 <= B) ? b1 : ((B & ~3) > b0 ? (B & ~3) : b0);  // groups below bmain are entirely real bins
+  int b = b0;
+  for (; b + 12 <= bmain; b += 12) phase_a_groups<3, false>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
+  for (; b < bmain; b += 4) phase_a_groups<1, false>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
+  for (; b < b1; b += 4) phase_a_groups<1, true>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
+  Z = Z2.x + Z2.y; S1 = S2.x + S2.y; xmax = m;
+}
+// fp64 atlas: per group of 2 bins three double2 {bx0,bx1} {by0,by1} {bz0,bz1}
+template <bool TAIL>
+__device__ __forceinline__ void phase_a_group(const double2* __restrict__ p, const double* __restrict__ tab, int b, int B, double d0,
+                                              double d1, double d2, double off, double* __restrict__ erow, double& z, double& s1,
+                                              double& m) {
+  const double2 ax = p[0], ay = p[1], az = p[2];
+  double x0 = fma(d0, ax.x, fma(d1, ay.x, fma(d2, az.x, off)));
+  double x1 = fma(d0, ax.y, fma(d1, ay.y, fma(d2, az.y, off)));
+  double e0 = exp2_128(x0, tab), e1 = exp2_128(x1, tab);
+  if (TAIL) {
+    if (b + 0 >= B) { e0 = 0.0; x0 = -1.0e300; }
+    if (b + 1 >= B) { e1 = 0.0; x1 = -1.0e300; }
+  }
+  *reinterpret_cast<double2*>(erow + b) = make_double2(e0, e1);
+  z += e0 + e1;
+  s1 = fma(e0, x0, s1); s1 = fma(e1, x1, s1);
+  m = fmax(m, fmax(x0, x1));
+}
+__device__ __forceinline__ void phase_a_bins(const double* __restrict__ atlas, const double* __restrict__ tab, int b0, int b1, int B,
+                                             double d0, double d1, double d2, double off, double* __restrict__ erow, double& Z,
+                                             double& S1, double& xmax) {
+  double z = 0.0, s1 = 0.0, m = -1.0e300;
+  const double2* p = reinterpret_cast<const double2*>(atlas);
+  const int bmain = (b1 <= B) ? b1 : ((B & ~1) > b0 ? (B & ~1) : b0);
+#pragma unroll 4
+  for (int b = b0; b < bmain; b += 2) phase_a_group<false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  for (int b = bmain; b < b1; b += 2) phase_a_group<true>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  Z = z; S1 = s1; xmax = m;
+}
+__device__ __forceinline__ float exp_of_max(float x, const double*) { return fast_exp2(x); }
+__device__ __forceinline__ double exp_of_max(double x, const double* tab) { return exp2_128(x, tab); }
+
+// row maximum of the scaled similarity over ALL bins (only when the fixed shift could underflow: tiny tau)
+__device__ __forceinline__ float sim_rowmax(const float* atlas, int B, float d0, float d1, float d2) {
+  float m = -3.0e38f;
+  for (int b = 0; b < B; ++b) {
+    const float* g = atlas + 12 * (b >> 2) + (b & 3);
+    m = fmaxf(m, fmaf(d0, g[0], fmaf(d1, g[4], d2 * g[8])));
+  }
+  return m;
+}
+__device__ __forceinline__ double sim_rowmax(const double* atlas, int B, double d0, double d1, double d2) {
+  double m = -1.0e300;
+  for (int b = 0; b < B; ++b) {
+    const double* g = atlas + 6 * (b >> 1) + (b & 1);
+    m = fmax(m, fma(d0, g[0], fma(d1, g[2], d2 * g[4])));
+  }
+  return m;
+}
+
+// ---- shared-memory plan (host and device agree through these) ----------------------------------------------------------------
+struct FusedPlan {
+  int G, L, TP, TA, BA, EP;   // bins/thread, bin lanes, points/tile, phase-A threads/point, bins per phase-A thread, e pitch
+  size_t o_tab, o_sd, o_zp, o_rows, o_etile, o_in, total;
+};
+__host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, int TP) {
+  FusedPlan p;
+  p.G = G; p.L = L; p.TP = TP; p.TA = kNT / TP;
+  const int vec = tsz == 4 ? 4 : 2;
+  p.BA = (((B + p.TA - 1) / p.TA) + vec - 1) / vec * vec;
+  const int cols = (G * L > p.TA * p.BA) ? G * L : p.TA * p.BA;
+  p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : e_pitch(cols, 4, 2);
+  size_t off = (size_t)(p.TA * p.BA) * 3 * tsz;                    // phase-A atlas, 3 components per bin
+  off = (off + 15) & ~(size_t)15;
+  p.o_tab = off;  off += 128 * 8;
+  p.o_sd = off;   off += (size_t)TP * 4 * tsz;
+  p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
+  off = (off + 15) & ~(size_t)15;
+  p.o_rows = off; off += (size_t)TP * kRowPitch * tsz;
+  p.o_in = off;   off += (size_t)TP * 5 * 8;
+  p.o_etile = off;
+  size_t et = (size_t)TP * p.EP * tsz;
+  const size_t stage = (size_t)(kNT / L) * kKC * (size_t)(G * L) * tsz;
+  if (stage > et) et = stage;
+  off += et;
+  p.total = off + 16;
+  return p;
+}
+
+template <typename T, int G, int MINB>
+__global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int B = P.n_bins, L = P.lanes;
+  __shared__ double s_red[kNT / 32][GCL_NCERT];
+
+  const int tid = threadIdx.x;
+  const gcl_job& J = P.jobs ? P.jobs[blockIdx.y] : P.job;
+  const ScanConst& C = P.c;
+
+  // --- this CTA's slice of the selected rows -----------------------------------------------------------------
+  const int64_t n_raw = J.n_raw;
+  const int64_t cap = J.n_points_cap > 0 ? J.n_points_cap : 1;
+  const int64_t stride0 = (n_raw + cap - 1) / cap;                 // ceil(n/cap), point_budget.py:160
+  const int64_t stride = stride0 > 1 ? stride0 : 1;
+  const int64_t n_sel_total = (n_raw + stride - 1) / stride;       // len(arange(0, n, stride))
+  const int64_t sel_begin = J.sel_begin;
+  const int64_t sel_end = (J.sel_end < 0 || J.sel_end > n_sel_total) ? n_sel_total : J.sel_end;
+  const int64_t rows = sel_end > sel_begin ? sel_end - sel_begin : 0;
+  const int64_t rpc = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t lo0 = sel_begin + (int64_t)blockIdx.x * rpc;
+  const int64_t lo = lo0 < sel_end ? lo0 : sel_end;
+  const int64_t hi = (lo + rpc < sel_end) ? lo + rpc : sel_end;
+  double* part = P.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * P.rec_doubles;
+  // points per tile: the launch's maximum (shared-memory bound), fewer when this CTA has few rows (then more threads
+  // share a point in phase A)
+  int TP = P.tile_points;
+  while (TP > 16 && (TP >> 1) >= rpc) TP >>= 1;
+  const FusedPlan pl = fused_plan(B, (int)sizeof(T), G, L, TP);
+  const int TA = pl.TA, BA = pl.BA, EP = pl.EP, PS = kNT / L, Bp = G * L;
+  T* s_atlas = reinterpret_cast<T*>(smem_raw);
+  double* s_tab = reinterpret_cast<double*>(smem_raw + pl.o_tab);
+  T* s_d = reinterpret_cast<T*>(smem_raw + pl.o_sd);
+  T* s_zp = reinterpret_cast<T*>(smem_raw + pl.o_zp);
+  T* s_rows = reinterpret_cast<T*>(smem_raw + pl.o_rows);
+  T* s_etile = reinterpret_cast<T*>(smem_raw + pl.o_etile);
+  T* s_stage = s_etile;  // flush staging aliases the e-tile (a flush happens between tiles)
+  double* s_in = reinterpret_cast<double*>(smem_raw + pl.o_in);
+
+  const double cscale_d = Num<T>::kScale / P.tau;
+  const T cscale = (T)cscale_d;
+
+  // --- zero this CTA's record; atlas (pre-scaled) and exp table to shared --------------------------------------------------
+  for (int i = tid; i < GCL_NM * B + GCL_NCERT; i += kNT) part[i] = 0.0;
+  {
+    const int nb = TA * BA;  // padded bin count of phase A
+    constexpr int V = Num<T>::kVec;
+    for (int i = tid; i < nb * 3; i += kNT) {   // group-major: [group][component][lane in group]
+      const int g = i / (3 * V), rem = i - g * 3 * V, c = rem / V, b = g * V + (rem - c * V);
+      s_atlas[i] = (b < B) ? (T)(P.bin_dirs[b * 3 + c] * cscale_d) : (T)0;
+    }
+    if (sizeof(T) == 8) {
+      if (tid < 128) s_tab[tid] = exp2((double)tid * (1.0 / 128.0));
+    }
+  }
+  const int binlane = tid & (L - 1);
+  const int slice = tid / L;
+  const int pi = tid & (TP - 1);   // phase-A point of this thread
+  const int pa = tid / TP;         // phase-A sub-thread
+  float xi32[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
+
+  constexpr int VB = Tile<T, G>::VB;
+  Tile<T, G> acc;
+  acc.zero();
+
+  double c_wraw = 0, c_wsel = 0, c_wsel2 = 0, c_wdesk = 0, c_ent = 0, c_maxr = 0, c_rows = 0;
+
+  // --- sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69) ------------------
+  if (stride > 1 && hi > lo) {
+    const int64_t rlo = lo * stride;
+    const int64_t rhi = (hi >= n_sel_total) ? n_raw : hi * stride;
+    if (P.layout == GCL_LAYOUT_REF_F64) {
+      const double* w = static_cast<const double*>(J.weights);
+      for (int64_t r = rlo + tid; r < rhi; r += kNT) c_wraw += w[r];
+    } else {
+      const float* w = static_cast<const float*>(J.weights);
+      for (int64_t r = rlo + tid; r < rhi; r += kNT) c_wraw += (double)w[r];
+    }
+  }
+
+  // fixed-order cross-slice reduction, kKC moments at a time, carried in fp64 in this CTA's record
+  auto flush = [&]() {
+#pragma unroll
+    for (int k0 = 0; k0 < GCL_NM; k0 += kKC) {
+#pragma unroll
+      for (int kc = 0; kc < kKC; ++kc) {
+        if (k0 + kc < GCL_NM) {
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            s_stage[((size_t)slice * kKC + kc) * Bp + (g / VB) * VB * L + VB * binlane + (g % VB)] = acc.get(g, (k0 + kc < GCL_NM) ? k0 + kc : 0);
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < kKC * Bp; e += kNT) {
+        const int kc = e / Bp, b = e - kc * Bp, k = k0 + kc;
+        if (k < GCL_NM && b < B) {
+          double s = 0.0;
+          for (int sl = 0; sl < PS; ++sl) s += (double)s_stage[((size_t)sl * kKC + kc) * Bp + b];
+          part[(size_t)k * B + b] += s;
+        }
+      }
+      __syncthreads();
+    }
+    acc.zero();
+  };
+
+  // raw rows of tile [t0, t0 + TP) -> s_in, asynchronously (one row per thread of the front group)
+  auto prefetch_tile = [&](int64_t t0) {
+    const int64_t srow = t0 + tid;
+    if (tid >= TP || srow >= hi) return;
+    const int64_t r = srow * stride;
+    if (P.layout == GCL_LAYOUT_REF_F64) {
+      const double* pts = static_cast<const double*>(J.points) + r * 3;
+      double* dst = s_in + (size_t)tid * 5;
+      cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
+      cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + r);
+      cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
+    } else {
+      float* base = reinterpret_cast<float*>(s_in);
+      cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + r);
+      cp_async4(base + (size_t)TP * 4 + tid, static_cast<const float*>(J.weights) + r);
+    }
+  };
+  prefetch_tile(lo);
+
+  int pts_since_flush = 0;
+  const int flush_points = (sizeof(T) == 4) ? 512 * PS : (1 << 30);  // per-thread chain length ~512 in fp32
+
+  for (int64_t tile0 = lo; tile0 < hi; tile0 += TP) {
+    const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+    cp_async_wait_all();
+    __syncthreads();  // raw rows landed; previous tile's phase B (e-tile, rows) is finished
+    // ======================================= front =============================================================
+    T q0 = 0, q1 = 0, q2 = 0, d0 = 0, d1 = 0, d2 = 0, wq = 0;
+    if (tid < count) {
+      const int64_t srow = tile0 + tid;   // selected-row index; raw index = srow * stride (PointBudget gather)
+      double w_sel, w_time;
+      if (P.layout == GCL_LAYOUT_REF_F64) {
+        const double* in = s_in + (size_t)tid * 5;  // {x, y, z, t, w}
+        const double px = in[0], py = in[1], pz = in[2], tt = in[3];
+        w_sel = in[4];
+        if (sizeof(T) == 8) {
+          PointOut64 o;
+          point_front64(J, C, px, py, pz, tt, o);
+          d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+          q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+          w_time = o.w_time;
+        } else {
+          PointOut32 o;
+          point_front32(J, C, xi32, (float)px, (float)py, (float)pz, (float)(tt - J.scan_start_time), o);
+          d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+          q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+          w_time = (double)o.w_time;
+        }
+      } else {
+        const float* base = reinterpret_cast<const float*>(s_in);
+        const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)tid * 4);
+        w_sel = (double)base[(size_t)TP * 4 + tid];
+        PointOut32 o;
+        point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
+        d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+        q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+        w_time = (double)o.w_time;
+      }
+      const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
+      const double w_desk = w_sel * w_time;
+      c_wsel += w_sel; c_wsel2 += w_sel * w_sel; c_wdesk += w_desk; c_rows += 1.0;
+      wq = (T)(w_desk * lam);
+      // Shift = the largest possible logit (|d.b| <= 1) when that cannot underflow, else the true row maximum
+      // (jax.nn.softmax, binning.py:69).
+      const T offv = (P.fixed_shift & 1) ? -cscale : -sim_rowmax(s_atlas, B, d0, d1, d2);
+      T* sd = s_d + (size_t)tid * 4;
+      sd[0] = d0; sd[1] = d1; sd[2] = d2; sd[3] = offv;
+    }
+    __syncthreads();
+    prefetch_tile(tile0 + TP);  // next tile's raw rows stream in while this tile is processed
+    // ======================================= phase A ===========================================================
+    if (pi < count) {
+      const T* sd = s_d + (size_t)pi * 4;
+      T Z, S1, xmax;
+      phase_a_bins(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+      T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
+      zp[0] = Z; zp[1] = S1; zp[2] = xmax;
+    }
+    __syncthreads();
+    // ======================================= scale =============================================================
+    if (tid < count) {
+      T Z = 0, S1 = 0, xmax = (T)-1.0e30;
+      for (int a = 0; a < TA; ++a) {
+        const T* zp = s_zp + ((size_t)a * TP + tid) * 3;
+        Z += zp[0]; S1 += zp[1]; xmax = zp[2] > xmax ? zp[2] : xmax;
+      }
+      // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in logit units
+      const double Zd = (double)Z;
+      if (sizeof(T) == 4) {
+        const float invZ = 1.f / (float)Z;
+        c_ent += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
+        const double mr = (double)(fast_exp2((float)xmax) * invZ);
+        c_maxr = mr > c_maxr ? mr : c_maxr;
+      } else {
+        c_ent += log(Zd) - Num<T>::kToNat * (double)S1 / Zd - (double)B * C.eps_mass;
+        const double mr = (double)exp_of_max(xmax, s_tab) / Zd;
+        c_maxr = mr > c_maxr ? mr : c_maxr;
+      }
+      const T w = wq / Z;
+      T f[kRowPitch];
+      f[0] = w;
+      f[1] = w * d0; f[2] = w * d1; f[3] = w * d2;
+      f[4] = f[1] * d0; f[5] = f[1] * d1; f[6] = f[1] * d2; f[7] = f[2] * d1; f[8] = f[2] * d2; f[9] = f[3] * d2;
+      f[10] = w * q0; f[11] = w * q1; f[12] = w * q2;
+      f[13] = f[10] * q0; f[14] = f[10] * q1; f[15] = f[10] * q2; f[16] = f[11] * q1; f[17] = f[11] * q2; f[18] = f[12] * q2;
+      f[19] = 0;
+      T* row = s_rows + (size_t)tid * kRowPitch;
+      if (sizeof(T) == 4) {
+        float4* r4 = reinterpret_cast<float4*>(row);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r4[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
+      } else {
+        double2* r2 = reinterpret_cast<double2*>(row);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) r2[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
+      }
+    }
+    __syncthreads();
+    // ======================================= phase B ===========================================================
+    {
+      const T* ebase = s_etile + (size_t)binlane * VB;
+#pragma unroll 2
+      for (int pt = slice; pt < count; pt += PS) acc.step(ebase + (size_t)pt * EP, L, s_rows + (size_t)pt * kRowPitch);
+    }
+    pts_since_flush += count;
+    if (pts_since_flush >= flush_points) {
+      __syncthreads();
+      flush();
+      pts_since_flush = 0;
+    }
+  }
+  __syncthreads();
+  if (pts_since_flush > 0) flush();
+
+  // --- certificate scalars of this CTA -------------------------------------------------------------------------
+  double cs[GCL_NCERT] = {c_wraw, c_wsel, c_wsel2, c_wdesk, c_ent, c_maxr, c_rows, 0.0};
+#pragma unroll
+  for (int k = 0; k < GCL_NCERT; ++k) {
+    double v = cs[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = (k == GCL_CS_MAX_RESP) ? fmax(v, other) : v + other;
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5][k] = v;
+  }
+  __syncthreads();
+  if (tid < GCL_NCERT) {
+    // at stride 1 the raw-weight sum IS the selected-weight sum (same numbers, same order)
+    const int src = (tid == GCL_CS_SUM_W_RAW && stride == 1) ? GCL_CS_SUM_W_SEL : tid;
+    double v = s_red[0][src];
+    for (int w = 1; w < kNT / 32; ++w) v = (src == GCL_CS_MAX_RESP) ? fmax(v, s_red[w][src]) : v + s_red[w][src];
+    part[(size_t)GCL_NM * B + tid] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------------------
+static inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// G bins per phase-B thread, L = pow2 bin lanes with G*L >= B; least padding first, then the larger G.
+// Two CTAs per SM (<= 128 registers: G = 4 fp32 / 2 fp64) let one CTA's exp phase overlap the other's accumulate phase.
+struct FusedCfg { int G, minb; };
+void plan_fused_bins(int n_bins, int precision, int* G_out, int* L_out, int* minb_out) {
+  static const FusedCfg c32[] = {{8, 1}, {6, 1}, {4, 2}}, c64[] = {{4, 1}, {3, 1}, {2, 2}};
+  const FusedCfg* cand = precision == GCL_F64 ? c64 : c32;
+  int force_g = 0;
+  if (const char* e = getenv("GCL_K1_G")) force_g = atoi(e);   // tuning aid
+  int bestG = cand[0].G, bestL = kNT, bestM = cand[0].minb, bestWaste = 1 << 30;
+  for (int i = 0; i < 3; ++i) {
+    const int G = cand[i].G;
+    if (force_g && G != force_g) continue;
+    const int L = pow2_ceil((n_bins + G - 1) / G);
+    if (L > kNT) continue;
+    const int waste = G * L - n_bins;
+    if (waste < bestWaste) { bestWaste = waste; bestG = G; bestL = L; bestM = cand[i].minb; }
+  }
+  *G_out = bestG; *L_out = bestL; *minb_out = bestM;
+}
+
+// points per tile: as many as fit in shared memory (the kernel lowers it for CTAs that see few rows), at least 256/16
+int plan_fused_tile(int n_bins, int precision, int G, int L, int minb) {
+  const int tsz = precision == GCL_F64 ? 8 : 4;
+  const size_t budget = (minb == 2 ? 110 : 220) * 1024;
+  int TP = kNT;
+  while (TP > 16 && fused_plan(n_bins, tsz, G, L, TP).total > budget) TP >>= 1;
+  return TP;
+}
+
+template <typename T, int G, int MINB>
+static cudaError_t launch_fused_one(const ScanParams& P, dim3 grid, size_t smem, cudaStream_t stream) {
+  auto kern = scan_moments_fused_kernel<T, G, MINB>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  kern<<<grid, kNT, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+int fused_ctas_per_sm(int n_bins, int precision) {
+  int G, L, M;
+  plan_fused_bins(n_bins, precision, &G, &L, &M);
+  return M;
+}
+
+cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_job, int precision, cudaStream_t stream) {
+  int G, L, M;
+  plan_fused_bins(P.n_bins, precision, &G, &L, &M);
+  const int TP = plan_fused_tile(P.n_bins, precision, G, L, M);
+  P.lanes = L; P.tile_points = TP; P.n_chunks = 1;
+  const size_t smem = fused_plan(P.n_bins, precision == GCL_F64 ? 8 : 4, G, L, TP).total;
+  dim3 grid(ctas_per_job, n_jobs);
+  if (precision == GCL_F64) {
+    switch (G) {
+      case 2: return launch_fused_one<double, 2, 2>(P, grid, smem, stream);
+      case 3: return launch_fused_one<double, 3, 1>(P, grid, smem, stream);
+      default: return launch_fused_one<double, 4, 1>(P, grid, smem, stream);
+    }
+  }
+  switch (G) {
+    case 4: return launch_fused_one<float, 4, 2>(P, grid, smem, stream);
+    case 6: return launch_fused_one<float, 6, 1>(P, grid, smem, stream);
+    default: return launch_fused_one<float, 8, 1>(P, grid, smem, stream);
+  }
+}
+
+}  // namespace gcl
