@@ -29,27 +29,6 @@ constexpr int kNT = 256;       // threads per CTA
 constexpr int kRowPitch = 20;  // values per scaled row: 19 moments + 1 pad (16-byte aligned rows)
 constexpr int kKC = 5;         // moments per flush pass
 
-// ---- fp64 exp for arguments in units of 1/128 octave ---------------------------------------------------------------------
-// 2^(t/128) = 2^k * T[j] * exp(r ln2/128), n = rint(t) = 128 k + j, r = t - n in [-1/2, 1/2].  T[j] = 2^(j/128) lives in
-// shared memory; the degree-5 polynomial has a truncation error below 1e-18.  Relative error vs libm exp <= ~3e-16.
-// Arguments below 2^-1000 (never reached for tau >= 0.003) return 0.
-__device__ __forceinline__ double exp2_128(double t, const double* __restrict__ tab) {
-  const double magic = 6755399441055744.0;  // 2^52 + 2^51
-  const double tm = t + magic;
-  const int n = __double2loint(tm);
-  const double r = t - (tm - magic);
-  double p = 3.8805761567865385e-14;
-  p = fma(p, r, 3.583032305400251e-11);
-  p = fma(p, r, 2.6466421444330967e-08);
-  p = fma(p, r, 1.4662262387640423e-05);
-  p = fma(p, r, 0.0054152123481245725);
-  p = fma(p, r, 1.0);
-  const int k = n >> 7;
-  const double y = tab[n & 127] * p;
-  const double z = __hiloint2double(__double2hiint(y) + (k << 20), __double2loint(y));
-  return (t < -128000.0) ? 0.0 : z;  // also covers the -1e300 marker of bins past the atlas
-}
-
 template <typename T> struct Num;
 template <> struct Num<float> {
   static constexpr double kScale = 1.4426950408889634;          // logits in octaves
@@ -178,6 +157,7 @@ __device__ __forceinline__ void phase_a_groups(const float4* __restrict__ p, int
     m = fmaxf(fmaxf(m, fmaxf(s0[g].x, s0[g].y)), fmaxf(s1[g].x, s1[g].y));
   }
 }
+template <int NGB>
 __device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, const double*, int b0, int b1, int B, float d0,
                                              float d1, float d2, float off, float* __restrict__ erow, float& Z, float& S1, float& xmax) {
   const float2 dx = make_float2(d0, d0), dy = make_float2(d1, d1), dz = make_float2(d2, d2), o2 = make_float2(off, off);
@@ -186,7 +166,7 @@ __device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, co
   const float4* p = reinterpret_cast<const float4*>(atlas);
   const int bmain = (b1 <= B) ? b1 : ((B & ~3) > b0 ? (B & ~3) : b0);  // groups below bmain are entirely real bins
   int b = b0;
-  for (; b + 12 <= bmain; b += 12) phase_a_groups<3, false>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
+  for (; b + 4 * NGB <= bmain; b += 4 * NGB) phase_a_groups<NGB, false>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
   for (; b < bmain; b += 4) phase_a_groups<1, false>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
   for (; b < b1; b += 4) phase_a_groups<1, true>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
   Z = Z2.x + Z2.y; S1 = S2.x + S2.y; xmax = m;
@@ -199,7 +179,7 @@ __device__ __forceinline__ void phase_a_group(const double2* __restrict__ p, con
   const double2 ax = p[0], ay = p[1], az = p[2];
   double x0 = fma(d0, ax.x, fma(d1, ay.x, fma(d2, az.x, off)));
   double x1 = fma(d0, ax.y, fma(d1, ay.y, fma(d2, az.y, off)));
-  double e0 = exp2_128(x0, tab), e1 = exp2_128(x1, tab);
+  double e0 = exp2_128<false>(x0, tab), e1 = exp2_128<false>(x1, tab);
   if (TAIL) {
     if (b + 0 >= B) { e0 = 0.0; x0 = -1.0e300; }
     if (b + 1 >= B) { e1 = 0.0; x1 = -1.0e300; }
@@ -209,19 +189,20 @@ __device__ __forceinline__ void phase_a_group(const double2* __restrict__ p, con
   s1 = fma(e0, x0, s1); s1 = fma(e1, x1, s1);
   m = fmax(m, fmax(x0, x1));
 }
+template <int NGB>
 __device__ __forceinline__ void phase_a_bins(const double* __restrict__ atlas, const double* __restrict__ tab, int b0, int b1, int B,
                                              double d0, double d1, double d2, double off, double* __restrict__ erow, double& Z,
                                              double& S1, double& xmax) {
   double z = 0.0, s1 = 0.0, m = -1.0e300;
   const double2* p = reinterpret_cast<const double2*>(atlas);
   const int bmain = (b1 <= B) ? b1 : ((B & ~1) > b0 ? (B & ~1) : b0);
-#pragma unroll 4
+#pragma unroll NGB
   for (int b = b0; b < bmain; b += 2) phase_a_group<false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
   for (int b = bmain; b < b1; b += 2) phase_a_group<true>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
   Z = z; S1 = s1; xmax = m;
 }
 __device__ __forceinline__ float exp_of_max(float x, const double*) { return fast_exp2(x); }
-__device__ __forceinline__ double exp_of_max(double x, const double* tab) { return exp2_128(x, tab); }
+__device__ __forceinline__ double exp_of_max(double x, const double* tab) { return exp2_128<true>(x, tab); }
 
 // row maximum of the scaled similarity over ALL bins (only when the fixed shift could underflow: tiny tau)
 __device__ __forceinline__ float sim_rowmax(const float* atlas, int B, float d0, float d1, float d2) {
@@ -275,6 +256,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int B = P.n_bins, L = P.lanes;
   __shared__ double s_red[kNT / 32][GCL_NCERT];
+  __shared__ double s_cert[kNT * GCL_NCERT];
 
   const int tid = threadIdx.x;
   const gcl_job& J = P.jobs ? P.jobs[blockIdx.y] : P.job;
@@ -329,15 +311,17 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   const int slice = tid / L;
   const int pi = tid & (TP - 1);   // phase-A point of this thread
   const int pa = tid / TP;         // phase-A sub-thread
-  float xi32[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
 
   constexpr int VB = Tile<T, G>::VB;
   Tile<T, G> acc;
   acc.zero();
 
-  double c_wraw = 0, c_wsel = 0, c_wsel2 = 0, c_wdesk = 0, c_ent = 0, c_maxr = 0, c_rows = 0;
+  const TimeConst tconst = time_const(J);
+  // per-thread certificate partials live in shared memory (they are touched once per tile; registers are for the tile)
+  double* my_cert = s_cert + (size_t)tid * GCL_NCERT;
+#pragma unroll
+  for (int k = 0; k < GCL_NCERT; ++k) my_cert[k] = 0.0;
+  double c_wraw = 0;
 
   // --- sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69) ------------------
   if (stride > 1 && hi > lo) {
@@ -350,6 +334,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       const float* w = static_cast<const float*>(J.weights);
       for (int64_t r = rlo + tid; r < rhi; r += kNT) c_wraw += (double)w[r];
     }
+    my_cert[GCL_CS_SUM_W_RAW] = c_wraw;
   }
 
   // fixed-order cross-slice reduction, kKC moments at a time, carried in fp64 in this CTA's record
@@ -407,6 +392,9 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     // ======================================= front =============================================================
     T q0 = 0, q1 = 0, q2 = 0, d0 = 0, d1 = 0, d2 = 0, wq = 0;
     if (tid < count) {
+      float xi32[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
       const int64_t srow = tile0 + tid;   // selected-row index; raw index = srow * stride (PointBudget gather)
       double w_sel, w_time;
       if (P.layout == GCL_LAYOUT_REF_F64) {
@@ -415,7 +403,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
         w_sel = in[4];
         if (sizeof(T) == 8) {
           PointOut64 o;
-          point_front64(J, C, px, py, pz, tt, o);
+          point_front64_fast(J, C, tconst, s_tab, px, py, pz, tt, o);
           d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
           q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
           w_time = o.w_time;
@@ -438,7 +426,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       }
       const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
       const double w_desk = w_sel * w_time;
-      c_wsel += w_sel; c_wsel2 += w_sel * w_sel; c_wdesk += w_desk; c_rows += 1.0;
+      my_cert[GCL_CS_SUM_W_SEL] += w_sel; my_cert[GCL_CS_SUM_W_SEL_SQ] += w_sel * w_sel; my_cert[GCL_CS_SUM_W_DESKEW] += w_desk;
+      my_cert[GCL_CS_ROWS] += 1.0;
       wq = (T)(w_desk * lam);
       // Shift = the largest possible logit (|d.b| <= 1) when that cannot underflow, else the true row maximum
       // (jax.nn.softmax, binning.py:69).
@@ -452,7 +441,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     if (pi < count) {
       const T* sd = s_d + (size_t)pi * 4;
       T Z, S1, xmax;
-      phase_a_bins(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+      phase_a_bins<(MINB > 1 ? 1 : (sizeof(T) == 4 ? 3 : 4))>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
       T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
       zp[0] = Z; zp[1] = S1; zp[2] = xmax;
     }
@@ -468,13 +457,13 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       const double Zd = (double)Z;
       if (sizeof(T) == 4) {
         const float invZ = 1.f / (float)Z;
-        c_ent += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
+        my_cert[GCL_CS_SUM_ENTROPY] += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
         const double mr = (double)(fast_exp2((float)xmax) * invZ);
-        c_maxr = mr > c_maxr ? mr : c_maxr;
+        if (mr > my_cert[GCL_CS_MAX_RESP]) my_cert[GCL_CS_MAX_RESP] = mr;
       } else {
-        c_ent += log(Zd) - Num<T>::kToNat * (double)S1 / Zd - (double)B * C.eps_mass;
+        my_cert[GCL_CS_SUM_ENTROPY] += log(Zd) - Num<T>::kToNat * (double)S1 / Zd - (double)B * C.eps_mass;
         const double mr = (double)exp_of_max(xmax, s_tab) / Zd;
-        c_maxr = mr > c_maxr ? mr : c_maxr;
+        if (mr > my_cert[GCL_CS_MAX_RESP]) my_cert[GCL_CS_MAX_RESP] = mr;
       }
       const T w = wq / Z;
       T f[kRowPitch];
@@ -513,10 +502,9 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   if (pts_since_flush > 0) flush();
 
   // --- certificate scalars of this CTA -------------------------------------------------------------------------
-  double cs[GCL_NCERT] = {c_wraw, c_wsel, c_wsel2, c_wdesk, c_ent, c_maxr, c_rows, 0.0};
 #pragma unroll
   for (int k = 0; k < GCL_NCERT; ++k) {
-    double v = cs[k];
+    double v = my_cert[k];
     for (int o = 16; o > 0; o >>= 1) {
       const double other = __shfl_xor_sync(0xffffffffu, v, o);
       v = (k == GCL_CS_MAX_RESP) ? fmax(v, other) : v + other;
@@ -539,10 +527,11 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 static inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 // G bins per phase-B thread, L = pow2 bin lanes with G*L >= B; least padding first, then the larger G.
-// Two CTAs per SM (<= 128 registers: G = 4 fp32 / 2 fp64) let one CTA's exp phase overlap the other's accumulate phase.
+// (Two CTAs per SM at <= 128 registers -- G = 4 fp32 / 2 fp64 -- were measured slower than one CTA with the larger tile:
+// 470 vs 420 us fp32 and 1470 vs 1200 us fp64 at 1M x 256; the smaller tile doubles the row traffic per multiply-add.)
 struct FusedCfg { int G, minb; };
 void plan_fused_bins(int n_bins, int precision, int* G_out, int* L_out, int* minb_out) {
-  static const FusedCfg c32[] = {{8, 1}, {6, 1}, {4, 2}}, c64[] = {{4, 1}, {3, 1}, {2, 2}};
+  static const FusedCfg c32[] = {{8, 1}, {6, 1}, {4, 1}}, c64[] = {{4, 1}, {3, 1}, {2, 1}};
   const FusedCfg* cand = precision == GCL_F64 ? c64 : c32;
   int force_g = 0;
   if (const char* e = getenv("GCL_K1_G")) force_g = atoi(e);   // tuning aid
@@ -561,7 +550,8 @@ void plan_fused_bins(int n_bins, int precision, int* G_out, int* L_out, int* min
 // points per tile: as many as fit in shared memory (the kernel lowers it for CTAs that see few rows), at least 256/16
 int plan_fused_tile(int n_bins, int precision, int G, int L, int minb) {
   const int tsz = precision == GCL_F64 ? 8 : 4;
-  const size_t budget = (minb == 2 ? 110 : 220) * 1024;
+  // 228 KB per SM, 1 KB reserved per CTA, ~17 KB static (certificate partials, reduction scratch)
+  const size_t budget = (minb == 2 ? 94 : 200) * 1024;
   int TP = kNT;
   while (TP > 16 && fused_plan(n_bins, tsz, G, L, TP).total > budget) TP >>= 1;
   return TP;
@@ -572,7 +562,7 @@ static cudaError_t launch_fused_one(const ScanParams& P, dim3 grid, size_t smem,
   auto kern = scan_moments_fused_kernel<T, G, MINB>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -595,13 +585,13 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   dim3 grid(ctas_per_job, n_jobs);
   if (precision == GCL_F64) {
     switch (G) {
-      case 2: return launch_fused_one<double, 2, 2>(P, grid, smem, stream);
+      case 2: return launch_fused_one<double, 2, 1>(P, grid, smem, stream);
       case 3: return launch_fused_one<double, 3, 1>(P, grid, smem, stream);
       default: return launch_fused_one<double, 4, 1>(P, grid, smem, stream);
     }
   }
   switch (G) {
-    case 4: return launch_fused_one<float, 4, 2>(P, grid, smem, stream);
+    case 4: return launch_fused_one<float, 4, 1>(P, grid, smem, stream);
     case 6: return launch_fused_one<float, 6, 1>(P, grid, smem, stream);
     default: return launch_fused_one<float, 8, 1>(P, grid, smem, stream);
   }
