@@ -31,6 +31,22 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_moments launch of this workload, from the ncu --set full
+# capture summarised in profiles/ (None until captured)
+TRAFFIC_BYTES_PER_LAUNCH = {"fp64": None, "fp32c": None}
+TRAFFIC_SOURCE = None
+
+
+# FMA-issue ceilings of scan_moments (rates measured with tools/microbench/ffma_rate.cu):
+# FMA-pipe lane operations per (point, bin) pair = 19 accumulate + 3 similarity + softmax bookkeeping (+ the fp64 exp)
+FMA_LANES_PER_CLK_SM = {"fp32c": 128.0, "fp64": 64.0}
+LANE_OPS_PER_PAIR = {"fp32c": 24.0, "fp64": 34.0}
+N_SM = 148
+
+
+def pair_ceiling(precision, sm_mhz):
+    """pairs/s at which the FP32 (FP64) FMA pipe of all SMs would be saturated by scan_moments' own instruction mix."""
+    return FMA_LANES_PER_CLK_SM[precision] / LANE_OPS_PER_PAIR[precision] * N_SM * sm_mhz * 1e6
 
 
 def load_peaks():
@@ -95,18 +111,22 @@ def make_stream(n_scans, seed0=1234 + 2):
     return scans, np.stack(poses)
 
 
-def cpu_stream_rate(n_sample, tau):
+def cpu_stream_rate(n_sample, tau, min_seconds=0.0):
     """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the SAME stream workload:
-    resample, deskew, soft assign, moment match, Matrix Fisher, planar translation, IW update, map update per scan."""
+    resample, deskew, soft assign, moment match, Matrix Fisher, planar translation, IW update, map update per scan.
+    The n_sample-scan stream is walked repeatedly until min_seconds of CPU work have been timed."""
     from oracle import gc_oracle as O
     scans, poses = make_stream(n_sample)
     bins = O.create_fibonacci_atlas(N_BINS)
-    t0 = time.perf_counter()
-    O.scan_stream(scans, poses, poses, n_points_cap=CAP, bin_directions=bins, tau=tau, lidar_origin=scans[0].lidar_origin,
-                  iw_state=O.iw_lidar_init(1e-3), use_sigma_meas=True)
-    dt = time.perf_counter() - t0
     pts = sum(s.points.shape[0] for s in scans)
-    return pts / dt, n_sample / dt, dt
+    dt, passes = 0.0, 0
+    while passes == 0 or dt < min_seconds:
+        t0 = time.perf_counter()
+        O.scan_stream(scans, poses, poses, n_points_cap=CAP, bin_directions=bins, tau=tau, lidar_origin=scans[0].lidar_origin,
+                      iw_state=O.iw_lidar_init(1e-3), use_sigma_meas=True)
+        dt += time.perf_counter() - t0
+        passes += 1
+    return passes * pts / dt, passes * n_sample / dt, dt
 
 
 def blas_threads():
@@ -124,13 +144,13 @@ def run_reference(args, rank):
         return
     from fl_slam_b200 import synth
     tau = synth.DEFAULT_TAU
-    n_sample = 6
+    n_sample = 100
     for _ in range(args.warmup):
-        cpu_stream_rate(2, tau)
+        cpu_stream_rate(10, tau)
     t_all, pts_all, scans_all = 0.0, 0.0, 0.0
     for _ in range(args.steps):
-        pps, sps, dt = cpu_stream_rate(n_sample, tau)
-        t_all += dt; pts_all += pps * dt; scans_all += n_sample
+        pps, sps, dt = cpu_stream_rate(n_sample, tau, min_seconds=3.0)
+        t_all += dt; pts_all += pps * dt; scans_all += sps * dt
     value = pts_all / t_all
     cores = blas_threads()
     line = {"impl": "reference", "metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value,
@@ -155,7 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2]/[3] side measurements")
-    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=100, help="scans in the CPU-baseline sample (walked repeatedly for >= 12 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -238,25 +258,27 @@ def main():
     def rest_only():
         pl.launch_finalize(b["partials"], ctas, pl.rec, pl.rec * ctas, jobs_dev, None, N_SCANS, True, b["reduced"], b["stats"])
         pl.launch_chain(b["stats"], N_SCANS, 1, ms, b["map_derived"], poses_dev, poses_dev, b["evidence"], iw, True, 0.99)
-    def _time(fn):
+    def _time(fn, n=max(args.steps, 100)):
         fn(); torch.cuda.synchronize()
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(n):
             fn()
         ev1.record(); torch.cuda.synchronize()
-        return ev0.elapsed_time(ev1) / args.steps
+        return ev0.elapsed_time(ev1) / n
     k1_ms = _time(moments_only)
     rest_ms = _time(rest_only)
     achieved = bytes_per_launch / (k1_ms * 1e-3) / 1e9
     pairs = float(sum(pl.selected_rows(s.points.shape[0], CAP)[1] for s in scans)) * N_BINS
-    roofline = {"bound": "hbm", "kernel": "scan_moments_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "scan_moments_fused_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src, "ms_per_launch": k1_ms,
                 "launches_per_step": 1, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "share_of_step": k1_ms / ms_per_step, "rest_of_step_ms": rest_ms,
                 "pairs_per_sec": pairs / (k1_ms * 1e-3),
-                "note": "one launch covers all 200 scans (7500 rows x 48 bins each); the kernel is bound by FP64 FMA/exp issue, "
-                        "not by HBM (DESIGN.md); the sequential chain launch dominates the step"}
-    clocks = sampler.stop()
+                "traffic_source": TRAFFIC_SOURCE,
+                "note": "one launch covers all 200 scans (7500 rows x 48 bins each); the kernel is bound by FMA-pipe issue, not by "
+                        "HBM: compute_frac = pairs/s over the FMA-issue ceiling of its own instruction mix at the sampled SM "
+                        "clock (DESIGN.md section 4)"}
+    roofline["traffic"] = TRAFFIC_BYTES_PER_LAUNCH.get(args.precision)
 
     # ---------------------------------------------------------------- e2e: the reference-facing host call, pinned buffers
     n_e2e = min(N_SCANS, 50)
@@ -306,11 +328,15 @@ def main():
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1:
-        pps, sps, dt = cpu_stream_rate(args.cpu_sample, tau)
+        pps, sps, dt = cpu_stream_rate(args.cpu_sample, tau, min_seconds=12.0)
         cpu = {"value": pps, "unit": "points/s", "cores": blas_threads(), "kind": "port", "scans_per_sec": sps,
-               "sample": f"first {args.cpu_sample} scans of the same stream ({dt:.1f} s); NumPy float64 restatement of the "
+               "sample": f"first {args.cpu_sample} scans of the same stream, walked repeatedly for {dt:.1f} s; NumPy float64 restatement of the "
                          f"reference operators (JAX unavailable); os.cpu_count()={os.cpu_count()}"}
 
+    clocks = sampler.stop()   # sampled over the timed stream passes, the per-kernel timing loops, e2e and the side measurements
+    ceiling = pair_ceiling(args.precision, clocks.get("sm_mhz") or 1965.0)
+    roofline["compute_ceiling_pairs_per_sec"] = ceiling
+    roofline["compute_frac"] = roofline["pairs_per_sec"] / ceiling
     if rank == 0:
         line = {"metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value, "unit": "points/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

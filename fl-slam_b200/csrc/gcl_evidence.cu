@@ -91,7 +91,7 @@ __device__ __forceinline__ void translation_sums_warp(int lane, int B, const dou
     mat3_mul(R_hat, Sig_p + b * 9, RS);
     mat3_mul_nt(RS, R_hat, RSR);
     for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? eps : 0.0);
-    mat3_inv_lu(Sg, Si);  // plain inverse, matrix_fisher_evidence.py:462-466
+    mat3_inv_adj(Sg, Si);  // plain inverse, matrix_fisher_evidence.py:462-466
     const double wb = sqrt(sN[b] * map_N_pos[b] + eps);
     for (int i = 0; i < 9; ++i) Si[i] *= wb;
     for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
@@ -105,12 +105,14 @@ __device__ __forceinline__ void translation_sums_warp(int lane, int B, const dou
 
 // t_wls = solve(L_full + eps I, h_full)  (jnp.linalg.solve, :479); evaluated identically on every lane
 __device__ __forceinline__ void translation_solve(const double* Lf, const double* hf, double eps, double* tw) {
-  double Lreg[9];
+  // L_full + eps I is symmetric positive definite: the cofactor inverse needs no pivot search (no dynamically indexed
+  // arrays => everything stays in registers) and is as accurate as LU here
+  double Lreg[9], Li[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) Lreg[i] = Lf[i] + ((i % 4 == 0) ? eps : 0.0);
-  int piv[3];
-  lu3(Lreg, piv);
-  tw[0] = hf[0]; tw[1] = hf[1]; tw[2] = hf[2];
-  lu3_solve(Lreg, piv, tw);
+  mat3_inv_adj(Lreg, Li);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tw[i] = Li[i * 3] * hf[0] + Li[i * 3 + 1] * hf[1] + Li[i * 3 + 2] * hf[2];
 }
 
 // planar mask, PSD projection, information vector, certificate and the 22-D blocks (one thread)
@@ -339,7 +341,12 @@ cudaError_t launch_map_update(const double* stats, const double* R, const double
 }
 
 // ---- LiDAR measurement-noise inverse-Wishart block -------------------------------------------------------------------
-__device__ __forceinline__ double softplus64(double x) { return (x > 0.0 ? x : 0.0) + log1p(exp(-fabs(x))); }
+// softplus(x) = max(x,0) + log1p(exp(-|x|)); beyond |x| = 40 the second term (< 4.3e-18) is below half an ulp of the first
+// whenever the first is non-zero, and for x < -40 it equals exp(x) to rounding: the shortcuts return the same doubles
+__device__ __forceinline__ double softplus64(double x) {
+  if (x > 40.0) return x;
+  return (x > 0.0 ? x : 0.0) + log1p(exp(-fabs(x)));
+}
 
 // IW mode Sigma = PSD(Psi / (nu + p + 1)), p = 3   (measurement_noise_iw_jax.py:37-57)
 __device__ inline void iw_sigma_mode(const double* iw /* [nu, Psi(9)] */, double eps_psd, double* Sigma) {
@@ -353,9 +360,9 @@ __device__ inline void iw_sigma_mode(const double* iw /* [nu, Psi(9)] */, double
 __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T (9), sum w] */, double rho, double nu_weak_add,
                                  double nu_max, double eps_mass, double eps_psd) {
   double rrT[9], dPsi[9];
-  const double wsum = rr_w[9] + eps_mass;
+  const double iw_ = 1.0 / (rr_w[9] + eps_mass);
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) rrT[i * 3 + j] = 0.5 * (rr_w[i * 3 + j] + rr_w[j * 3 + i]) / wsum;
+    for (int j = 0; j < 3; ++j) rrT[i * 3 + j] = 0.5 * (rr_w[i * 3 + j] + rr_w[j * 3 + i]) * iw_;
   psd_project3_fast(rrT, eps_psd, dPsi);
   double Praw[9], Ppsd[9];
   for (int i = 0; i < 9; ++i) Praw[i] = rho * iw[1 + i] + dPsi[i];
@@ -547,42 +554,51 @@ __global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __
 
 // S4a: IW recurrence alone (the residual statistics do not depend on the IW state when Sigma_meas is not fed back)
 __global__ void stream_iw_recurrence_kernel(const __grid_constant__ ChainParams P) {
-  if (threadIdx.x != 0) return;
   const StreamWs W(P.workspace, P.n_scans, P.n_bins);
+  __shared__ double s_rr[32][10];   // residual statistics of the next 32 scans (one global round trip per 32 scans)
   double iw[10];
   for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
-  for (int s = 0; s < P.n_scans; ++s)
-    iw_update(iw, W.tpart + ((size_t)s * P.n_hyp) * 32 + 13, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
-  for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
+  for (int s0 = 0; s0 < P.n_scans; s0 += 32) {
+    const int n = P.n_scans - s0 < 32 ? P.n_scans - s0 : 32;
+    for (int i = threadIdx.x; i < n * 10; i += 32) s_rr[i / 10][i % 10] = W.tpart[((size_t)(s0 + i / 10) * P.n_hyp) * 32 + 13 + i % 10];
+    __syncwarp();
+    for (int s = 0; s < n; ++s) iw_update(iw, s_rr[s], P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);  // every lane, same values
+    __syncwarp();
+  }
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
 }
 
 // S4b: the sequential core with Sigma_meas fed back.  Warp 0 computes, warp 1 stages the next scan's inputs in shared memory.
 //      staged block per scan (doubles): N[B] p_bar[3B] sum_ppT[9B] | cen[3B] Sig_c[9B] | N_pos[B] | R_hat[9]
 __device__ __forceinline__ size_t seq_block_doubles(int B) { return 26 * (size_t)B + 9; }
-__global__ void __launch_bounds__(64) stream_sigma_chain_kernel(const __grid_constant__ ChainParams P, int use_smem) {
+constexpr int kSeqHelpers = 3;  // warps that stage the next scan's inputs while warp 0 computes
+__global__ void __launch_bounds__(32 * (1 + kSeqHelpers)) stream_sigma_chain_kernel(const __grid_constant__ ChainParams P, int use_smem) {
   extern __shared__ __align__(16) double s_stage[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = P.n_bins, H = P.n_hyp, S = P.n_scans;
   const StatsLayout SL(B);
   const StreamWs W(P.workspace, S, B);
   const size_t blk = seq_block_doubles(B);
-  auto stage = [&](int s, double* dst) {  // all 32 lanes of the calling warp
+  const int hl = tid - 32, HN = 32 * kSeqHelpers;  // helper-thread index / count
+  auto stage = [&](int s, double* dst) {  // all helper threads
     const double* st = P.stats + (size_t)s * H * P.stats_stride;
     const double* md = W.mder + (size_t)s * 16 * B;
     const MapView mv = map_view(P, W, s);
     const double* ev = P.evidence + (size_t)s * H * GCL_EVID_DOUBLES;
-    for (int i = lane; i < B; i += 32) { dst[i] = st[SL.N() + i]; dst[25 * B + i] = mv.N_pos[i]; }
-    for (int i = lane; i < 3 * B; i += 32) { dst[B + i] = st[SL.p_bar() + i]; dst[13 * B + i] = md[4 * B + i]; }
-    for (int i = lane; i < 9 * B; i += 32) { dst[4 * B + i] = st[SL.sum_ppT() + i]; dst[16 * B + i] = md[7 * B + i]; }
-    if (lane < 9) dst[26 * B + lane] = ev[GCL_EV_R_MF + lane];
+    for (int i = hl; i < B; i += HN) { dst[i] = st[SL.N() + i]; dst[25 * B + i] = mv.N_pos[i]; }
+    for (int i = hl; i < 3 * B; i += HN) { dst[B + i] = st[SL.p_bar() + i]; dst[13 * B + i] = md[4 * B + i]; }
+#pragma unroll 4
+    for (int i = hl; i < 9 * B; i += HN) { dst[4 * B + i] = st[SL.sum_ppT() + i]; dst[16 * B + i] = md[7 * B + i]; }
+    if (hl < 9) dst[26 * B + hl] = ev[GCL_EV_R_MF + hl];
   };
   if (use_smem) {
-    if (warp == 1) stage(0, s_stage);
+    if (warp >= 1) stage(0, s_stage);
     __syncthreads();
   }
   double iw[10];
   for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
   for (int s = 0; s < S; ++s) {
-    if (warp == 1) {
+    if (warp >= 1) {
       if (use_smem && s + 1 < S) stage(s + 1, s_stage + ((s + 1) & 1) * blk);
     } else {
       double* st0 = P.stats + (size_t)s * H * P.stats_stride;
@@ -618,7 +634,7 @@ __global__ void __launch_bounds__(64) stream_sigma_chain_kernel(const __grid_con
         mat3_mul(R_hat, Sp, RS);
         mat3_mul_nt(RS, R_hat, RSR);
         for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
-        mat3_inv_lu(Sg, Si);
+        mat3_inv_adj(Sg, Si);
         const double wb = sqrt(N * Npos[b] + P.eps_mass);
         for (int i = 0; i < 9; ++i) Si[i] *= wb;
         for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
@@ -700,7 +716,7 @@ cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launche
       if (e != cudaSuccess) return e;
       attr_done = true;
     }
-    stream_sigma_chain_kernel<<<1, 64, use_smem ? smem : 0, stream>>>(P, use_smem);
+    stream_sigma_chain_kernel<<<1, 32 * (1 + kSeqHelpers), use_smem ? smem : 0, stream>>>(P, use_smem);
     stream_translation_finish_kernel<<<S * P.n_hyp, 32, 0, stream>>>(P);
     *launches += 2;
   } else if (P.iw_state) {

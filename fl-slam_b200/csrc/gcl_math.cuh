@@ -285,6 +285,18 @@ __host__ __device__ inline void mat3_inv_lu(const double* A, double* Ainv) {
   }
 }
 
+// 3x3 inverse by cofactors: one division, no pivot search.  Used for the per-bin covariance sums of the translation evidence
+// (matrix_fisher_evidence.py:462-466 calls jnp.linalg.inv): those matrices are symmetric positive definite up to round-off, for
+// which the cofactor formula is as accurate as partially pivoted LU (relative error ~ cond * eps in both cases).
+__host__ __device__ inline void mat3_inv_adj(const double* A, double* Ainv) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double id = 1.0 / det;
+  Ainv[0] = c00 * id; Ainv[3] = c01 * id; Ainv[6] = c02 * id;
+  Ainv[1] = (A[2] * A[7] - A[1] * A[8]) * id; Ainv[4] = (A[0] * A[8] - A[2] * A[6]) * id; Ainv[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+  Ainv[2] = (A[1] * A[5] - A[2] * A[4]) * id; Ainv[5] = (A[2] * A[3] - A[0] * A[5]) * id; Ainv[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
 // ---- kappa, pkg/backend/operators/kappa.py:130-169 -----------------------------------------------------------
 __host__ __device__ inline double kappa_from_resultant(double Rbar, double eps_r, double d, double r0, double tau) {
   const double R = fmin(fmax(Rbar, 0.0), 1.0 - eps_r);

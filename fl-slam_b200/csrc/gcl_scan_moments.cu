@@ -1,4 +1,6 @@
-// gcl_scan_moments.cu -- K1: the one kernel that touches O(N) data.
+// gcl_scan_moments.cu -- moment sums from MATERIALISED responsibilities (the stand-alone ScanBinMomentMatch operator,
+// archive/legacy_operators/binning.py:212-324, with per-point covariances).  The fused hot path is gcl_scan_fused.cu; only the
+// FROM_RESP instantiations of the kernel below are built.
 //
 // One pass over the raw points fuses: PointBudget gather (stride), constant-twist deskew + time-window weights,
 // ray directions, softmax responsibilities over the bin atlas and the per-bin weighted moment sums
@@ -543,15 +545,8 @@ cudaError_t launch_scan_moments(const ScanParams& P, int n_jobs, int ctas_per_jo
     if (G == 1) return launch_one<double, 1, 28, true, 256>(P, grid, smem, stream);
     return launch_one<double, 2, 28, true, 256>(P, grid, smem, stream);
   }
-  if (precision == GCL_F64) {
-    if (G == 1) return launch_one<double, 1, 19, false, 256>(P, grid, smem, stream);
-    return launch_one<double, 2, 19, false, 256>(P, grid, smem, stream);
-  }
-  switch (G) {
-    case 2: return launch_one<float, 2, 19, false, GCL_NT_F32>(P, grid, smem, stream);
-    case 4: return launch_one<float, 4, 19, false, GCL_NT_F32>(P, grid, smem, stream);
-    default: return launch_one<float, 6, 19, false, GCL_NT_F32>(P, grid, smem, stream);
-  }
+  (void)precision;
+  return cudaErrorNotSupported;  // the fused path lives in gcl_scan_fused.cu
 }
 
 }  // namespace gcl
