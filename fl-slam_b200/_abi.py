@@ -30,7 +30,7 @@ class GclJob(C.Structure):
     """Mirror of struct gcl_job."""
     _fields_ = [("points", C.c_void_p), ("timestamps", C.c_void_p), ("weights", C.c_void_p),
                 ("point_lambda", C.c_void_p), ("n_raw", C.c_int64), ("n_points_cap", C.c_int32),
-                ("sel_begin", C.c_int32), ("sel_end", C.c_int32), ("reserved", C.c_int32),
+                ("sel_begin", C.c_int32), ("sel_end", C.c_int32), ("flags", C.c_int32),
                 ("scan_start_time", C.c_double), ("scan_end_time", C.c_double), ("xi_body", C.c_double * 6)]
 
 
@@ -74,6 +74,8 @@ def _load():
                                  f64, f64, vp]),
         "gcl_scan_chain_workspace_doubles": (C.c_size_t, [i32, i32, i32]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
+        "gcl_scan_submit_host": (i32, [vp, i32, vp, vp, vp, i64, C.c_int32, f64, f64, vp, i32, vp, vp, i32, f64, i32, f64, f64]),
+        "gcl_scan_evidence_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, vp, vp]),
         "gcl_lidar_scan_evidence_host": (i32, [vp, vp, vp, vp, i64, C.c_int32, f64, f64, vp, vp, i32, vp, vp, i32, f64, i32,
                                                vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, vp, vp]),
     }

@@ -4,6 +4,10 @@
 #include <cstring>
 #include <string>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "gcl_internal.cuh"
 
 using namespace gcl;
@@ -66,7 +70,15 @@ int gcl_create(int device, gcl_handle* out) {
 void gcl_destroy(gcl_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->stream1) { cudaStreamSynchronize(h->stream1); cudaStreamDestroy(h->stream1); }
+  if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
+  for (int i = 0; i < 2; ++i) {
+    if (h->slot[i].ev_copy) cudaEventDestroy(h->slot[i].ev_copy);
+    if (h->slot[i].ev_stage1) cudaEventDestroy(h->slot[i].ev_stage1);
+    if (h->slot[i].d_buf) cudaFree(h->slot[i].d_buf);
+    if (h->slot[i].h_buf) cudaFreeHost(h->slot[i].h_buf);
+  }
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->h_buf) cudaFreeHost(h->h_buf);
   delete h;
@@ -350,7 +362,7 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
   P.map_sum_ppT = msum_ppT; P.workspace = map_derived; P.pose_pred = pose_pred; P.pose_update = pose_update;
   P.iw_state = iw_state; P.evidence = evidence; P.n_scans = n_scans; P.n_hyp = n_hyp; P.n_bins = n_bins;
   P.use_sigma_meas = use_sigma_meas; P.forgetting = forgetting; P.iw_rho = iw_rho; P.iw_nu_weak_add = iw_nu_weak_add;
-  P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass;
+  P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.chain_smem = 0;
   cudaSetDevice(h->device);
   int l = 0;
   GCL_CUDA(h, launch_chain(P, (cudaStream_t)stream, &l));
@@ -369,30 +381,220 @@ int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const 
   return GCL_OK;
 }
 
-// ---- reference-facing call with HOST buffers -------------------------------------------------------------------------------
-static int ensure_buffers(gcl_handle h, size_t dbytes, size_t hbytes) {
-  if (!h->stream) GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  if (dbytes > h->d_bytes) {
-    if (h->d_buf) cudaFree(h->d_buf);
-    h->d_buf = nullptr; h->d_bytes = 0;
-    GCL_CUDA(h, cudaMalloc(&h->d_buf, dbytes));
-    h->d_bytes = dbytes;
+// ---- reference-facing calls with HOST buffers ---------------------------------------------------------------------------------
+// Two stages per scan.  Stage 1 (submit) needs only the scan and the twist: H2D of the scan on the copy stream, then
+// scan_moments + reduce_finalize on the stage-1 stream; it returns without waiting.  Stage 2 (evidence) needs the pose
+// prediction and the map: it waits (on the GPU) for stage 1 of the same slot, runs the chain step, copies every output back
+// in ONE D2H and synchronises.  Two slots let the upload and the moment pass of scan k+1 overlap the evidence step (and the
+// caller's own fusion work) of scan k; gcl_lidar_scan_evidence_host is submit + evidence on slot 0.
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int grow(gcl_handle h, void** d, size_t* dcap, void** hp, size_t* hcap, size_t dbytes, size_t hbytes) {
+  if (dbytes > *dcap) {
+    if (*d) cudaFree(*d);
+    *d = nullptr; *dcap = 0;
+    GCL_CUDA(h, cudaMalloc(d, dbytes));
+    *dcap = dbytes;
   }
-  if (hbytes > h->h_bytes) {
-    if (h->h_buf) cudaFreeHost(h->h_buf);
-    h->h_buf = nullptr; h->h_bytes = 0;
-    GCL_CUDA(h, cudaMallocHost(&h->h_buf, hbytes));
-    h->h_bytes = hbytes;
+  if (hbytes > *hcap) {
+    if (*hp) cudaFreeHost(*hp);
+    *hp = nullptr; *hcap = 0;
+    GCL_CUDA(h, cudaMallocHost(hp, hbytes));
+    *hcap = hbytes;
   }
   return GCL_OK;
 }
 
-static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static int ensure_streams(gcl_handle h) {
+  if (h->stream) return GCL_OK;
+  GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream1, cudaStreamNonBlocking));
+  GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_copy, cudaEventDisableTiming));
+    GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_stage1, cudaEventDisableTiming));
+  }
+  return GCL_OK;
+}
+
+// GCL_HOST_TIMING=1: per-stage wall clock of the blocking host entry (the streams are synchronised at each mark, so this mode
+// serialises the stages -- for diagnosis only), averaged and printed every 64 calls
+struct HostTiming {
+  bool on; int n; double acc[8]; std::chrono::steady_clock::time_point t;
+  HostTiming() : on(getenv("GCL_HOST_TIMING") != nullptr), n(0) { for (double& a : acc) a = 0; }
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void mark(int i, gcl_handle h, bool sync = true) {
+    if (!on) return;
+    if (sync) { cudaStreamSynchronize(h->stream_copy); cudaStreamSynchronize(h->stream1); cudaStreamSynchronize(h->stream); }
+    const auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  void done() {
+    if (!on || ++n < 64) return;
+    fprintf(stderr, "[gcl host timing, us/call] stage+enqueue H2D %.1f | H2D done %.1f | scan_moments %.1f | reduce_finalize %.1f | chain %.1f | D2H+sync %.1f | copy-out %.1f\n",
+            acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n);
+    n = 0; for (double& a : acc) a = 0;
+  }
+};
+static HostTiming g_ht;
 
 static bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
+}
+
+int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
+                         const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1, const double* xi_host,
+                         int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
+                         double eps_psd, double eps_mass) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index == 0 || slot_index == 1, "slot must be 0 or 1");
+  GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
+  GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
+  GCL_REQUIRE(h, xi_host && origin_host && bins_host, "NULL pointer");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  cudaSetDevice(h->device);
+  g_ht.start();
+  int rc = ensure_streams(h);
+  if (rc != GCL_OK) return rc;
+  gcl_handle_s::Slot& S = h->slot[slot_index];
+  if (S.pending) {  // a scan that was submitted and never collected is dropped
+    cudaStreamSynchronize(h->stream1);
+    S.pending = false;
+  }
+  const size_t B = n_bins, H = n_hyp, n = (size_t)n_raw;
+  int64_t stride = (n_raw + cap - 1) / cap; if (stride < 1) stride = 1;
+  const int64_t n_sel = (n_raw + stride - 1) / stride;
+  const int ctas = gcl_plan_ctas_per_job(h, n_hyp, n_sel, n_bins, precision);
+  const size_t rec = gcl_partial_record_doubles(n_bins), srec = gcl_stats_record_doubles(n_bins);
+  // slot block (device, mirrored in pinned memory up to o_parts): [points][timestamps][weights] | [bins][jobs] | work
+  // (With stride > 1 only the selected rows of points / timestamps are needed; gathering them on the host first was
+  // measured: the strided CPU reads of a cold 1.2 MB scan cost 33 us against 13 us of PCIe time saved.  A caller whose
+  // producer already emits compact rows can use the device-pointer API with GCL_JOB_COMPACT_ROWS.)
+  const size_t o_pts = 0, o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), o_bins = al(o_w + n * 8);
+  const size_t o_jobs = al(o_bins + B * 24), in_end = al(o_jobs + H * sizeof(gcl_job));
+  const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
+  const size_t d_end = al(o_stats + H * srec * 8);
+  rc = grow(h, &S.d_buf, &S.d_bytes, &S.h_buf, &S.h_bytes, d_end, in_end);
+  if (rc != GCL_OK) return rc;
+  unsigned char* hb = static_cast<unsigned char*>(S.h_buf);
+  unsigned char* db = static_cast<unsigned char*>(S.d_buf);
+  // Scan arrays that already live in page-locked memory are copied straight from the caller's buffers (they must stay
+  // untouched until the matching evidence call returns); pageable arrays go through the pinned block.
+  const bool direct = n > 0 && is_pinned(points_host) && is_pinned(timestamps_host) && is_pinned(weights_host);
+  if (!direct && n > 0) {
+    memcpy(hb + o_pts, points_host, n * 24);
+    memcpy(hb + o_ts, timestamps_host, n * 8);
+    memcpy(hb + o_w, weights_host, n * 8);
+  }
+  memcpy(hb + o_bins, bins_host, B * 24);
+  gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
+  for (int i = 0; i < n_hyp; ++i) {
+    gcl_job& j = hj[i];
+    memset(&j, 0, sizeof(j));
+    j.points = db + o_pts; j.timestamps = db + o_ts; j.weights = db + o_w; j.point_lambda = nullptr;
+    j.n_raw = n_raw; j.n_points_cap = cap; j.sel_begin = 0; j.sel_end = -1;
+    j.scan_start_time = t0; j.scan_end_time = t1;
+    for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host[i * 6 + k];
+  }
+  cudaStream_t sc = h->stream_copy, s1 = h->stream1;
+  if (direct) {
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_pts, points_host, n * 24, cudaMemcpyHostToDevice, sc));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_ts, timestamps_host, n * 8, cudaMemcpyHostToDevice, sc));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_w, weights_host, n * 8, cudaMemcpyHostToDevice, sc));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, in_end - o_bins, cudaMemcpyHostToDevice, sc));
+  } else {
+    GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, sc));
+  }
+  GCL_CUDA(h, cudaEventRecord(S.ev_copy, sc));
+  GCL_CUDA(h, cudaStreamWaitEvent(s1, S.ev_copy, 0));
+  g_ht.mark(0, h, false);
+  g_ht.mark(1, h);
+  const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
+  const gcl_job* d_jobs = reinterpret_cast<const gcl_job*>(db + o_jobs);
+  double* d_parts = reinterpret_cast<double*>(db + o_parts);
+  double* d_red = reinterpret_cast<double*>(db + o_red);
+  double* d_stats = reinterpret_cast<double*>(db + o_stats);
+  rc = gcl_scan_moments(h, s1, d_jobs, nullptr, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host,
+                        eps_mass, d_parts);
+  if (rc != GCL_OK) return rc;
+  g_ht.mark(2, h);
+  rc = gcl_reduce_finalize(h, s1, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
+                           origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
+  if (rc != GCL_OK) return rc;
+  GCL_CUDA(h, cudaEventRecord(S.ev_stage1, s1));
+  g_ht.mark(3, h);
+  S.n_hyp = n_hyp; S.n_bins = n_bins; S.d_stats = d_stats; S.pending = true;
+  S.eps_psd = eps_psd; S.eps_mass = eps_mass;
+  return GCL_OK;
+}
+
+int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host, double* mS_dir, double* mS_sc, double* mN_dir,
+                           double* mN_pos, double* msum_p, double* msum_ppT, const double* pose_update_host, double forgetting,
+                           double* iw_state_host, int use_sigma_meas, double* stats_host, double* evidence_host) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index == 0 || slot_index == 1, "slot must be 0 or 1");
+  gcl_handle_s::Slot& S = h->slot[slot_index];
+  GCL_REQUIRE(h, S.pending, "no scan was submitted to this slot");
+  GCL_REQUIRE(h, pose_host && stats_host && evidence_host, "NULL pointer");
+  GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
+  GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
+  GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
+  cudaSetDevice(h->device);
+  const size_t B = S.n_bins, H = S.n_hyp;
+  const size_t srec = gcl_stats_record_doubles(S.n_bins);
+  // stage-2 block, mirrored in pinned memory: [pose][pose_update][map][iw] | [stats][evidence] | map-derived scratch
+  // ONE H2D carries pose .. iw, ONE D2H carries map .. evidence.
+  const size_t o_pose = 0, o_pupd = al(o_pose + H * 48), o_map = al(o_pupd + 48);  // S_dir 3B, S_sc 9B, N_dir B, N_pos B, sum_p 3B, sum_ppT 9B
+  const size_t o_iw = al(o_map + B * 26 * 8), o_stats = al(o_iw + 80);
+  const size_t o_evid = al(o_stats + H * srec * 8), io_end = al(o_evid + H * GCL_EVID_DOUBLES * 8);
+  const size_t d_end = al(io_end + B * 16 * 8);
+  int rc = grow(h, &h->d_buf, &h->d_bytes, &h->h_buf, &h->h_bytes, d_end, io_end);
+  if (rc != GCL_OK) return rc;
+  unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
+  unsigned char* db = static_cast<unsigned char*>(h->d_buf);
+  cudaStream_t st = h->stream;
+  double* hm = reinterpret_cast<double*>(hb + o_map);
+  memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
+  memcpy(hm + 13 * B, mN_pos, B * 8); memcpy(hm + 14 * B, msum_p, B * 24); memcpy(hm + 17 * B, msum_ppT, B * 72);
+  memcpy(hb + o_pose, pose_host, H * 48);
+  if (pose_update_host) memcpy(hb + o_pupd, pose_update_host, 48);
+  if (iw_state_host) memcpy(hb + o_iw, iw_state_host, 80);
+  GCL_CUDA(h, cudaMemcpyAsync(db + o_pose, hb + o_pose, (o_iw + 80) - o_pose, cudaMemcpyHostToDevice, st));
+  GCL_CUDA(h, cudaStreamWaitEvent(st, S.ev_stage1, 0));
+  double* dm = reinterpret_cast<double*>(db + o_map);
+  double* d_stats = reinterpret_cast<double*>(db + o_stats);
+  double* d_evid = reinterpret_cast<double*>(db + o_evid);
+  double* d_mder = reinterpret_cast<double*>(db + io_end);
+  double* d_iw = iw_state_host ? reinterpret_cast<double*>(db + o_iw) : nullptr;
+  // the chain step rewrites Sigma_p in the stats records: work on the copy that travels back
+  GCL_CUDA(h, cudaMemcpyAsync(d_stats, S.d_stats, H * srec * 8, cudaMemcpyDeviceToDevice, st));
+  rc = gcl_scan_chain(h, st, d_stats, (int64_t)srec, 1, S.n_hyp, S.n_bins, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, dm + 14 * B,
+                      dm + 17 * B, d_mder, reinterpret_cast<const double*>(db + o_pose),
+                      pose_update_host ? reinterpret_cast<const double*>(db + o_pupd) : nullptr, forgetting, d_iw, use_sigma_meas,
+                      0.99 /* GC_IW_RHO_MEAS_LIDAR, constants.py:281 */, 0.5 /* GC_IW_NU_WEAK_ADD, :164 */, 1000.0, S.eps_psd,
+                      S.eps_mass, d_evid);
+  if (rc != GCL_OK) return rc;
+  g_ht.mark(4, h);
+  // one D2H for every output: [map][iw][stats][evidence] (the map / IW blocks ride along even when they were not updated)
+  GCL_CUDA(h, cudaMemcpyAsync(hb + o_map, db + o_map, io_end - o_map, cudaMemcpyDeviceToHost, st));
+  GCL_CUDA(h, cudaStreamSynchronize(st));
+  S.pending = false;
+  g_ht.mark(5, h, false);
+  memcpy(stats_host, hb + o_stats, H * srec * 8);
+  memcpy(evidence_host, hb + o_evid, H * GCL_EVID_DOUBLES * 8);
+  if (pose_update_host) {
+    const double* om = reinterpret_cast<const double*>(hb + o_map);
+    memcpy(mS_dir, om, B * 24); memcpy(mS_sc, om + 3 * B, B * 72); memcpy(mN_dir, om + 12 * B, B * 8);
+    memcpy(mN_pos, om + 13 * B, B * 8); memcpy(msum_p, om + 14 * B, B * 24); memcpy(msum_ppT, om + 17 * B, B * 72);
+  }
+  if (iw_state_host) memcpy(iw_state_host, hb + o_iw, 80);
+  g_ht.mark(6, h, false);
+  g_ht.done();
+  return GCL_OK;
 }
 
 int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,
@@ -403,103 +605,15 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
                                  double forgetting, double* iw_state_host, int use_sigma_meas, double eps_psd, double eps_mass,
                                  double* stats_host, double* evidence_host) {
   if (!h) return GCL_ERR_ARG;
-  GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
-  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
-  GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
-  GCL_REQUIRE(h, xi_host && pose_host && origin_host && bins_host && stats_host && evidence_host, "NULL pointer");
+  GCL_REQUIRE(h, pose_host && stats_host && evidence_host, "NULL pointer");
   GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
-  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
   GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
   GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
-  cudaSetDevice(h->device);
-  const size_t B = n_bins, H = n_hyp, n = (size_t)n_raw;
-  int64_t stride = (n_raw + cap - 1) / cap; if (stride < 1) stride = 1;
-  const int64_t n_sel = (n_raw + stride - 1) / stride;
-  const int ctas = gcl_plan_ctas_per_job(h, n_hyp, n_sel, n_bins, precision);
-  const size_t rec = gcl_partial_record_doubles(n_bins), srec = gcl_stats_record_doubles(n_bins);
-  // one pinned staging block (inputs) and one device block, carved identically
-  const size_t o_pts = 0, o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), o_bins = al(o_w + n * 8);
-  const size_t o_map = al(o_bins + B * 24);                    // S_dir 3B, S_sc 9B, N_dir B, N_pos B, sum_p 3B, sum_ppT 9B
-  const size_t o_pose = al(o_map + B * 26 * 8), o_pupd = al(o_pose + H * 48), o_iw = al(o_pupd + 48);
-  const size_t o_jobs = al(o_iw + 80), in_end = al(o_jobs + H * sizeof(gcl_job));
-  const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
-  const size_t o_evid = al(o_stats + H * srec * 8), o_mder = al(o_evid + H * GCL_EVID_DOUBLES * 8);
-  const size_t d_end = al(o_mder + B * 16 * 8);
-  const size_t out_bytes = al(H * srec * 8) + al(H * GCL_EVID_DOUBLES * 8) + al(B * 26 * 8) + 256;
-  int rc = ensure_buffers(h, d_end, in_end + out_bytes);
+  int rc = gcl_scan_submit_host(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
+                                bins_host, n_bins, tau, precision, eps_psd, eps_mass);
   if (rc != GCL_OK) return rc;
-  unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
-  unsigned char* db = static_cast<unsigned char*>(h->d_buf);
-  cudaStream_t st = h->stream;
-  // Scan arrays that already live in page-locked memory are copied straight from the caller's buffers; pageable
-  // arrays go through the pinned staging block (the memcpy is the price of pageable inputs).
-  const bool direct = n > 0 && is_pinned(points_host) && is_pinned(timestamps_host) && is_pinned(weights_host);
-  if (!direct) {
-    memcpy(hb + o_pts, points_host, n * 24);
-    memcpy(hb + o_ts, timestamps_host, n * 8);
-    memcpy(hb + o_w, weights_host, n * 8);
-  }
-  memcpy(hb + o_bins, bins_host, B * 24);
-  double* hm = reinterpret_cast<double*>(hb + o_map);
-  memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
-  memcpy(hm + 13 * B, mN_pos, B * 8); memcpy(hm + 14 * B, msum_p, B * 24); memcpy(hm + 17 * B, msum_ppT, B * 72);
-  memcpy(hb + o_pose, pose_host, H * 48);
-  if (pose_update_host) memcpy(hb + o_pupd, pose_update_host, 48);
-  if (iw_state_host) memcpy(hb + o_iw, iw_state_host, 80);
-  gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
-  for (int i = 0; i < n_hyp; ++i) {
-    gcl_job& j = hj[i];
-    memset(&j, 0, sizeof(j));
-    j.points = db + o_pts; j.timestamps = db + o_ts; j.weights = db + o_w; j.point_lambda = nullptr;
-    j.n_raw = n_raw; j.n_points_cap = cap; j.sel_begin = 0; j.sel_end = -1;
-    j.scan_start_time = t0; j.scan_end_time = t1;
-    for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host[i * 6 + k];
-  }
-  if (direct) {
-    GCL_CUDA(h, cudaMemcpyAsync(db + o_pts, points_host, n * 24, cudaMemcpyHostToDevice, st));
-    GCL_CUDA(h, cudaMemcpyAsync(db + o_ts, timestamps_host, n * 8, cudaMemcpyHostToDevice, st));
-    GCL_CUDA(h, cudaMemcpyAsync(db + o_w, weights_host, n * 8, cudaMemcpyHostToDevice, st));
-    GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, in_end - o_bins, cudaMemcpyHostToDevice, st));
-  } else {
-    GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, st));
-  }
-  const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
-  double* dm = reinterpret_cast<double*>(db + o_map);
-  const gcl_job* d_jobs = reinterpret_cast<const gcl_job*>(db + o_jobs);
-  double* d_parts = reinterpret_cast<double*>(db + o_parts);
-  double* d_red = reinterpret_cast<double*>(db + o_red);
-  double* d_stats = reinterpret_cast<double*>(db + o_stats);
-  double* d_evid = reinterpret_cast<double*>(db + o_evid);
-  double* d_mder = reinterpret_cast<double*>(db + o_mder);
-  double* d_iw = iw_state_host ? reinterpret_cast<double*>(db + o_iw) : nullptr;
-  rc = gcl_scan_moments(h, st, d_jobs, nullptr, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host,
-                        eps_mass, d_parts);
-  if (rc != GCL_OK) return rc;
-  rc = gcl_reduce_finalize(h, st, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
-                           origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
-  if (rc != GCL_OK) return rc;
-  rc = gcl_scan_chain(h, st, d_stats, (int64_t)srec, 1, n_hyp, n_bins, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, dm + 14 * B,
-                      dm + 17 * B, d_mder, reinterpret_cast<const double*>(db + o_pose),
-                      pose_update_host ? reinterpret_cast<const double*>(db + o_pupd) : nullptr, forgetting, d_iw, use_sigma_meas,
-                      0.99 /* GC_IW_RHO_MEAS_LIDAR, constants.py:281 */, 0.5 /* GC_IW_NU_WEAK_ADD, :164 */, 1000.0, eps_psd,
-                      eps_mass, d_evid);
-  if (rc != GCL_OK) return rc;
-  unsigned char* hout = hb + in_end;
-  const size_t oo_ev = al(H * srec * 8), oo_map = oo_ev + al(H * GCL_EVID_DOUBLES * 8), oo_iw = oo_map + al(B * 26 * 8);
-  GCL_CUDA(h, cudaMemcpyAsync(hout, d_stats, H * srec * 8, cudaMemcpyDeviceToHost, st));
-  GCL_CUDA(h, cudaMemcpyAsync(hout + oo_ev, d_evid, H * GCL_EVID_DOUBLES * 8, cudaMemcpyDeviceToHost, st));
-  if (pose_update_host) GCL_CUDA(h, cudaMemcpyAsync(hout + oo_map, dm, B * 26 * 8, cudaMemcpyDeviceToHost, st));
-  if (iw_state_host) GCL_CUDA(h, cudaMemcpyAsync(hout + oo_iw, d_iw, 80, cudaMemcpyDeviceToHost, st));
-  GCL_CUDA(h, cudaStreamSynchronize(st));
-  memcpy(stats_host, hout, H * srec * 8);
-  memcpy(evidence_host, hout + oo_ev, H * GCL_EVID_DOUBLES * 8);
-  if (pose_update_host) {
-    const double* om = reinterpret_cast<const double*>(hout + oo_map);
-    memcpy(mS_dir, om, B * 24); memcpy(mS_sc, om + 3 * B, B * 72); memcpy(mN_dir, om + 12 * B, B * 8);
-    memcpy(mN_pos, om + 13 * B, B * 8); memcpy(msum_p, om + 14 * B, B * 24); memcpy(msum_ppT, om + 17 * B, B * 72);
-  }
-  if (iw_state_host) memcpy(iw_state_host, hout + oo_iw, 80);
-  return GCL_OK;
+  return gcl_scan_evidence_host(h, 0, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host, forgetting,
+                                iw_state_host, use_sigma_meas, stats_host, evidence_host);
 }
 
 }  // extern "C"

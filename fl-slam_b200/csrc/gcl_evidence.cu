@@ -170,7 +170,11 @@ __device__ __forceinline__ void residual_sums_warp(int lane, int B, const double
 __device__ void pose_evidence_warp(int lane, const double* st, const double* map_S_dir, const double* map_S_sc,
                                    const double* map_N_dir, const double* map_N_pos, const double* map_derived,
                                    const double* pose, const double* R_hat_override, int B, double eps_psd, double eps,
-                                   int do_rotation, int do_translation, double* ev, double* iw_out) {
+                                   int do_rotation, int do_translation, double* ev, double* iw_out, int role = 0,
+                                   double* s_l13 = nullptr, int bar_id = 0) {
+  // role 0: everything on this warp.  Roles 1 / 2 split one hypothesis over a PAIR of warps (the latency-critical single-scan
+  // chain): role 2 computes the scan / map scatter metrics (two symmetric eigen problems) while role 1 runs the SVD chain;
+  // they meet at named barrier `bar_id` (64 threads) where role 2 hands over the map eigenvalues through s_l13.
   const StatsLayout SL(B);
   const double* sN = st + SL.N();
   const double* s_dir = st + SL.s_dir();
@@ -179,7 +183,9 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
   const double* Sig_p = st + SL.Sigma_p();
   const double* m_cen = map_derived + 4 * B;
   const double* m_Sig = map_derived + 7 * B;
-  for (int i = lane; i < GCL_EVID_DOUBLES; i += 32) ev[i] = 0.0;
+  if (role != 2)
+    for (int i = lane; i < GCL_EVID_DOUBLES; i += 32)
+      if (role == 0 || i < GCL_EV_SCAN_METRICS || i >= GCL_EV_T_WLS) ev[i] = 0.0;   // role 2 owns [SCAN_METRICS, T_WLS)
   __syncwarp();
 
   // ---- pass 1 over bins: cross-covariance H, effective mass, scatter totals ------------------------------------
@@ -187,6 +193,11 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
   double sumNs = 0, sumNm = 0;
   for (int b = lane; b < B; b += 32) {
     const double Ns = sN[b], Nm = map_N_dir[b];
+    if (role != 1) {
+      for (int i = 0; i < 9; ++i) { scanT[i] += sS[b * 9 + i]; mapT[i] += map_S_sc[b * 9 + i]; }
+      sumNs += Ns; sumNm += Nm;
+    }
+    if (role == 2) continue;
     const double ss[3] = {s_dir[b * 3], s_dir[b * 3 + 1], s_dir[b * 3 + 2]};
     const double sm[3] = {map_S_dir[b * 3], map_S_dir[b * 3 + 1], map_S_dir[b * 3 + 2]};
     const double wb = sqrt(Ns * Nm + eps);
@@ -198,11 +209,15 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) H[i * 3 + j] += w * (sm[i] * inm) * (ss[j] * ins);
     Neff += w;
-    for (int i = 0; i < 9; ++i) { scanT[i] += sS[b * 9 + i]; mapT[i] += map_S_sc[b * 9 + i]; }
-    sumNs += Ns; sumNm += Nm;
   }
-  for (int i = 0; i < 9; ++i) { H[i] = warp_sum(H[i]); scanT[i] = warp_sum(scanT[i]); mapT[i] = warp_sum(mapT[i]); }
-  Neff = warp_sum(Neff); sumNs = warp_sum(sumNs); sumNm = warp_sum(sumNm);
+  if (role != 2) {
+    for (int i = 0; i < 9; ++i) H[i] = warp_sum(H[i]);
+    Neff = warp_sum(Neff);
+  }
+  if (role != 1) {
+    for (int i = 0; i < 9; ++i) { scanT[i] = warp_sum(scanT[i]); mapT[i] = warp_sum(mapT[i]); }
+    sumNs = warp_sum(sumNs); sumNm = warp_sum(sumNm);
+  }
 
   double R_hat[9];
   double Rp[9];
@@ -210,7 +225,7 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
   // independent 3x3 eigen problems run on separate lanes: 0 = SVD chain, 1 = scan scatter metrics, 2 = map scatter metrics
   double map_eval[3] = {0, 0, 0};
   // lanes 1 and 2 run the same code on different matrices (scan / map scatter), so they execute together
-  if (lane == 1 || lane == 2) {
+  if (role != 1 && (lane == 1 || lane == 2)) {
     double m8[8], v9[9];
     scatter_metrics(lane == 1 ? scanT : mapT, lane == 1 ? sumNs : sumNm, eps, m8, v9);  // map: same matrix as T_map (:572-587)
     if (do_rotation) {
@@ -219,6 +234,11 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
       for (int i = 0; i < 9; ++i) ev[ov + i] = v9[i];
     }
     map_eval[0] = m8[0]; map_eval[2] = m8[2];
+    if (role == 2 && lane == 2) { s_l13[0] = m8[0]; s_l13[1] = m8[2]; }
+  }
+  if (role == 2) {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    return;
   }
   if (do_rotation) {
     if (lane == 0) {
@@ -258,7 +278,11 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
     }
     for (int i = 0; i < 9; ++i) R_hat[i] = __shfl_sync(0xffffffffu, R_hat[i], 0);
   }
-  const double l1m = __shfl_sync(0xffffffffu, map_eval[0], 2), l3m = __shfl_sync(0xffffffffu, map_eval[2], 2);
+  double l1m = __shfl_sync(0xffffffffu, map_eval[0], 2), l3m = __shfl_sync(0xffffffffu, map_eval[2], 2);
+  if (role == 1) {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    l1m = s_l13[0]; l3m = s_l13[1];
+  }
   if (R_hat_override)
     for (int i = 0; i < 9; ++i) R_hat[i] = R_hat_override[i];
   if (!do_translation) return;
@@ -408,6 +432,9 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
   const StatsLayout SL(B);
   __shared__ double s_iw[10];
   __shared__ double s_sigma[9];
+  __shared__ double s_l13[kChainThreads / 64][2];
+  extern __shared__ __align__(16) double s_mder_dyn[];
+  double* mder = P.chain_smem ? s_mder_dyn : P.workspace;   // map-derived statistics stay on chip when they fit
   for (int s = 0; s < P.n_scans; ++s) {
     double* st0 = P.stats + (size_t)s * H * P.stats_stride;
     // 1. measurement noise enters every bin covariance
@@ -424,13 +451,14 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     }
     // 2. map-derived statistics
     for (int b = tid; b < B; b += kChainThreads)
-      map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, P.workspace);
+      map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, mder);
     __syncthreads();
-    // 3. pose evidence, one warp per hypothesis
-    for (int h = warp; h < H; h += kChainThreads / 32)
+    // 3. pose evidence, one PAIR of warps per hypothesis (SVD chain | scatter metrics)
+    for (int h = warp >> 1; h < H; h += kChainThreads / 64)
       pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
-                         P.workspace, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
-                         P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr);
+                         mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                         P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr,
+                         1 + (warp & 1), s_l13[warp >> 1], 1 + (warp >> 1));
     __syncthreads();
     // 4. IW update from hypothesis 0's translation residuals
     if (P.iw_state && tid == 0) iw_update(P.iw_state, s_iw, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
@@ -695,7 +723,10 @@ __global__ void __launch_bounds__(32) stream_translation_finish_kernel(const __g
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches) {
   *launches = 0;
   if (P.n_scans < kStagedMinScans) {
-    chain_kernel<<<1, kChainThreads, 0, stream>>>(P);
+    ChainParams Q = P;
+    const size_t smem = 16 * (size_t)P.n_bins * sizeof(double);
+    Q.chain_smem = smem <= 40 * 1024;
+    chain_kernel<<<1, kChainThreads, Q.chain_smem ? smem : 0, stream>>>(Q);
     *launches = 1;
     return cudaGetLastError();
   }

@@ -9,7 +9,7 @@
 
 namespace gcl {
 
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 512;
 
 __device__ __forceinline__ double block_reduce(double v, bool is_max, double* s_buf) {
   // fixed shuffle tree inside a warp, then warps in index order

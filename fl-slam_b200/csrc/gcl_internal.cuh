@@ -23,10 +23,21 @@ struct gcl_handle_s {
   int sm_count = 148;
   int64_t launches = 0;
   std::string err;
-  // resources of the *_host entry point (allocated on first use, grown on demand)
-  cudaStream_t stream = nullptr;
-  void* d_buf = nullptr; size_t d_bytes = 0;
+  // resources of the *_host entry points (allocated on first use, grown on demand)
+  cudaStream_t stream = nullptr;       // stage 2: chain step + D2H
+  cudaStream_t stream1 = nullptr;      // stage 1: scan_moments + reduce_finalize
+  cudaStream_t stream_copy = nullptr;  // H2D of the scans
+  void* d_buf = nullptr; size_t d_bytes = 0;   // stage-2 block
   void* h_buf = nullptr; size_t h_bytes = 0;
+  struct Slot {                         // one scan in flight
+    void* d_buf = nullptr; size_t d_bytes = 0;
+    void* h_buf = nullptr; size_t h_bytes = 0;
+    cudaEvent_t ev_copy = nullptr, ev_stage1 = nullptr;
+    double* d_stats = nullptr;
+    int n_hyp = 0, n_bins = 0;
+    double eps_psd = 0, eps_mass = 0;
+    bool pending = false;
+  } slot[2];
 };
 
 namespace gcl {
@@ -103,6 +114,7 @@ struct ChainParams {
   double* iw_state;         // [nu, Psi(9)] LiDAR measurement-noise block, or nullptr
   double* evidence;         // (n_scans * n_hyp) records
   int n_scans, n_hyp, n_bins, use_sigma_meas;
+  int chain_smem;           // single-launch chain: map-derived statistics live in dynamic shared memory
   double forgetting, iw_rho, iw_nu_weak_add, iw_nu_max, eps_psd, eps_mass;
 };
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches);

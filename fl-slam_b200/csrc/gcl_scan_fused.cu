@@ -367,16 +367,17 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   auto prefetch_tile = [&](int64_t t0) {
     const int64_t srow = t0 + tid;
     if (tid >= TP || srow >= hi) return;
-    const int64_t r = srow * stride;
+    const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
+    const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;         // row in the points / timestamps arrays
     if (P.layout == GCL_LAYOUT_REF_F64) {
-      const double* pts = static_cast<const double*>(J.points) + r * 3;
+      const double* pts = static_cast<const double*>(J.points) + rp * 3;
       double* dst = s_in + (size_t)tid * 5;
       cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
-      cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + r);
+      cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
       cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
     } else {
       float* base = reinterpret_cast<float*>(s_in);
-      cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + r);
+      cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + rp);
       cp_async4(base + (size_t)TP * 4 + tid, static_cast<const float*>(J.weights) + r);
     }
   };

@@ -140,6 +140,8 @@ class LidarEvidencePipeline:
         self.srec = int(_lib.gcl_stats_record_doubles(self.n_bins))
         self._bufs: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self._origin_c = _abi.dvec(self.origin)
+        self._ptr_cache: Dict[int, Tuple[np.ndarray, int]] = {}
+        self._inflight: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     def manifest_entries(self, n_gpus: int = 1, shard_mode: str = "none") -> Dict[str, Any]:
@@ -303,26 +305,66 @@ class LidarEvidencePipeline:
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=b["stats"], evidence=b["evidence"], n_input=scan.n_raw,
                                  n_points_cap=self.n_points_cap)
 
-    # ---- the reference-facing call: host arrays in, certificates out ------------------------------------------------------
-    def process_scan_host(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body, pose_pred,
-                          map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0, chart_id: str = constants.GC_CHART_ID,
-                          anchor_id: str = "initial", pose_update=None, forgetting: float = 0.99,
-                          iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> LidarScanEvidence:
-        """One call of gcl_lidar_scan_evidence_host: H2D of the scan, three kernels, D2H of stats + evidence.
+    # ---- the reference-facing calls: host arrays in, certificates out -----------------------------------------------------
+    _MAP_KEYS = ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT")
 
-        With ``pose_update`` (6,) the six arrays of ``map_stats_host`` (float64, C-contiguous) are updated IN PLACE
-        (forgetting + this scan's bin sums in the world frame); ``iw_state_host`` (10,) likewise."""
-        f = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
+    def _map_shapes(self):
+        B = self.n_bins
+        return (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))
+
+    @staticmethod
+    def _f64(a, shape):
+        """float64 C-contiguous view/copy of `a` with `shape` (no copy, no new object when `a` already is one)."""
+        if type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous:
+            return a if a.shape == shape else a.reshape(shape)
+        return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
+
+    def _addr(self, a: Optional[np.ndarray]) -> Optional[int]:
+        """Address of a NumPy array; arrays that come back call after call (map statistics, IW state) are looked up."""
+        if a is None:
+            return None
+        hit = self._ptr_cache.get(id(a))
+        if hit is not None and hit[0] is a:
+            return hit[1]
+        addr = a.ctypes.data
+        if len(self._ptr_cache) > 64:
+            self._ptr_cache.clear()
+        self._ptr_cache[id(a)] = (a, addr)   # holding `a` keeps id(a) from being reused by another object
+        return addr
+
+    def submit_scan_host(self, slot: int, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body) -> int:
+        """Stage 1 of the host call (gcl_scan_submit_host): asynchronous upload + moment pass of one scan under H twists.
+        Returns H.  Page-locked inputs are read in place: keep them unchanged until ``evidence_host(slot, ...)`` returns."""
+        f = self._f64
         pts, ts, w = f(points, (-1, 3)), f(timestamps, (-1,)), f(weights, (-1,))
         n = pts.shape[0]
         if ts.shape[0] != n or w.shape[0] != n:
-            raise ValueError("points / timestamps / weights disagree on N")
-        xi, poses = f(xi_body, (-1, 6)), f(pose_pred, (-1, 6))
+            raise ValueError("points, timestamps and weights must have the same length")
+        xi = f(xi_body, (-1, 6))
+        bins_host = getattr(self, "_bins_host", None)
+        if bins_host is None:
+            bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
+        p = lambda a: a.ctypes.data
+        self._inflight[slot] = (pts, ts, w, xi, n)           # keep the arrays alive while the copy is in flight
+        _abi.check(_lib.gcl_scan_submit_host(self.handle, int(slot), p(pts), p(ts), p(w), n, self.n_points_cap, float(scan_start_time),
+                                             float(scan_end_time), p(xi), xi.shape[0], self._addr(self.origin), self._addr(bins_host), self.n_bins,
+                                             self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
+        return xi.shape[0]
+
+    def evidence_host(self, slot: int, pose_pred, map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0,
+                      chart_id: str = constants.GC_CHART_ID, anchor_id: str = "initial", pose_update=None, forgetting: float = 0.99,
+                      iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> LidarScanEvidence:
+        """Stage 2 of the host call (gcl_scan_evidence_host): chain step for the scan submitted to ``slot``, one D2H, sync.
+
+        With ``pose_update`` (6,) the six arrays of ``map_stats_host`` (float64, C-contiguous) are updated IN PLACE
+        (forgetting + this scan's bin sums in the world frame); ``iw_state_host`` (10,) likewise."""
+        f = self._f64
+        pts, ts, w, xi, n = self._inflight.pop(slot)
         H = xi.shape[0]
+        poses = f(pose_pred, (-1, 6))
         if poses.shape[0] != H:
             raise ValueError("xi_body and pose_pred must have one row per hypothesis")
-        B = self.n_bins
-        shapes = (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))
+        shapes = self._map_shapes()
         if pose_update is not None:
             for k, sh in shapes:   # in/out: the caller's arrays are written, so they must be usable as they are
                 a = map_stats_host[k]
@@ -331,24 +373,33 @@ class LidarEvidencePipeline:
             m = map_stats_host
         else:
             m = {k: f(map_stats_host[k], sh) for k, sh in shapes}
-        bins_host = getattr(self, "_bins_host", None)
-        if bins_host is None:
-            bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
         stats = np.empty((H, self.srec), dtype=np.float64)
         evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
-        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        p = self._addr
         pu = None if pose_update is None else f(pose_update, (6,))
         if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
                                               and iw_state_host.shape == (10,) and iw_state_host.flags.c_contiguous):
             raise ValueError("iw_state_host must be a C-contiguous float64 array of shape (10,)")
-        _abi.check(_lib.gcl_lidar_scan_evidence_host(
-            self.handle, p(pts), p(ts), p(w), n, self.n_points_cap, float(scan_start_time), float(scan_end_time), p(xi), p(poses),
-            H, p(self.origin), p(bins_host), B, self.tau, PRECISIONS[self.precision], p(m["S_dir"]), p(m["S_dir_scatter"]),
-            p(m["N_dir"]), p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting), p(iw_state_host),
-            1 if use_sigma_meas else 0, self.eps_psd, self.eps_mass, p(stats), p(evid)), self.handle)
-        return LidarScanEvidence(n_bins=B, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
+        _abi.check(_lib.gcl_scan_evidence_host(self.handle, int(slot), p(poses), p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]),
+                                               p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting),
+                                               p(iw_state_host), 1 if use_sigma_meas else 0, p(stats), p(evid)), self.handle)
+        return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
                                  stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
                                  n_points_cap=self.n_points_cap, ess_imu=ess_imu)
+
+    def process_scan_host(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body, pose_pred,
+                          map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0, chart_id: str = constants.GC_CHART_ID,
+                          anchor_id: str = "initial", pose_update=None, forgetting: float = 0.99,
+                          iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> LidarScanEvidence:
+        """The blocking reference-facing call (= gcl_lidar_scan_evidence_host): stage 1 and stage 2 back to back on slot 0."""
+        xi = np.asarray(xi_body, dtype=np.float64).reshape(-1, 6)
+        poses = np.asarray(pose_pred, dtype=np.float64).reshape(-1, 6)
+        if poses.shape[0] != xi.shape[0]:
+            raise ValueError("xi_body and pose_pred must have one row per hypothesis")
+        self.submit_scan_host(0, points, timestamps, weights, scan_start_time, scan_end_time, xi)
+        return self.evidence_host(0, poses, map_stats_host, ess_imu=ess_imu, chart_id=chart_id, anchor_id=anchor_id,
+                                  pose_update=pose_update, forgetting=forgetting, iw_state_host=iw_state_host,
+                                  use_sigma_meas=use_sigma_meas)
 
 
 def lidar_scan_evidence(points, timestamps, weights, *, scan_start_time: float, scan_end_time: float, xi_body, belief_pred,

@@ -64,11 +64,14 @@ typedef struct gcl_job {
   int32_t n_points_cap;    /* PointBudget cap; stride = max(1, ceil(n_raw / cap)) (point_budget.py:160) */
   int32_t sel_begin;       /* this rank's slice of the selected-row index space [sel_begin, sel_end) ... */
   int32_t sel_end;         /* ... (0, n_sel) on one GPU; a contiguous sub-range when points are sharded */
-  int32_t reserved;
+  int32_t flags;           /* GCL_JOB_COMPACT_ROWS: points/timestamps hold only the SELECTED rows (row k = raw row k*stride),
+                              already gathered by the caller; weights stay raw (all n_raw, needed for the mass sum) */
   double scan_start_time;
   double scan_end_time;
   double xi_body[6];       /* constant twist over the sweep, [rho, phi] (deskew_constant_twist.py:31-69) */
 } gcl_job;
+
+#define GCL_JOB_COMPACT_ROWS 1
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
 int gcl_abi_version(void);
@@ -262,6 +265,26 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
                                  int use_sigma_meas, double eps_psd, double eps_mass,
                                  double* stats_host /* n_hyp stats records */,
                                  double* evidence_host /* n_hyp evidence records */);
+
+/* The same call in two stages, for callers that want the upload and the moment pass of scan k+1 to overlap the evidence
+ * step of scan k (and their own fusion work between the two).  Stage 1 needs only the scan and the IMU twist
+ * (pkg/backend/pipeline.py:400-593 up to the moment match: nothing there depends on the pose prediction or the map);
+ * stage 2 needs the pose prediction and the map (archive/legacy_operators/matrix_fisher_evidence.py:264-275, :502-516).
+ *   gcl_scan_submit_host    asynchronous: H2D on a copy stream, scan_moments + reduce_finalize on a second stream; returns
+ *                           at once.  Page-locked input arrays are read in place and must stay untouched until the matching
+ *                           gcl_scan_evidence_host returns.  slot is 0 or 1 (two scans may be in flight).
+ *   gcl_scan_evidence_host  waits on the GPU for stage 1 of `slot`, runs the chain step, ONE D2H of map / IW / stats /
+ *                           evidence, synchronises.  Arguments as in gcl_lidar_scan_evidence_host. */
+int gcl_scan_submit_host(gcl_handle h, int slot, const double* points_host, const double* timestamps_host,
+                         const double* weights_host, int64_t n_raw, int32_t n_points_cap, double scan_start_time,
+                         double scan_end_time, const double* xi_body_host, int n_hyp, const double* lidar_origin_host,
+                         const double* bin_dirs_host, int n_bins, double tau, int precision, double eps_psd,
+                         double eps_mass);
+int gcl_scan_evidence_host(gcl_handle h, int slot, const double* pose_pred_host, double* map_S_dir_host,
+                           double* map_S_dir_scatter_host, double* map_N_dir_host, double* map_N_pos_host,
+                           double* map_sum_p_host, double* map_sum_ppT_host, const double* pose_update_host,
+                           double forgetting, double* iw_state_host, int use_sigma_meas, double* stats_host,
+                           double* evidence_host);
 
 #ifdef __cplusplus
 }

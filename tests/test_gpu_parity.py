@@ -448,3 +448,38 @@ def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
     if use_iw:
         assert torch.equal(iw_a, iw_b)
     assert float(ev_a[:, g._abi.EV['T_WLS']:g._abi.EV['T_WLS'] + 3].abs().sum()) > 0
+
+
+def test_two_stage_host_api_equals_blocking_call(g):
+    """submit (upload + moment pass, asynchronous, two slots) / evidence (chain step + D2H): overlapping scan k+1's stage 1
+    with scan k's stage 2 must give exactly what the blocking call gives, scan after scan with the map and IW state carried
+    through the host arrays."""
+    S, B, cap, tau = 6, 48, 4096, 0.1
+    scans = [g.synth.make_scan(9000 + 101 * k, seed=700 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
+    poses = np.stack([np.array([0.05 * k, 0.01 * k, 0.0, 0.0, 0.0, 0.01 * k]) for k in range(S)])
+    pinned = [[torch.from_numpy(a).pin_memory().numpy() for a in (s.points, s.timestamps, s.weights)] for s in scans]
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=scans[0].lidar_origin)
+
+    def fresh():
+        m = {k: np.zeros(v) for k, v in (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))}
+        return m, np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
+
+    m_a, iw_a = fresh()
+    out_a = []
+    for k in range(S):
+        ev = pl.process_scan_host(*pinned[k], scans[k].scan_start_time, scans[k].scan_end_time, scans[k].xi_body[None], poses[k][None],
+                                  m_a, pose_update=poses[k], iw_state_host=iw_a, use_sigma_meas=True)
+        out_a.append((ev.stats_host.copy(), ev.evidence_host.copy()))
+    m_b, iw_b = fresh()
+    out_b = []
+    pl.submit_scan_host(0, *pinned[0], scans[0].scan_start_time, scans[0].scan_end_time, scans[0].xi_body[None])
+    for k in range(S):
+        if k + 1 < S:
+            pl.submit_scan_host((k + 1) % 2, *pinned[k + 1], scans[k + 1].scan_start_time, scans[k + 1].scan_end_time, scans[k + 1].xi_body[None])
+        ev = pl.evidence_host(k % 2, poses[k][None], m_b, pose_update=poses[k], iw_state_host=iw_b, use_sigma_meas=True)
+        out_b.append((ev.stats_host.copy(), ev.evidence_host.copy()))
+    for (sa, ea), (sb, eb) in zip(out_a, out_b):
+        assert np.array_equal(sa, sb) and np.array_equal(ea, eb)
+    for k in m_a:
+        assert np.array_equal(m_a[k], m_b[k]), k
+    assert np.array_equal(iw_a, iw_b)
