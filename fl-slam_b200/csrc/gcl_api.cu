@@ -97,9 +97,10 @@ int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_
   if (n_jobs < 1) n_jobs = 1;
   if (max_sel_rows < 1) max_sel_rows = 1;
   // at least one 256-row tile of work per CTA; when that would leave SMs idle (one small scan: the latency case),
-  // go down to 64 rows per CTA so that phase B of every CTA is short
+  // go down to 96 rows per CTA: shorter CTAs, but not so many partial records that reduce_finalize pays for them
+  // (measured at 7500 rows x 48 bins: 118 / 74 / 37 CTAs -> scan_moments 13.1 / 14.4 / 17.0 us, reduce_finalize 22.7 / 18.7 / 14.7 us)
   int64_t by_rows = (max_sel_rows + 255) / 256;
-  if ((int64_t)n_jobs * by_rows < sms) by_rows = (max_sel_rows + 63) / 64;
+  if ((int64_t)n_jobs * by_rows < sms) by_rows = (max_sel_rows + 95) / 96;
   // one job: one CTA per SM (equal slices, no tail).  several jobs: about four waves of CTAs in total
   int64_t want = (n_jobs == 1) ? sms : (4 * sms + n_jobs - 1) / n_jobs;
   if (want < 1) want = 1;

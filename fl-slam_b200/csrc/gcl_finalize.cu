@@ -10,6 +10,7 @@
 namespace gcl {
 
 constexpr int kFinThreads = 512;
+constexpr int kRedSmem = 5120;   // doubles of the reduced record kept in shared memory (19 * 256 + 8 fits)
 
 __device__ __forceinline__ double block_reduce(double v, bool is_max, double* s_buf) {
   // fixed shuffle tree inside a warp, then warps in index order
@@ -27,6 +28,8 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double* s_
 
 __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __grid_constant__ FinalizeParams P) {
   __shared__ double s_buf[kFinThreads / 32];
+  __shared__ double s_pad[2];
+  __shared__ double s_redrec[kRedSmem];
   const int job = blockIdx.x;
   const int tid = threadIdx.x;
   const int B = P.n_bins, NMOM = P.nmom;
@@ -34,8 +37,48 @@ __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __gr
   const double* src = P.parts + (size_t)job * P.job_stride;
   double* red = P.reduced + (size_t)job * rec;
 
-  // ---- step 1: fixed-order sum over parts ---------------------------------------------------------------------
-  for (int e = tid; e < rec; e += kFinThreads) {
+  // ---- padded rows of the soft-assign certificate (all identical: p = 0, t = 0, w = 0): the LAST warp evaluates one such row
+  //      with warp-level reductions while the other warps run step 1 -------------------------------------------------------
+  const gcl_job& J = P.jobs ? P.jobs[job] : P.job;
+  const int64_t cap = J.n_points_cap > 0 ? J.n_points_cap : 1;
+  const int64_t stride0 = (J.n_raw + cap - 1) / cap;
+  const int64_t stride = stride0 > 1 ? stride0 : 1;
+  const int64_t n_sel = (J.n_raw + stride - 1) / stride;
+  const int64_t n_pad = cap > n_sel ? cap - n_sel : 0;
+  const bool pad_warp = P.finalize && !P.from_resp && n_pad > 0 && (tid >> 5) == kFinThreads / 32 - 1;
+  if (pad_warp) {
+    const int lane = tid & 31;
+    // deskew of the padded row exactly as the reference evaluates it (epoch-scale alpha, SURVEY.md 7.2)
+    const double denomt = fmax(J.scan_end_time - J.scan_start_time, 1e-12);
+    const double alpha = (0.0 - J.scan_start_time) / denomt;
+    const double pz[3] = {0.0, 0.0, 0.0};
+    double p0[3];
+    deskew_point64(J.xi_body, alpha, pz, p0);
+    const double r0 = p0[0] - P.origin[0], r1 = p0[1] - P.origin[1], r2 = p0[2] - P.origin[2];
+    const double inv = 1.0 / (sqrt(r0 * r0 + r1 * r1 + r2 * r2) + P.eps_mass);
+    const double d[3] = {r0 * inv, r1 * inv, r2 * inv};
+    double mx = -1e300;
+    for (int b = lane; b < B; b += 32)
+      mx = fmax(mx, (d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double z = 0;
+    for (int b = lane; b < B; b += 32)
+      z += exp((d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau - mx);
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    double h = 0, rm = 0;
+    for (int b = lane; b < B; b += 32) {
+      const double r = exp((d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau - mx) / z;
+      h -= r * log(r + P.eps_mass);
+      rm = fmax(rm, r);
+    }
+    for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o)); }
+    if (lane == 0) { s_pad[0] = h; s_pad[1] = rm; }
+  }
+
+  // ---- step 1: fixed-order sum over parts (the reduced record also stays in shared memory when it fits) -----------------
+  const int nred = pad_warp ? 0 : ((P.finalize && !P.from_resp && n_pad > 0) ? kFinThreads - 32 : kFinThreads);
+  const bool red_smem = rec <= kRedSmem;
+  for (int e = tid; nred > 0 && e < rec; e += nred) {
     const bool is_max = (e == NMOM * B + GCL_CS_MAX_RESP);
     double s = src[e];
     for (int p = 1; p < P.n_parts; ++p) {
@@ -43,15 +86,16 @@ __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __gr
       s = is_max ? fmax(s, v) : s + v;
     }
     red[e] = s;
+    if (red_smem) s_redrec[e] = s;
   }
   if (!P.finalize) return;
   __syncthreads();
 
-  const gcl_job& J = P.jobs ? P.jobs[job] : P.job;
   const StatsLayout SL(B);
   double* st = P.stats + (size_t)job * SL.total();
   const double eps = P.eps_mass;
-  const double* cert = red + (size_t)NMOM * B;
+  const double* redv = red_smem ? s_redrec : red;   // step 1's result, read back from shared memory when it fits
+  const double* cert = redv + (size_t)NMOM * B;
 
   // ---- scalars of the resample / deskew steps -------------------------------------------------------------------
   const double W_raw = cert[GCL_CS_SUM_W_RAW], W_sel = cert[GCL_CS_SUM_W_SEL];
@@ -61,7 +105,7 @@ __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __gr
   double a_N = 0, a_N2 = 0, a_sf = 0, a_psd = 0, a_ratio = 0;
   for (int b = tid; b < B; b += kFinThreads) {
     double m[28];
-    for (int k = 0; k < NMOM; ++k) m[k] = mass_scale * red[(size_t)k * B + b];
+    for (int k = 0; k < NMOM; ++k) m[k] = mass_scale * redv[(size_t)k * B + b];
     const double N = m[0];
     const double denom = N + eps + kF64Eps;  // inv_mass_core, primitives.py:205-212
     const double invN = 1.0 / denom;
@@ -97,44 +141,11 @@ __global__ void __launch_bounds__(kFinThreads) reduce_finalize_kernel(const __gr
   const double tpsd = block_reduce(a_psd, false, s_buf);
   const double tratio = block_reduce(a_ratio, true, s_buf);
 
-  // ---- soft-assign certificate: add the padded rows (all identical: p = 0, t = 0, w = 0) ----------------------------
-  const int64_t cap = J.n_points_cap > 0 ? J.n_points_cap : 1;
-  const int64_t stride0 = (J.n_raw + cap - 1) / cap;
-  const int64_t stride = stride0 > 1 ? stride0 : 1;
-  const int64_t n_sel = (J.n_raw + stride - 1) / stride;
-  const int64_t n_pad = cap > n_sel ? cap - n_sel : 0;
+  // ---- soft-assign certificate: add the padded rows (evaluated by the last warp above; visible after block_reduce's barriers)
   double ent_total = cert[GCL_CS_SUM_ENTROPY], max_resp = cert[GCL_CS_MAX_RESP];
-  if (!P.from_resp && n_pad > 0) {  // uniform branch: every thread takes it
-    ScanConst C;
-    C.origin[0] = P.origin[0]; C.origin[1] = P.origin[1]; C.origin[2] = P.origin[2];
-    C.eps_mass = eps;
-    // deskew of the padded row exactly as the reference evaluates it (epoch-scale alpha, SURVEY.md 7.2)
-    const double denomt = fmax(J.scan_end_time - J.scan_start_time, 1e-12);
-    const double alpha = (0.0 - J.scan_start_time) / denomt;
-    const double pz[3] = {0.0, 0.0, 0.0};
-    double p0[3];
-    deskew_point64(J.xi_body, alpha, pz, p0);
-    const double r0 = p0[0] - C.origin[0], r1 = p0[1] - C.origin[1], r2 = p0[2] - C.origin[2];
-    const double inv = 1.0 / (sqrt(r0 * r0 + r1 * r1 + r2 * r2) + eps);
-    const double d[3] = {r0 * inv, r1 * inv, r2 * inv};
-    double mx = -1e300;
-    for (int b = tid; b < B; b += kFinThreads)
-      mx = fmax(mx, (d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau);
-    mx = block_reduce(mx, true, s_buf);
-    double z = 0;
-    for (int b = tid; b < B; b += kFinThreads)
-      z += exp((d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau - mx);
-    z = block_reduce(z, false, s_buf);
-    double h = 0, rm = 0;
-    for (int b = tid; b < B; b += kFinThreads) {
-      const double r = exp((d[0] * P.bin_dirs[b * 3] + d[1] * P.bin_dirs[b * 3 + 1] + d[2] * P.bin_dirs[b * 3 + 2]) / P.tau - mx) / z;
-      h -= r * log(r + eps);
-      rm = fmax(rm, r);
-    }
-    h = block_reduce(h, false, s_buf);
-    rm = block_reduce(rm, true, s_buf);
-    ent_total += (double)n_pad * h;
-    max_resp = fmax(max_resp, rm);
+  if (!P.from_resp && n_pad > 0) {
+    ent_total += (double)n_pad * s_pad[0];
+    max_resp = fmax(max_resp, s_pad[1]);
   }
 
   if (tid == 0) {
