@@ -33,8 +33,9 @@ if ROOT not in sys.path:
 N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_moments launch of this workload, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
-TRAFFIC_BYTES_PER_LAUNCH = {"fp64": None, "fp32c": None}
-TRAFFIC_SOURCE = None
+TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.16128e6 + 8.16e6, "fp32c": None}
+TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch; the "
+                  "stride-4 gather of 24-byte rows touches every 32-byte sector, hence ~2.3x the algorithmic bytes)")
 
 
 # FMA-issue ceilings of scan_moments (rates measured with tools/microbench/ffma_rate.cu):
@@ -175,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2]/[3] side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=100, help="scans in the CPU-baseline sample (walked repeatedly for >= 12 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -351,7 +353,7 @@ def main():
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         pps, sps, dt = cpu_stream_rate(args.cpu_sample, tau, min_seconds=12.0)
         cpu = {"value": pps, "unit": "points/s", "cores": blas_threads(), "kind": "port", "scans_per_sec": sps,
                "sample": f"first {args.cpu_sample} scans of the same stream, walked repeatedly for {dt:.1f} s; NumPy float64 restatement of the "

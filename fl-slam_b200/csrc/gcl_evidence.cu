@@ -539,11 +539,19 @@ __global__ void stream_map_recurrence_kernel(const __grid_constant__ ChainParams
   const double g = P.forgetting;
   double* slot = W.map_pre + e;
   const size_t pitch = 26 * (size_t)B;
-#pragma unroll 8
-  for (int s = 0; s < P.n_scans; ++s) {
-    const double inc = slot[s * pitch];
-    slot[s * pitch] = m;
-    m = g * m + inc;
+  // increments are read eight scans ahead of the stores (the compiler cannot prove that slot[s] and slot[s+1] differ, and a
+  // load that waits for the previous store makes every step an L2 round trip)
+  for (int s0 = 0; s0 < P.n_scans; s0 += 8) {
+    double inc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) inc[j] = (s0 + j < P.n_scans) ? slot[(size_t)(s0 + j) * pitch] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (s0 + j < P.n_scans) {
+        slot[(size_t)(s0 + j) * pitch] = m;
+        m = g * m + inc[j];
+      }
+    }
   }
   *arr = m;
 }
