@@ -483,3 +483,41 @@ def test_two_stage_host_api_equals_blocking_call(g):
     for k in m_a:
         assert np.array_equal(m_a[k], m_b[k]), k
     assert np.array_equal(iw_a, iw_b)
+
+
+@pytest.mark.parametrize("n,B", [(1 << 20, 256), (1 << 24, 1024)])   # BASELINE.json configs[3] and configs[4] at FULL size
+def test_full_size_properties(g, n, B):
+    """Size-independent properties at the named full sizes (the oracle cannot finish these in seconds):
+    (i) responsibilities sum to one => sum_b N_b = sum of the deskewed weights (a separately accumulated certificate scalar);
+    (ii) linearity in the points: the sums of two halves add up to the sums of the whole;
+    (iii) fp32-compensated against fp64 within the 1e-5 bar on every raw sum."""
+    tau = 0.1
+    sc = g.synth.make_scan(n, seed=1234 + (4 if B == 256 else 5), dense=True)
+    zero_pose = torch.zeros(1, 6, dtype=torch.float64, device="cuda")
+    res = {}
+    for precision in ("fp64", "fp32c"):
+        pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision=precision, n_points_cap=n, lidar_origin=sc.lidar_origin)
+        scan = pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+        ev = pl.run_resident(scan, sc.xi_body[None], zero_pose, g.create_empty_map_stats(B))
+        st = H(ev.stats)[0].copy()
+        s = ev.scalars(0)
+        tol = 1e-9 if precision == "fp64" else 1e-5
+        assert abs(st[:B].sum() / s["SUM_W_OUT"] - 1) < tol                                    # (i)
+        if precision == "fp64":                                                                # (ii)
+            ctas = pl.plan_ctas(1, n // 2)
+            parts = []
+            for lo_, hi_ in ((0, n // 2), (n // 2, n)):
+                b = pl._buffers(1, ctas)
+                job = pl.make_job(scan, sc.xi_body, sel_range=(lo_, hi_))
+                pl.launch_moments(None, job, 1, ctas, scan.layout, b["partials"])
+                pl.launch_finalize(b["partials"], ctas, pl.rec, pl.rec * ctas, None, job, 1, False, b["reduced"], None)
+                parts.append(H(b["reduced"])[0, :19 * B].copy())
+            whole_raw = np.concatenate([st[:B], st[B:4 * B].reshape(B, 3).T.reshape(-1)])     # N and s_dir, moment-major
+            halves = parts[0] + parts[1]
+            assert rel_err(halves[:B], whole_raw[:B]) < 1e-12
+            assert rel_err(halves[B:4 * B], whole_raw[B:4 * B]) < 1e-12
+        res[precision] = st
+        del scan, pl
+        torch.cuda.empty_cache()
+    for lo_, hi_ in ((0, B), (B, 4 * B), (4 * B, 13 * B), (26 * B, 29 * B), (29 * B, 38 * B)):  # N, s_dir, S, sum_p, sum_ppT
+        assert rel_err(res["fp32c"][lo_:hi_], res["fp64"][lo_:hi_]) < 1e-5                     # (iii)

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: 16M points x 1024 bins, fp64 vs fp32-compensated accumulation -- timing, roofline fractions and a
+tolerance report (fp32c against fp64 on the GPU; fp64 against the CPU oracle, chunked, on the first --oracle-points rows).
+
+    python tools/sweep_cfg5.py [--points 16777216] [--bins 1024] [--oracle-points 2097152] > gpurun_out/cfg5_sweep.md
+"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import fl_slam_b200 as g
+import bench
+from oracle import gc_oracle as O
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--points", type=int, default=1 << 24)
+ap.add_argument("--bins", type=int, default=1024)
+ap.add_argument("--oracle-points", type=int, default=1 << 21)
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+n, B, tau = a.points, a.bins, g.synth.DEFAULT_TAU
+sc = g.synth.make_scan(n, seed=1234 + 5, dense=True)
+Rs, ts = g.synth.known_map_transform(0)
+peak_gbs, _ = bench.load_peaks()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+out, stats, evid = {}, {}, {}
+for prec in ("fp64", "fp32c"):
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision=prec, n_points_cap=n, lidar_origin=sc.lidar_origin)
+    scan = pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+    ctas = pl.plan_ctas(1, n); bufs = pl._buffers(1, ctas); job = pl.make_job(scan, sc.xi_body)
+    k1 = lambda: pl.launch_moments(None, job, 1, ctas, scan.layout, bufs["partials"])
+    k1(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.iters): k1()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    if prec == "fp64":   # a map = this scan's own sums moved by a known transform, so that the evidence step is well posed
+        pl.launch_finalize(bufs["partials"], ctas, pl.rec, pl.rec * ctas, None, job, 1, True, bufs["reduced"], bufs["stats"])
+        st = bufs["stats"][0].cpu().numpy()
+        raw = {"N": st[:B], "s_dir": st[B:4 * B].reshape(B, 3), "S_dir_scatter": st[4 * B:13 * B].reshape(B, 3, 3),
+               "sum_p": st[26 * B:29 * B].reshape(B, 3), "sum_ppT": st[29 * B:38 * B].reshape(B, 3, 3)}
+        map_stats = g.MapBinStats.from_arrays(g.synth.map_stats_from_scan_sums(raw, Rs, ts, seed=0))
+    ev = pl.run_resident(scan, sc.xi_body[None], torch.zeros(1, 6, dtype=torch.float64, device="cuda"), map_stats)
+    torch.cuda.synchronize()
+    stats[prec], evid[prec] = ev.stats[0].cpu().numpy().copy(), ev.evidence[0].cpu().numpy().copy()
+    bpp = scan.bytes_per_point
+    out[prec] = dict(ms=ms, pairs=n * B / (ms * 1e-3), gbs=n * bpp / (ms * 1e-3) / 1e9, bpp=bpp, ctas=ctas)
+    del scan, pl, bufs
+    torch.cuda.empty_cache()
+
+def views(st):
+    return {"N": st[:B], "s_dir": st[B:4 * B], "S_dir_scatter": st[4 * B:13 * B], "p_bar": st[13 * B:16 * B], "Sigma_p": st[16 * B:25 * B],
+            "kappa": st[25 * B:26 * B], "sum_p": st[26 * B:29 * B], "sum_ppT": st[29 * B:38 * B]}
+def rel(a_, b_):
+    s = np.max(np.abs(b_)) + 1e-300
+    d = np.abs(a_ - b_) / s
+    return float(d.max()), float(d.mean())
+def geodesic(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return float(np.arccos(min(1.0, max(-1.0, c))))
+
+print(f"# configs[4] sweep: {n} points x {B} bins, tau = {tau}, one B200\n")
+print("| mode | layout | scan_moments ms | pairs/s | GB/s (algorithmic) | frac of HBM peak | frac of FMA-issue ceiling @1965 MHz |")
+print("|---|---|---|---|---|---|---|")
+for prec in ("fp64", "fp32c"):
+    o = out[prec]
+    print(f"| {prec} | {o['bpp']} B/point | {o['ms']:.2f} | {o['pairs']:.3e} | {o['gbs']:.1f} | {o['gbs'] / peak_gbs:.4f} | {o['pairs'] / bench.pair_ceiling(prec, 1965.0):.3f} |")
+v64, v32 = views(stats["fp64"]), views(stats["fp32c"])
+print("\n## fp32c against fp64 (both on the GPU), error relative to the largest entry of each array\n")
+print("| quantity | max rel | mean rel |\n|---|---|---|")
+for k in ("N", "s_dir", "S_dir_scatter", "sum_p", "sum_ppT", "p_bar", "Sigma_p", "kappa"):
+    mx, mn = rel(v32[k], v64[k])
+    print(f"| {k} | {mx:.2e} | {mn:.2e} |")
+print(f"| R_mf geodesic (rad) | {geodesic(evid['fp32c'][:9].reshape(3, 3), evid['fp64'][:9].reshape(3, 3)):.2e} | |")
+print(f"| t_wls abs (m) | {float(np.max(np.abs(evid['fp32c'][71:74] - evid['fp64'][71:74]))):.2e} | |")
+print(f"\nconservation (sum_b N_b vs the deskewed weight total is a size-independent property): fp64 sum N = {v64['N'].sum():.12e}, fp32c sum N = {v32['N'].sum():.12e}, ratio - 1 = {v32['N'].sum() / v64['N'].sum() - 1:.2e}")
+
+m = min(a.oracle_points, n)
+if m > 0:
+    t0 = time.perf_counter()
+    sub = slice(0, m)
+    dk = O.deskew_constant_twist(sc.points[sub], sc.timestamps[sub], sc.weights[sub], sc.scan_start_time, sc.scan_end_time, sc.xi_body)
+    bins = O.create_fibonacci_atlas(B)
+    raw = O.fused_scan_raw_sums(dk["points"], dk["weights"], bins, tau, sc.lidar_origin)
+    dt = time.perf_counter() - t0
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=m, lidar_origin=sc.lidar_origin, bin_directions=bins)
+    scan = pl.upload_scan(sc.points[sub], sc.timestamps[sub], sc.weights[sub], sc.scan_start_time, sc.scan_end_time)
+    ev = pl.run_resident(scan, sc.xi_body[None], torch.zeros(1, 6, dtype=torch.float64, device="cuda"), g.create_empty_map_stats(B))
+    vg = views(ev.stats[0].cpu().numpy())
+    print(f"\n## fp64 GPU against the CPU oracle on the first {m} rows (oracle: {dt:.1f} s on the host, chunked)\n")
+    print("| quantity | max rel |\n|---|---|")
+    for k in ("N", "s_dir", "S_dir_scatter", "sum_p", "sum_ppT"):
+        print(f"| {k} | {rel(vg[k], np.asarray(raw[k]).reshape(-1))[0]:.2e} |")
