@@ -101,12 +101,19 @@ int gcl_plan_ctas_per_job(gcl_handle h, int n_jobs, int64_t max_sel_rows, int n_
   // (measured at 7500 rows x 48 bins: 118 / 74 / 37 CTAs -> scan_moments 13.1 / 14.4 / 17.0 us, reduce_finalize 22.7 / 18.7 / 14.7 us)
   int64_t by_rows = (max_sel_rows + 255) / 256;
   if ((int64_t)n_jobs * by_rows < sms) by_rows = (max_sel_rows + 95) / 96;
-  // one job: one CTA per SM (equal slices, no tail).  several jobs: about four waves of CTAs in total
-  int64_t want = (n_jobs == 1) ? sms : (4 * sms + n_jobs - 1) / n_jobs;
-  if (want < 1) want = 1;
-  int64_t c = want < by_rows ? want : by_rows;
-  if (c > 65535) c = 65535;
-  return (int)c;
+  // one job: one CTA per SM (equal slices, no tail)
+  if (n_jobs == 1) return (int)(sms < by_rows ? sms : by_rows);
+  // several jobs: the grid runs in waves of `sms` CTAs and the last wave is rarely full (200 jobs x 3 CTAs = 4.05 waves cost
+  // 5).  Pick the CTAs per job that minimise  waves x (rows per CTA + fixed cost per CTA), the fixed cost (record zeroing,
+  // atlas set-up, flush, certificate reduction: ~6 us) being worth about 128 rows of a 48-bin fp64 pass.
+  int64_t cmax = by_rows < 64 ? by_rows : 64, best_c = 1;
+  double best = 1e300;
+  for (int64_t c = 1; c <= cmax; ++c) {
+    const int64_t waves = (n_jobs * c + sms - 1) / sms;
+    const double cost = (double)waves * ((double)((max_sel_rows + c - 1) / c) + 128.0);
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  return (int)best_c;
 }
 
 int gcl_scan_moments(gcl_handle h, void* stream, const gcl_job* jobs_dev, const gcl_job* job_host, int n_jobs,
