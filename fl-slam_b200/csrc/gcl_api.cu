@@ -378,6 +378,26 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
   return GCL_OK;
 }
 
+int gcl_imu_preintegrate(gcl_handle h, void* stream, const double* stamps, const double* gyro, const double* accel,
+                         const double* weights, int n_samples, double t0, double t1, double sigma, const double* rotvec_start,
+                         const double* gyro_bias, const double* accel_bias, const double* gravity_host, int rotation_only,
+                         int n_hyp, double* out, double* weights_out, gcl_job* jobs_out) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_samples >= 1 && n_hyp >= 1, "n_samples and n_hyp must be >= 1");
+  GCL_REQUIRE(h, stamps && gyro && accel && rotvec_start && gyro_bias && accel_bias && gravity_host && out, "NULL pointer");
+  ImuParams P;
+  P.stamps = stamps; P.gyro = gyro; P.accel = accel; P.weights = weights; P.M = n_samples;
+  P.t0 = t0; P.t1 = t1; P.sigma = sigma;
+  P.rotvec_start = rotvec_start; P.gyro_bias = gyro_bias; P.accel_bias = accel_bias;
+  P.gravity[0] = gravity_host[0]; P.gravity[1] = gravity_host[1]; P.gravity[2] = gravity_host[2];
+  P.trans_scale = rotation_only ? 0.0 : 1.0;
+  P.out = out; P.weights_out = weights_out; P.jobs_out = jobs_out;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_imu_preintegrate(P, n_hyp, (cudaStream_t)stream));
+  h->launches += 1;
+  return GCL_OK;
+}
+
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps, const double* weights,
                         int64_t n, double t0, void* packed_xyzt, float* packed_w) {
   if (!h) return GCL_ERR_ARG;

@@ -126,6 +126,19 @@ cudaError_t launch_map_update(const double* stats, const double* R, const double
                               double* S_dir, double* S_dir_scatter, double* N_dir, double* N_pos, double* sum_p,
                               double* sum_ppT, cudaStream_t stream);
 
+struct ImuParams {
+  const double *stamps, *gyro, *accel, *weights;  // (M,), (M,3), (M,3), optional (M,) -- NULL: window weights computed here
+  int M;
+  double t0, t1, sigma;                           // window of smooth_window_weights (used when weights == NULL)
+  const double *rotvec_start, *gyro_bias, *accel_bias;  // (H,3) each
+  double gravity[3];
+  double trans_scale;                             // 0 = rotation-only deskew, 1 = full twist
+  double* out;                                    // (H, GCL_IMU_DOUBLES)
+  double* weights_out;                            // optional (M,)
+  gcl_job* jobs_out;                              // optional (H): xi_body is written into the jobs
+};
+cudaError_t launch_imu_preintegrate(const ImuParams& P, int n_hyp, cudaStream_t stream);
+
 // standalone operators (gcl_ops.cu)
 cudaError_t op_point_budget(const double* pts, const double* ts, const double* w, const uint8_t* ring, const uint8_t* tag,
                             int64_t n, int cap, double eps, double* pts_out, double* ts_out, double* w_out,

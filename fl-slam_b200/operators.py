@@ -282,6 +282,70 @@ def scan_bin_moment_match(points, point_covariances, weights, responsibilities, 
     return stats_views(rec, nb), cert, effect
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# IMU preintegration -> deskew twist ("next" row)
+# ----------------------------------------------------------------------------------------------------------------
+IMU = dict(DELTA_POSE=0, DELTA_R=6, DELTA_P=15, DELTA_V=18, ESS=21, A_BODY_MEAN=22, A_WORLD_NOG_MEAN=25, A_WORLD_MEAN=28,
+           DT_SUM=31, XI_BODY=32)
+GCL_IMU_DOUBLES = 40
+
+
+def _imu_launch(imu_stamps, imu_gyro, imu_accel, weights, window, rotvec_start_WB, gyro_bias, accel_bias, gravity_W,
+                rotation_only: bool, want_weights: bool, jobs_dev: Optional[torch.Tensor] = None):
+    t, gy, ac = _dev(imu_stamps).reshape(-1), _dev(imu_gyro).reshape(-1, 3), _dev(imu_accel).reshape(-1, 3)
+    M = t.shape[0]
+    if gy.shape[0] != M or ac.shape[0] != M:
+        raise ValueError("imu_stamps, imu_gyro and imu_accel must have the same length")
+    rv, bg, ba = _dev(rotvec_start_WB).reshape(-1, 3), _dev(gyro_bias).reshape(-1, 3), _dev(accel_bias).reshape(-1, 3)
+    H = rv.shape[0]
+    if bg.shape[0] != H or ba.shape[0] != H:
+        raise ValueError("rotvec_start_WB, gyro_bias and accel_bias must have one row per hypothesis")
+    w = None if weights is None else _dev(weights).reshape(-1)
+    if w is not None and w.shape[0] != M:
+        raise ValueError("weights must have one entry per IMU sample")
+    t0, t1, sigma = window
+    out = _empty(H, GCL_IMU_DOUBLES)
+    w_out = _empty(M) if want_weights else None
+    h = _h()
+    _abi.check(_lib.gcl_imu_preintegrate(h, _stream(), _ptr(t), _ptr(gy), _ptr(ac), _ptr(w), M, float(t0), float(t1), float(sigma),
+                                         _ptr(rv), _ptr(bg), _ptr(ba), _abi.dvec(np.asarray(gravity_W, dtype=np.float64).reshape(3)),
+                                         1 if rotation_only else 0, H, _ptr(out), _ptr(w_out), _ptr(jobs_dev)), h)
+    return out, w_out
+
+
+def smooth_window_weights(imu_stamps, scan_start_time: float, scan_end_time: float, sigma: float) -> torch.Tensor:
+    """pkg/backend/operators/imu_preintegration.py:19-43."""
+    z = np.zeros((1, 3))
+    M = int(np.asarray(imu_stamps.shape if hasattr(imu_stamps, "shape") else [len(imu_stamps)]).prod())
+    _, w = _imu_launch(imu_stamps, np.zeros((M, 3)), np.zeros((M, 3)), None, (scan_start_time, scan_end_time, sigma), z, z, z,
+                       np.zeros(3), False, True)
+    return w
+
+
+def preintegrate_imu_relative_pose(imu_stamps, imu_gyro, imu_accel, weights, rotvec_start_WB, gyro_bias, accel_bias, gravity_W):
+    """preintegrate_imu_relative_pose_jax, pkg/backend/operators/imu_preintegration.py:46-147: the same nine outputs
+    (delta_pose_se3, delta_R, delta_p, delta_v, ess, a_body_mean, a_world_nog_mean, a_world_mean, dt_eff_sum)."""
+    out, _ = _imu_launch(imu_stamps, imu_gyro, imu_accel, weights, (0.0, 0.0, 1.0), rotvec_start_WB, gyro_bias, accel_bias,
+                         gravity_W, False, False)
+    o = out[0]
+    return (o[0:6], o[6:15].view(3, 3), o[15:18], o[18:21], o[21], o[22:25], o[25:28], o[28:31], o[31])
+
+
+preintegrate_imu_relative_pose_jax = preintegrate_imu_relative_pose   # the reference's name
+
+
+def imu_deskew_twist(imu_stamps, imu_gyro, imu_accel, scan_start_time: float, scan_end_time: float, sigma: float,
+                     rotvec_start_WB, gyro_bias, accel_bias, gravity_W, deskew_rotation_only: bool = False,
+                     jobs_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Window weights -> preintegration -> xi_body = se3_log(delta_pose) in one launch, batched over hypotheses (rows of
+    rotvec_start_WB / gyro_bias / accel_bias); pkg/backend/pipeline.py:437-483.  With ``jobs_dev`` (a device array of H
+    gcl_job records) the twists are written straight into the jobs of the fused LiDAR kernel."""
+    out, w = _imu_launch(imu_stamps, imu_gyro, imu_accel, None, (scan_start_time, scan_end_time, sigma), rotvec_start_WB,
+                         gyro_bias, accel_bias, gravity_W, deskew_rotation_only, True, jobs_dev)
+    return {"record": out, "xi_body": out[:, IMU["XI_BODY"]:IMU["XI_BODY"] + 6], "delta_pose": out[:, 0:6], "ess": out[:, IMU["ESS"]],
+            "dt_sum": out[:, IMU["DT_SUM"]], "weights": w}
+
+
 def kappa_from_resultant_batch(R_bar, eps_r: float = constants.GC_EPS_R, d: int = 3, r0: float = constants.GC_KAPPA_BLEND_R0,
                                tau: float = constants.GC_KAPPA_BLEND_TAU) -> torch.Tensor:
     """pkg/backend/operators/kappa.py:130-169."""

@@ -243,6 +243,25 @@ int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const 
                         const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,
                         float* packed_w);
 
+/* ---- IMU preintegration -> deskew twist ("next" row) ---------------------------------------- */
+/* smooth_window_weights + preintegrate_imu_relative_pose_jax + se3_log as called at pkg/backend/pipeline.py:437-483
+ * (pkg/backend/operators/imu_preintegration.py:19-43, :46-147; pkg/common/geometry/se3_jax.py:179-256), batched over
+ * n_hyp hypotheses (start orientation + biases), one warp each; the sequential lax.scan becomes a prefix product of
+ * rotations and prefix sums.  weights == NULL: the window weights of (scan_start_time, scan_end_time, sigma) are used.
+ * out: n_hyp records of GCL_IMU_DOUBLES doubles (offsets GCL_IMU_*).  jobs_out (optional): xi_body is also written into
+ * n_hyp gcl_job records, so that the twist never leaves the device. */
+#define GCL_IMU_DOUBLES 40
+enum {
+  GCL_IMU_DELTA_POSE = 0, GCL_IMU_DELTA_R = 6, GCL_IMU_DELTA_P = 15, GCL_IMU_DELTA_V = 18, GCL_IMU_ESS = 21,
+  GCL_IMU_A_BODY_MEAN = 22, GCL_IMU_A_WORLD_NOG_MEAN = 25, GCL_IMU_A_WORLD_MEAN = 28, GCL_IMU_DT_SUM = 31,
+  GCL_IMU_XI_BODY = 32
+};
+int gcl_imu_preintegrate(gcl_handle h, void* stream, const double* imu_stamps, const double* imu_gyro,
+                         const double* imu_accel, const double* weights, int n_samples, double scan_start_time,
+                         double scan_end_time, double sigma, const double* rotvec_start_WB, const double* gyro_bias,
+                         const double* accel_bias, const double* gravity_W_host, int deskew_rotation_only, int n_hyp,
+                         double* out, double* weights_out, gcl_job* jobs_out);
+
 /* ---- reference-facing call with HOST buffers ------------------------------------------------------------- */
 /* The whole chain for one scan and n_hyp hypotheses: H2D of the scan, fused moments, finalize, the chain step (map
  * derived statistics, pose evidence, optional IW + map update), D2H of the stats and evidence records; synchronises.

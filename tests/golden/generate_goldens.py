@@ -203,6 +203,39 @@ def run_pieces(ref):
     np.savez_compressed(os.path.join(HERE, "ref_pieces.npz"), **out)
 
 
+def run_imu(ref):
+    """IMU preintegration -> deskew twist: the reference's own smooth_window_weights,
+    preintegrate_imu_relative_pose_jax (imu_preintegration.py:46-147) and se3_log (se3_jax.py:221-256) on seeded IMU streams."""
+    rng = np.random.default_rng(77)
+    pre, se3 = ref["imu_preintegration"], ref["se3_jax"]
+    out = {}
+    cases = {"a": dict(M=200, rate=200.0, w_scale=0.5, lead=0.02), "b": dict(M=512, rate=400.0, w_scale=1.5, lead=0.3),
+             "c": dict(M=37, rate=100.0, w_scale=0.05, lead=0.0)}
+    for name, c in cases.items():
+        M = c["M"]
+        t0 = 1.7e9
+        stamps = t0 - c["lead"] + np.arange(M) / c["rate"] + rng.uniform(0, 2e-4, M)
+        gyro = c["w_scale"] * rng.normal(size=(M, 3)) + np.array([0.0, 0.0, 0.8])
+        accel = rng.normal(size=(M, 3)) * 0.5 + np.array([0.0, 0.0, 9.81])
+        rotvec0 = 0.3 * rng.normal(size=3)
+        bg, ba = 0.01 * rng.normal(size=3), 0.05 * rng.normal(size=3)
+        grav = np.array([0.0, 0.0, -9.81])
+        w = np.asarray(pre.smooth_window_weights(stamps, t0, t0 + 0.1, 0.01))
+        res = pre.preintegrate_imu_relative_pose_jax(stamps, gyro, accel, w, rotvec0, bg, ba, grav)
+        xi = np.asarray(se3.se3_log(res[0]))
+        out.update({f"{name}_stamps": stamps, f"{name}_gyro": gyro, f"{name}_accel": accel, f"{name}_rotvec0": rotvec0,
+                    f"{name}_bg": bg, f"{name}_ba": ba, f"{name}_grav": grav, f"{name}_t0": t0, f"{name}_t1": t0 + 0.1,
+                    f"{name}_sigma": 0.01, f"{name}_w": w, f"{name}_xi": xi})
+        for k, nm in enumerate(("delta_pose", "delta_R", "delta_p", "delta_v", "ess", "a_body_mean", "a_world_nog_mean",
+                                "a_world_mean", "dt_sum")):
+            out[f"{name}_{nm}"] = np.asarray(res[k])
+    # se3_log known answers, including the small-angle branch
+    poses = rng.normal(size=(8, 6)) * np.array([[1e-9], [1e-5], [1e-3], [0.05], [0.3], [1.0], [2.5], [3.1]])
+    out["se3log_in"] = poses
+    out["se3log_out"] = np.stack([np.asarray(se3.se3_log(p)) for p in poses])
+    np.savez_compressed(os.path.join(HERE, "ref_imu.npz"), **out)
+
+
 def main():
     ref = _jaxshim.load_reference("/root/reference", n_bins=48, tau=0.1)
     synth = _load_synth()
@@ -221,6 +254,7 @@ def main():
     with open(os.path.join(HERE, "ref_certs.json"), "w") as f:
         json.dump(certs, f, indent=1, sort_keys=True, default=float)
     run_pieces(ref)
+    run_imu(ref)
     print("wrote goldens to", HERE)
 
 

@@ -521,3 +521,51 @@ def test_full_size_properties(g, n, B):
         torch.cuda.empty_cache()
     for lo_, hi_ in ((0, B), (B, 4 * B), (4 * B, 13 * B), (26 * B, 29 * B), (29 * B, 38 * B)):  # N, s_dir, S, sum_p, sum_ppT
         assert rel_err(res["fp32c"][lo_:hi_], res["fp64"][lo_:hi_]) < 1e-5                     # (iii)
+
+
+# ---------------------------------------------------------------- IMU preintegration -> deskew twist
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_imu_preintegration_against_reference_goldens(g, case):
+    """The warp-scan preintegration against the reference's own sample-by-sample lax.scan (run under the shim): the
+    re-association of the rotation products and of the sums shows at the 1e-15 level; bar 1e-11."""
+    z = np.load(os.path.join(GOLDEN, "ref_imu.npz"))
+    r = lambda k: z[f"{case}_{k}"]
+    out = g.imu_deskew_twist(r("stamps"), r("gyro"), r("accel"), float(r("t0")), float(r("t1")), float(r("sigma")), r("rotvec0")[None],
+                             r("bg")[None], r("ba")[None], r("grav"))
+    np.testing.assert_allclose(H(out["weights"]), r("w"), rtol=1e-12, atol=1e-300)
+    rec = H(out["record"])[0]
+    I = g.operators.IMU
+    for k, off, n in (("delta_pose", I["DELTA_POSE"], 6), ("delta_R", I["DELTA_R"], 9), ("delta_p", I["DELTA_P"], 3),
+                      ("delta_v", I["DELTA_V"], 3), ("a_body_mean", I["A_BODY_MEAN"], 3), ("a_world_nog_mean", I["A_WORLD_NOG_MEAN"], 3),
+                      ("a_world_mean", I["A_WORLD_MEAN"], 3)):
+        np.testing.assert_allclose(rec[off:off + n], np.asarray(r(k)).reshape(-1), rtol=1e-11, atol=1e-13, err_msg=k)
+    assert abs(rec[I["ESS"]] / float(r("ess")) - 1) < 1e-12 and abs(rec[I["DT_SUM"]] / float(r("dt_sum")) - 1) < 1e-12
+    np.testing.assert_allclose(H(out["xi_body"])[0], r("xi"), rtol=1e-10, atol=1e-13)
+    # the nine-output form with explicit weights (the reference signature)
+    res = g.preintegrate_imu_relative_pose(r("stamps"), r("gyro"), r("accel"), r("w"), r("rotvec0"), r("bg"), r("ba"), r("grav"))
+    np.testing.assert_allclose(H(res[0]), r("delta_pose"), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(H(res[1]), r("delta_R"), rtol=1e-11, atol=1e-13)
+
+
+def test_imu_twist_batch_feeds_the_jobs(g, O):
+    """Several hypotheses (start orientation, biases) in one launch, odd sample counts, rotation-only deskew, and the twist
+    written straight into gcl_job records on the device."""
+    rng = np.random.default_rng(9)
+    for M in (1, 31, 33, 700):
+        Hn = 5
+        t0 = 1.7e9
+        stamps = t0 - 0.01 + np.arange(M) / 250.0
+        gyro, accel = rng.normal(size=(M, 3)), rng.normal(size=(M, 3)) + np.array([0, 0, 9.81])
+        rv, bg, ba = 0.4 * rng.normal(size=(Hn, 3)), 0.02 * rng.normal(size=(Hn, 3)), 0.1 * rng.normal(size=(Hn, 3))
+        grav = np.array([0.0, 0.0, -9.81])
+        for rot_only in (False, True):
+            import ctypes
+            jsz, joff = ctypes.sizeof(g._abi.GclJob), g._abi.GclJob.xi_body.offset
+            jobs = torch.zeros((Hn, jsz), dtype=torch.uint8, device="cuda")
+            out = g.imu_deskew_twist(stamps, gyro, accel, t0, t0 + 0.1, 0.01, rv, bg, ba, grav, deskew_rotation_only=rot_only, jobs_dev=jobs)
+            xi = H(out["xi_body"])
+            for h in range(Hn):
+                ref = O.imu_deskew_twist(stamps, gyro, accel, t0, t0 + 0.1, 0.01, rv[h], bg[h], ba[h], grav, rotation_only=rot_only)
+                np.testing.assert_allclose(xi[h], ref["xi_body"], rtol=1e-9, atol=1e-12)
+            in_jobs = np.frombuffer(jobs.cpu().numpy().tobytes(), dtype=np.float64).reshape(Hn, jsz // 8)[:, joff // 8:joff // 8 + 6]
+            assert np.array_equal(in_jobs, xi)

@@ -257,3 +257,27 @@ def test_appendix_b_known_answers():
         pb = O.point_budget_resample(np.zeros((n, 3)), np.zeros(n), np.ones(n), n_points_cap=cap)
         assert (pb["stride"], pb["n_output"]) == (stride, nsel)
         assert np.array_equal(pb["indices"], np.arange(0, n, max(1, int(np.ceil(n / cap)))))
+
+
+# ---------------------------------------------------------------- IMU preintegration -> deskew twist
+@pytest.fixture(scope="module")
+def imu_ref():
+    return np.load(os.path.join(GOLDEN, "ref_imu.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_imu_preintegration_matches_reference(imu_ref, case):
+    z = imu_ref
+    g = lambda k: z[f"{case}_{k}"]
+    out = O.imu_deskew_twist(g("stamps"), g("gyro"), g("accel"), float(g("t0")), float(g("t1")), float(g("sigma")), g("rotvec0"),
+                             g("bg"), g("ba"), g("grav"))
+    np.testing.assert_allclose(out["weights"], g("w"), rtol=1e-13, atol=1e-300)
+    for k in ("delta_pose", "delta_R", "delta_p", "delta_v", "a_body_mean", "a_world_nog_mean", "a_world_mean"):
+        np.testing.assert_allclose(out[k], g(k), rtol=1e-11, atol=1e-13, err_msg=k)
+    assert abs(out["ess"] / float(g("ess")) - 1) < 1e-13 and abs(out["dt_sum"] / float(g("dt_sum")) - 1) < 1e-13
+    np.testing.assert_allclose(out["xi_body"], g("xi"), rtol=1e-10, atol=1e-13)
+
+
+def test_se3_log_matches_reference(imu_ref):
+    for p, ref in zip(imu_ref["se3log_in"], imu_ref["se3log_out"]):
+        np.testing.assert_allclose(O.se3_log(p), ref, rtol=1e-10, atol=1e-13)
