@@ -9,7 +9,8 @@ from .operators import (BinAtlas, BinSoftAssignResult, DeskewConstantTwistResult
                         apply_forgetting, bin_soft_assign, build_combined_lidar_evidence_22d, compute_map_derived_stats,
                         create_empty_map_stats, create_fibonacci_atlas, deskew_constant_twist, imu_deskew_twist,
                         kappa_from_resultant_batch,
-                        map_update_inplace, matrix_fisher_rotation_evidence, planar_translation_evidence, point_budget_resample,
+                        map_update_inplace, matrix_fisher_rotation_evidence, parse_pointcloud2_vlp16, planar_translation_evidence,
+                        point_budget_resample,
                         point_directions, preintegrate_imu_relative_pose, preintegrate_imu_relative_pose_jax,
                         scan_bin_moment_match, smooth_window_weights, update_map_stats)
 from .pipeline import LidarEvidencePipeline, LidarScanEvidence, ResidentScan, lidar_scan_evidence  # noqa: F401

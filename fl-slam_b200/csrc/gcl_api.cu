@@ -378,6 +378,38 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
   return GCL_OK;
 }
 
+int gcl_pointcloud2_ingest(gcl_handle h, void* stream, const uint8_t* data, int64_t n_points, int32_t point_step,
+                           const int32_t* off, const int32_t* dt, double header_stamp, const double* R_host, const double* t_host,
+                           double* points_out, double* timestamps_out, double* weights_out, uint8_t* ring_out, uint8_t* tag_out,
+                           void* packed_xyzt, float* packed_w, double packed_t0, double* workspace) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, n_points >= 0 && point_step >= 1 && point_step <= 512, "n_points >= 0 and 1 <= point_step <= 512 required");
+  GCL_REQUIRE(h, off && dt && workspace && (n_points == 0 || data), "NULL pointer");
+  GCL_REQUIRE(h, (R_host == nullptr) == (t_host == nullptr), "R_base_lidar and t_base_lidar go together");
+  GCL_REQUIRE(h, (packed_xyzt == nullptr) == (packed_w == nullptr), "packed_xyzt and packed_w go together");
+  static const int width[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+  IngestParams P;
+  memset(&P, 0, sizeof(P));
+  for (int k = 0; k < 5; ++k) {
+    const bool optional = (k == 4) && off[k] < 0;
+    GCL_REQUIRE(h, optional || (dt[k] >= 1 && dt[k] <= 8), "Unsupported PointField datatype");   // backend_node.py:374
+    GCL_REQUIRE(h, optional || (off[k] >= 0 && off[k] + width[dt[k]] <= point_step), "field does not fit in point_step");
+    P.off[k] = off[k]; P.dtype[k] = optional ? 0 : dt[k];
+  }
+  P.data = data; P.n_points = n_points; P.point_step = point_step; P.header_stamp = header_stamp;
+  P.sentinel = 1e6; P.sigma = 0.25; P.min_r = 0.5; P.max_r = 50.0; P.weight_floor = 1e-12;   // constants.py:256-262
+  P.transform = R_host != nullptr;
+  if (R_host) { for (int k = 0; k < 9; ++k) P.R[k] = R_host[k]; for (int k = 0; k < 3; ++k) P.t[k] = t_host[k]; }
+  P.points_out = points_out; P.timestamps_out = timestamps_out; P.weights_out = weights_out; P.ring_out = ring_out; P.tag_out = tag_out;
+  P.packed_xyzt = static_cast<float4*>(packed_xyzt); P.packed_w = packed_w; P.packed_t0 = packed_t0;
+  P.flag = reinterpret_cast<int*>(workspace);
+  int l = 0;
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, launch_ingest(P, (cudaStream_t)stream, &l));
+  h->launches += l;
+  return GCL_OK;
+}
+
 int gcl_imu_preintegrate(gcl_handle h, void* stream, const double* stamps, const double* gyro, const double* accel,
                          const double* weights, int n_samples, double t0, double t1, double sigma, const double* rotvec_start,
                          const double* gyro_bias, const double* accel_bias, const double* gravity_host, int rotation_only,

@@ -126,6 +126,22 @@ cudaError_t launch_map_update(const double* stats, const double* R, const double
                               double* S_dir, double* S_dir_scatter, double* N_dir, double* N_pos, double* sum_p,
                               double* sum_ppT, cudaStream_t stream);
 
+struct IngestParams {
+  const unsigned char* data;   // raw PointCloud2 bytes (device)
+  int64_t n_points;
+  int point_step;
+  int off[5], dtype[5];        // x, y, z, ring, time (off[4] < 0: no per-point time)
+  double header_stamp;
+  double sentinel, sigma, min_r, max_r, weight_floor;
+  int transform;
+  double R[9], t[3];
+  double* points_out; double* timestamps_out; double* weights_out;
+  unsigned char* ring_out; unsigned char* tag_out;
+  float4* packed_xyzt; float* packed_w; double packed_t0;
+  int* flag;                   // device scratch: "per-point time is in nanoseconds"
+};
+cudaError_t launch_ingest(const IngestParams& P, cudaStream_t stream, int* launches);
+
 struct ImuParams {
   const double *stamps, *gyro, *accel, *weights;  // (M,), (M,3), (M,3), optional (M,) -- NULL: window weights computed here
   int M;

@@ -283,6 +283,49 @@ def scan_bin_moment_match(points, point_covariances, weights, responsibilities, 
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# PointCloud2 ingest ("next" row)
+# ----------------------------------------------------------------------------------------------------------------
+def parse_pointcloud2_vlp16(msg=None, *, data=None, fields=None, point_step: Optional[int] = None, n_points: Optional[int] = None,
+                            header_stamp_sec: float = 0.0, R_base_lidar=None, t_base_lidar=None, packed_t0: Optional[float] = None):
+    """parse_pointcloud2_vlp16 (pkg/backend/backend_node.py:377-468) on the GPU: the raw message bytes are uploaded as they are
+    (point_step bytes per point) and decoded there.  Pass a sensor_msgs/PointCloud2-like ``msg`` (``data``, ``fields`` with
+    ``name`` / ``offset`` / ``datatype``, ``point_step``, ``width``, ``height``, ``header.stamp``) or the pieces by keyword
+    (``fields`` as (name, offset, datatype) triples).  With ``R_base_lidar`` / ``t_base_lidar`` the points come back in the
+    base frame (backend_node.py:1675-1681).  Returns ``(points, timestamps, weights, ring, tag)`` like the reference; with
+    ``packed_t0`` also the 20 B/point layout ``(xyzt float4, w float)`` as a sixth and seventh element."""
+    if msg is not None:
+        data, point_step, n_points = msg.data, int(msg.point_step), int(msg.width) * int(msg.height)
+        fields = [(f.name, int(f.offset), int(f.datatype)) for f in msg.fields]
+        header_stamp_sec = msg.header.stamp.sec + msg.header.stamp.nanosec * 1e-9
+    fmap = {f[0]: (int(f[1]), int(f[2])) for f in fields}
+    missing = [k for k in ("x", "y", "z", "ring") if k not in fmap]
+    if missing:
+        raise RuntimeError(f"PointCloud2 (VLP-16 layout) missing required fields: {missing}. Present fields: {sorted(fmap)}")
+    tname = "t" if "t" in fmap else ("time" if "time" in fmap else None)
+    order = ["x", "y", "z", "ring"] + ([tname] if tname else [])
+    off = np.array([fmap[k][0] for k in order] + ([] if tname else [-1]), dtype=np.int32)
+    dt = np.array([fmap[k][1] for k in order] + ([] if tname else [0]), dtype=np.int32)
+    if any(d < 1 or d > 8 for d in dt[:len(order)]):
+        raise ValueError(f"Unsupported PointField datatype: {[int(d) for d in dt]}")
+    n = int(n_points)
+    dev = _device()
+    raw = torch.frombuffer(bytearray(bytes(data)[:n * point_step]), dtype=torch.uint8).to(dev) if n > 0 else torch.zeros(0, dtype=torch.uint8, device=dev)
+    pts, ts, w = _empty(n, 3), _empty(n), _empty(n)
+    ring, tag = _empty(n, dtype=torch.uint8), _empty(n, dtype=torch.uint8)
+    xyzt = _empty(n, 4, dtype=torch.float32) if packed_t0 is not None else None
+    wf = _empty(n, dtype=torch.float32) if packed_t0 is not None else None
+    ws = _empty(2)
+    R = None if R_base_lidar is None else np.ascontiguousarray(np.asarray(R_base_lidar, dtype=np.float64).reshape(9))
+    t = None if t_base_lidar is None else np.ascontiguousarray(np.asarray(t_base_lidar, dtype=np.float64).reshape(3))
+    h = _h()
+    _abi.check(_lib.gcl_pointcloud2_ingest(h, _stream(), _ptr(raw), n, int(point_step), off.ctypes.data, dt.ctypes.data,
+                                           float(header_stamp_sec), None if R is None else R.ctypes.data,
+                                           None if t is None else t.ctypes.data, _ptr(pts), _ptr(ts), _ptr(w), _ptr(ring), _ptr(tag),
+                                           _ptr(xyzt), _ptr(wf), 0.0 if packed_t0 is None else float(packed_t0), _ptr(ws)), h)
+    return (pts, ts, w, ring, tag) if packed_t0 is None else (pts, ts, w, ring, tag, xyzt, wf)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # IMU preintegration -> deskew twist ("next" row, SURVEY.md 8f-3)
 # ----------------------------------------------------------------------------------------------------------------
 IMU = dict(DELTA_POSE=0, DELTA_R=6, DELTA_P=15, DELTA_V=18, ESS=21, A_BODY_MEAN=22, A_WORLD_NOG_MEAN=25, A_WORLD_MEAN=28,

@@ -243,6 +243,22 @@ int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const 
                         const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,
                         float* packed_w);
 
+/* ---- PointCloud2 ingest ("next" row) ------------------------------------------------------- */
+/* parse_pointcloud2_vlp16 (pkg/backend/backend_node.py:377-468; datatype codes :351-374) + the base-frame transform
+ * (:1675-1681) on the raw message bytes in DEVICE memory: n_points records of point_step bytes.
+ *   field_offsets / field_datatypes  5 entries each: x, y, z, ring, per-point time ("t" else "time"; offset -1 if absent).
+ *                                    Datatypes are sensor_msgs/PointField codes 1..8.
+ *   R_base_lidar_host, t_base_lidar_host   (9,), (3,) or NULL/NULL for no transform (points stay in the LiDAR frame)
+ *   outputs (any may be NULL): points (n,3) f64, timestamps (n,) f64, weights (n,) f64, ring (n,) u8, tag (n,) u8; and / or
+ *   the packed 20 B/point layout (float4 {x,y,z,t - packed_t0} + float w) that the fp32c kernel reads.
+ *   workspace: at least 1 double of device scratch.
+ * Constants of the reference: sentinel 1e6 (GC_NONFINITE_SENTINEL), range window 0.25 / 0.5 / 50 m, weight floor 1e-12. */
+int gcl_pointcloud2_ingest(gcl_handle h, void* stream, const uint8_t* data, int64_t n_points, int32_t point_step,
+                           const int32_t* field_offsets_host, const int32_t* field_datatypes_host,
+                           double header_stamp_sec, const double* R_base_lidar_host, const double* t_base_lidar_host,
+                           double* points_out, double* timestamps_out, double* weights_out, uint8_t* ring_out,
+                           uint8_t* tag_out, void* packed_xyzt, float* packed_w, double packed_t0, double* workspace);
+
 /* ---- IMU preintegration -> deskew twist ("next" row) ---------------------------------------- */
 /* smooth_window_weights + preintegrate_imu_relative_pose_jax + se3_log as called at pkg/backend/pipeline.py:437-483
  * (pkg/backend/operators/imu_preintegration.py:19-43, :46-147; pkg/common/geometry/se3_jax.py:179-256), batched over

@@ -236,6 +236,77 @@ def run_imu(ref):
     np.savez_compressed(os.path.join(HERE, "ref_imu.npz"), **out)
 
 
+def _load_pointcloud2_parser():
+    """parse_pointcloud2_vlp16 and _pointfield_to_dtype cut out of the reference's backend_node.py (the module itself imports
+    rclpy / sensor_msgs, which are not installed): the two function bodies are executed unmodified against a stand-in
+    PointField (sensor_msgs/msg/PointField datatype codes) and the reference's own constants module."""
+    import ast, importlib.util, types
+    path = "/root/reference/fl_ws/src/fl_slam_poc/fl_slam_poc/backend/backend_node.py"
+    src = open(path).read()
+    tree = ast.parse(src)
+    wanted = {"_pointfield_to_dtype", "parse_pointcloud2_vlp16"}
+    chunks = [ast.get_source_segment(src, n) for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert len(chunks) == 2
+    spec = importlib.util.spec_from_file_location("ref_constants", "/root/reference/fl_ws/src/fl_slam_poc/fl_slam_poc/common/constants.py")
+    constants = importlib.util.module_from_spec(spec); spec.loader.exec_module(constants)
+    PointField = types.SimpleNamespace(INT8=1, UINT8=2, INT16=3, UINT16=4, INT32=5, UINT32=6, FLOAT32=7, FLOAT64=8)
+    from typing import Tuple
+    ns = {"np": np, "constants": constants, "PointField": PointField, "PointCloud2": object, "Tuple": Tuple}
+    exec("\n\n".join(chunks), ns)
+    return ns["parse_pointcloud2_vlp16"]
+
+
+def _make_msg(data, fields, point_step, n, stamp):
+    import types
+    return types.SimpleNamespace(width=n, height=1, point_step=point_step, data=bytes(data),
+                                 fields=[types.SimpleNamespace(name=f[0], offset=f[1], datatype=f[2]) for f in fields],
+                                 header=types.SimpleNamespace(stamp=types.SimpleNamespace(sec=int(stamp[0]), nanosec=int(stamp[1]))))
+
+
+def run_pointcloud2():
+    """PointCloud2 ingest: the reference's parse_pointcloud2_vlp16 (backend_node.py:377-468) and the base-frame
+    transform (:1675-1681) on synthetic VLP-16 messages: the Kimera layout (x y z f32, intensity f32, ring u16, time f32,
+    point_step 22), per-point time in nanoseconds as u32, a layout without per-point time, doubles, and non-finite points."""
+    parse = _load_pointcloud2_parser()
+    rng = np.random.default_rng(31)
+    out = {}
+    R_bl = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]) @ np.array([[1, 0, 0], [0, 0.9998, -0.02], [0, 0.02, 0.9998]])
+    t_bl = np.array([-0.065447, -0.100474, 0.108987])
+    layouts = {
+        "kimera": dict(step=22, fields=[("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("intensity", 12, 7), ("ring", 16, 4), ("time", 18, 7)]),
+        "ns_u32": dict(step=24, fields=[("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("ring", 12, 2), ("t", 16, 6)]),
+        "no_time": dict(step=16, fields=[("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("ring", 12, 4)]),
+        "f64": dict(step=40, fields=[("x", 0, 8), ("y", 8, 8), ("z", 16, 8), ("ring", 24, 5), ("time", 32, 8)]),
+    }
+    npd = {1: "i1", 2: "u1", 3: "<i2", 4: "<u2", 5: "<i4", 6: "<u4", 7: "<f4", 8: "<f8"}
+    for name, L in layouts.items():
+        n = 777
+        dt = np.dtype({"names": [f[0] for f in L["fields"]], "formats": [npd[f[2]] for f in L["fields"]],
+                       "offsets": [f[1] for f in L["fields"]], "itemsize": L["step"]})
+        arr = np.zeros(n, dtype=dt)
+        rngm = rng.uniform(0.2, 60.0, n)
+        d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        xyz = d * rngm[:, None]
+        xyz[5] = [np.nan, 1.0, 2.0]; xyz[17] = [np.inf, -np.inf, 0.0]; xyz[40] = [0.0, 0.0, 0.0]
+        arr["x"], arr["y"], arr["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        arr["ring"] = rng.integers(0, 16, n)
+        if "intensity" in dt.names:
+            arr["intensity"] = rng.uniform(0, 255, n)
+        tf = [f for f in L["fields"] if f[0] in ("t", "time")]
+        if tf:
+            arr[tf[0][0]] = (rng.uniform(0, 0.1, n) * (1e9 if tf[0][2] == 6 else 1.0))
+        raw = arr.tobytes()
+        stamp = (1700000000, 123456789)
+        pts, ts, w, ring, tag = parse(_make_msg(raw, L["fields"], L["step"], n, stamp))
+        pts_base = (R_bl @ pts.T).T + t_bl[None, :]
+        out.update({f"{name}_raw": np.frombuffer(raw, dtype=np.uint8), f"{name}_step": L["step"], f"{name}_n": n,
+                    f"{name}_fields": np.array([[{"x": 0, "y": 1, "z": 2, "ring": 3, "t": 4, "time": 4, "intensity": 5}[f[0]], f[1], f[2]] for f in L["fields"]]),
+                    f"{name}_stamp": np.array(stamp), f"{name}_points_lidar": pts, f"{name}_points_base": pts_base, f"{name}_t": ts,
+                    f"{name}_w": w, f"{name}_ring": ring, f"{name}_tag": tag})
+    out["R_base_lidar"], out["t_base_lidar"] = R_bl, t_bl
+    np.savez_compressed(os.path.join(HERE, "ref_pointcloud2.npz"), **out)
+
+
 def main():
     ref = _jaxshim.load_reference("/root/reference", n_bins=48, tau=0.1)
     synth = _load_synth()
@@ -255,6 +326,7 @@ def main():
         json.dump(certs, f, indent=1, sort_keys=True, default=float)
     run_pieces(ref)
     run_imu(ref)
+    run_pointcloud2()
     print("wrote goldens to", HERE)
 
 

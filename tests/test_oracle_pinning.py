@@ -281,3 +281,25 @@ def test_imu_preintegration_matches_reference(imu_ref, case):
 def test_se3_log_matches_reference(imu_ref):
     for p, ref in zip(imu_ref["se3log_in"], imu_ref["se3log_out"]):
         np.testing.assert_allclose(O.se3_log(p), ref, rtol=1e-10, atol=1e-13)
+
+
+# ---------------------------------------------------------------- PointCloud2 ingest
+PC2_FIELD_NAMES = {0: "x", 1: "y", 2: "z", 3: "ring", 4: "time", 5: "intensity"}
+
+
+def pc2_case(z, name):
+    fields = [(PC2_FIELD_NAMES[int(k)], int(off), int(dt)) for k, off, dt in z[f"{name}_fields"]]
+    return z[f"{name}_raw"], fields, int(z[f"{name}_step"]), int(z[f"{name}_n"]), tuple(int(v) for v in z[f"{name}_stamp"])
+
+
+@pytest.mark.parametrize("name", ["kimera", "ns_u32", "no_time", "f64"])
+def test_pointcloud2_parse_matches_reference(name):
+    z = np.load(os.path.join(GOLDEN, "ref_pointcloud2.npz"))
+    raw, fields, step, n, stamp = pc2_case(z, name)
+    out = O.parse_pointcloud2_vlp16(raw, fields, step, n, stamp)
+    assert np.array_equal(out["points"], z[f"{name}_points_lidar"])          # byte work: bit-exact
+    assert np.array_equal(out["timestamps"], z[f"{name}_t"])
+    assert np.array_equal(out["ring"], z[f"{name}_ring"]) and np.array_equal(out["tag"], z[f"{name}_tag"])
+    np.testing.assert_allclose(out["weights"], z[f"{name}_w"], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(O.lidar_points_to_base(out["points"], z["R_base_lidar"], z["t_base_lidar"]), z[f"{name}_points_base"],
+                               rtol=1e-15, atol=1e-15)
