@@ -381,8 +381,16 @@ __device__ inline void iw_sigma_mode(const double* iw /* [nu, Psi(9)] */, double
 }
 
 // suffstats from residuals (:104-127) then the forgetful update with the smooth nu projection (:60-100)
+// nu' = nu_max - softplus(nu_max - (nu_min + softplus(rho nu + 1 - nu_min))): the degrees of freedom follow a recurrence of
+// their own, independent of the data
+__device__ inline double iw_nu_next(double nu, double rho, double nu_weak_add, double nu_max) {
+  const double nu_raw = rho * nu + 1.0;
+  const double nu_min = 3.0 + 1.0 + nu_weak_add;
+  const double nu_floor = nu_min + softplus64(nu_raw - nu_min);
+  return nu_max - softplus64(nu_max - nu_floor);
+}
 __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T (9), sum w] */, double rho, double nu_weak_add,
-                                 double nu_max, double eps_mass, double eps_psd) {
+                                 double nu_max, double eps_mass, double eps_psd, bool update_nu = true) {
   double rrT[9], dPsi[9];
   const double iw_ = 1.0 / (rr_w[9] + eps_mass);
   for (int i = 0; i < 3; ++i)
@@ -391,10 +399,7 @@ __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T 
   double Praw[9], Ppsd[9];
   for (int i = 0; i < 9; ++i) Praw[i] = rho * iw[1 + i] + dPsi[i];
   psd_project3_fast(Praw, eps_psd, Ppsd);  // symmetrises first
-  const double nu_raw = rho * iw[0] + 1.0;
-  const double nu_min = 3.0 + 1.0 + nu_weak_add;
-  const double nu_floor = nu_min + softplus64(nu_raw - nu_min);
-  iw[0] = nu_max - softplus64(nu_max - nu_floor);
+  if (update_nu) iw[0] = iw_nu_next(iw[0], rho, nu_weak_add, nu_max);
   for (int i = 0; i < 9; ++i) iw[1 + i] = Ppsd[i];
 }
 
@@ -476,18 +481,28 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
 
 // ---- staged stream ----------------------------------------------------------------------------------------------------
 // workspace carve (doubles): [single-scan map-derived 16B][map_pre: S x 26B][mder: S x 16B][sigma: S x 16][tpart: S*H x 32]
+//                           [pre: S x (32 + 16B)]
 struct StreamWs {
-  double *map_pre, *mder, *sigma, *tpart;
-  __host__ __device__ StreamWs(double* ws, int S, int B) {
+  double *map_pre, *mder, *sigma, *tpart, *pre;
+  __host__ __device__ StreamWs(double* ws, int S, int B, int H) {
     map_pre = ws + 16 * (size_t)B;
     mder = map_pre + (size_t)S * 26 * B;
     sigma = mder + (size_t)S * 16 * B;
     tpart = sigma + (size_t)S * 16;
+    pre = tpart + (size_t)S * H * 32;
   }
 };
+__host__ __device__ inline size_t pre_block_doubles(int B) { return 32 + 16 * (size_t)B; }
 size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins) {
-  return 16 * (size_t)n_bins + (size_t)n_scans * (26 * (size_t)n_bins + 16 * (size_t)n_bins + 16) + (size_t)n_scans * n_hyp * 32;
+  return 16 * (size_t)n_bins + (size_t)n_scans * (26 * (size_t)n_bins + 16 * (size_t)n_bins + 16) + (size_t)n_scans * n_hyp * 32 +
+         (size_t)n_scans * pre_block_doubles(n_bins);
 }
+// pre block of one scan (hypothesis 0), everything of the translation step that does NOT depend on Sigma_meas:
+//   header: R_hat[0..9) | S_wtt[9..18) = sum_b w_b t_b t_b^T | S_wt[18..21) | S_w[21]
+//   per bin (16): M_b[0..9) = Sigma_c,b + R A_b R^T + eps I | c_b = N/(N+eps) | t_b[10..13) | w_b | flag (A_b provably >= eps_psd)
+// with A_b = sum_ppT/N - p_bar p_bar^T, so that  Sigma_c,b + R Sigma_p,b R^T + eps I = M_b + c_b (R Sigma_meas R^T)  whenever the
+// PSD projection of A_b + c_b Sigma_meas is the identity (flag), and
+//   sum_b w_b r_b r_b^T = S_wtt - S_wt t^T - t S_wt^T + S_w t t^T   for r_b = t_b - t.
 // tpart record: Lf[0..9) tw[9..12) NeffT[12] rr[13..22) ws[22]
 
 // S1: world-frame increments of every scan's bin sums (same expressions as map_update_bin, without the recurrence);
@@ -495,7 +510,7 @@ size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins) {
 __global__ void stream_increments_kernel(const __grid_constant__ ChainParams P) {
   const int s = blockIdx.x, B = P.n_bins;
   const StatsLayout SL(B);
-  const StreamWs W(P.workspace, P.n_scans, B);
+  const StreamWs W(P.workspace, P.n_scans, B, P.n_hyp);
   const double* stats = P.stats + (size_t)s * P.n_hyp * P.stats_stride;
   const double* pu = P.pose_update + (size_t)s * 6;
   double R[9];
@@ -532,7 +547,7 @@ __global__ void stream_increments_kernel(const __grid_constant__ ChainParams P) 
 __global__ void stream_map_recurrence_kernel(const __grid_constant__ ChainParams P) {
   const int B = P.n_bins, e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 26 * B) return;
-  const StreamWs W(P.workspace, P.n_scans, B);
+  const StreamWs W(P.workspace, P.n_scans, B, P.n_hyp);
   double* arr = e < 3 * B ? P.map_S_dir + e : e < 12 * B ? P.map_S_dir_scatter + (e - 3 * B) : e < 13 * B ? P.map_N_dir + (e - 12 * B)
               : e < 14 * B ? P.map_N_pos + (e - 13 * B) : e < 17 * B ? P.map_sum_p + (e - 14 * B) : P.map_sum_ppT + (e - 17 * B);
   double m = *arr;
@@ -574,7 +589,7 @@ __device__ __forceinline__ MapView map_view(const ChainParams& P, const StreamWs
 //     With use_sigma_meas only the rotation part can run here (the bin covariances are not known yet).
 __global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __grid_constant__ ChainParams P) {
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = P.n_bins, H = P.n_hyp;
-  const StreamWs W(P.workspace, P.n_scans, B);
+  const StreamWs W(P.workspace, P.n_scans, B, P.n_hyp);
   const MapView mv = map_view(P, W, s);
   double* mder = W.mder + (size_t)s * 16 * B;
   for (int b = tid; b < B; b += kChainThreads)
@@ -586,11 +601,58 @@ __global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __
                        P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, sig ? 0 : 1,
                        P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES,
                        (h == 0 && P.iw_state && !sig) ? W.tpart + ((size_t)s * H) * 32 + 13 : nullptr);
+  if (!sig) return;
+  // everything of hypothesis 0's translation step that does not depend on Sigma_meas (see the pre block above)
+  __syncthreads();
+  const StatsLayout SL(B);
+  const double* st = P.stats + ((size_t)s * H) * P.stats_stride;
+  const double* ev = P.evidence + ((size_t)s * H) * GCL_EVID_DOUBLES;
+  double* pre = W.pre + (size_t)s * pre_block_doubles(B);
+  double R[9];
+  for (int i = 0; i < 9; ++i) R[i] = ev[GCL_EV_R_MF + i];
+  for (int b = tid; b < B; b += kChainThreads) {
+    const double N = st[SL.N() + b];
+    const double invN = 1.0 / (N + P.eps_mass + kF64Eps);
+    const double* pb = st + SL.p_bar() + b * 3;
+    const double* spp = st + SL.sum_ppT() + b * 9;
+    double A[9], As[9], RA[9], RAR[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) A[i * 3 + j] = spp[i * 3 + j] * invN - pb[i] * pb[j];
+    const double a = A[0], d = A[4], f = A[8], bb = 0.5 * (A[1] + A[3]), c = 0.5 * (A[2] + A[6]), e2 = 0.5 * (A[5] + A[7]);
+    const double m2 = a * d - bb * bb, det = a * (d * f - e2 * e2) - bb * (bb * f - e2 * c) + c * (bb * e2 - d * c), tr = a + d + f;
+    const bool pd = a > 0.0 && m2 > 0.0 && det > 0.0 && 4.0 * det > 2.0 * P.eps_psd * tr * tr;   // as psd_project3_fast
+    As[0] = a; As[1] = bb; As[2] = c; As[3] = bb; As[4] = d; As[5] = e2; As[6] = c; As[7] = e2; As[8] = f;
+    mat3_mul(R, As, RA);
+    mat3_mul_nt(RA, R, RAR);
+    double* q = pre + 32 + 16 * (size_t)b;
+    for (int i = 0; i < 9; ++i) q[i] = mder[7 * B + b * 9 + i] + RAR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
+    q[9] = N * invN;
+    for (int i = 0; i < 3; ++i) q[10 + i] = mder[4 * B + b * 3 + i] - (R[i * 3] * pb[0] + R[i * 3 + 1] * pb[1] + R[i * 3 + 2] * pb[2]);
+    q[13] = sqrt(N * mv.N_pos[b] + P.eps_mass);
+    q[14] = pd ? 1.0 : 0.0;
+    q[15] = 0.0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = lane; b < B; b += 32) {
+      const double* q = pre + 32 + 16 * (size_t)b;
+      const double w = q[13];
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) acc[i * 3 + j] += w * q[10 + i] * q[10 + j];
+        acc[9 + i] += w * q[10 + i];
+      }
+      acc[12] += w;
+    }
+    for (int i = 0; i < 13; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane < 9) pre[lane] = R[lane];
+    if (lane < 13) pre[9 + lane] = acc[lane];
+  }
 }
 
 // S4a: IW recurrence alone (the residual statistics do not depend on the IW state when Sigma_meas is not fed back)
 __global__ void stream_iw_recurrence_kernel(const __grid_constant__ ChainParams P) {
-  const StreamWs W(P.workspace, P.n_scans, P.n_bins);
+  const StreamWs W(P.workspace, P.n_scans, P.n_bins, P.n_hyp);
   __shared__ double s_rr[32][10];   // residual statistics of the next 32 scans (one global round trip per 32 scans)
   double iw[10];
   for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
@@ -605,93 +667,86 @@ __global__ void stream_iw_recurrence_kernel(const __grid_constant__ ChainParams 
     for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
 }
 
-// S4b: the sequential core with Sigma_meas fed back.  Warp 0 computes, warp 1 stages the next scan's inputs in shared memory.
-//      staged block per scan (doubles): N[B] p_bar[3B] sum_ppT[9B] | cen[3B] Sig_c[9B] | N_pos[B] | R_hat[9]
-__device__ __forceinline__ size_t seq_block_doubles(int B) { return 26 * (size_t)B + 9; }
+// S4b: the sequential core with Sigma_meas fed back.  Warp 0 computes, the other warps stage the next scan's pre block in
+//      shared memory.  Per scan:  Sigma_meas -> S = R Sigma_meas R^T -> per bin inv(M_b + c_b S) -> L, h -> t_wls -> residual
+//      statistics from the pre-computed sums -> IW update.  Bins whose A_b is not provably >= eps_psd (flag 0: e.g. empty
+//      bins) take the full route: PSD projection of A_b + c_b Sigma_meas, R . R^T, map covariance.
+__device__ __forceinline__ size_t seq_block_doubles(int B) { return pre_block_doubles(B); }
 constexpr int kSeqHelpers = 3;  // warps that stage the next scan's inputs while warp 0 computes
 __global__ void __launch_bounds__(32 * (1 + kSeqHelpers)) stream_sigma_chain_kernel(const __grid_constant__ ChainParams P, int use_smem) {
   extern __shared__ __align__(16) double s_stage[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = P.n_bins, H = P.n_hyp, S = P.n_scans;
   const StatsLayout SL(B);
-  const StreamWs W(P.workspace, S, B);
+  const StreamWs W(P.workspace, S, B, P.n_hyp);
   const size_t blk = seq_block_doubles(B);
   const int hl = tid - 32, HN = 32 * kSeqHelpers;  // helper-thread index / count
-  auto stage = [&](int s, double* dst) {  // all helper threads
-    const double* st = P.stats + (size_t)s * H * P.stats_stride;
-    const double* md = W.mder + (size_t)s * 16 * B;
-    const MapView mv = map_view(P, W, s);
-    const double* ev = P.evidence + (size_t)s * H * GCL_EVID_DOUBLES;
-    for (int i = hl; i < B; i += HN) { dst[i] = st[SL.N() + i]; dst[25 * B + i] = mv.N_pos[i]; }
-    for (int i = hl; i < 3 * B; i += HN) { dst[B + i] = st[SL.p_bar() + i]; dst[13 * B + i] = md[4 * B + i]; }
+  auto stage = [&](int s, double* dst) {  // all helper threads; 16-byte copies
+    const double2* src = reinterpret_cast<const double2*>(W.pre + (size_t)s * blk);
+    double2* d2 = reinterpret_cast<double2*>(dst);
 #pragma unroll 4
-    for (int i = hl; i < 9 * B; i += HN) { dst[4 * B + i] = st[SL.sum_ppT() + i]; dst[16 * B + i] = md[7 * B + i]; }
-    if (hl < 9) dst[26 * B + hl] = ev[GCL_EV_R_MF + hl];
+    for (int i = hl; i < (int)(blk / 2); i += HN) d2[i] = src[i];
   };
   if (use_smem) {
     if (warp >= 1) stage(0, s_stage);
     __syncthreads();
   }
+  // the degrees of freedom nu_s do not depend on the data: a helper thread runs their recurrence one scan ahead (two softplus
+  // evaluations off the critical path); the compute warp picks nu_s up after the barrier
+  __shared__ double s_nu[2];
   double iw[10];
   for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
+  double nu_h = iw[0];
   for (int s = 0; s < S; ++s) {
     if (warp >= 1) {
+      if (hl == 0) { nu_h = iw_nu_next(nu_h, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max); s_nu[(s + 1) & 1] = nu_h; }
       if (use_smem && s + 1 < S) stage(s + 1, s_stage + ((s + 1) & 1) * blk);
     } else {
-      double* st0 = P.stats + (size_t)s * H * P.stats_stride;
-      double sigma[9];
+      if (s > 0) iw[0] = s_nu[s & 1];
+      const double* in = use_smem ? s_stage + (s & 1) * blk : W.pre + (size_t)s * blk;
+      double sigma[9], R[9], RS[9], Sc[9];
       iw_sigma_mode(iw, P.eps_psd, sigma);
-      const double *sN, *p_bar, *spp, *m_cen, *m_Sig, *Npos;
-      double R_hat[9];
-      if (use_smem) {
-        const double* in = s_stage + (s & 1) * blk;
-        sN = in; p_bar = in + B; spp = in + 4 * B; m_cen = in + 13 * B; m_Sig = in + 16 * B; Npos = in + 25 * B;
-        for (int i = 0; i < 9; ++i) R_hat[i] = in[26 * B + i];
-      } else {
-        const double* md = W.mder + (size_t)s * 16 * B;
-        sN = st0 + SL.N(); p_bar = st0 + SL.p_bar(); spp = st0 + SL.sum_ppT(); m_cen = md + 4 * B; m_Sig = md + 7 * B;
-        Npos = map_view(P, W, s).N_pos;
-        for (int i = 0; i < 9; ++i) R_hat[i] = P.evidence[(size_t)s * H * GCL_EVID_DOUBLES + GCL_EV_R_MF + i];
-      }
-      // bin covariances with the measurement noise (written back: they are an output), then the WLS sums
-      double Lf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hf[3] = {0, 0, 0}, NeffT = 0;
+      for (int i = 0; i < 9; ++i) R[i] = in[i];
+      mat3_mul(R, sigma, RS);
+      mat3_mul_nt(RS, R, Sc);   // S = R Sigma_meas R^T
+      double Lf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hf[3] = {0, 0, 0};
       for (int b = lane; b < B; b += 32) {
-        const double N = sN[b];
-        const double invN = 1.0 / (N + P.eps_mass + kF64Eps);
-        double Sraw[9], Sp[9];
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j)
-            Sraw[i * 3 + j] = spp[b * 9 + i * 3 + j] * invN - p_bar[b * 3 + i] * p_bar[b * 3 + j] + sigma[i * 3 + j] * (N * invN);
-        psd_project3_fast(Sraw, P.eps_psd, Sp);
-        for (int i = 0; i < 9; ++i) st0[SL.Sigma_p() + b * 9 + i] = Sp[i];
-        double tb[3];
-        for (int i = 0; i < 3; ++i)
-          tb[i] = m_cen[b * 3 + i] - (R_hat[i * 3] * p_bar[b * 3] + R_hat[i * 3 + 1] * p_bar[b * 3 + 1] + R_hat[i * 3 + 2] * p_bar[b * 3 + 2]);
-        double RS[9], RSR[9], Sg[9], Si[9];
-        mat3_mul(R_hat, Sp, RS);
-        mat3_mul_nt(RS, R_hat, RSR);
-        for (int i = 0; i < 9; ++i) Sg[i] = m_Sig[b * 9 + i] + RSR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
+        const double* q = in + 32 + 16 * (size_t)b;
+        double Sg[9], Si[9];
+        if (q[14] != 0.0) {
+          for (int i = 0; i < 9; ++i) Sg[i] = q[i] + q[9] * Sc[i];
+        } else {   // full route for this bin
+          const double* st0 = P.stats + (size_t)s * H * P.stats_stride;
+          const double* md = W.mder + (size_t)s * 16 * B;
+          double Sp[9], T1[9], RSR[9];
+          sigma_p_with_meas(st0, SL, b, sigma, P.eps_mass, P.eps_psd, Sp);
+          mat3_mul(R, Sp, T1);
+          mat3_mul_nt(T1, R, RSR);
+          for (int i = 0; i < 9; ++i) Sg[i] = md[7 * B + b * 9 + i] + RSR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
+        }
         mat3_inv_adj(Sg, Si);
-        const double wb = sqrt(N * Npos[b] + P.eps_mass);
-        for (int i = 0; i < 9; ++i) Si[i] *= wb;
-        for (int i = 0; i < 9; ++i) Lf[i] += Si[i];
-        for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * tb[0] + Si[i * 3 + 1] * tb[1] + Si[i * 3 + 2] * tb[2];
-        NeffT += wb;
+        const double wb = q[13];
+        for (int i = 0; i < 9; ++i) { Si[i] *= wb; Lf[i] += Si[i]; }
+        for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * q[10] + Si[i * 3 + 1] * q[11] + Si[i * 3 + 2] * q[12];
       }
       for (int i = 0; i < 9; ++i) Lf[i] = warp_sum(Lf[i]);
       for (int i = 0; i < 3; ++i) hf[i] = warp_sum(hf[i]);
-      NeffT = warp_sum(NeffT);
       double tw[3], rr_w[10];
       translation_solve(Lf, hf, P.eps_mass, tw);
-      residual_sums_warp(lane, B, R_hat, p_bar, sN, m_cen, Npos, tw, P.eps_mass, rr_w, rr_w[9]);
+      const double* Swtt = in + 9; const double* Swt = in + 18; const double Sw = in[21];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) rr_w[i * 3 + j] = Swtt[i * 3 + j] - Swt[i] * tw[j] - tw[i] * Swt[j] + Sw * tw[i] * tw[j];
+      rr_w[9] = Sw;
       double* tp = W.tpart + ((size_t)s * H) * 32;
       if (lane < 9) { tp[lane] = Lf[lane]; W.sigma[(size_t)s * 16 + lane] = sigma[lane]; }
-      if (lane == 0) { tp[9] = tw[0]; tp[10] = tw[1]; tp[11] = tw[2]; tp[12] = NeffT; }
-      iw_update(iw, rr_w, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);  // identical on every lane
+      if (lane == 0) { tp[9] = tw[0]; tp[10] = tw[1]; tp[11] = tw[2]; tp[12] = Sw; }
+      iw_update(iw, rr_w, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd, false);  // identical on every lane
     }
-    if (use_smem) __syncthreads();
+    __syncthreads();
   }
-  if (tid == 0)
-    for (int i = 0; i < 10; ++i) P.iw_state[i] = iw[i];
+  if (tid == 0) {
+    P.iw_state[0] = s_nu[S & 1];
+    for (int i = 1; i < 10; ++i) P.iw_state[i] = iw[i];
+  }
 }
 
 // S5: finish the translation evidence in parallel: hypothesis 0 from the stored sums, the others from scratch with the
@@ -700,24 +755,24 @@ __global__ void __launch_bounds__(32) stream_translation_finish_kernel(const __g
   const int job = blockIdx.x, lane = threadIdx.x, B = P.n_bins, H = P.n_hyp;
   const int s = job / H, h = job - s * H;
   const StatsLayout SL(B);
-  const StreamWs W(P.workspace, P.n_scans, B);
+  const StreamWs W(P.workspace, P.n_scans, B, P.n_hyp);
   double* st = P.stats + (size_t)job * P.stats_stride;
   double* ev = P.evidence + (size_t)job * GCL_EVID_DOUBLES;
   const double* pose = P.pose_pred + (size_t)job * 6;
   const double l1m = ev[GCL_EV_MAP_METRICS + 0], l3m = ev[GCL_EV_MAP_METRICS + 2];
   double Lf[9], tw[3], NeffT;
+  const double* sigma = W.sigma + (size_t)s * 16;
+  for (int b = lane; b < B; b += 32) {   // the bin covariances with the measurement noise are an output of the chain
+    double Sp[9];
+    sigma_p_with_meas(st, SL, b, sigma, P.eps_mass, P.eps_psd, Sp);
+    for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Sp[i];
+  }
+  __syncwarp();
   if (h == 0) {
     const double* tp = W.tpart + ((size_t)s * H) * 32;
     for (int i = 0; i < 9; ++i) Lf[i] = tp[i];
     tw[0] = tp[9]; tw[1] = tp[10]; tw[2] = tp[11]; NeffT = tp[12];
   } else {
-    const double* sigma = W.sigma + (size_t)s * 16;
-    for (int b = lane; b < B; b += 32) {
-      double Sp[9];
-      sigma_p_with_meas(st, SL, b, sigma, P.eps_mass, P.eps_psd, Sp);
-      for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Sp[i];
-    }
-    __syncwarp();
     const double* md = W.mder + (size_t)s * 16 * B;
     double R_hat[9], hf[3];
     for (int i = 0; i < 9; ++i) R_hat[i] = ev[GCL_EV_R_MF + i];
@@ -747,7 +802,7 @@ cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launche
   stream_evidence_kernel<<<S, kChainThreads, 0, stream>>>(P);
   *launches += 1;
   if (P.iw_state && P.use_sigma_meas) {
-    const size_t smem = 2 * (26 * (size_t)B + 9) * sizeof(double);
+    const size_t smem = 2 * pre_block_doubles(B) * sizeof(double);
     const int use_smem = smem <= 200 * 1024;
     static bool attr_done = false;
     if (!attr_done) {

@@ -406,7 +406,8 @@ def test_stream_chain_with_map_and_iw_state(g, O):
 @pytest.mark.parametrize("variant", ["sigma", "iw_only", "plain", "read_only_map"])
 def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
     """The staged stream chain (parallel map recurrence / rotation evidence, sequential IW core) must give exactly what
-    walking the scans one launch at a time gives, for several hypotheses per scan."""
+    walking the scans one launch at a time gives, for several hypotheses per scan (to re-association when Sigma_meas is fed
+    back: see the branch below)."""
     S, Hh, B, cap, tau = 7, 3, 48, 2048, 0.1
     rng = np.random.default_rng(5)
     scans = [g.synth.make_scan(4000 + 53 * k, seed=500 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
@@ -441,12 +442,22 @@ def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
         pl.launch_chain(st_b[k * Hh:(k + 1) * Hh], 1, Hh, ms_b, ws, poses_pred[k * Hh:(k + 1) * Hh],
                         poses_upd[k:k + 1] if upd else None, ev_b[k * Hh:(k + 1) * Hh], iw_b, use_sigma, 0.97)
     torch.cuda.synchronize()
-    assert torch.equal(st_a, st_b)
-    assert torch.equal(ev_a, ev_b)
     for name in ("S_dir", "S_dir_scatter", "N_dir", "N_pos", "sum_p", "sum_ppT"):
         assert torch.equal(getattr(ms_a, name), getattr(ms_b, name)), name
-    if use_iw:
-        assert torch.equal(iw_a, iw_b)
+    if variant != "sigma":
+        assert torch.equal(st_a, st_b)
+        assert torch.equal(ev_a, ev_b)
+        if use_iw:
+            assert torch.equal(iw_a, iw_b)
+    else:
+        # With Sigma_meas fed back the staged chain evaluates the translation step through an algebraic split
+        # (M_b + c_b R Sigma_meas R^T; residual statistics from pre-computed sums): same numbers up to re-association.
+        EVo = g._abi.EV
+        assert rel_err(H(st_a), H(st_b)) < 1e-12
+        for lo_, hi_ in ((EVo["R_MF"], EVo["SVD_S"] + 3), (EVo["T_WLS"], EVo["T_WLS"] + 3), (EVo["L_TRANS"], EVo["L_TRANS"] + 9),
+                         (EVo["H_TRANS"], EVo["H_TRANS"] + 3), (EVo["L22"], EVo["L22"] + 484)):
+            assert rel_err(H(ev_a)[:, lo_:hi_], H(ev_b)[:, lo_:hi_]) < 1e-9, (lo_, hi_)
+        assert rel_err(H(iw_a), H(iw_b)) < 1e-9
     assert float(ev_a[:, g._abi.EV['T_WLS']:g._abi.EV['T_WLS'] + 3].abs().sum()) > 0
 
 
