@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the LiDAR evidence hot path on B200 (contract in the task brief, section 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp64|fp32c] [--no-extra] [--no-cpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Default workload = BASELINE.json configs[1]: a Kimera-jackal-shaped synthetic scan stream (200 scans of ~30k points,
 cap 8192 => stride 4 / 7500 selected rows, 48 bins, 1 hypothesis) with the map bin statistics carried from scan to scan
-(forgetting 0.99).  One "step" = one pass over the whole stream.  `value` = raw points per second with the scans
-resident in HBM (one CUDA graph per stream pass); `e2e` = the same stream through the reference-facing host call
-(pinned host buffers, H2D + kernels + D2H per scan).  `roofline` is for the dominant kernel, scan_moments.
+(forgetting 0.99) and the LiDAR measurement-noise IW block adapted every scan.  One "step" = one pass over the whole stream
+(seven launches).  `value` = raw points per second with the scans resident in HBM; `e2e` = the same stream through the
+reference-facing host calls (pinned host buffers; every scan's H2D, kernels and D2H inside the timed region).  `roofline` is for the dominant kernel, scan_moments.
 `extra` carries the 1M-point x 256-bin cloud (configs[3]) -- the configuration the HBM target is quoted on -- and
 the 64-hypothesis batch (configs[2]).  At N > 1 the stream workload runs as N independent replicas (scan k+1 depends on
 scan k's map: it does not shard); configs[3] shards by points with one all-gather of the per-bin moment
@@ -345,6 +345,19 @@ def main():
 
     # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
     extra = {}
+    if not args.no_extra and args.precision == "fp64":
+        # the same stream in fp32c mode (packed 20 B/point layout, <= 1e-5 on the moments): side figure
+        pl32 = g.LidarEvidencePipeline(n_bins=N_BINS, tau=tau, precision="fp32c", n_points_cap=CAP, lidar_origin=scans[0].lidar_origin)
+        res32 = [pl32.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
+        jobs32 = pl32.jobs_to_device([pl32.make_job(res32[k], xis[k]) for k in range(N_SCANS)])
+        ms32, iw32 = g.create_empty_map_stats(N_BINS), pl32.create_lidar_iw_state(1e-3)
+        ctas32 = pl32.plan_ctas(N_SCANS, max_sel)
+        b32 = pl32._buffers(N_SCANS, ctas32)
+        step32 = _time(lambda: pl32.run_stream(res32, xis, poses_dev, poses_dev, ms32, iw_state=iw32, use_sigma_meas=True, jobs_dev=jobs32, ctas=ctas32), n=max(args.steps, 20))
+        k132 = _time(lambda: pl32.launch_moments(jobs32, None, N_SCANS, ctas32, res32[0].layout, b32["partials"]))
+        extra["stream_fp32c"] = {"ms_per_step": step32, "points_per_sec": world * total_points / (step32 * 1e-3), "scan_moments_ms": k132,
+                                 "pairs_per_sec": pairs / (k132 * 1e-3), "layout": "packed_f32 (20 B/point)"}
+        del pl32, res32
     if not args.no_extra:
         extra["cfg4_1Mx256"] = sharding.bench_points_sharded(g, n_points=1 << 20, n_bins=256, tau=tau, steps=max(args.steps, 10),
                                                             warmup=args.warmup, rank=rank, world=world, peak_gbs=peak_gbs)

@@ -1,12 +1,9 @@
 // gcl_api.cu -- the C ABI declared in include/gcl_b200.h: argument checks, launch planning, error text.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
-
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
 
 #include "gcl_internal.cuh"
 
@@ -302,7 +299,7 @@ int gcl_scan_bin_moment_match(gcl_handle h, void* stream, const double* points, 
   plan_bins(n_bins, GCL_F64, &G, &L, &chunks);
   P.lanes = L; P.n_chunks = chunks; P.layout = GCL_LAYOUT_REF_F64; P.fixed_shift = 1;
   cudaSetDevice(h->device);
-  GCL_CUDA(h, launch_scan_moments(P, 1, ctas, GCL_F64, G, 28, true, (cudaStream_t)stream));
+  GCL_CUDA(h, launch_moments_from_resp(P, ctas, G, (cudaStream_t)stream));
   FinalizeParams F;
   memset(&F, 0, sizeof(F));
   F.parts = workspace; F.n_parts = ctas; F.part_stride = rec; F.job_stride = 0;

@@ -67,12 +67,9 @@ struct ScanParams {
 };
 
 void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_out);
-int scan_moments_threads(int precision);
-size_t scan_moments_smem_bytes(int precision, int G, int L, int n_chunks, int nmom);
 int fused_ctas_per_sm(int n_bins, int precision);
 cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_job, int precision, cudaStream_t stream);
-cudaError_t launch_scan_moments(const ScanParams& P, int n_jobs, int ctas_per_job, int precision, int G, int nmom,
-                                bool from_resp, cudaStream_t stream);
+cudaError_t launch_moments_from_resp(const ScanParams& P, int ctas, int G, cudaStream_t stream);
 
 struct FinalizeParams {
   const double* parts;
