@@ -414,7 +414,7 @@ __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T 
 //     scan, so ONE warp walks the scans doing just  Sigma_meas -> bin covariances -> t_wls -> residuals -> IW update
 //     (inputs of scan s+1 are staged into shared memory by a helper warp meanwhile); the planar mask / PSD projection /
 //     certificates of the translation evidence are finished in parallel afterwards.  Same arithmetic, same order within
-//     a scan as (a): results are bit-identical.
+//     a scan as (a): results agree to the last ulps (to re-association with Sigma_meas fed back, see S4b).
 constexpr int kChainThreads = 128;
 constexpr int kStagedMinScans = 4;
 

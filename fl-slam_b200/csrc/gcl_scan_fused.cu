@@ -171,23 +171,49 @@ __device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, co
   for (; b < b1; b += 4) phase_a_groups<1, true>(p + 3 * (b >> 2), b, B, dx, dy, dz, o2, erow, Z2, S2, m);
   Z = Z2.x + Z2.y; S1 = S2.x + S2.y; xmax = m;
 }
-// fp64 atlas: per group of 2 bins three double2 {bx0,bx1} {by0,by1} {bz0,bz1}
-template <bool TAIL>
-__device__ __forceinline__ void phase_a_group(const double2* __restrict__ p, const double* __restrict__ tab, int b, int B, double d0,
-                                              double d1, double d2, double off, double* __restrict__ erow, double& z, double& s1,
-                                              double& m) {
-  const double2 ax = p[0], ay = p[1], az = p[2];
-  double x0 = fma(d0, ax.x, fma(d1, ay.x, fma(d2, az.x, off)));
-  double x1 = fma(d0, ax.y, fma(d1, ay.y, fma(d2, az.y, off)));
-  double e0 = exp2_128<false>(x0, tab), e1 = exp2_128<false>(x1, tab);
-  if (TAIL) {
-    if (b + 0 >= B) { e0 = 0.0; x0 = -1.0e300; }
-    if (b + 1 >= B) { e1 = 0.0; x1 = -1.0e300; }
+// fp64 atlas: per group of 2 bins three double2 {bx0,bx1} {by0,by1} {bz0,bz1}.  NG groups (2 NG bins) at a time, written
+// stage by stage: the exp is a chain of ~13 dependent FP64 operations, and with two warps per scheduler the FP64 pipe only
+// fills when each warp carries 2 NG independent chains (measured: one group in flight ran phase A at 2.5x its FP64 bound).
+template <int NG, bool TAIL>
+__device__ __forceinline__ void phase_a_groups(const double2* __restrict__ p, const double* __restrict__ tab, int b, int B, double d0,
+                                               double d1, double d2, double off, double* __restrict__ erow, double& z, double& s1,
+                                               double& m) {
+  constexpr int N = 2 * NG;
+  const double magic = 6755399441055744.0;  // 2^52 + 2^51
+  double x[N], tm[N], r[N], q[N], e[N];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const double2 ax = p[3 * g], ay = p[3 * g + 1], az = p[3 * g + 2];
+    x[2 * g] = fma(d0, ax.x, fma(d1, ay.x, fma(d2, az.x, off)));
+    x[2 * g + 1] = fma(d0, ax.y, fma(d1, ay.y, fma(d2, az.y, off)));
   }
-  *reinterpret_cast<double2*>(erow + b) = make_double2(e0, e1);
-  z += e0 + e1;
-  s1 = fma(e0, x0, s1); s1 = fma(e1, x1, s1);
-  m = fmax(m, fmax(x0, x1));
+#pragma unroll
+  for (int k = 0; k < N; ++k) tm[k] = x[k] + magic;
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = x[k] - (tm[k] - magic);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(3.583032305400251e-11, r[k], 2.6466421444330967e-08);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 1.4662262387640423e-05);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 0.0054152123481245725);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int n = __double2loint(tm[k]);
+    const double y = tab[n & 127] * q[k];
+    e[k] = __hiloint2double(__double2hiint(y) + ((n >> 7) << 20), __double2loint(y));
+  }
+  if (TAIL) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (b + k >= B) { e[k] = 0.0; x[k] = -1.0e300; }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) *reinterpret_cast<double2*>(erow + b + 2 * g) = make_double2(e[2 * g], e[2 * g + 1]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) { z += e[k]; s1 = fma(e[k], x[k], s1); m = fmax(m, x[k]); }
 }
 template <int NGB>
 __device__ __forceinline__ void phase_a_bins(const double* __restrict__ atlas, const double* __restrict__ tab, int b0, int b1, int B,
@@ -196,9 +222,10 @@ __device__ __forceinline__ void phase_a_bins(const double* __restrict__ atlas, c
   double z = 0.0, s1 = 0.0, m = -1.0e300;
   const double2* p = reinterpret_cast<const double2*>(atlas);
   const int bmain = (b1 <= B) ? b1 : ((B & ~1) > b0 ? (B & ~1) : b0);
-#pragma unroll NGB
-  for (int b = b0; b < bmain; b += 2) phase_a_group<false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
-  for (int b = bmain; b < b1; b += 2) phase_a_group<true>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  int b = b0;
+  for (; b + 2 * NGB <= bmain; b += 2 * NGB) phase_a_groups<NGB, false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  for (; b < bmain; b += 2) phase_a_groups<1, false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  for (; b < b1; b += 2) phase_a_groups<1, true>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
   Z = z; S1 = s1; xmax = m;
 }
 __device__ __forceinline__ float exp_of_max(float x, const double*) { return fast_exp2(x); }
@@ -442,7 +469,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     if (pi < count) {
       const T* sd = s_d + (size_t)pi * 4;
       T Z, S1, xmax;
-      phase_a_bins<(MINB > 1 ? 1 : (sizeof(T) == 4 ? 3 : 4))>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+      phase_a_bins<(sizeof(T) == 4 ? 3 : (G >= 4 ? 2 : 4))>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
       T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
       zp[0] = Z; zp[1] = S1; zp[2] = xmax;
     }

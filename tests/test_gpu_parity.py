@@ -404,10 +404,11 @@ def test_stream_chain_with_map_and_iw_state(g, O):
 
 
 @pytest.mark.parametrize("variant", ["sigma", "iw_only", "plain", "read_only_map"])
-def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
-    """The staged stream chain (parallel map recurrence / rotation evidence, sequential IW core) must give exactly what
-    walking the scans one launch at a time gives, for several hypotheses per scan (to re-association when Sigma_meas is fed
-    back: see the branch below)."""
+def test_staged_stream_chain_matches_scan_by_scan(g, variant):
+    """The staged stream chain (parallel map recurrence / rotation evidence, sequential IW core) must give what walking the
+    scans one launch at a time gives, for several hypotheses per scan: the map recurrence exactly; the evidence to the last
+    ulps (same arithmetic, but the two kernels are compiled separately and may contract multiply-adds differently); to
+    re-association when Sigma_meas is fed back (see the branch below)."""
     S, Hh, B, cap, tau = 7, 3, 48, 2048, 0.1
     rng = np.random.default_rng(5)
     scans = [g.synth.make_scan(4000 + 53 * k, seed=500 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
@@ -446,9 +447,9 @@ def test_staged_stream_chain_is_bit_identical_to_scan_by_scan(g, variant):
         assert torch.equal(getattr(ms_a, name), getattr(ms_b, name)), name
     if variant != "sigma":
         assert torch.equal(st_a, st_b)
-        assert torch.equal(ev_a, ev_b)
+        np.testing.assert_allclose(H(ev_a), H(ev_b), rtol=1e-12, atol=1e-15 * float(ev_b.abs().max()))
         if use_iw:
-            assert torch.equal(iw_a, iw_b)
+            np.testing.assert_allclose(H(iw_a), H(iw_b), rtol=1e-12, atol=0)
     else:
         # With Sigma_meas fed back the staged chain evaluates the translation step through an algebraic split
         # (M_b + c_b R Sigma_meas R^T; residual statistics from pre-computed sums): same numbers up to re-association.
