@@ -77,6 +77,8 @@ def _load():
         "gcl_imu_preintegrate": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
         "gcl_scan_submit_host": (i32, [vp, i32, vp, vp, vp, i64, C.c_int32, f64, f64, vp, i32, vp, vp, i32, f64, i32, f64, f64]),
+        "gcl_scan_evidence_begin_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32]),
+        "gcl_scan_evidence_end_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gcl_scan_evidence_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, vp, vp]),
         "gcl_lidar_scan_evidence_host": (i32, [vp, vp, vp, vp, i64, C.c_int32, f64, f64, vp, vp, i32, vp, vp, i32, f64, i32,
                                                vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, vp, vp]),

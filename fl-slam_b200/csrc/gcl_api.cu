@@ -589,14 +589,17 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   return GCL_OK;
 }
 
-int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host, double* mS_dir, double* mS_sc, double* mN_dir,
-                           double* mN_pos, double* msum_p, double* msum_ppT, const double* pose_update_host, double forgetting,
-                           double* iw_state_host, int use_sigma_meas, double* stats_host, double* evidence_host) {
+// stage 2, first half: everything is enqueued (H2D of pose / map / IW, chain step, the one D2H); no waiting
+int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pose_host, const double* mS_dir, const double* mS_sc,
+                                 const double* mN_dir, const double* mN_pos, const double* msum_p, const double* msum_ppT,
+                                 const double* pose_update_host, double forgetting, const double* iw_state_host,
+                                 int use_sigma_meas) {
   if (!h) return GCL_ERR_ARG;
   GCL_REQUIRE(h, slot_index == 0 || slot_index == 1, "slot must be 0 or 1");
   gcl_handle_s::Slot& S = h->slot[slot_index];
   GCL_REQUIRE(h, S.pending, "no scan was submitted to this slot");
-  GCL_REQUIRE(h, pose_host && stats_host && evidence_host, "NULL pointer");
+  GCL_REQUIRE(h, h->stage2_slot < 0, "an evidence step is already in flight: call gcl_scan_evidence_end_host first");
+  GCL_REQUIRE(h, pose_host, "NULL pointer");
   GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
   GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
   GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
@@ -638,8 +641,33 @@ int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host
   g_ht.mark(4, h);
   // one D2H for every output: [map][iw][stats][evidence] (the map / IW blocks ride along even when they were not updated)
   GCL_CUDA(h, cudaMemcpyAsync(hb + o_map, db + o_map, io_end - o_map, cudaMemcpyDeviceToHost, st));
+  h->stage2_slot = slot_index;
+  h->stage2_has_update = pose_update_host != nullptr;
+  h->stage2_has_iw = iw_state_host != nullptr;
+  return GCL_OK;
+}
+
+// stage 2, second half: wait for the D2H and hand the results out
+int gcl_scan_evidence_end_host(gcl_handle h, double* mS_dir, double* mS_sc, double* mN_dir, double* mN_pos, double* msum_p,
+                               double* msum_ppT, double* iw_state_host, double* stats_host, double* evidence_host) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, h->stage2_slot >= 0, "no evidence step is in flight");
+  GCL_REQUIRE(h, stats_host && evidence_host, "NULL pointer");
+  gcl_handle_s::Slot& S = h->slot[h->stage2_slot];
+  const bool pose_update_host = h->stage2_has_update;
+  GCL_REQUIRE(h, !pose_update_host || (mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT), "NULL map statistics");
+  GCL_REQUIRE(h, !h->stage2_has_iw || iw_state_host, "iw_state_host is NULL but the step carried an IW state");
+  cudaSetDevice(h->device);
+  const size_t B = S.n_bins, H = S.n_hyp;
+  const size_t srec = gcl_stats_record_doubles(S.n_bins);
+  const size_t o_pose = 0, o_pupd = al(o_pose + H * 48), o_map = al(o_pupd + 48);
+  const size_t o_iw = al(o_map + B * 26 * 8), o_stats = al(o_iw + 80);
+  const size_t o_evid = al(o_stats + H * srec * 8);
+  unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
+  cudaStream_t st = h->stream;
   GCL_CUDA(h, cudaStreamSynchronize(st));
   S.pending = false;
+  h->stage2_slot = -1;
   g_ht.mark(5, h, false);
   memcpy(stats_host, hb + o_stats, H * srec * 8);
   memcpy(evidence_host, hb + o_evid, H * GCL_EVID_DOUBLES * 8);
@@ -648,10 +676,21 @@ int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host
     memcpy(mS_dir, om, B * 24); memcpy(mS_sc, om + 3 * B, B * 72); memcpy(mN_dir, om + 12 * B, B * 8);
     memcpy(mN_pos, om + 13 * B, B * 8); memcpy(msum_p, om + 14 * B, B * 24); memcpy(msum_ppT, om + 17 * B, B * 72);
   }
-  if (iw_state_host) memcpy(iw_state_host, hb + o_iw, 80);
+  if (h->stage2_has_iw) memcpy(iw_state_host, hb + o_iw, 80);
   g_ht.mark(6, h, false);
   g_ht.done();
   return GCL_OK;
+}
+
+int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host, double* mS_dir, double* mS_sc, double* mN_dir,
+                           double* mN_pos, double* msum_p, double* msum_ppT, const double* pose_update_host, double forgetting,
+                           double* iw_state_host, int use_sigma_meas, double* stats_host, double* evidence_host) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, stats_host && evidence_host, "NULL pointer");
+  int rc = gcl_scan_evidence_begin_host(h, slot_index, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host,
+                                        forgetting, iw_state_host, use_sigma_meas);
+  if (rc != GCL_OK) return rc;
+  return gcl_scan_evidence_end_host(h, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, iw_state_host, stats_host, evidence_host);
 }
 
 int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const double* timestamps_host,

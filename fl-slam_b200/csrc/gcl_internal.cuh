@@ -38,6 +38,8 @@ struct gcl_handle_s {
     double eps_psd = 0, eps_mass = 0;
     bool pending = false;
   } slot[2];
+  int stage2_slot = -1;                 // slot whose evidence step is enqueued and not yet collected
+  bool stage2_has_update = false, stage2_has_iw = false;
 };
 
 namespace gcl {

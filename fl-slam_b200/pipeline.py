@@ -351,13 +351,14 @@ class LidarEvidencePipeline:
                                              self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
         return xi.shape[0]
 
-    def evidence_host(self, slot: int, pose_pred, map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0,
-                      chart_id: str = constants.GC_CHART_ID, anchor_id: str = "initial", pose_update=None, forgetting: float = 0.99,
-                      iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> LidarScanEvidence:
-        """Stage 2 of the host call (gcl_scan_evidence_host): chain step for the scan submitted to ``slot``, one D2H, sync.
+    def evidence_begin_host(self, slot: int, pose_pred, map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0,
+                            chart_id: str = constants.GC_CHART_ID, anchor_id: str = "initial", pose_update=None,
+                            forgetting: float = 0.99, iw_state_host: Optional[np.ndarray] = None, use_sigma_meas: bool = False) -> None:
+        """First half of stage 2 (gcl_scan_evidence_begin_host): the chain step of the scan submitted to ``slot`` and its one
+        D2H are enqueued; nothing is waited for, so the next scan can be submitted while the GPU works.
 
-        With ``pose_update`` (6,) the six arrays of ``map_stats_host`` (float64, C-contiguous) are updated IN PLACE
-        (forgetting + this scan's bin sums in the world frame); ``iw_state_host`` (10,) likewise."""
+        With ``pose_update`` (6,) the six arrays of ``map_stats_host`` (float64, C-contiguous) are updated IN PLACE by
+        ``evidence_end_host`` (forgetting + this scan's bin sums in the world frame); ``iw_state_host`` (10,) likewise."""
         f = self._f64
         pts, ts, w, xi, n = self._inflight.pop(slot)
         H = xi.shape[0]
@@ -373,19 +374,34 @@ class LidarEvidencePipeline:
             m = map_stats_host
         else:
             m = {k: f(map_stats_host[k], sh) for k, sh in shapes}
-        stats = np.empty((H, self.srec), dtype=np.float64)
-        evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
         p = self._addr
         pu = None if pose_update is None else f(pose_update, (6,))
         if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
                                               and iw_state_host.shape == (10,) and iw_state_host.flags.c_contiguous):
             raise ValueError("iw_state_host must be a C-contiguous float64 array of shape (10,)")
-        _abi.check(_lib.gcl_scan_evidence_host(self.handle, int(slot), p(poses), p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]),
-                                               p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting),
-                                               p(iw_state_host), 1 if use_sigma_meas else 0, p(stats), p(evid)), self.handle)
+        _abi.check(_lib.gcl_scan_evidence_begin_host(self.handle, int(slot), p(poses), p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]),
+                                                     p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting),
+                                                     p(iw_state_host), 1 if use_sigma_meas else 0), self.handle)
+        self._stage2 = (H, n, m, iw_state_host, ess_imu, chart_id, anchor_id, poses, pu)
+
+    def evidence_end_host(self) -> LidarScanEvidence:
+        """Second half of stage 2 (gcl_scan_evidence_end_host): wait for the D2H, write the map / IW arrays back, return."""
+        H, n, m, iw_state_host, ess_imu, chart_id, anchor_id, _poses, _pu = self._stage2
+        self._stage2 = None
+        stats = np.empty((H, self.srec), dtype=np.float64)
+        evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
+        p = self._addr
+        _abi.check(_lib.gcl_scan_evidence_end_host(self.handle, p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]), p(m["N_pos"]),
+                                                   p(m["sum_p"]), p(m["sum_ppT"]), p(iw_state_host), stats.ctypes.data, evid.ctypes.data),
+                   self.handle)
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
                                  stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
                                  n_points_cap=self.n_points_cap, ess_imu=ess_imu)
+
+    def evidence_host(self, slot: int, pose_pred, map_stats_host: Dict[str, np.ndarray], **kw) -> LidarScanEvidence:
+        """Stage 2 of the host call (= gcl_scan_evidence_host): chain step for the scan submitted to ``slot``, one D2H, sync."""
+        self.evidence_begin_host(slot, pose_pred, map_stats_host, **kw)
+        return self.evidence_end_host()
 
     def process_scan_host(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body, pose_pred,
                           map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0, chart_id: str = constants.GC_CHART_ID,

@@ -315,6 +315,18 @@ int gcl_scan_submit_host(gcl_handle h, int slot, const double* points_host, cons
                          double scan_end_time, const double* xi_body_host, int n_hyp, const double* lidar_origin_host,
                          const double* bin_dirs_host, int n_bins, double tau, int precision, double eps_psd,
                          double eps_mass);
+/* gcl_scan_evidence_host in two halves, so that the caller can issue the next scan's gcl_scan_submit_host while the GPU runs
+ * this scan's chain step: _begin enqueues everything (H2D of pose / map / IW, chain step, the one D2H) and returns; _end
+ * waits for the D2H and hands out the results (map / IW arrays are written only if the step carried an update / an IW state).
+ * One evidence step may be in flight at a time. */
+int gcl_scan_evidence_begin_host(gcl_handle h, int slot, const double* pose_pred_host, const double* map_S_dir_host,
+                                 const double* map_S_dir_scatter_host, const double* map_N_dir_host,
+                                 const double* map_N_pos_host, const double* map_sum_p_host,
+                                 const double* map_sum_ppT_host, const double* pose_update_host, double forgetting,
+                                 const double* iw_state_host, int use_sigma_meas);
+int gcl_scan_evidence_end_host(gcl_handle h, double* map_S_dir_host, double* map_S_dir_scatter_host, double* map_N_dir_host,
+                               double* map_N_pos_host, double* map_sum_p_host, double* map_sum_ppT_host,
+                               double* iw_state_host, double* stats_host, double* evidence_host);
 int gcl_scan_evidence_host(gcl_handle h, int slot, const double* pose_pred_host, double* map_S_dir_host,
                            double* map_S_dir_scatter_host, double* map_N_dir_host, double* map_N_pos_host,
                            double* map_sum_p_host, double* map_sum_ppT_host, const double* pose_update_host,

@@ -486,9 +486,17 @@ def test_two_stage_host_api_equals_blocking_call(g):
     out_b = []
     pl.submit_scan_host(0, *pinned[0], scans[0].scan_start_time, scans[0].scan_end_time, scans[0].xi_body[None])
     for k in range(S):
-        if k + 1 < S:
-            pl.submit_scan_host((k + 1) % 2, *pinned[k + 1], scans[k + 1].scan_start_time, scans[k + 1].scan_end_time, scans[k + 1].xi_body[None])
-        ev = pl.evidence_host(k % 2, poses[k][None], m_b, pose_update=poses[k], iw_state_host=iw_b, use_sigma_meas=True)
+        nxt = lambda: pl.submit_scan_host((k + 1) % 2, *pinned[k + 1], scans[k + 1].scan_start_time, scans[k + 1].scan_end_time,
+                                          scans[k + 1].xi_body[None])
+        if k % 2 == 0:    # next scan submitted before this scan's evidence step
+            if k + 1 < S:
+                nxt()
+            ev = pl.evidence_host(k % 2, poses[k][None], m_b, pose_update=poses[k], iw_state_host=iw_b, use_sigma_meas=True)
+        else:             # next scan submitted between the two halves of this scan's evidence step
+            pl.evidence_begin_host(k % 2, poses[k][None], m_b, pose_update=poses[k], iw_state_host=iw_b, use_sigma_meas=True)
+            if k + 1 < S:
+                nxt()
+            ev = pl.evidence_end_host()
         out_b.append((ev.stats_host.copy(), ev.evidence_host.copy()))
     for (sa, ea), (sb, eb) in zip(out_a, out_b):
         assert np.array_equal(sa, sb) and np.array_equal(ea, eb)
