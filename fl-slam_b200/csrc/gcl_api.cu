@@ -70,7 +70,7 @@ void gcl_destroy(gcl_handle h) {
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream1) { cudaStreamSynchronize(h->stream1); cudaStreamDestroy(h->stream1); }
   if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < GCL_HOST_SLOTS; ++i) {
     if (h->slot[i].ev_copy) cudaEventDestroy(h->slot[i].ev_copy);
     if (h->slot[i].ev_stage1) cudaEventDestroy(h->slot[i].ev_stage1);
     if (h->slot[i].d_buf) cudaFree(h->slot[i].d_buf);
@@ -442,8 +442,8 @@ int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const 
 // Two stages per scan.  Stage 1 (submit) needs only the scan and the twist: H2D of the scan on the copy stream, then
 // scan_moments + reduce_finalize on the stage-1 stream; it returns without waiting.  Stage 2 (evidence) needs the pose
 // prediction and the map: it waits (on the GPU) for stage 1 of the same slot, runs the chain step, copies every output back
-// in ONE D2H and synchronises.  Two slots let the upload and the moment pass of scan k+1 overlap the evidence step (and the
-// caller's own fusion work) of scan k; gcl_lidar_scan_evidence_host is submit + evidence on slot 0.
+// in ONE D2H and synchronises.  GCL_HOST_SLOTS slots let the uploads and moment passes of the next scans overlap the evidence
+// step (and the caller's own fusion work) of scan k; gcl_lidar_scan_evidence_host is submit + evidence on slot 0.
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int grow(gcl_handle h, void** d, size_t* dcap, void** hp, size_t* hcap, size_t dbytes, size_t hbytes) {
@@ -467,7 +467,7 @@ static int ensure_streams(gcl_handle h) {
   GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream1, cudaStreamNonBlocking));
   GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < GCL_HOST_SLOTS; ++i) {
     GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_copy, cudaEventDisableTiming));
     GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_stage1, cudaEventDisableTiming));
   }
@@ -496,10 +496,17 @@ struct HostTiming {
 };
 static HostTiming g_ht;
 
-static bool is_pinned(const void* p) {
+// Is this host pointer page-locked?  The answer only selects between copying straight from the caller's array and staging
+// through the pinned block -- both are correct whatever the truth is -- so the last few answers are remembered per handle
+// (cudaPointerGetAttributes costs ~1 us a call; a scan stream reuses the same buffers).
+static bool is_pinned(gcl_handle h, const void* p) {
+  for (int i = 0; i < 8; ++i)
+    if (h->pin_ptr[i] == p) return h->pin_val[i];
   cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
+  bool v = false;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess) v = a.type == cudaMemoryTypeHost; else cudaGetLastError();
+  h->pin_ptr[h->pin_next] = p; h->pin_val[h->pin_next] = v; h->pin_next = (h->pin_next + 1) & 7;
+  return v;
 }
 
 int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
@@ -507,7 +514,7 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
                          int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
                          double eps_psd, double eps_mass) {
   if (!h) return GCL_ERR_ARG;
-  GCL_REQUIRE(h, slot_index == 0 || slot_index == 1, "slot must be 0 or 1");
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
   GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
   GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
   GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
@@ -527,12 +534,13 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   const int64_t n_sel = (n_raw + stride - 1) / stride;
   const int ctas = gcl_plan_ctas_per_job(h, n_hyp, n_sel, n_bins, precision);
   const size_t rec = gcl_partial_record_doubles(n_bins), srec = gcl_stats_record_doubles(n_bins);
-  // slot block (device, mirrored in pinned memory up to o_parts): [points][timestamps][weights] | [bins][jobs] | work
+  // slot block (device, mirrored in pinned memory up to o_parts): [bins][jobs] | [points][timestamps][weights] | work
   // (With stride > 1 only the selected rows of points / timestamps are needed; gathering them on the host first was
   // measured: the strided CPU reads of a cold 1.2 MB scan cost 33 us against 13 us of PCIe time saved.  A caller whose
   // producer already emits compact rows can use the device-pointer API with GCL_JOB_COMPACT_ROWS.)
-  const size_t o_pts = 0, o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), o_bins = al(o_w + n * 8);
-  const size_t o_jobs = al(o_bins + B * 24), in_end = al(o_jobs + H * sizeof(gcl_job));
+  // (the atlas and the jobs come first so that their device addresses do not move with the scan size)
+  const size_t o_bins = 0, o_jobs = al(o_bins + B * 24), o_pts = al(o_jobs + H * sizeof(gcl_job));
+  const size_t o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), in_end = al(o_w + n * 8);
   const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
   const size_t d_end = al(o_stats + H * srec * 8);
   rc = grow(h, &S.d_buf, &S.d_bytes, &S.h_buf, &S.h_bytes, d_end, in_end);
@@ -541,12 +549,17 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   unsigned char* db = static_cast<unsigned char*>(S.d_buf);
   // Scan arrays that already live in page-locked memory are copied straight from the caller's buffers (they must stay
   // untouched until the matching evidence call returns); pageable arrays go through the pinned block.
-  const bool direct = n > 0 && is_pinned(points_host) && is_pinned(timestamps_host) && is_pinned(weights_host);
+  const bool direct = n > 0 && is_pinned(h, points_host) && is_pinned(h, timestamps_host) && is_pinned(h, weights_host);
   if (!direct && n > 0) {
     memcpy(hb + o_pts, points_host, n * 24);
     memcpy(hb + o_ts, timestamps_host, n * 8);
     memcpy(hb + o_w, weights_host, n * 8);
   }
+  // the atlas rarely changes: it is re-uploaded only when its bytes differ from what this slot already holds on the device;
+  // a single hypothesis travels as a kernel argument (by-value job), so the common call has no small H2D at all
+  const bool atlas_same = S.atlas_bins == n_bins && S.atlas_copy.size() == B * 24 && memcmp(S.atlas_copy.data(), bins_host, B * 24) == 0
+                          && S.atlas_dev == static_cast<void*>(db + o_bins);
+  if (!atlas_same) { S.atlas_copy.assign(reinterpret_cast<const char*>(bins_host), reinterpret_cast<const char*>(bins_host) + B * 24); }
   memcpy(hb + o_bins, bins_host, B * 24);
   gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
   for (int i = 0; i < n_hyp; ++i) {
@@ -562,10 +575,12 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
     GCL_CUDA(h, cudaMemcpyAsync(db + o_pts, points_host, n * 24, cudaMemcpyHostToDevice, sc));
     GCL_CUDA(h, cudaMemcpyAsync(db + o_ts, timestamps_host, n * 8, cudaMemcpyHostToDevice, sc));
     GCL_CUDA(h, cudaMemcpyAsync(db + o_w, weights_host, n * 8, cudaMemcpyHostToDevice, sc));
-    GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, in_end - o_bins, cudaMemcpyHostToDevice, sc));
+    if (!atlas_same || n_hyp > 1)
+      GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, o_pts - o_bins, cudaMemcpyHostToDevice, sc));
   } else {
     GCL_CUDA(h, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, sc));
   }
+  S.atlas_bins = n_bins; S.atlas_dev = db + o_bins;
   GCL_CUDA(h, cudaEventRecord(S.ev_copy, sc));
   GCL_CUDA(h, cudaStreamWaitEvent(s1, S.ev_copy, 0));
   g_ht.mark(0, h, false);
@@ -575,12 +590,13 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   double* d_parts = reinterpret_cast<double*>(db + o_parts);
   double* d_red = reinterpret_cast<double*>(db + o_red);
   double* d_stats = reinterpret_cast<double*>(db + o_stats);
-  rc = gcl_scan_moments(h, s1, d_jobs, nullptr, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host,
-                        eps_mass, d_parts);
+  const gcl_job* jd = n_hyp == 1 ? nullptr : d_jobs;   // one hypothesis: the job is a kernel argument
+  const gcl_job* jv = n_hyp == 1 ? hj : nullptr;
+  rc = gcl_scan_moments(h, s1, jd, jv, n_hyp, ctas, GCL_LAYOUT_REF_F64, precision, d_bins, n_bins, tau, origin_host, eps_mass, d_parts);
   if (rc != GCL_OK) return rc;
   g_ht.mark(2, h);
-  rc = gcl_reduce_finalize(h, s1, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
-                           origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
+  rc = gcl_reduce_finalize(h, s1, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, jd, jv, n_hyp, n_bins, d_bins, tau, origin_host,
+                           eps_psd, eps_mass, 1, d_red, d_stats);
   if (rc != GCL_OK) return rc;
   GCL_CUDA(h, cudaEventRecord(S.ev_stage1, s1));
   g_ht.mark(3, h);
@@ -595,7 +611,7 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
                                  const double* pose_update_host, double forgetting, const double* iw_state_host,
                                  int use_sigma_meas) {
   if (!h) return GCL_ERR_ARG;
-  GCL_REQUIRE(h, slot_index == 0 || slot_index == 1, "slot must be 0 or 1");
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
   gcl_handle_s::Slot& S = h->slot[slot_index];
   GCL_REQUIRE(h, S.pending, "no scan was submitted to this slot");
   GCL_REQUIRE(h, h->stage2_slot < 0, "an evidence step is already in flight: call gcl_scan_evidence_end_host first");

@@ -37,7 +37,12 @@ struct gcl_handle_s {
     int n_hyp = 0, n_bins = 0;
     double eps_psd = 0, eps_mass = 0;
     bool pending = false;
-  } slot[2];
+    std::string atlas_copy;             // bytes of the atlas this slot holds on the device
+    int atlas_bins = 0; void* atlas_dev = nullptr;
+  } slot[GCL_HOST_SLOTS];
+  const void* pin_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pin_val[8] = {false, false, false, false, false, false, false, false};
+  int pin_next = 0;
   int stage2_slot = -1;                 // slot whose evidence step is enqueued and not yet collected
   bool stage2_has_update = false, stage2_has_iw = false;
 };

@@ -72,6 +72,7 @@ typedef struct gcl_job {
 } gcl_job;
 
 #define GCL_JOB_COMPACT_ROWS 1
+#define GCL_HOST_SLOTS 4       /* scans that may be in flight through gcl_scan_submit_host */
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
 int gcl_abi_version(void);
@@ -307,7 +308,7 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
  * stage 2 needs the pose prediction and the map (archive/legacy_operators/matrix_fisher_evidence.py:264-275, :502-516).
  *   gcl_scan_submit_host    asynchronous: H2D on a copy stream, scan_moments + reduce_finalize on a second stream; returns
  *                           at once.  Page-locked input arrays are read in place and must stay untouched until the matching
- *                           gcl_scan_evidence_host returns.  slot is 0 or 1 (two scans may be in flight).
+ *                           gcl_scan_evidence_host returns.  slot is in [0, GCL_HOST_SLOTS).
  *   gcl_scan_evidence_host  waits on the GPU for stage 1 of `slot`, runs the chain step, ONE D2H of map / IW / stats /
  *                           evidence, synchronises.  Arguments as in gcl_lidar_scan_evidence_host. */
 int gcl_scan_submit_host(gcl_handle h, int slot, const double* points_host, const double* timestamps_host,
