@@ -286,7 +286,13 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   __shared__ double s_cert[kNT * GCL_NCERT];
 
   const int tid = threadIdx.x;
-  const gcl_job& J = P.jobs ? P.jobs[blockIdx.y] : P.job;
+  // the job record is read all through the kernel (array pointers at every prefetch, times and twist at every front end): keep
+  // it in shared memory instead of going back to global memory for every field
+  __shared__ gcl_job s_job;
+  if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
+    reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
+  __syncthreads();
+  const gcl_job& J = s_job;
   const ScanConst& C = P.c;
 
   // --- this CTA's slice of the selected rows -----------------------------------------------------------------
