@@ -170,7 +170,9 @@ int gcl_reduce_finalize(gcl_handle h, void* stream, const double* parts, int n_p
   P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.finalize = finalize; P.from_resp = 0;
   P.reduced = reduced; P.stats = stats;
   cudaSetDevice(h->device);
-  GCL_CUDA(h, launch_reduce_finalize(P, n_jobs, (cudaStream_t)stream));
+  int l = 0;
+  GCL_CUDA(h, launch_reduce_finalize(P, n_jobs, (cudaStream_t)stream, &l));
+  h->launches += l - 1;
   h->launches += 1;
   return GCL_OK;
 }
@@ -306,7 +308,9 @@ int gcl_scan_bin_moment_match(gcl_handle h, void* stream, const double* points, 
   F.job = P.job; F.n_bins = n_bins; F.nmom = 28; F.tau = 1.0;
   F.eps_psd = eps_psd; F.eps_mass = eps_mass; F.finalize = 1; F.from_resp = 1;
   F.reduced = workspace + (size_t)rec * ctas; F.stats = stats;
-  GCL_CUDA(h, launch_reduce_finalize(F, 1, (cudaStream_t)stream));
+  int lf = 0;
+  GCL_CUDA(h, launch_reduce_finalize(F, 1, (cudaStream_t)stream, &lf));
+  h->launches += lf - 1;
   h->launches += 2;
   return GCL_OK;
 }

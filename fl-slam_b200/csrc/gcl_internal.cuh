@@ -94,7 +94,7 @@ struct FinalizeParams {
   double* reduced;
   double* stats;
 };
-cudaError_t launch_reduce_finalize(const FinalizeParams& P, int n_jobs, cudaStream_t stream);
+cudaError_t launch_reduce_finalize(const FinalizeParams& P, int n_jobs, cudaStream_t stream, int* launches);
 
 struct EvidenceParams {
   const double* stats;
