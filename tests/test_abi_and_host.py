@@ -120,3 +120,18 @@ def test_manifest_entries(g):
         assert "sm_100a" in m["backends"][k]
     assert m["B_BINS"] == 48 and m["tau_soft_assign"] == 0.1 and m["precision_mode"] == "fp64"
     assert m["n_gpus"] == 8 and m["shard_mode"] == "points" and m["pose_evidence_backend"] == "bins"
+
+
+def test_launch_planning_without_a_gpu(g):
+    """Host-side planning entry points need no device: CTAs per job fill whole waves of 148 SMs, workspaces grow with the
+    problem."""
+    lib = g._abi.lib
+    assert lib.gcl_plan_ctas_per_job(None, 1, 1 << 20, 256, 1) == 148           # one big scan: one CTA per SM
+    assert lib.gcl_plan_ctas_per_job(None, 1, 7500, 48, 0) == 79                # one small scan: 96-row CTAs
+    c = lib.gcl_plan_ctas_per_job(None, 200, 7500, 48, 0)                       # a stream: waves x (rows per CTA + fixed cost) minimal
+    waves = -(-200 * c // 148)
+    cost = lambda k: -(-200 * k // 148) * (-(-7500 // k) + 128)
+    assert cost(c) == min(cost(k) for k in range(1, 30)) and waves * 148 - 200 * c < 148
+    assert lib.gcl_plan_ctas_per_job(None, 1, 0, 48, 0) >= 1
+    w = [lib.gcl_scan_chain_workspace_doubles(s, h, b) for s, h, b in ((1, 1, 48), (200, 1, 48), (200, 4, 48), (200, 4, 256))]
+    assert w == sorted(w) and w[0] >= 16 * 48
