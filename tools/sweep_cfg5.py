@@ -55,8 +55,7 @@ def rel(a_, b_):
     d = np.abs(a_ - b_) / s
     return float(d.max()), float(d.mean())
 def geodesic(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return float(np.arccos(min(1.0, max(-1.0, c))))
+    return float(np.linalg.norm(Ra - Rb) / np.sqrt(2.0))   # = 2 sin(theta/2): the arccos form bottoms out at 1.5e-8
 
 print(f"# configs[4] sweep: {n} points x {B} bins, tau = {tau}, one B200\n")
 print("| mode | layout | scan_moments ms | pairs/s | GB/s (algorithmic) | frac of HBM peak | frac of FMA-issue ceiling @1965 MHz |")
