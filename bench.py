@@ -279,7 +279,9 @@ def main():
                 "traffic_source": TRAFFIC_SOURCE,
                 "note": "one launch covers all 200 scans (7500 rows x 48 bins each); the kernel is bound by FMA-pipe issue, not by "
                         "HBM: compute_frac = pairs/s over the FMA-issue ceiling of its own instruction mix at the sampled SM "
-                        "clock (DESIGN.md section 4)"}
+                        "clock (DESIGN.md section 4).  The other large launch of a step is the sequential measurement-noise core "
+                        "(stream_sigma_chain_kernel, one warp walking the 200 scans, ~2.6 us per scan: latency-bound by construction); "
+                        "the remaining five launches take ~0.1 ms together (profiles/r1_launches_bench_stream_fp64.csv)"}
     roofline["traffic"] = TRAFFIC_BYTES_PER_LAUNCH.get(args.precision)
 
     # ---------------------------------------------------------------- e2e: the reference-facing host call, pinned buffers
