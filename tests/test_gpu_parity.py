@@ -622,3 +622,39 @@ def test_pointcloud2_ingest_errors_and_empty(g):
         g.parse_pointcloud2_vlp16(data=bytes(16), fields=[("x", 0, 9), ("y", 4, 7), ("z", 8, 7), ("ring", 12, 4)], point_step=16, n_points=1)
     out = g.parse_pointcloud2_vlp16(data=b"", fields=[("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("ring", 12, 4)], point_step=16, n_points=0)
     assert out[0].shape == (0, 3) and out[3].shape == (0,)
+
+
+@pytest.mark.parametrize("case", ["zero_weights", "one_point_repeated", "sentinel_points"])
+def test_degenerate_scans_against_oracle(g, O, case):
+    """Inputs the reference pipeline can legitimately produce: a scan whose weights all vanish (every bin mass 0: the eps_mass
+    guards and the PSD floor decide the result), a cloud collapsed to one point (zero scatter), and points replaced by the
+    non-finite sentinel 1e6 (backend_node.py:431-433)."""
+    n, cap, B, tau = 3000, 4096, 48, 0.1
+    sc = g.synth.make_scan(n, seed=4242)
+    pts, w = sc.points.copy(), sc.weights.copy()
+    if case == "zero_weights":
+        w[:] = 0.0
+    elif case == "one_point_repeated":
+        pts[:] = pts[7]
+    else:
+        pts[::97] = np.array([1e6, -1e6, 1e6])
+    bins = O.create_fibonacci_atlas(B)
+    pb = O.point_budget_resample(pts, sc.timestamps, w, sc.ring, sc.tag, cap)
+    dk = O.deskew_constant_twist(pb["points"], pb["timestamps"], pb["weights"], sc.scan_start_time, sc.scan_end_time, sc.xi_body)
+    raw = O.fused_scan_raw_sums(dk["points"], dk["weights"], bins, tau, sc.lidar_origin)
+    fin = O.scan_bin_finalize(raw)
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=sc.lidar_origin, bin_directions=bins)
+    scan = pl.upload_scan(pts, sc.timestamps, w, sc.scan_start_time, sc.scan_end_time)
+    ev = pl.run_resident(scan, sc.xi_body[None], torch.zeros(1, 6, dtype=torch.float64, device="cuda"), g.create_empty_map_stats(B))
+    sb = ev.scan_bins(0)
+    st = H(ev.stats)
+    assert np.all(np.isfinite(st))
+    scale = max(float(np.max(np.abs(fin["N"]))), 1e-300)
+    assert float(np.max(np.abs(H(sb.N) - fin["N"]))) <= 1e-9 * scale
+    for k, ref in (("s_dir", fin["s_dir"]), ("S_dir_scatter", fin["S_dir_scatter"]), ("p_bar", fin["p_bar"]), ("Sigma_p", fin["Sigma_p"])):
+        got = H(getattr(sb, k))
+        assert float(np.max(np.abs(got - ref))) <= 1e-9 * max(float(np.max(np.abs(ref))), 1e-12), k
+    # kappa amplifies near R = 1 (a collapsed cloud has R -> 1): compare where the resultant length leaves room
+    Rbar = np.linalg.norm(fin["s_dir"], axis=1) / (fin["N"] + 1e-12 + 2.220446049250313e-16)
+    ok = Rbar < 1 - 1e-3
+    assert float(np.max(np.abs(H(sb.kappa_scan)[ok] - fin["kappa_scan"][ok]), initial=0.0)) <= 1e-7 * max(float(np.max(np.abs(fin["kappa_scan"][ok]), initial=0.0)), 1.0)
