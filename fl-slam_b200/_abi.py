@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libgcl_b200.so")
 GCL_F64, GCL_F32C = 0, 1
 GCL_LAYOUT_REF_F64, GCL_LAYOUT_PACKED_F32 = 0, 1
 GCL_NM, GCL_NCERT, GCL_STATS_SCALARS, GCL_EVID_DOUBLES, GCL_MAX_BINS = 19, 8, 24, 640, 1024
+GCL_MSG_INFO_HEADER = 8
 
 # scalar tail of a stats record (enum GCL_SS_* in the header)
 SS = dict(TOTAL_MASS_IN=0, TOTAL_MASS_SEL=1, MASS_SCALE=2, PB_ESS=3, N_SELECTED=4, STRIDE=5, DESKEW_RETAINED=6,
@@ -77,6 +78,9 @@ def _load():
         "gcl_imu_preintegrate": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
         "gcl_scan_submit_host": (i32, [vp, i32, vp, vp, vp, i64, C.c_int32, f64, f64, vp, i32, vp, vp, i32, f64, i32, f64, f64]),
+        "gcl_scan_submit_msg_host": (i32, [vp, i32, vp, i64, C.c_int32, vp, vp, f64, vp, vp, C.c_int32, vp, vp, vp, vp, i32, f64, vp, vp, vp,
+                                           vp, i32, i32, vp, vp, i32, f64, i32, f64, f64]),
+        "gcl_scan_msg_info_host": (i32, [vp, i32, vp, i64]),
         "gcl_scan_evidence_begin_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32]),
         "gcl_scan_evidence_end_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gcl_scan_evidence_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, vp, vp]),

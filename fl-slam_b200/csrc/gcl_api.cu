@@ -420,7 +420,7 @@ int gcl_imu_preintegrate(gcl_handle h, void* stream, const double* stamps, const
   GCL_REQUIRE(h, stamps && gyro && accel && rotvec_start && gyro_bias && accel_bias && gravity_host && out, "NULL pointer");
   ImuParams P;
   P.stamps = stamps; P.gyro = gyro; P.accel = accel; P.weights = weights; P.M = n_samples;
-  P.t0 = t0; P.t1 = t1; P.sigma = sigma;
+  P.t0 = t0; P.t1 = t1; P.sigma = sigma; P.bounds_dev = nullptr;
   P.rotvec_start = rotvec_start; P.gyro_bias = gyro_bias; P.accel_bias = accel_bias;
   P.gravity[0] = gravity_host[0]; P.gravity[1] = gravity_host[1]; P.gravity[2] = gravity_host[2];
   P.trans_scale = rotation_only ? 0.0 : 1.0;
@@ -606,6 +606,162 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   g_ht.mark(3, h);
   S.n_hyp = n_hyp; S.n_bins = n_bins; S.d_stats = d_stats; S.pending = true;
   S.eps_psd = eps_psd; S.eps_mass = eps_mass;
+  return GCL_OK;
+}
+
+// Stage 1 from the MESSAGE: the raw PointCloud2 bytes (point_step bytes per point, 22 for the Kimera VLP-16 layout against 40
+// bytes of parsed float64) and, optionally, the IMU buffer cross PCIe; everything between the message and the bin statistics
+// runs on the device without a host round trip:
+//   pass 1 (time unit + extrema) -> scan bounds (backend_node.py:1776-1786) -> [IMU preintegration over those bounds ->
+//   deskew twist into the jobs] -> decode + range weights + base-frame transform into COMPACT rows (only the rows
+//   PointBudgetResample keeps; every raw weight) -> scan_moments -> reduce_finalize -> D2H of the info record.
+// The reference does this with a NumPy parse on the host, five H2D copies, one D2H sync for the bounds and a 512-step lax.scan.
+int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_host, int64_t n_points, int32_t point_step,
+                             const int32_t* off, const int32_t* dt, double header_stamp, const double* R_host,
+                             const double* t_host, int32_t cap, const double* xi_host, const double* imu_stamps_host,
+                             const double* imu_gyro_host, const double* imu_accel_host, int imu_samples, double imu_sigma,
+                             const double* rotvec_start_host, const double* gyro_bias_host, const double* accel_bias_host,
+                             const double* gravity_host, int rotation_only, int n_hyp, const double* origin_host,
+                             const double* bins_host, int n_bins, double tau, int precision, double eps_psd, double eps_mass) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
+  GCL_REQUIRE(h, n_points >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_points >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
+  GCL_REQUIRE(h, point_step >= 1 && point_step <= 512, "1 <= point_step <= 512 required");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
+  GCL_REQUIRE(h, off && dt && origin_host && bins_host && (n_points == 0 || msg_host), "NULL pointer");
+  GCL_REQUIRE(h, (R_host == nullptr) == (t_host == nullptr), "R_base_lidar and t_base_lidar go together");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  const bool imu = imu_stamps_host != nullptr;
+  GCL_REQUIRE(h, imu != (xi_host != nullptr), "exactly one of xi_body_host and the IMU buffer must be given");
+  GCL_REQUIRE(h, !imu || (imu_gyro_host && imu_accel_host && rotvec_start_host && gyro_bias_host && accel_bias_host && gravity_host
+                          && imu_samples >= 1), "incomplete IMU buffer");
+  static const int width[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+  IngestParams IP;
+  memset(&IP, 0, sizeof(IP));
+  for (int k = 0; k < 5; ++k) {
+    const bool optional = (k == 4) && off[k] < 0;
+    GCL_REQUIRE(h, optional || (dt[k] >= 1 && dt[k] <= 8), "Unsupported PointField datatype");   // backend_node.py:374
+    GCL_REQUIRE(h, optional || (off[k] >= 0 && off[k] + width[dt[k]] <= point_step), "field does not fit in point_step");
+    IP.off[k] = off[k]; IP.dtype[k] = optional ? 0 : dt[k];
+  }
+  cudaSetDevice(h->device);
+  int rc = ensure_streams(h);
+  if (rc != GCL_OK) return rc;
+  gcl_handle_s::Slot& S = h->slot[slot_index];
+  if (S.pending) { cudaStreamSynchronize(h->stream1); S.pending = false; }
+  const size_t B = n_bins, H = n_hyp, n = (size_t)n_points, M = imu ? (size_t)imu_samples : 0;
+  int64_t stride = (n_points + cap - 1) / cap; if (stride < 1) stride = 1;
+  const int64_t n_sel = (n_points + stride - 1) / stride;
+  const int ctas = gcl_plan_ctas_per_job(h, n_hyp, n_sel, n_bins, precision);
+  const size_t rec = gcl_partial_record_doubles(n_bins), srec = gcl_stats_record_doubles(n_bins);
+  const size_t info_doubles = GCL_MSG_INFO_HEADER + H * GCL_IMU_DOUBLES;
+  const int grid_ingest = (int)((n_points + 255) / 256);
+  // slot block, mirrored in pinned memory up to in_end: [bins][jobs][info][imu stamps|gyro|accel|rotvec|bg|ba][message bytes]
+  // device only: [bounds parts][flag][points][timestamps][weights] | partials | reduced | stats
+  const size_t o_bins = 0, o_jobs = al(o_bins + B * 24), o_info = al(o_jobs + H * sizeof(gcl_job));
+  const size_t o_imu = al(o_info + info_doubles * 8), o_msg = al(o_imu + (7 * M + 9 * H) * 8), in_end = al(o_msg + n * point_step);
+  const size_t o_bparts = in_end, o_flag = al(o_bparts + (size_t)(grid_ingest > 0 ? grid_ingest : 1) * 16);
+  const bool packed = precision == GCL_F32C;
+  const size_t o_pts = al(o_flag + 16), o_ts = al(o_pts + (size_t)n_sel * (packed ? 16 : 24));
+  const size_t o_w = al(o_ts + (packed ? 0 : (size_t)n_sel * 8)), o_parts = al(o_w + n * (packed ? 4 : 8));
+  const size_t o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8), d_end = al(o_stats + H * srec * 8);
+  rc = grow(h, &S.d_buf, &S.d_bytes, &S.h_buf, &S.h_bytes, d_end, in_end);
+  if (rc != GCL_OK) return rc;
+  unsigned char* hb = static_cast<unsigned char*>(S.h_buf);
+  unsigned char* db = static_cast<unsigned char*>(S.d_buf);
+  S.atlas_bins = 0; S.atlas_dev = nullptr; S.atlas_copy.clear();   // this path always uploads the head of the block
+  memcpy(hb + o_bins, bins_host, B * 24);
+  gcl_job* hj = reinterpret_cast<gcl_job*>(hb + o_jobs);
+  for (int i = 0; i < n_hyp; ++i) {
+    gcl_job& j = hj[i];
+    memset(&j, 0, sizeof(j));
+    j.points = db + o_pts; j.timestamps = db + o_ts; j.weights = db + o_w; j.point_lambda = nullptr;
+    j.n_raw = n_points; j.n_points_cap = cap; j.sel_begin = 0; j.sel_end = -1;
+    j.flags = GCL_JOB_COMPACT_ROWS;
+    j.scan_start_time = header_stamp; j.scan_end_time = header_stamp;   // patched on the device by scan_bounds_kernel
+    for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host ? xi_host[i * 6 + k] : 0.0;
+  }
+  double* hinfo = reinterpret_cast<double*>(hb + o_info);
+  memset(hinfo, 0, info_doubles * 8);
+  hinfo[GCL_MSG_INFO_N_POINTS] = (double)n_points; hinfo[GCL_MSG_INFO_STRIDE] = (double)stride; hinfo[GCL_MSG_INFO_N_SEL] = (double)n_sel;
+  if (xi_host)
+    for (size_t i = 0; i < H; ++i)
+      for (int k = 0; k < 6; ++k) hinfo[GCL_MSG_INFO_HEADER + i * GCL_IMU_DOUBLES + GCL_IMU_XI_BODY + k] = xi_host[i * 6 + k];
+  double* himu = reinterpret_cast<double*>(hb + o_imu);
+  if (imu) {
+    memcpy(himu, imu_stamps_host, M * 8); memcpy(himu + M, imu_gyro_host, M * 24); memcpy(himu + 4 * M, imu_accel_host, M * 24);
+    memcpy(himu + 7 * M, rotvec_start_host, H * 24); memcpy(himu + 7 * M + 3 * H, gyro_bias_host, H * 24);
+    memcpy(himu + 7 * M + 6 * H, accel_bias_host, H * 24);
+  }
+  cudaStream_t sc = h->stream_copy, s1 = h->stream1;
+  const bool direct = n > 0 && is_pinned(h, msg_host);
+  if (direct) {
+    GCL_CUDA(h, cudaMemcpyAsync(db, hb, o_msg, cudaMemcpyHostToDevice, sc));
+    GCL_CUDA(h, cudaMemcpyAsync(db + o_msg, msg_host, n * point_step, cudaMemcpyHostToDevice, sc));
+  } else {
+    if (n > 0) memcpy(hb + o_msg, msg_host, n * point_step);
+    GCL_CUDA(h, cudaMemcpyAsync(db, hb, n > 0 ? in_end : o_msg, cudaMemcpyHostToDevice, sc));
+  }
+  GCL_CUDA(h, cudaEventRecord(S.ev_copy, sc));
+  GCL_CUDA(h, cudaStreamWaitEvent(s1, S.ev_copy, 0));
+  gcl_job* d_jobs = reinterpret_cast<gcl_job*>(db + o_jobs);
+  double* d_info = reinterpret_cast<double*>(db + o_info);
+  IP.data = db + o_msg; IP.n_points = n_points; IP.point_step = point_step; IP.header_stamp = header_stamp;
+  IP.sentinel = 1e6; IP.sigma = 0.25; IP.min_r = 0.5; IP.max_r = 50.0; IP.weight_floor = 1e-12;   // constants.py:256-262
+  IP.transform = R_host != nullptr;
+  if (R_host) { for (int k = 0; k < 9; ++k) IP.R[k] = R_host[k]; for (int k = 0; k < 3; ++k) IP.t[k] = t_host[k]; }
+  if (packed) { IP.packed_xyzt = reinterpret_cast<float4*>(db + o_pts); IP.packed_w = reinterpret_cast<float*>(db + o_w); }
+  else { IP.points_out = reinterpret_cast<double*>(db + o_pts); IP.timestamps_out = reinterpret_cast<double*>(db + o_ts);
+         IP.weights_out = reinterpret_cast<double*>(db + o_w); }
+  IP.flag = reinterpret_cast<int*>(db + o_flag);
+  IP.compact_stride = (int)stride;
+  IP.bounds_parts = reinterpret_cast<double*>(db + o_bparts);
+  IP.bounds_out = d_info; IP.bounds_jobs = d_jobs; IP.bounds_n_jobs = n_hyp; IP.bounds_dev = d_info;
+  IP.defer_decode = 1;
+  int l = 0;
+  GCL_CUDA(h, launch_ingest(IP, s1, &l));        // time unit + extrema, scan bounds into the info record and the jobs
+  if (imu) {
+    const double* dimu = reinterpret_cast<const double*>(db + o_imu);
+    ImuParams P;
+    P.stamps = dimu; P.gyro = dimu + M; P.accel = dimu + 4 * M; P.weights = nullptr; P.M = imu_samples;
+    P.t0 = 0; P.t1 = 0; P.sigma = imu_sigma; P.bounds_dev = d_info;
+    P.rotvec_start = dimu + 7 * M; P.gyro_bias = dimu + 7 * M + 3 * H; P.accel_bias = dimu + 7 * M + 6 * H;
+    P.gravity[0] = gravity_host[0]; P.gravity[1] = gravity_host[1]; P.gravity[2] = gravity_host[2];
+    P.trans_scale = rotation_only ? 0.0 : 1.0;
+    P.out = d_info + GCL_MSG_INFO_HEADER; P.weights_out = nullptr; P.jobs_out = d_jobs;
+    GCL_CUDA(h, launch_imu_preintegrate(P, n_hyp, s1));
+    l += 1;
+  }
+  GCL_CUDA(h, launch_ingest_decode(IP, s1, &l));
+  h->launches += l;
+  const double* d_bins = reinterpret_cast<const double*>(db + o_bins);
+  double* d_parts = reinterpret_cast<double*>(db + o_parts);
+  double* d_red = reinterpret_cast<double*>(db + o_red);
+  double* d_stats = reinterpret_cast<double*>(db + o_stats);
+  rc = gcl_scan_moments(h, s1, d_jobs, nullptr, n_hyp, ctas, packed ? GCL_LAYOUT_PACKED_F32 : GCL_LAYOUT_REF_F64, precision, d_bins,
+                        n_bins, tau, origin_host, eps_mass, d_parts);
+  if (rc != GCL_OK) return rc;
+  rc = gcl_reduce_finalize(h, s1, d_parts, ctas, (int64_t)rec, (int64_t)rec * ctas, d_jobs, nullptr, n_hyp, n_bins, d_bins, tau,
+                           origin_host, eps_psd, eps_mass, 1, d_red, d_stats);
+  if (rc != GCL_OK) return rc;
+  GCL_CUDA(h, cudaMemcpyAsync(hb + o_info, d_info, info_doubles * 8, cudaMemcpyDeviceToHost, s1));
+  GCL_CUDA(h, cudaEventRecord(S.ev_stage1, s1));
+  S.n_hyp = n_hyp; S.n_bins = n_bins; S.d_stats = d_stats; S.pending = true;
+  S.eps_psd = eps_psd; S.eps_mass = eps_mass;
+  S.info_off = o_info; S.info_doubles = info_doubles;
+  return GCL_OK;
+}
+
+// the info record of the last gcl_scan_submit_msg_host on `slot`: waits for stage 1 of that slot only
+int gcl_scan_msg_info_host(gcl_handle h, int slot_index, double* info_host, int64_t n_doubles) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
+  gcl_handle_s::Slot& S = h->slot[slot_index];
+  GCL_REQUIRE(h, S.info_doubles > 0 && S.h_buf, "no message was submitted to this slot");
+  GCL_REQUIRE(h, info_host && n_doubles >= (int64_t)S.info_doubles, "info buffer too small (GCL_MSG_INFO_HEADER + n_hyp * GCL_IMU_DOUBLES doubles)");
+  cudaSetDevice(h->device);
+  GCL_CUDA(h, cudaEventSynchronize(S.ev_stage1));
+  memcpy(info_host, static_cast<unsigned char*>(S.h_buf) + S.info_off, S.info_doubles * 8);
   return GCL_OK;
 }
 

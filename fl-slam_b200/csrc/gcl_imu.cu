@@ -34,7 +34,8 @@ __device__ __forceinline__ void se3_log6(const double* T, double* xi) {   // se3
 __device__ __forceinline__ double imu_weight(const ImuParams& P, int i) {
   if (P.weights) return P.weights[i];
   const double sigma = fmax(P.sigma, 1e-6);
-  return window_weight64(P.stamps[i], P.t0, P.t1, sigma, 1e-12);   // GC_WEIGHT_FLOOR, constants.py:256
+  const double t0 = P.bounds_dev ? P.bounds_dev[0] : P.t0, t1 = P.bounds_dev ? P.bounds_dev[1] : P.t1;
+  return window_weight64(P.stamps[i], t0, t1, sigma, 1e-12);   // GC_WEIGHT_FLOOR, constants.py:256
 }
 
 __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_constant__ ImuParams P) {

@@ -31,12 +31,64 @@ __device__ __forceinline__ double decode_field(const unsigned char* p, int datat
 }
 
 // pass 1 (only when the message carries per-point time): does ANY raw time value exceed 1e6?  (backend_node.py:437-441:
-// such a message is in nanoseconds and every value is scaled by 1e-9)
+// such a message is in nanoseconds and every value is scaled by 1e-9).  With bounds_parts it also leaves this CTA's
+// minimum / maximum raw time value (scaling by a positive constant is monotone, so the unit can be applied afterwards).
 __global__ void __launch_bounds__(kIngestThreads) ingest_time_unit_kernel(const __grid_constant__ IngestParams P) {
   const int64_t i = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
   bool big = false;
-  if (i < P.n_points) big = decode_field(P.data + i * P.point_step + P.off[4], P.dtype[4]) > 1e6;
+  double lo = 1.0e300, hi = -1.0e300;
+  if (i < P.n_points) {
+    const double v = decode_field(P.data + i * P.point_step + P.off[4], P.dtype[4]);
+    big = v > 1e6;
+    lo = hi = v;
+  }
   if (__syncthreads_or(big) && threadIdx.x == 0) atomicOr(P.flag, 1);
+  if (P.bounds_parts) {
+    __shared__ double s_lo[kIngestThreads / 32], s_hi[kIngestThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kIngestThreads / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+      P.bounds_parts[2 * blockIdx.x] = lo; P.bounds_parts[2 * blockIdx.x + 1] = hi;
+    }
+  }
+}
+
+// Scan time bounds from the per-point times and the header stamp (pkg/backend/backend_node.py:1776-1786):
+//   |max - min| < 1e-9 : start = min, end = header stamp;   else  start = min(stamp, min), end = max(stamp, max).
+// One CTA: reduces the per-CTA extrema of pass 1, applies the time unit, writes the bounds record
+// [start, end, min, max, unit flag] and patches the window of the n_jobs job records of this scan.
+__global__ void __launch_bounds__(kIngestThreads) scan_bounds_kernel(const __grid_constant__ IngestParams P, int n_parts, gcl_job* jobs, int n_jobs) {
+  __shared__ double s_lo[kIngestThreads / 32], s_hi[kIngestThreads / 32];
+  __shared__ double s_b[2];
+  double lo = 1.0e300, hi = -1.0e300;
+  if (P.off[4] >= 0) {
+    for (int k = threadIdx.x; k < n_parts; k += kIngestThreads) { lo = fmin(lo, P.bounds_parts[2 * k]); hi = fmax(hi, P.bounds_parts[2 * k + 1]); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kIngestThreads / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+    const int ns = *P.flag;
+    double tmin, tmax;
+    if (P.off[4] >= 0 && P.n_points > 0) { tmin = ns ? lo * 1e-9 : lo; tmax = ns ? hi * 1e-9 : hi; }
+    else { tmin = tmax = P.header_stamp; }
+    double t0, t1;
+    if (fabs(tmax - tmin) < 1e-9) { t0 = tmin; t1 = P.header_stamp; }
+    else { t0 = fmin(P.header_stamp, tmin); t1 = fmax(P.header_stamp, tmax); }
+    P.bounds_out[0] = t0; P.bounds_out[1] = t1; P.bounds_out[2] = tmin; P.bounds_out[3] = tmax; P.bounds_out[4] = (double)ns;
+    s_b[0] = t0; s_b[1] = t1;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_jobs; j += kIngestThreads) { jobs[j].scan_start_time = s_b[0]; jobs[j].scan_end_time = s_b[1]; }
 }
 
 __global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const __grid_constant__ IngestParams P) {
@@ -83,31 +135,50 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const __grid_con
   } else {
     q[0] = c[0]; q[1] = c[1]; q[2] = c[2];
   }
-  if (P.points_out) { P.points_out[i * 3] = q[0]; P.points_out[i * 3 + 1] = q[1]; P.points_out[i * 3 + 2] = q[2]; }
-  if (P.timestamps_out) P.timestamps_out[i] = t;
+  // compact rows (GCL_JOB_COMPACT_ROWS): points / times only for the rows PointBudgetResample selects (raw row = k * stride,
+  // point_budget.py:160-163), at index k; weights for EVERY raw row (mass preservation needs their sum, :69)
+  const int64_t cs = P.compact_stride > 1 ? P.compact_stride : 1;
+  const bool keep = (i % cs) == 0;
+  const int64_t ip = i / cs;
+  if (P.points_out && keep) { P.points_out[ip * 3] = q[0]; P.points_out[ip * 3 + 1] = q[1]; P.points_out[ip * 3 + 2] = q[2]; }
+  if (P.timestamps_out && keep) P.timestamps_out[ip] = t;
   if (P.weights_out) P.weights_out[i] = w;
   if (P.ring_out) P.ring_out[i] = (unsigned char)(long long)ringv;   // astype(uint8) keeps the low byte
   if (P.tag_out) P.tag_out[i] = 0;
   if (P.packed_xyzt) {
-    P.packed_xyzt[i] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)(t - P.packed_t0));
+    const double pt0 = P.bounds_dev ? P.bounds_dev[0] : P.packed_t0;
+    if (keep) P.packed_xyzt[ip] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)(t - pt0));
     P.packed_w[i] = (float)w;
   }
 }
 
 cudaError_t launch_ingest(const IngestParams& P, cudaStream_t stream, int* launches) {
   *launches = 0;
-  if (P.n_points <= 0) return cudaSuccess;
+  if (P.n_points <= 0 && !P.bounds_out) return cudaSuccess;
   const int grid = (int)((P.n_points + kIngestThreads - 1) / kIngestThreads);
   cudaError_t e = cudaMemsetAsync(P.flag, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
-  if (P.off[4] >= 0) {
+  if (P.off[4] >= 0 && grid > 0) {
     ingest_time_unit_kernel<<<grid, kIngestThreads, 0, stream>>>(P);
     *launches += 1;
   }
+  if (P.bounds_out) {
+    scan_bounds_kernel<<<1, kIngestThreads, 0, stream>>>(P, grid, P.bounds_jobs, P.bounds_n_jobs);
+    *launches += 1;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (P.defer_decode || grid == 0) return cudaGetLastError();
+  return launch_ingest_decode(P, stream, launches);
+}
+
+// the decode pass alone (after launch_ingest with defer_decode: other work that needs the bounds may be enqueued in between)
+cudaError_t launch_ingest_decode(const IngestParams& P, cudaStream_t stream, int* launches) {
+  if (P.n_points <= 0) return cudaSuccess;
+  const int grid = (int)((P.n_points + kIngestThreads - 1) / kIngestThreads);
   const size_t smem = (size_t)kIngestThreads * P.point_step;
   static bool attr_done = false;
   if (!attr_done) {
-    e = cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }

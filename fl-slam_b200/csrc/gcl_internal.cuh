@@ -39,6 +39,7 @@ struct gcl_handle_s {
     bool pending = false;
     std::string atlas_copy;             // bytes of the atlas this slot holds on the device
     int atlas_bins = 0; void* atlas_dev = nullptr;
+    size_t info_off = 0, info_doubles = 0;   // info record of the last gcl_scan_submit_msg_host (pinned block)
   } slot[GCL_HOST_SLOTS];
   const void* pin_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool pin_val[8] = {false, false, false, false, false, false, false, false};
@@ -143,13 +144,22 @@ struct IngestParams {
   unsigned char* ring_out; unsigned char* tag_out;
   float4* packed_xyzt; float* packed_w; double packed_t0;
   int* flag;                   // device scratch: "per-point time is in nanoseconds"
+  // message -> evidence path (gcl_scan_submit_msg_host): everything below may stay zero for the stand-alone operator
+  int compact_stride;          // > 1: points / times are written only for raw rows k * stride, at index k (weights: every row)
+  double* bounds_parts;        // device scratch, 2 doubles per CTA of pass 1: extrema of the raw per-point time
+  double* bounds_out;          // device, 5 doubles [scan start, scan end, min t, max t, unit flag] (backend_node.py:1776-1786)
+  gcl_job* bounds_jobs; int bounds_n_jobs;   // job records whose time window is patched with the bounds
+  const double* bounds_dev;    // decode pass: packed_t0 is read from here (the scan start computed on the device)
+  int defer_decode;            // launch_ingest stops after the bounds; launch_ingest_decode runs the decode pass
 };
 cudaError_t launch_ingest(const IngestParams& P, cudaStream_t stream, int* launches);
+cudaError_t launch_ingest_decode(const IngestParams& P, cudaStream_t stream, int* launches);
 
 struct ImuParams {
   const double *stamps, *gyro, *accel, *weights;  // (M,), (M,3), (M,3), optional (M,) -- NULL: window weights computed here
   int M;
   double t0, t1, sigma;                           // window of smooth_window_weights (used when weights == NULL)
+  const double* bounds_dev;                       // optional: [t0, t1] read from device memory instead (scan bounds of the ingest)
   const double *rotvec_start, *gyro_bias, *accel_bias;  // (H,3) each
   double gravity[3];
   double trans_scale;                             // 0 = rotation-only deskew, 1 = full twist

@@ -142,6 +142,7 @@ class LidarEvidencePipeline:
         self._origin_c = _abi.dvec(self.origin)
         self._ptr_cache: Dict[int, Tuple[np.ndarray, int]] = {}
         self._inflight: Dict[int, tuple] = {}
+        self._msg_layouts: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     def manifest_entries(self, n_gpus: int = 1, shard_mode: str = "none") -> Dict[str, Any]:
@@ -350,6 +351,82 @@ class LidarEvidencePipeline:
                                              float(scan_end_time), p(xi), xi.shape[0], self._addr(self.origin), self._addr(bins_host), self.n_bins,
                                              self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
         return xi.shape[0]
+
+    def submit_scan_msg_host(self, slot: int, msg=None, *, data=None, fields=None, point_step: Optional[int] = None,
+                             n_points: Optional[int] = None, header_stamp_sec: float = 0.0, R_base_lidar=None, t_base_lidar=None,
+                             xi_body=None, imu: Optional[Dict[str, Any]] = None) -> int:
+        """Stage 1 from the MESSAGE (gcl_scan_submit_msg_host): the raw PointCloud2 bytes are uploaded as they are and parsed,
+        windowed, transformed to the base frame and resampled on the device; the scan time bounds
+        (pkg/backend/backend_node.py:1776-1786) are computed there too.  The deskew twist is either ``xi_body`` (H,6) or comes
+        from ``imu`` = dict(stamps, gyro, accel, sigma, rotvec_start_WB (H,3), gyro_bias (H,3), accel_bias (H,3), gravity_W,
+        deskew_rotation_only=False), preintegrated on the device over those bounds (pkg/backend/pipeline.py:437-483).
+        ``msg`` is a sensor_msgs/PointCloud2-like object, or pass the pieces by keyword (``fields`` as (name, offset,
+        datatype) triples).  A page-locked ``data`` array (np.uint8) is read in place.  Returns H."""
+        if (xi_body is None) == (imu is None):
+            raise ValueError("exactly one of xi_body and imu must be given")
+        if msg is not None:
+            data, point_step, n_points = msg.data, int(msg.point_step), int(msg.width) * int(msg.height)
+            fields = [(f.name, int(f.offset), int(f.datatype)) for f in msg.fields]
+            header_stamp_sec = msg.header.stamp.sec + msg.header.stamp.nanosec * 1e-9
+        key = (tuple(fields), int(point_step))
+        lay = self._msg_layouts.get(key)
+        if lay is None:
+            fmap = {f[0]: (int(f[1]), int(f[2])) for f in fields}
+            missing = [k for k in ("x", "y", "z", "ring") if k not in fmap]
+            if missing:
+                raise RuntimeError(f"PointCloud2 (VLP-16 layout) missing required fields: {missing}. Present fields: {sorted(fmap)}")
+            tname = "t" if "t" in fmap else ("time" if "time" in fmap else None)
+            order = ["x", "y", "z", "ring"] + ([tname] if tname else [])
+            off = np.array([fmap[k][0] for k in order] + ([] if tname else [-1]), dtype=np.int32)
+            dt = np.array([fmap[k][1] for k in order] + ([] if tname else [0]), dtype=np.int32)
+            if any(d < 1 or d > 8 for d in dt[:len(order)]):
+                raise ValueError(f"Unsupported PointField datatype: {[int(d) for d in dt]}")
+            lay = self._msg_layouts[key] = (off, dt)
+        off, dt = lay
+        n = int(n_points)
+        raw = data if (type(data) is np.ndarray and data.dtype == np.uint8 and data.flags.c_contiguous) else np.frombuffer(bytes(data), dtype=np.uint8)
+        if raw.size < n * int(point_step):
+            raise ValueError("message data is shorter than n_points * point_step")
+        f = self._f64
+        R = None if R_base_lidar is None else f(R_base_lidar, (9,))
+        t = None if t_base_lidar is None else f(t_base_lidar, (3,))
+        p = lambda a: None if a is None else a.ctypes.data
+        if xi_body is not None:
+            xi = f(xi_body, (-1, 6))
+            H = xi.shape[0]
+            imu_args = (p(xi), None, None, None, 0, 0.0, None, None, None, None, 0)
+            keep = (xi,)
+        else:
+            st, gy, ac = f(imu["stamps"], (-1,)), f(imu["gyro"], (-1, 3)), f(imu["accel"], (-1, 3))
+            M = st.shape[0]
+            if gy.shape[0] != M or ac.shape[0] != M:
+                raise ValueError("imu stamps, gyro and accel must have the same length")
+            rv, bg, ba = f(imu["rotvec_start_WB"], (-1, 3)), f(imu["gyro_bias"], (-1, 3)), f(imu["accel_bias"], (-1, 3))
+            H = rv.shape[0]
+            if bg.shape[0] != H or ba.shape[0] != H:
+                raise ValueError("rotvec_start_WB, gyro_bias and accel_bias must have one row per hypothesis")
+            grav = f(imu["gravity_W"], (3,))
+            imu_args = (None, p(st), p(gy), p(ac), M, float(imu["sigma"]), p(rv), p(bg), p(ba), p(grav),
+                        1 if imu.get("deskew_rotation_only", False) else 0)
+            keep = (st, gy, ac, rv, bg, ba, grav)
+        bins_host = getattr(self, "_bins_host", None)
+        if bins_host is None:
+            bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
+        self._inflight[slot] = (raw, keep, None, np.empty((H, 0)), n)     # keep the arrays alive while the copy is in flight
+        _abi.check(_lib.gcl_scan_submit_msg_host(self.handle, int(slot), p(raw), n, int(point_step), p(off), p(dt), float(header_stamp_sec),
+                                                 p(R), p(t), self.n_points_cap, *imu_args, H, self._addr(self.origin), self._addr(bins_host),
+                                                 self.n_bins, self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
+        return H
+
+    def msg_info_host(self, slot: int, n_hyp: int = 1) -> Dict[str, Any]:
+        """What the device derived from the message submitted to ``slot`` (gcl_scan_msg_info_host): the scan time bounds, the
+        time unit, the resample stride and, per hypothesis, the IMU preintegration record with the deskew twist."""
+        out = np.empty(_abi.GCL_MSG_INFO_HEADER + n_hyp * ops.GCL_IMU_DOUBLES)
+        _abi.check(_lib.gcl_scan_msg_info_host(self.handle, int(slot), out.ctypes.data, out.size), self.handle)
+        recs = out[_abi.GCL_MSG_INFO_HEADER:].reshape(n_hyp, ops.GCL_IMU_DOUBLES)
+        return {"scan_start_time": float(out[0]), "scan_end_time": float(out[1]), "t_min": float(out[2]), "t_max": float(out[3]),
+                "time_in_nanoseconds": bool(out[4]), "n_points": int(out[5]), "stride": int(out[6]), "n_selected": int(out[7]),
+                "imu_records": recs, "xi_body": recs[:, ops.IMU["XI_BODY"]:ops.IMU["XI_BODY"] + 6], "ess_imu": recs[:, ops.IMU["ESS"]]}
 
     def evidence_begin_host(self, slot: int, pose_pred, map_stats_host: Dict[str, np.ndarray], ess_imu: float = 0.0,
                             chart_id: str = constants.GC_CHART_ID, anchor_id: str = "initial", pose_update=None,

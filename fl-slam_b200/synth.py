@@ -126,3 +126,53 @@ def map_stats_from_scan_sums(raw: Dict[str, np.ndarray], R: np.ndarray, t: np.nd
         "sum_p": f[:, None] * sum_p,
         "sum_ppT": f[:, None, None] * sum_ppT,
     }
+
+
+def make_pointcloud2(scan: SyntheticScan, R_base_lidar=None, t_base_lidar=None, *, time_field: Optional[str] = "time_f32",
+                     time_base: Optional[float] = None, header_stamp_sec: Optional[float] = None) -> Dict[str, object]:
+    """The synthetic scan as the raw bytes of a VLP-16 PointCloud2 message (what pkg/backend/backend_node.py:377-468 parses):
+    x, y, z float32 in the LiDAR frame, intensity float32, ring uint16, and a per-point time field --
+    "time_f32" (the Kimera layout, 22 bytes per point: float32 seconds since ``time_base``), "t_f64" (float64 seconds since ``time_base``, 26 bytes; the reference parser reads any
+    value above 1e6 as nanoseconds, so absolute epoch seconds cannot be carried), "t_u32ns" (uint32 nanoseconds since ``time_base``, 22 bytes; any value > 1e6 switches the reference
+    parser to nanoseconds) or None (no time field, 18 bytes: every point takes the header stamp)."""
+    n = scan.points.shape[0]
+    R = np.eye(3) if R_base_lidar is None else np.asarray(R_base_lidar, dtype=np.float64).reshape(3, 3)
+    t = np.zeros(3) if t_base_lidar is None else np.asarray(t_base_lidar, dtype=np.float64).reshape(3)
+    p_lidar = (scan.points - t[None, :]) @ R                      # R^T (p_base - t)
+    base = scan.scan_start_time if time_base is None else float(time_base)
+    cols = [("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("intensity", "<f4"), ("ring", "<u2")]
+    if time_field == "time_f32":
+        cols.append(("time", "<f4"))
+    elif time_field == "t_f64":
+        cols.append(("t", "<f8"))
+    elif time_field == "t_u32ns":
+        cols.append(("t", "<u4"))
+    elif time_field is not None:
+        raise ValueError(time_field)
+    dt = np.dtype(cols)                                            # packed, unaligned offsets like the real message
+    rec = np.zeros(n, dtype=dt)
+    rec["x"], rec["y"], rec["z"] = p_lidar[:, 0], p_lidar[:, 1], p_lidar[:, 2]
+    rec["intensity"] = 1.0
+    rec["ring"] = scan.ring
+    if time_field == "time_f32":
+        rec["time"] = (scan.timestamps - base).astype(np.float32)
+    elif time_field == "t_f64":
+        rec["t"] = scan.timestamps - base
+    elif time_field == "t_u32ns":
+        rec["t"] = np.round((scan.timestamps - base) * 1e9).astype(np.uint32)
+    code = {"<f4": 7, "<f8": 8, "<u2": 4, "<u4": 6}
+    fields = [(name, int(dt.fields[name][1]), code[fmt]) for name, fmt in cols]
+    stamp = (scan.scan_start_time - base if time_field is not None else scan.scan_start_time) \
+        if header_stamp_sec is None else float(header_stamp_sec)
+    return {"data": np.frombuffer(rec.tobytes(), dtype=np.uint8).copy(), "fields": fields, "point_step": int(dt.itemsize),
+            "n_points": n, "header_stamp_sec": float(stamp)}
+
+
+def make_imu_buffer(t0: float, t1: float, n_samples: int = 512, seed: int = 0) -> Dict[str, np.ndarray]:
+    """A padded IMU buffer around the scan window [t0, t1] (pkg/backend/pipeline.py:437-483 takes M = 512 samples)."""
+    rng = np.random.default_rng(seed)
+    pad = 0.5 * (t1 - t0) + 0.02
+    stamps = np.linspace(t0 - pad, t1 + pad, n_samples)
+    gyro = np.array([0.02, -0.03, 0.8])[None, :] + 0.01 * rng.normal(size=(n_samples, 3))
+    accel = np.array([0.3, -0.1, 9.81])[None, :] + 0.05 * rng.normal(size=(n_samples, 3))
+    return {"stamps": stamps, "gyro": gyro, "accel": accel}

@@ -316,6 +316,34 @@ int gcl_scan_submit_host(gcl_handle h, int slot, const double* points_host, cons
                          double scan_end_time, const double* xi_body_host, int n_hyp, const double* lidar_origin_host,
                          const double* bin_dirs_host, int n_bins, double tau, int precision, double eps_psd,
                          double eps_mass);
+/* Stage 1 straight from the MESSAGE (the callers either side of the path, SURVEY.md 8f-3 / 8f-4 joined to stage 1): replaces
+ * parse_pointcloud2_vlp16 (pkg/backend/backend_node.py:377-468), the base-frame transform (:1675-1681), the scan time bounds
+ * (:1776-1786: |max - min| < 1e-9 ? [min, stamp] : [min(stamp, min), max(stamp, max)]) and, when the IMU buffer is given,
+ * smooth_window_weights + preintegrate_imu_relative_pose_jax + se3_log over those bounds (pkg/backend/pipeline.py:437-483),
+ * followed by the same moment pass as gcl_scan_submit_host.  The raw message bytes (point_step per point) are what crosses
+ * PCIe; nothing returns to the host between the message and the bin statistics.
+ *   field_offsets / field_datatypes   as in gcl_pointcloud2_ingest (x, y, z, ring, per-point time or -1)
+ *   xi_body_host (n_hyp,6)            the deskew twist, OR (exactly one of the two)
+ *   imu_*                             the IMU buffer (n_imu samples; stamps (M,), gyro (M,3), accel (M,3)), window width
+ *                                     imu_sigma, and per hypothesis the start orientation and biases (n_hyp,3) each
+ * The evidence step is the usual gcl_scan_evidence_begin_host / _end_host on the same slot.  gcl_scan_msg_info_host returns
+ * GCL_MSG_INFO_HEADER doubles [scan start, scan end, min t, max t, time-unit flag (1 = nanoseconds), n_points, stride,
+ * n_selected] followed by n_hyp IMU records of GCL_IMU_DOUBLES doubles (only XI_BODY is set when the twist was given). */
+#define GCL_MSG_INFO_HEADER 8
+enum {
+  GCL_MSG_INFO_T0 = 0, GCL_MSG_INFO_T1 = 1, GCL_MSG_INFO_TMIN = 2, GCL_MSG_INFO_TMAX = 3, GCL_MSG_INFO_NS = 4,
+  GCL_MSG_INFO_N_POINTS = 5, GCL_MSG_INFO_STRIDE = 6, GCL_MSG_INFO_N_SEL = 7
+};
+int gcl_scan_submit_msg_host(gcl_handle h, int slot, const uint8_t* msg_data_host, int64_t n_points, int32_t point_step,
+                             const int32_t* field_offsets_host, const int32_t* field_datatypes_host, double header_stamp_sec,
+                             const double* R_base_lidar_host, const double* t_base_lidar_host, int32_t n_points_cap,
+                             const double* xi_body_host, const double* imu_stamps_host, const double* imu_gyro_host,
+                             const double* imu_accel_host, int n_imu, double imu_sigma, const double* rotvec_start_WB_host,
+                             const double* gyro_bias_host, const double* accel_bias_host, const double* gravity_W_host,
+                             int deskew_rotation_only, int n_hyp, const double* lidar_origin_host, const double* bin_dirs_host,
+                             int n_bins, double tau, int precision, double eps_psd, double eps_mass);
+int gcl_scan_msg_info_host(gcl_handle h, int slot, double* info_host, int64_t n_doubles);
+
 /* gcl_scan_evidence_host in two halves, so that the caller can issue the next scan's gcl_scan_submit_host while the GPU runs
  * this scan's chain step: _begin enqueues everything (H2D of pose / map / IW, chain step, the one D2H) and returns; _end
  * waits for the D2H and hands out the results (map / IW arrays are written only if the step carried an update / an IW state).

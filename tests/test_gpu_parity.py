@@ -658,3 +658,102 @@ def test_degenerate_scans_against_oracle(g, O, case):
     Rbar = np.linalg.norm(fin["s_dir"], axis=1) / (fin["N"] + 1e-12 + 2.220446049250313e-16)
     ok = Rbar < 1 - 1e-3
     assert float(np.max(np.abs(H(sb.kappa_scan)[ok] - fin["kappa_scan"][ok]), initial=0.0)) <= 1e-7 * max(float(np.max(np.abs(fin["kappa_scan"][ok]), initial=0.0)), 1.0)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# message -> evidence: raw PointCloud2 bytes (+ IMU buffer) in, bin statistics and evidence out, nothing parsed on the host
+# --------------------------------------------------------------------------------------------------------------
+def _msg_case(g, O, time_field, n, seed):
+    sc = g.synth.make_scan(n, seed=seed, with_times=time_field is not None)
+    R_bl = g.synth.rotation_from_rotvec(np.array([0.02, -0.01, 0.3]))
+    t_bl = sc.lidar_origin.copy()
+    # per-point times in the message's own time base: 12.25 .. 12.35 s, or 0.5e9 .. 0.6e9 ns for the uint32 field
+    base = sc.scan_start_time - (0.5 if time_field == "t_u32ns" else 12.25)
+    stamp = {"time_f32": 12.0, "t_u32ns": 0.55, "t_f64": 12.3, None: 12.0}[time_field]
+    msg = g.synth.make_pointcloud2(sc, R_bl, t_bl, time_field=time_field, time_base=base, header_stamp_sec=stamp)
+    par = O.parse_pointcloud2_vlp16(msg["data"], msg["fields"], msg["point_step"], msg["n_points"], header_stamp=(stamp, 0))
+    pts_base = O.lidar_points_to_base(par["points"], R_bl, t_bl)
+    t0, t1 = O.scan_time_bounds(par["timestamps"], stamp)
+    return sc, msg, R_bl, t_bl, par, pts_base, t0, t1
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-9), ("fp32c", 1e-5)])
+@pytest.mark.parametrize("time_field,n,cap,use_imu", [("time_f32", 30011, 8192, True), ("time_f32", 30011, 8192, False),
+                                                      ("t_f64", 8192, 8192, True), ("t_u32ns", 12000, 8192, False),
+                                                      (None, 5000, 8192, False), ("t_f64", 777, 256, True)])
+def test_message_to_evidence_against_oracle(g, O, precision, tol, time_field, n, cap, use_imu):
+    """gcl_scan_submit_msg_host against the oracle's parse -> base frame -> time bounds -> (IMU twist) -> chain on the SAME
+    bytes: bounds, time unit and stride exact; the twist to re-association; moments / rotation to the usual bars."""
+    B, tau = 48, g.synth.DEFAULT_TAU
+    sc, msg, R_bl, t_bl, par, pts_base, t0, t1 = _msg_case(g, O, time_field, n, seed=4100 + n)
+    bins = O.create_fibonacci_atlas(B)
+    if use_imu:
+        imu = g.synth.make_imu_buffer(t0, t1, 512, seed=n)
+        rv, bg, ba, grav = np.array([0.01, -0.02, 0.4]), np.array([1e-3, -2e-3, 5e-4]), np.array([0.02, 0.01, -0.03]), np.array([0.0, 0.0, -9.81])
+        io = O.imu_deskew_twist(imu["stamps"], imu["gyro"], imu["accel"], t0, t1, 0.01, rv, bg, ba, grav)
+        xi = io["xi_body"]
+    else:
+        xi = sc.xi_body
+    pb = O.point_budget_resample(pts_base, par["timestamps"], par["weights"], par["ring"], par["tag"], cap)
+    dk = O.deskew_constant_twist(pb["points"], pb["timestamps"], pb["weights"], t0, t1, xi)
+    raw = O.fused_scan_raw_sums(dk["points"], dk["weights"], bins, tau, sc.lidar_origin)
+    fin = O.scan_bin_finalize(raw)
+    Rs, ts_ = g.synth.known_map_transform(0)
+    ms = g.synth.map_stats_from_scan_sums(raw, Rs, ts_, seed=0)
+    pose = np.zeros(6)
+    mf = O.matrix_fisher_rotation_evidence(pose, fin["s_dir"], fin["S_dir_scatter"], fin["N"], ms["S_dir"], ms["S_dir_scatter"], ms["N_dir"])
+
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision=precision, n_points_cap=cap, lidar_origin=sc.lidar_origin, bin_directions=bins)
+    kw = dict(data=msg["data"], fields=msg["fields"], point_step=msg["point_step"], n_points=msg["n_points"],
+              header_stamp_sec=msg["header_stamp_sec"], R_base_lidar=R_bl, t_base_lidar=t_bl)
+    if use_imu:
+        kw["imu"] = dict(stamps=imu["stamps"], gyro=imu["gyro"], accel=imu["accel"], sigma=0.01, rotvec_start_WB=rv[None], gyro_bias=bg[None],
+                         accel_bias=ba[None], gravity_W=grav)
+    else:
+        kw["xi_body"] = xi[None]
+    assert pl.submit_scan_msg_host(1, **kw) == 1
+    ev = pl.evidence_host(1, pose[None], ms)
+    info = pl.msg_info_host(1)
+    assert (info["scan_start_time"], info["scan_end_time"]) == (t0, t1)            # bit exact
+    assert (info["t_min"], info["t_max"]) == (float(par["timestamps"].min()), float(par["timestamps"].max()))
+    assert info["time_in_nanoseconds"] == (time_field == "t_u32ns")
+    stride = max(1, -(-n // cap))
+    assert (info["n_points"], info["stride"], info["n_selected"]) == (n, stride, len(range(0, n, stride)))
+    np.testing.assert_allclose(info["xi_body"][0], xi, rtol=0, atol=1e-11)
+    if use_imu:
+        assert abs(info["ess_imu"][0] - io["ess"]) < 1e-9 * max(1.0, io["ess"])
+    sb = ev.scan_bins(0)
+    for name in ("N", "s_dir", "S_dir_scatter", "p_bar"):
+        assert rel_err(H(getattr(sb, name)), fin[name]) < tol, name
+    R = H(ev.evidence)[0, :9].reshape(3, 3)
+    assert np.linalg.norm(R - mf["R_mf"]) / math.sqrt(2.0) < (1e-8 if precision == "fp64" else 1e-4)
+
+
+def test_message_path_matches_parsed_array_path(g, O):
+    """The same scan through the message entry and through the parsed-array entry (arrays = the GPU ingest of the same bytes,
+    bounds and twist = what the message path derived): identical bin statistics in fp64 (same rows, same order of summation)."""
+    B, tau, n, cap = 48, g.synth.DEFAULT_TAU, 30011, 8192
+    sc, msg, R_bl, t_bl, par, pts_base, t0, t1 = _msg_case(g, O, "time_f32", n, seed=99)
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=sc.lidar_origin)
+    ms = {k: np.zeros(v) for k, v in (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)),
+                                      ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))}
+    pl.submit_scan_msg_host(0, data=msg["data"], fields=msg["fields"], point_step=msg["point_step"], n_points=n,
+                            header_stamp_sec=msg["header_stamp_sec"], R_base_lidar=R_bl, t_base_lidar=t_bl, xi_body=sc.xi_body[None])
+    ev_a = pl.evidence_host(0, np.zeros((1, 6)), ms)
+    out = g.parse_pointcloud2_vlp16(data=msg["data"], fields=msg["fields"], point_step=msg["point_step"], n_points=n,
+                                    header_stamp_sec=msg["header_stamp_sec"], R_base_lidar=R_bl, t_base_lidar=t_bl)
+    ev_b = pl.process_scan_host(H(out[0]), H(out[1]), H(out[2]), t0, t1, sc.xi_body[None], np.zeros((1, 6)), ms)
+    assert np.array_equal(H(ev_a.stats), H(ev_b.stats))
+
+
+def test_message_path_errors(g):
+    pl = g.LidarEvidencePipeline(n_bins=16, tau=0.1, precision="fp64", n_points_cap=64, lidar_origin=np.zeros(3))
+    f3 = [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)]
+    with pytest.raises(RuntimeError):
+        pl.submit_scan_msg_host(0, data=bytes(12), fields=f3, point_step=12, n_points=1, xi_body=np.zeros((1, 6)))
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(16), fields=f3 + [("ring", 12, 4)], point_step=16, n_points=1)
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(8), fields=f3 + [("ring", 12, 4)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(16), fields=f3 + [("ring", 12, 9)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
