@@ -315,6 +315,33 @@ def main():
             pl.evidence_end_host()
         return m
 
+    # the same stream from the MESSAGES: 22 bytes per point of raw PointCloud2 + the 512-sample IMU buffer per scan cross PCIe;
+    # parse, range weights, base-frame transform, scan time bounds, IMU preintegration -> twist, resample, moments on the device
+    R_bl, t_bl = synth.rotation_from_rotvec(np.array([0.02, -0.01, 0.3])), scans[0].lidar_origin.copy()
+    msgs = []
+    for k, s in enumerate(scans[:n_e2e]):
+        m = synth.make_pointcloud2(s, R_bl, t_bl, time_field="time_f32", time_base=s.scan_start_time - 0.1 * k - 5.0)
+        buf = torch.from_numpy(m["data"]).pin_memory()
+        imu = synth.make_imu_buffer(5.0 + 0.1 * k, 5.1 + 0.1 * k, 512, seed=k)
+        imu.update(sigma=0.01, rotvec_start_WB=np.zeros((1, 3)), gyro_bias=np.zeros((1, 3)), accel_bias=np.zeros((1, 3)),
+                   gravity_W=np.array([0.0, 0.0, -9.81]))
+        msgs.append((buf.numpy(), m, imu, buf))
+
+    def e2e_pass_messages():
+        m = {k: np.zeros(v) for k, v in (("S_dir", (N_BINS, 3)), ("S_dir_scatter", (N_BINS, 3, 3)), ("N_dir", (N_BINS,)),
+                                         ("N_pos", (N_BINS,)), ("sum_p", (N_BINS, 3)), ("sum_ppT", (N_BINS, 3, 3)))}
+        iw_h = np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
+        sub = lambda k: pl.submit_scan_msg_host(k % 4, data=msgs[k][0], fields=msgs[k][1]["fields"], point_step=msgs[k][1]["point_step"],
+                                                n_points=msgs[k][1]["n_points"], header_stamp_sec=msgs[k][1]["header_stamp_sec"],
+                                                R_base_lidar=R_bl, t_base_lidar=t_bl, imu=msgs[k][2])
+        sub(0); sub(1)
+        for k in range(n_e2e):
+            pl.evidence_begin_host(k % 4, poses[k][None], m, pose_update=poses[k], iw_state_host=iw_h, use_sigma_meas=True)
+            if k + 2 < n_e2e:
+                sub(k + 2)
+            pl.evidence_end_host()
+        return m
+
     def _time_e2e(fn):
         fn()
         if world > 1:
@@ -332,6 +359,7 @@ def main():
     n_rep = max(1, args.steps // 2)
     e2e_blocking_s = _time_e2e(e2e_pass)
     e2e_s = _time_e2e(e2e_pass_pipelined)
+    e2e_msg_s = _time_e2e(e2e_pass_messages)
     e2e_points = sum(s.points.shape[0] for s in scans[:n_e2e])
     rec_bytes = (38 * N_BINS + 24 + 640 + 26 * N_BINS + 10) * 8
     e2e = {"value": world * n_rep * e2e_points / e2e_s, "unit": "points/s",
@@ -341,6 +369,12 @@ def main():
            "blocking_call": {"value": world * n_rep * e2e_points / e2e_blocking_s, "unit": "points/s",
                              "us_per_scan": 1e6 * e2e_blocking_s / (n_rep * n_e2e),
                              "note": "one gcl_lidar_scan_evidence_host call per scan, nothing overlapped"},
+           "from_message": {"value": world * n_rep * e2e_points / e2e_msg_s, "unit": "points/s", "us_per_scan": 1e6 * e2e_msg_s / (n_rep * n_e2e),
+                            "h2d_bytes_per_step": int(e2e_points * msgs[0][1]["point_step"] + n_e2e * (512 * 7 * 8 + N_BINS * 26 * 8 + N_BINS * 24 + 400)),
+                            "note": "gcl_scan_submit_msg_host: the raw PointCloud2 bytes (22 B/point, Kimera VLP-16 layout) and the 512-sample IMU "
+                                    "buffer are the inputs; parse, range weights, base-frame transform, scan time bounds, IMU preintegration -> "
+                                    "deskew twist, resample, moments and finalize run on the device (the reference does the parse in NumPy and the "
+                                    "preintegration as a 512-step lax.scan before the operators timed by the other figures)"},
            "note": f"{n_e2e} scans per pass through the two-stage host API with pinned host arrays: gcl_scan_submit_host (H2D of "
                    "the scan, scan_moments, reduce_finalize; asynchronous) for scan k+2 is issued between "
                    "gcl_scan_evidence_begin_host (H2D of pose/map/IW, chain step incl. IW + map update, one D2H of "

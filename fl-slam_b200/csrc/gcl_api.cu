@@ -659,10 +659,11 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
   // slot block, mirrored in pinned memory up to in_end: [bins][jobs][info][imu stamps|gyro|accel|rotvec|bg|ba][message bytes]
   // device only: [bounds parts][flag][points][timestamps][weights] | partials | reduced | stats
   const size_t o_bins = 0, o_jobs = al(o_bins + B * 24), o_info = al(o_jobs + H * sizeof(gcl_job));
-  const size_t o_imu = al(o_info + info_doubles * 8), o_msg = al(o_imu + (7 * M + 9 * H) * 8), in_end = al(o_msg + n * point_step);
-  const size_t o_bparts = in_end, o_flag = al(o_bparts + (size_t)(grid_ingest > 0 ? grid_ingest : 1) * 16);
+  const size_t o_flag = al(o_info + info_doubles * 8);   // time-unit flag + ticket: zero in the upload, so no memset
+  const size_t o_imu = al(o_flag + 16), o_msg = al(o_imu + (7 * M + 9 * H) * 8), in_end = al(o_msg + n * point_step);
+  const size_t o_bparts = in_end;
   const bool packed = precision == GCL_F32C;
-  const size_t o_pts = al(o_flag + 16), o_ts = al(o_pts + (size_t)n_sel * (packed ? 16 : 24));
+  const size_t o_pts = al(o_bparts + (size_t)(grid_ingest > 0 ? grid_ingest : 1) * 16), o_ts = al(o_pts + (size_t)n_sel * (packed ? 16 : 24));
   const size_t o_w = al(o_ts + (packed ? 0 : (size_t)n_sel * 8)), o_parts = al(o_w + n * (packed ? 4 : 8));
   const size_t o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8), d_end = al(o_stats + H * srec * 8);
   rc = grow(h, &S.d_buf, &S.d_bytes, &S.h_buf, &S.h_bytes, d_end, in_end);
@@ -683,6 +684,7 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
   }
   double* hinfo = reinterpret_cast<double*>(hb + o_info);
   memset(hinfo, 0, info_doubles * 8);
+  memset(hb + o_flag, 0, 16);
   hinfo[GCL_MSG_INFO_N_POINTS] = (double)n_points; hinfo[GCL_MSG_INFO_STRIDE] = (double)stride; hinfo[GCL_MSG_INFO_N_SEL] = (double)n_sel;
   if (xi_host)
     for (size_t i = 0; i < H; ++i)
@@ -713,7 +715,7 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
   if (packed) { IP.packed_xyzt = reinterpret_cast<float4*>(db + o_pts); IP.packed_w = reinterpret_cast<float*>(db + o_w); }
   else { IP.points_out = reinterpret_cast<double*>(db + o_pts); IP.timestamps_out = reinterpret_cast<double*>(db + o_ts);
          IP.weights_out = reinterpret_cast<double*>(db + o_w); }
-  IP.flag = reinterpret_cast<int*>(db + o_flag);
+  IP.flag = reinterpret_cast<int*>(db + o_flag); IP.flag_is_zero = 1;
   IP.compact_stride = (int)stride;
   IP.bounds_parts = reinterpret_cast<double*>(db + o_bparts);
   IP.bounds_out = d_info; IP.bounds_jobs = d_jobs; IP.bounds_n_jobs = n_hyp; IP.bounds_dev = d_info;

@@ -3,9 +3,9 @@
 // Replaces smooth_window_weights + preintegrate_imu_relative_pose_jax (pkg/backend/operators/imu_preintegration.py:19-43,
 // :46-147) + se3_log (pkg/common/geometry/se3_jax.py:179-256) as called at pkg/backend/pipeline.py:437-483.  The reference
 // walks the M samples with a sequential lax.scan (its dominant per-scan cost, docs/PIPELINE_DESIGN_GAPS.md:200-214).  Here
-// one warp handles one hypothesis (start orientation + biases); the recurrences are evaluated as scans:
-//   R_k = R_start dR_0 ... dR_{k-1}      exclusive prefix PRODUCT of the per-sample rotations (lane-local products, then a
-//                                        warp scan of 3x3 matrices)
+// one CTA of 256 threads handles one hypothesis (start orientation + biases); the recurrences are evaluated as scans:
+//   R_k = R_start dR_0 ... dR_{k-1}      exclusive prefix PRODUCT of the per-sample rotations (thread-local products, then a
+//                                        warp scan of 3x3 matrices and a pass over the warp totals)
 //   v, p                                 prefix sums once R_k is known (p needs the incoming v of every lane's chunk)
 // Re-association changes the result at the 1e-15 level against the sample-by-sample order.
 #include "gcl_internal.cuh"
@@ -38,16 +38,22 @@ __device__ __forceinline__ double imu_weight(const ImuParams& P, int i) {
   return window_weight64(P.stamps[i], t0, t1, sigma, 1e-12);   // GC_WEIGHT_FLOOR, constants.py:256
 }
 
-__global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_constant__ ImuParams P) {
-  const int h = blockIdx.x, lane = threadIdx.x, M = P.M;
-  const int C = (M + 31) / 32;
-  const int i0 = lane * C < M ? lane * C : M, i1 = (lane + 1) * C < M ? (lane + 1) * C : M;
+constexpr int kImuThreads = 256;            // one CTA per hypothesis; 512 samples -> 2 per thread
+constexpr int kImuWarps = kImuThreads / 32;
+
+__global__ void __launch_bounds__(kImuThreads) imu_preintegrate_kernel(const __grid_constant__ ImuParams P) {
+  __shared__ double s_wtot[kImuWarps][9];   // per-warp rotation products
+  __shared__ double s_vtot[kImuWarps][3];   // per-warp velocity gains
+  __shared__ double s_sum[kImuWarps][17];   // per-warp totals
+  const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = P.M;
+  const int C = (M + kImuThreads - 1) / kImuThreads;
+  const int i0 = tid * C < M ? tid * C : M, i1 = (tid + 1) * C < M ? (tid + 1) * C : M;
   const double bg[3] = {P.gyro_bias[h * 3], P.gyro_bias[h * 3 + 1], P.gyro_bias[h * 3 + 2]};
   const double ba[3] = {P.accel_bias[h * 3], P.accel_bias[h * 3 + 1], P.accel_bias[h * 3 + 2]};
   double R_start[9];
   so3_exp(P.rotvec_start + h * 3, R_start);
 
-  // ---- pass 1: product of this lane's per-sample rotations, sum of weights ---------------------------------------------
+  // ---- pass 1: product of this thread's per-sample rotations, sum of weights --------------------------------------------
   double Pm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ess = 0.0;
   for (int i = i0; i < i1; ++i) {
     const double w = imu_weight(P, i);
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_const
     for (int k = 0; k < 9; ++k) Pm[k] = T[k];
     ess += w;
   }
-  // ---- inclusive warp scan of the lane products (earlier lanes multiply from the LEFT) -----------------------------------
+  // ---- inclusive scan of the thread products (earlier threads multiply from the LEFT): warp scan, then warp totals --------
   double Q[9];
   for (int k = 0; k < 9; ++k) Q[k] = Pm[k];
   for (int o = 1; o < 32; o <<= 1) {
@@ -72,14 +78,28 @@ __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_const
       for (int k = 0; k < 9; ++k) Q[k] = T[k];
     }
   }
-  double Rc[9], E[9];   // orientation at the start of this lane's chunk = R_start * (exclusive prefix)
+  if (lane == 31)
+    for (int k = 0; k < 9; ++k) s_wtot[warp][k] = Q[k];
+  __syncthreads();
+  double E[9];   // exclusive prefix of this thread = (warps before) * (lanes before)
   for (int k = 0; k < 9; ++k) {
     const double up = __shfl_up_sync(0xffffffffu, Q[k], 1);
     E[k] = (lane == 0) ? ((k % 4 == 0) ? 1.0 : 0.0) : up;
   }
-  mat3_mul(R_start, E, Rc);
-  double Qtot[9];
-  for (int k = 0; k < 9; ++k) Qtot[k] = __shfl_sync(0xffffffffu, Q[k], 31);
+  double Wp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Qtot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int w = 0; w < kImuWarps; ++w) {
+    double T[9];
+    if (w == warp)
+      for (int k = 0; k < 9; ++k) Wp[k] = Qtot[k];
+    mat3_mul(Qtot, s_wtot[w], T);
+    for (int k = 0; k < 9; ++k) Qtot[k] = T[k];
+  }
+  double Rc[9];   // orientation at the start of this thread's chunk
+  {
+    double T[9];
+    mat3_mul(Wp, E, T);
+    mat3_mul(R_start, T, Rc);
+  }
 
   // ---- pass 2: accelerations in the world frame, local velocity / position integrals, weighted means ---------------------
   double v[3] = {0, 0, 0}, p[3] = {0, 0, 0}, Tl = 0.0, s_ab[3] = {0, 0, 0}, s_awn[3] = {0, 0, 0}, s_aw[3] = {0, 0, 0};
@@ -99,11 +119,13 @@ __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_const
       p[r] = p[r] + v[r] * dte + 0.5 * aw[r] * (dte * dte);
       v[r] = v[r] + aw[r] * dte;
     }
-    const double om[3] = {(P.gyro[i * 3] - bg[0]) * dte, (P.gyro[i * 3 + 1] - bg[1]) * dte, (P.gyro[i * 3 + 2] - bg[2]) * dte};
-    double dR[9], T[9];
-    so3_exp(om, dR);
-    mat3_mul(Rc, dR, T);
-    for (int k = 0; k < 9; ++k) Rc[k] = T[k];
+    if (i + 1 < i1) {
+      const double om[3] = {(P.gyro[i * 3] - bg[0]) * dte, (P.gyro[i * 3 + 1] - bg[1]) * dte, (P.gyro[i * 3 + 2] - bg[2]) * dte};
+      double dR[9], T[9];
+      so3_exp(om, dR);
+      mat3_mul(Rc, dR, T);
+      for (int k = 0; k < 9; ++k) Rc[k] = T[k];
+    }
   }
   // incoming velocity of every chunk = exclusive prefix sum of the local velocity gains; position: p_end = sum_l (p_l + v_in,l T_l)
   double vin[3];
@@ -113,16 +135,28 @@ __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_const
       const double up = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += up;
     }
+    if (lane == 31) s_vtot[warp][r] = inc;
     vin[r] = inc - v[r];
   }
-  double tot[22];
+  __syncthreads();
+  for (int r = 0; r < 3; ++r)
+    for (int w = 0; w < warp; ++w) vin[r] += s_vtot[w][r];
+  double tot[17];
   for (int r = 0; r < 3; ++r) {
     tot[r] = p[r] + vin[r] * Tl; tot[3 + r] = v[r]; tot[6 + r] = s_ab[r]; tot[9 + r] = s_awn[r]; tot[12 + r] = s_aw[r];
   }
   tot[15] = Tl; tot[16] = ess;
-  for (int k = 0; k < 17; ++k)
+  for (int k = 0; k < 17; ++k) {
     for (int o = 16; o > 0; o >>= 1) tot[k] += __shfl_xor_sync(0xffffffffu, tot[k], o);
-  if (lane != 0) return;
+    if (lane == 0) s_sum[warp][k] = tot[k];
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  for (int k = 0; k < 17; ++k) {
+    double a = s_sum[0][k];
+    for (int w = 1; w < kImuWarps; ++w) a += s_sum[w][k];
+    tot[k] = a;
+  }
 
   double* out = P.out + (size_t)h * GCL_IMU_DOUBLES;
   double R_end[9], dR[9], rot[3];
@@ -153,7 +187,7 @@ __global__ void __launch_bounds__(32) imu_preintegrate_kernel(const __grid_const
 }
 
 cudaError_t launch_imu_preintegrate(const ImuParams& P, int n_hyp, cudaStream_t stream) {
-  imu_preintegrate_kernel<<<n_hyp, 32, 0, stream>>>(P);
+  imu_preintegrate_kernel<<<n_hyp, kImuThreads, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

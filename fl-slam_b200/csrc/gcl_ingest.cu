@@ -30,54 +30,27 @@ __device__ __forceinline__ double decode_field(const unsigned char* p, int datat
   }
 }
 
-// pass 1 (only when the message carries per-point time): does ANY raw time value exceed 1e6?  (backend_node.py:437-441:
-// such a message is in nanoseconds and every value is scaled by 1e-9).  With bounds_parts it also leaves this CTA's
-// minimum / maximum raw time value (scaling by a positive constant is monotone, so the unit can be applied afterwards).
-__global__ void __launch_bounds__(kIngestThreads) ingest_time_unit_kernel(const __grid_constant__ IngestParams P) {
-  const int64_t i = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
-  bool big = false;
-  double lo = 1.0e300, hi = -1.0e300;
-  if (i < P.n_points) {
-    const double v = decode_field(P.data + i * P.point_step + P.off[4], P.dtype[4]);
-    big = v > 1e6;
-    lo = hi = v;
-  }
-  if (__syncthreads_or(big) && threadIdx.x == 0) atomicOr(P.flag, 1);
-  if (P.bounds_parts) {
-    __shared__ double s_lo[kIngestThreads / 32], s_hi[kIngestThreads / 32];
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kIngestThreads / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
-      P.bounds_parts[2 * blockIdx.x] = lo; P.bounds_parts[2 * blockIdx.x + 1] = hi;
-    }
-  }
-}
-
 // Scan time bounds from the per-point times and the header stamp (pkg/backend/backend_node.py:1776-1786):
 //   |max - min| < 1e-9 : start = min, end = header stamp;   else  start = min(stamp, min), end = max(stamp, max).
 // One CTA: reduces the per-CTA extrema of pass 1, applies the time unit, writes the bounds record
-// [start, end, min, max, unit flag] and patches the window of the n_jobs job records of this scan.
-__global__ void __launch_bounds__(kIngestThreads) scan_bounds_kernel(const __grid_constant__ IngestParams P, int n_parts, gcl_job* jobs, int n_jobs) {
+// [start, end, min, max, unit flag] and patches the window of the job records of this scan.
+__device__ __forceinline__ void scan_bounds_block(const IngestParams& P, int n_parts) {
   __shared__ double s_lo[kIngestThreads / 32], s_hi[kIngestThreads / 32];
   __shared__ double s_b[2];
   double lo = 1.0e300, hi = -1.0e300;
   if (P.off[4] >= 0) {
-    for (int k = threadIdx.x; k < n_parts; k += kIngestThreads) { lo = fmin(lo, P.bounds_parts[2 * k]); hi = fmax(hi, P.bounds_parts[2 * k + 1]); }
+    for (int k = threadIdx.x; k < n_parts; k += kIngestThreads) { lo = fmin(lo, __ldcg(P.bounds_parts + 2 * k)); hi = fmax(hi, __ldcg(P.bounds_parts + 2 * k + 1)); }
   }
   for (int o = 16; o > 0; o >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
+  __syncthreads();   // (the caller's use of these arrays is over)
   if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < kIngestThreads / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
-    const int ns = *P.flag;
+    const int ns = __ldcg(P.flag);
     double tmin, tmax;
     if (P.off[4] >= 0 && P.n_points > 0) { tmin = ns ? lo * 1e-9 : lo; tmax = ns ? hi * 1e-9 : hi; }
     else { tmin = tmax = P.header_stamp; }
@@ -88,8 +61,44 @@ __global__ void __launch_bounds__(kIngestThreads) scan_bounds_kernel(const __gri
     s_b[0] = t0; s_b[1] = t1;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < n_jobs; j += kIngestThreads) { jobs[j].scan_start_time = s_b[0]; jobs[j].scan_end_time = s_b[1]; }
+  for (int j = threadIdx.x; j < P.bounds_n_jobs; j += kIngestThreads) { P.bounds_jobs[j].scan_start_time = s_b[0]; P.bounds_jobs[j].scan_end_time = s_b[1]; }
 }
+
+// pass 1 (only when the message carries per-point time): does ANY raw time value exceed 1e6?  (backend_node.py:437-441:
+// such a message is in nanoseconds and every value is scaled by 1e-9).  With bounds_parts it also leaves this CTA's
+// minimum / maximum raw time value (scaling by a positive constant is monotone, so the unit can be applied afterwards), and
+// the CTA that finishes last (ticket in flag[1]) turns the extrema into the scan bounds.
+__global__ void __launch_bounds__(kIngestThreads) ingest_time_unit_kernel(const __grid_constant__ IngestParams P) {
+  const int64_t i = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
+  bool big = false;
+  double lo = 1.0e300, hi = -1.0e300;
+  if (i < P.n_points) {
+    const double v = decode_field(P.data + i * P.point_step + P.off[4], P.dtype[4]);
+    big = v > 1e6;
+    lo = hi = v;
+  }
+  if (__syncthreads_or(big) && threadIdx.x == 0) atomicOr(P.flag, 1);
+  if (!P.bounds_parts) return;
+  __shared__ double s_lo[kIngestThreads / 32], s_hi[kIngestThreads / 32];
+  __shared__ int s_last;
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kIngestThreads / 32; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+    P.bounds_parts[2 * blockIdx.x] = lo; P.bounds_parts[2 * blockIdx.x + 1] = hi;
+    __threadfence();
+    s_last = atomicAdd(P.flag + 1, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && P.bounds_out) { __threadfence(); scan_bounds_block(P, (int)gridDim.x); }
+}
+
+// the bounds alone (message without a per-point time field, or an empty message)
+__global__ void __launch_bounds__(kIngestThreads) scan_bounds_kernel(const __grid_constant__ IngestParams P) { scan_bounds_block(P, 0); }
 
 __global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const __grid_constant__ IngestParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -156,18 +165,17 @@ cudaError_t launch_ingest(const IngestParams& P, cudaStream_t stream, int* launc
   *launches = 0;
   if (P.n_points <= 0 && !P.bounds_out) return cudaSuccess;
   const int grid = (int)((P.n_points + kIngestThreads - 1) / kIngestThreads);
-  cudaError_t e = cudaMemsetAsync(P.flag, 0, sizeof(int), stream);
-  if (e != cudaSuccess) return e;
+  cudaError_t e;
+  if (!P.flag_is_zero && (e = cudaMemsetAsync(P.flag, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
   if (P.off[4] >= 0 && grid > 0) {
-    ingest_time_unit_kernel<<<grid, kIngestThreads, 0, stream>>>(P);
+    ingest_time_unit_kernel<<<grid, kIngestThreads, 0, stream>>>(P);   // with bounds_out: its last CTA writes the bounds
+    *launches += 1;
+  } else if (P.bounds_out) {
+    scan_bounds_kernel<<<1, kIngestThreads, 0, stream>>>(P);
     *launches += 1;
   }
-  if (P.bounds_out) {
-    scan_bounds_kernel<<<1, kIngestThreads, 0, stream>>>(P, grid, P.bounds_jobs, P.bounds_n_jobs);
-    *launches += 1;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
-  if (P.defer_decode || grid == 0) return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (P.defer_decode || grid == 0) return cudaSuccess;
   return launch_ingest_decode(P, stream, launches);
 }
 

@@ -143,7 +143,8 @@ struct IngestParams {
   double* points_out; double* timestamps_out; double* weights_out;
   unsigned char* ring_out; unsigned char* tag_out;
   float4* packed_xyzt; float* packed_w; double packed_t0;
-  int* flag;                   // device scratch: "per-point time is in nanoseconds"
+  int* flag;                   // device scratch, 2 ints: "per-point time is in nanoseconds", ticket counter of pass 1
+  int flag_is_zero;            // the caller already zeroed flag[0..1] (e.g. as part of an upload): no memset
   // message -> evidence path (gcl_scan_submit_msg_host): everything below may stay zero for the stand-alone operator
   int compact_stride;          // > 1: points / times are written only for raw rows k * stride, at index k (weights: every row)
   double* bounds_parts;        // device scratch, 2 doubles per CTA of pass 1: extrema of the raw per-point time

@@ -24,6 +24,9 @@ _lib = _abi.lib
 PRECISIONS = {"fp64": _abi.GCL_F64, "fp32c": _abi.GCL_F32C}
 
 
+_EMPTY_XI: Dict[int, np.ndarray] = {}   # (H, 0) placeholders: the message path carries no host-side twist array
+
+
 @dataclass
 class ResidentScan:
     """A raw scan resident in HBM, in one of the two layouts of include/gcl_b200.h."""
@@ -328,7 +331,7 @@ class LidarEvidencePipeline:
         if hit is not None and hit[0] is a:
             return hit[1]
         addr = a.ctypes.data
-        if len(self._ptr_cache) > 64:
+        if len(self._ptr_cache) > 512:   # small arrays only (map statistics, IW state, IMU buffers, extrinsics)
             self._ptr_cache.clear()
         self._ptr_cache[id(a)] = (a, addr)   # holding `a` keeps id(a) from being reused by another object
         return addr
@@ -381,42 +384,54 @@ class LidarEvidencePipeline:
             dt = np.array([fmap[k][1] for k in order] + ([] if tname else [0]), dtype=np.int32)
             if any(d < 1 or d > 8 for d in dt[:len(order)]):
                 raise ValueError(f"Unsupported PointField datatype: {[int(d) for d in dt]}")
-            lay = self._msg_layouts[key] = (off, dt)
-        off, dt = lay
+            lay = self._msg_layouts[key] = (off, dt, off.ctypes.data, dt.ctypes.data)
+        off_p, dt_p = lay[2], lay[3]
         n = int(n_points)
         raw = data if (type(data) is np.ndarray and data.dtype == np.uint8 and data.flags.c_contiguous) else np.frombuffer(bytes(data), dtype=np.uint8)
         if raw.size < n * int(point_step):
             raise ValueError("message data is shorter than n_points * point_step")
-        f = self._f64
-        R = None if R_base_lidar is None else f(R_base_lidar, (9,))
-        t = None if t_base_lidar is None else f(t_base_lidar, (3,))
-        p = lambda a: None if a is None else a.ctypes.data
+        c, ad = self._c64, self._addr
+        R = None if R_base_lidar is None else c(R_base_lidar, 9)
+        t = None if t_base_lidar is None else c(t_base_lidar, 3)
         if xi_body is not None:
-            xi = f(xi_body, (-1, 6))
-            H = xi.shape[0]
-            imu_args = (p(xi), None, None, None, 0, 0.0, None, None, None, None, 0)
+            xi = c(xi_body, 0, 6)
+            H = xi.size // 6
+            imu_args = (ad(xi), None, None, None, 0, 0.0, None, None, None, None, 0)
             keep = (xi,)
         else:
-            st, gy, ac = f(imu["stamps"], (-1,)), f(imu["gyro"], (-1, 3)), f(imu["accel"], (-1, 3))
-            M = st.shape[0]
-            if gy.shape[0] != M or ac.shape[0] != M:
+            st, gy, ac = c(imu["stamps"], 0, 1), c(imu["gyro"], 0, 3), c(imu["accel"], 0, 3)
+            M = st.size
+            if gy.size != 3 * M or ac.size != 3 * M:
                 raise ValueError("imu stamps, gyro and accel must have the same length")
-            rv, bg, ba = f(imu["rotvec_start_WB"], (-1, 3)), f(imu["gyro_bias"], (-1, 3)), f(imu["accel_bias"], (-1, 3))
-            H = rv.shape[0]
-            if bg.shape[0] != H or ba.shape[0] != H:
+            rv, bg, ba = c(imu["rotvec_start_WB"], 0, 3), c(imu["gyro_bias"], 0, 3), c(imu["accel_bias"], 0, 3)
+            H = rv.size // 3
+            if bg.size != 3 * H or ba.size != 3 * H:
                 raise ValueError("rotvec_start_WB, gyro_bias and accel_bias must have one row per hypothesis")
-            grav = f(imu["gravity_W"], (3,))
-            imu_args = (None, p(st), p(gy), p(ac), M, float(imu["sigma"]), p(rv), p(bg), p(ba), p(grav),
+            grav = c(imu["gravity_W"], 3)
+            imu_args = (None, ad(st), ad(gy), ad(ac), M, float(imu["sigma"]), ad(rv), ad(bg), ad(ba), ad(grav),
                         1 if imu.get("deskew_rotation_only", False) else 0)
             keep = (st, gy, ac, rv, bg, ba, grav)
         bins_host = getattr(self, "_bins_host", None)
         if bins_host is None:
             bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
-        self._inflight[slot] = (raw, keep, None, np.empty((H, 0)), n)     # keep the arrays alive while the copy is in flight
-        _abi.check(_lib.gcl_scan_submit_msg_host(self.handle, int(slot), p(raw), n, int(point_step), p(off), p(dt), float(header_stamp_sec),
-                                                 p(R), p(t), self.n_points_cap, *imu_args, H, self._addr(self.origin), self._addr(bins_host),
+        ph = _EMPTY_XI.get(H)
+        if ph is None:
+            ph = _EMPTY_XI[H] = np.empty((H, 0))
+        self._inflight[slot] = (raw, keep, None, ph, n)   # arrays stay alive while the copy is in flight
+        _abi.check(_lib.gcl_scan_submit_msg_host(self.handle, int(slot), raw.ctypes.data, n, int(point_step), off_p, dt_p, float(header_stamp_sec),
+                                                 ad(R), ad(t), self.n_points_cap, *imu_args, H, ad(self.origin), ad(bins_host),
                                                  self.n_bins, self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
         return H
+
+    @staticmethod
+    def _c64(a, size: int, mult: int = 1):
+        """``a`` as a float64 C-contiguous array whose size is ``size`` (or, with size 0, a multiple of ``mult``): no copy and no
+        new object when it already is one (only its address is needed, so the shape itself does not matter)."""
+        if not (type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous):
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if (size and a.size != size) or (not size and a.size % mult):
+            raise ValueError(f"array of {a.size} elements where {'%d' % size if size else 'a multiple of %d' % mult} were expected")
+        return a
 
     def msg_info_host(self, slot: int, n_hyp: int = 1) -> Dict[str, Any]:
         """What the device derived from the message submitted to ``slot`` (gcl_scan_msg_info_host): the scan time bounds, the
