@@ -78,6 +78,7 @@ void gcl_destroy(gcl_handle h) {
   }
   if (h->d_buf) cudaFree(h->d_buf);
   if (h->h_buf) cudaFreeHost(h->h_buf);
+  if (h->done_flag) cudaFreeHost(h->done_flag);
   delete h;
 }
 
@@ -500,6 +501,18 @@ struct HostTiming {
 };
 static HostTiming g_ht;
 
+// GCL_STAGE2_TRACE=1: host-side timeline of the single-launch evidence step, averaged over 64 calls (begin: enqueue;
+// gap: between begin returning and end being called; wait: polling in end; out: copying the results to the caller) and the
+// chain kernel's own duration from a pair of events
+struct Stage2Trace {
+  bool on; int n; double acc[5]; std::chrono::steady_clock::time_point t0, t1; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  Stage2Trace() : on(getenv("GCL_STAGE2_TRACE") != nullptr), n(0) { for (double& a : acc) a = 0; }
+  static double us(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  }
+};
+static Stage2Trace g_s2;
+
 // Is this host pointer page-locked?  The answer only selects between copying straight from the caller's array and staging
 // through the pinned block -- both are correct whatever the truth is -- so the last few answers are remembered per handle
 // (cudaPointerGetAttributes costs ~1 us a call; a scan stream reuses the same buffers).
@@ -782,6 +795,7 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
   GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
   cudaSetDevice(h->device);
+  if (g_s2.on) g_s2.t0 = std::chrono::steady_clock::now();
   const size_t B = S.n_bins, H = S.n_hyp;
   const size_t srec = gcl_stats_record_doubles(S.n_bins);
   // stage-2 block, mirrored in pinned memory: [pose][pose_update][map][iw] | [stats][evidence] | map-derived scratch
@@ -792,16 +806,24 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   const size_t d_end = al(io_end + B * 16 * 8);
   int rc = grow(h, &h->d_buf, &h->d_bytes, &h->h_buf, &h->h_bytes, d_end, io_end);
   if (rc != GCL_OK) return rc;
+  if (!h->done_flag) {
+    GCL_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->done_flag), 64));
+    *h->done_flag = 0;
+  }
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
   unsigned char* db = static_cast<unsigned char*>(h->d_buf);
   cudaStream_t st = h->stream;
+  // small blocks (one or a few hypotheses): ONE launch, the chain kernel stages its own inputs and outputs across PCIe and the
+  // host polls a ticket; large blocks (many hypotheses) go through the copy engine
+  static const bool single_launch_ok = !(getenv("GCL_HOST_SINGLE_LAUNCH") && atoi(getenv("GCL_HOST_SINGLE_LAUNCH")) == 0);
+  const bool single = single_launch_ok && !g_ht.on && (io_end - o_map) <= 96 * 1024;
   double* hm = reinterpret_cast<double*>(hb + o_map);
   memcpy(hm, mS_dir, B * 24); memcpy(hm + 3 * B, mS_sc, B * 72); memcpy(hm + 12 * B, mN_dir, B * 8);
   memcpy(hm + 13 * B, mN_pos, B * 8); memcpy(hm + 14 * B, msum_p, B * 24); memcpy(hm + 17 * B, msum_ppT, B * 72);
   memcpy(hb + o_pose, pose_host, H * 48);
   if (pose_update_host) memcpy(hb + o_pupd, pose_update_host, 48);
   if (iw_state_host) memcpy(hb + o_iw, iw_state_host, 80);
-  GCL_CUDA(h, cudaMemcpyAsync(db + o_pose, hb + o_pose, (o_iw + 80) - o_pose, cudaMemcpyHostToDevice, st));
+  if (!single) GCL_CUDA(h, cudaMemcpyAsync(db + o_pose, hb + o_pose, (o_iw + 80) - o_pose, cudaMemcpyHostToDevice, st));
   GCL_CUDA(h, cudaStreamWaitEvent(st, S.ev_stage1, 0));
   double* dm = reinterpret_cast<double*>(db + o_map);
   double* d_stats = reinterpret_cast<double*>(db + o_stats);
@@ -809,6 +831,37 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   double* d_mder = reinterpret_cast<double*>(db + io_end);
   double* d_iw = iw_state_host ? reinterpret_cast<double*>(db + o_iw) : nullptr;
   // the chain step rewrites Sigma_p in the stats records: work on the copy that travels back
+  if (single) {
+    ChainParams P;
+    P.stats = d_stats; P.stats_stride = (int64_t)srec;
+    P.map_S_dir = dm; P.map_S_dir_scatter = dm + 3 * B; P.map_N_dir = dm + 12 * B; P.map_N_pos = dm + 13 * B; P.map_sum_p = dm + 14 * B;
+    P.map_sum_ppT = dm + 17 * B; P.workspace = d_mder; P.pose_pred = reinterpret_cast<const double*>(db + o_pose);
+    P.pose_update = pose_update_host ? reinterpret_cast<const double*>(db + o_pupd) : nullptr;
+    P.iw_state = d_iw; P.evidence = d_evid; P.n_scans = 1; P.n_hyp = S.n_hyp; P.n_bins = S.n_bins;
+    P.use_sigma_meas = use_sigma_meas; P.forgetting = forgetting; P.iw_rho = 0.99 /* GC_IW_RHO_MEAS_LIDAR, constants.py:281 */;
+    P.iw_nu_weak_add = 0.5 /* GC_IW_NU_WEAK_ADD, :164 */; P.iw_nu_max = 1000.0; P.eps_psd = S.eps_psd; P.eps_mass = S.eps_mass;
+    P.chain_smem = 0;
+    P.stage_in_src = reinterpret_cast<const double*>(hb + o_pose); P.stage_in_dst = reinterpret_cast<double*>(db + o_pose);
+    P.stage_in_doubles = (int)(((o_iw + 80) - o_pose) / 8);
+    P.stats_src = S.d_stats; P.stats_doubles = (int)(H * srec);
+    P.stage_out_src = reinterpret_cast<const double*>(db + o_map); P.stage_out_dst = reinterpret_cast<double*>(hb + o_map);
+    P.stage_out_doubles = (int)((io_end - o_map) / 8);
+    P.done_flag = h->done_flag; P.done_value = ++h->done_seq;
+    int l = 0;
+    if (g_s2.on) {
+      if (!g_s2.e0) { cudaEventCreate(&g_s2.e0); cudaEventCreate(&g_s2.e1); }
+      cudaEventRecord(g_s2.e0, st);
+    }
+    GCL_CUDA(h, launch_chain(P, st, &l));
+    if (g_s2.on) { cudaEventRecord(g_s2.e1, st); g_s2.t1 = std::chrono::steady_clock::now(); g_s2.acc[0] += Stage2Trace::us(g_s2.t0, g_s2.t1); }
+    h->launches += l;
+    h->stage2_slot = slot_index;
+    h->stage2_has_update = pose_update_host != nullptr;
+    h->stage2_has_iw = iw_state_host != nullptr;
+    h->stage2_single = true;
+    return GCL_OK;
+  }
+  h->stage2_single = false;
   GCL_CUDA(h, cudaMemcpyAsync(d_stats, S.d_stats, H * srec * 8, cudaMemcpyDeviceToDevice, st));
   rc = gcl_scan_chain(h, st, d_stats, (int64_t)srec, 1, S.n_hyp, S.n_bins, dm, dm + 3 * B, dm + 12 * B, dm + 13 * B, dm + 14 * B,
                       dm + 17 * B, d_mder, reinterpret_cast<const double*>(db + o_pose),
@@ -843,7 +896,28 @@ int gcl_scan_evidence_end_host(gcl_handle h, double* mS_dir, double* mS_sc, doub
   const size_t o_evid = al(o_stats + H * srec * 8);
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
   cudaStream_t st = h->stream;
-  GCL_CUDA(h, cudaStreamSynchronize(st));
+  std::chrono::steady_clock::time_point tr_a;
+  if (g_s2.on && h->stage2_single) { tr_a = std::chrono::steady_clock::now(); g_s2.acc[1] += Stage2Trace::us(g_s2.t1, tr_a); }
+  if (h->stage2_single) {
+    // poll the ticket the chain kernel writes after its outputs (a stream synchronisation costs ~8 us of wake-up latency);
+    // fall back to the stream if it does not arrive, which also surfaces a kernel fault
+    const unsigned long long want = h->done_seq;
+    const auto t_start = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (__atomic_load_n(h->done_flag, __ATOMIC_ACQUIRE) != want) {
+      if ((++spins & 0x3ff) == 0 && std::chrono::steady_clock::now() - t_start > std::chrono::seconds(2)) {
+        GCL_CUDA(h, cudaStreamSynchronize(st));
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  } else {
+    GCL_CUDA(h, cudaStreamSynchronize(st));
+  }
+  std::chrono::steady_clock::time_point tr_b;
+  if (g_s2.on && h->stage2_single) { tr_b = std::chrono::steady_clock::now(); g_s2.acc[2] += Stage2Trace::us(tr_a, tr_b); }
   S.pending = false;
   h->stage2_slot = -1;
   g_ht.mark(5, h, false);
@@ -857,6 +931,18 @@ int gcl_scan_evidence_end_host(gcl_handle h, double* mS_dir, double* mS_sc, doub
   if (h->stage2_has_iw) memcpy(iw_state_host, hb + o_iw, 80);
   g_ht.mark(6, h, false);
   g_ht.done();
+  if (g_s2.on && h->stage2_single) {
+    g_s2.acc[3] += Stage2Trace::us(tr_b, std::chrono::steady_clock::now());
+    float ms = 0.f;
+    cudaEventSynchronize(g_s2.e1);
+    cudaEventElapsedTime(&ms, g_s2.e0, g_s2.e1);
+    g_s2.acc[4] += 1e3 * ms;
+    if (++g_s2.n == 64) {
+      fprintf(stderr, "[gcl stage 2, us/call] begin %.1f | gap %.1f | wait %.1f | out %.1f | chain kernel (events) %.1f\n", g_s2.acc[0] / 64,
+              g_s2.acc[1] / 64, g_s2.acc[2] / 64, g_s2.acc[3] / 64, g_s2.acc[4] / 64);
+      g_s2.n = 0; for (double& a : g_s2.acc) a = 0;
+    }
+  }
   return GCL_OK;
 }
 

@@ -6,9 +6,18 @@
 // metrics), :155-256 + :264-394 (Matrix Fisher), :413-499 + :502-671 (planar translation), :729-756 (22-D);
 // pkg/backend/operators/measurement_noise_iw_jax.py:37-127 (LiDAR measurement-noise inverse-Wishart block).
 // The 3x3 SVD / symmetric eigen / LU routines are in gcl_math.cuh.  All arithmetic is binary64.
+#define GCL_HEAVY __noinline__   // see gcl_math.cuh
 #include "gcl_internal.cuh"
 
 namespace gcl {
+
+constexpr int kChainThreads = 128;   // CTA of the chain / evidence kernels
+#ifdef GCL_CHAIN_TRACE
+__device__ long long g_chain_trace[32];
+#define TR(i) do { if ((threadIdx.x & 31) == 0) { g_chain_trace[i] = clock64(); if ((i) == 0 || (i) == 19) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_chain_trace[(i) == 0 ? 30 : 31] = gt; } } } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
 
 // ---- map-derived statistics of one bin (archive/bin_atlas.py:166-200) -----------------------------------------------
 __device__ __forceinline__ void map_derived_bin(const double* S_dir, const double* N_dir, const double* N_pos,
@@ -171,10 +180,14 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
                                    const double* map_N_dir, const double* map_N_pos, const double* map_derived,
                                    const double* pose, const double* R_hat_override, int B, double eps_psd, double eps,
                                    int do_rotation, int do_translation, double* ev, double* iw_out, int role = 0,
-                                   double* s_l13 = nullptr, int bar_id = 0) {
+                                   double* s_l13 = nullptr, int bar_id = 0, int pre_bar = 0, int iw_bar = 0) {
   // role 0: everything on this warp.  Roles 1 / 2 split one hypothesis over a PAIR of warps (the latency-critical single-scan
   // chain): role 2 computes the scan / map scatter metrics (two symmetric eigen problems) while role 1 runs the SVD chain;
   // they meet at named barrier `bar_id` (64 threads) where role 2 hands over the map eigenvalues through s_l13.
+  // pre_bar (role 1, single-scan chain): the rotation part needs neither the bin covariances nor the map-derived statistics,
+  // so it runs while other warps prepare those; this warp waits on named barrier `pre_bar` (whole CTA) only before the
+  // translation part.  iw_bar: the residual statistics are handed to the warp that runs the IW update (arrive, 64 threads)
+  // BEFORE this warp's lane 0 finishes the translation evidence, so the two run side by side.
   const StatsLayout SL(B);
   const double* sN = st + SL.N();
   const double* s_dir = st + SL.s_dir();
@@ -210,10 +223,12 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
       for (int j = 0; j < 3; ++j) H[i * 3 + j] += w * (sm[i] * inm) * (ss[j] * ins);
     Neff += w;
   }
+  if (role == 1) TR(2);
   if (role != 2) {
     for (int i = 0; i < 9; ++i) H[i] = warp_sum(H[i]);
     Neff = warp_sum(Neff);
   }
+  if (role == 1) TR(3);
   if (role != 1) {
     for (int i = 0; i < 9; ++i) { scanT[i] = warp_sum(scanT[i]); mapT[i] = warp_sum(mapT[i]); }
     sumNs = warp_sum(sumNs); sumNm = warp_sum(sumNm);
@@ -237,6 +252,7 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
     if (role == 2 && lane == 2) { s_l13[0] = m8[0]; s_l13[1] = m8[2]; }
   }
   if (role == 2) {
+    TR(14);
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     return;
   }
@@ -278,6 +294,7 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
     }
     for (int i = 0; i < 9; ++i) R_hat[i] = __shfl_sync(0xffffffffu, R_hat[i], 0);
   }
+  if (role == 1) TR(4);
   double l1m = __shfl_sync(0xffffffffu, map_eval[0], 2), l3m = __shfl_sync(0xffffffffu, map_eval[2], 2);
   if (role == 1) {
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
@@ -288,9 +305,12 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
   if (!do_translation) return;
 
   double Lf[9], hf[3], NeffT, tw[3];
+  if (role == 1) TR(5);
+  if (pre_bar) asm volatile("bar.sync %0, %1;" ::"r"(pre_bar), "r"(kChainThreads) : "memory");
+  if (role == 1) TR(6);
   translation_sums_warp(lane, B, R_hat, p_bar, Sig_p, sN, m_cen, m_Sig, map_N_pos, eps, Lf, hf, NeffT);
   translation_solve(Lf, hf, eps, tw);
-  if (lane == 0) translation_finish(Lf, tw, NeffT, l1m, l3m, pose, eps_psd, eps, ev);
+  if (role == 1) TR(7);
   if (iw_out) {  // residual sufficient statistics for the measurement-noise IW update (uniform branch)
     double rr[9], ws;
     residual_sums_warp(lane, B, R_hat, p_bar, sN, m_cen, map_N_pos, tw, eps, rr, ws);
@@ -298,7 +318,15 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
       for (int i = 0; i < 9; ++i) iw_out[i] = rr[i];
       iw_out[9] = ws;
     }
+    if (iw_bar) {
+      __threadfence_block();
+      __syncwarp();
+      asm volatile("bar.arrive %0, 64;" ::"r"(iw_bar) : "memory");
+    }
   }
+  if (role == 1) TR(8);
+  if (lane == 0) translation_finish(Lf, tw, NeffT, l1m, l3m, pose, eps_psd, eps, ev);
+  if (role == 1) TR(9);
 }
 
 __global__ void __launch_bounds__(32) pose_evidence_kernel(const __grid_constant__ EvidenceParams P) {
@@ -415,7 +443,6 @@ __device__ inline void iw_update(double* iw, const double* rr_w /* [sum w r r^T 
 //     (inputs of scan s+1 are staged into shared memory by a helper warp meanwhile); the planar mask / PSD projection /
 //     certificates of the translation evidence are finished in parallel afterwards.  Same arithmetic, same order within
 //     a scan as (a): results agree to the last ulps (to re-association with Sigma_meas fed back, see S4b).
-constexpr int kChainThreads = 128;
 constexpr int kStagedMinScans = 4;
 
 __device__ __forceinline__ void sigma_p_with_meas(const double* st, const StatsLayout& SL, int b, const double* sigma,
@@ -431,6 +458,24 @@ __device__ __forceinline__ void sigma_p_with_meas(const double* st, const StatsL
   psd_project3_fast(Sraw, eps_psd, Spsd);
 }
 
+// CTA-wide copy of n2 16-byte words, eight loads of a thread in flight before its first store (a dependent load / store pair
+// per iteration would pay the full L2 latency every time)
+__device__ __forceinline__ void copy_batched(double2* __restrict__ dst, const double2* __restrict__ src, int n2, int tid) {
+  for (int base = 0; base < n2; base += 8 * kChainThreads) {
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * kChainThreads + tid;
+      v[k] = i < n2 ? src[i] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * kChainThreads + tid;
+      if (i < n2) dst[i] = v[k];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_constant__ ChainParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = P.n_bins, H = P.n_hyp;
@@ -440,33 +485,98 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
   __shared__ double s_l13[kChainThreads / 64][2];
   extern __shared__ __align__(16) double s_mder_dyn[];
   double* mder = P.chain_smem ? s_mder_dyn : P.workspace;   // map-derived statistics stay on chip when they fit
-  for (int s = 0; s < P.n_scans; ++s) {
-    double* st0 = P.stats + (size_t)s * H * P.stats_stride;
-    // 1. measurement noise enters every bin covariance
-    if (P.iw_state && P.use_sigma_meas) {
-      if (tid == 0) iw_sigma_mode(P.iw_state, P.eps_psd, s_sigma);
-      __syncthreads();
-      for (int idx = tid; idx < B * H; idx += kChainThreads) {
-        const int h = idx / B, b = idx - h * B;
-        double* st = st0 + (size_t)h * P.stats_stride;
-        double Spsd[9];
-        sigma_p_with_meas(st, SL, b, s_sigma, P.eps_mass, P.eps_psd, Spsd);
-        for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Spsd[i];
+  if (tid == 0) TR(0);
+  if (P.stage_in_src) {
+    // pose / map / IW out of page-locked host memory (16-byte loads, all of a thread's loads in flight before its first store:
+    // a PCIe read takes ~1.5 us), and the stage-1 records into the working copy that the chain step rewrites
+    const double2* src = reinterpret_cast<const double2*>(P.stage_in_src);
+    double2* dst = reinterpret_cast<double2*>(P.stage_in_dst);
+    const int n2 = P.stage_in_doubles >> 1;
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // first batch of PCIe reads goes out ...
+      const int i = k * kChainThreads + tid;
+      v[k] = i < n2 ? __ldcv(src + i) : make_double2(0.0, 0.0);
+    }
+    copy_batched(reinterpret_cast<double2*>(P.stats), reinterpret_cast<const double2*>(P.stats_src), P.stats_doubles >> 1, tid);   // ... while the records are copied
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = k * kChainThreads + tid;
+      if (i < n2) dst[i] = v[k];
+    }
+    for (int base = 8 * kChainThreads; base < n2; base += 8 * kChainThreads) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k * kChainThreads + tid;
+        v[k] = i < n2 ? __ldcv(src + i) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + k * kChainThreads + tid;
+        if (i < n2) dst[i] = v[k];
       }
     }
-    // 2. map-derived statistics
-    for (int b = tid; b < B; b += kChainThreads)
-      map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, mder);
     __syncthreads();
-    // 3. pose evidence, one PAIR of warps per hypothesis (SVD chain | scatter metrics)
-    for (int h = warp >> 1; h < H; h += kChainThreads / 64)
-      pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
-                         mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
-                         P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr,
-                         1 + (warp & 1), s_l13[warp >> 1], 1 + (warp >> 1));
+  }
+  for (int s = 0; s < P.n_scans; ++s) {
+    double* st0 = P.stats + (size_t)s * H * P.stats_stride;
+    // Warp roles: even warps with a hypothesis run the rotation chain at once (it needs neither the bin covariances nor the
+    // map-derived statistics) and wait on barrier 8 only before their translation part; all other warps first prepare
+    //   1. the measurement noise in every bin covariance (Sigma_meas on one thread, then bins x hypotheses in parallel),
+    //   2. the map-derived statistics,
+    // arrive on barrier 8, and then the odd ones take the scatter-metric half of their hypothesis; warp 1 finally runs
+    //   4. the IW update as soon as hypothesis 0's residual statistics are there (barrier 9), next to the translation finish.
+    if (tid == 0) TR(1);
+    const bool role1 = (warp & 1) == 0 && (warp >> 1) < H;
+    const bool sigma_step = P.iw_state && P.use_sigma_meas;
+    if (role1) {
+      bool first = true;
+      for (int h = warp >> 1; h < H; h += kChainThreads / 64) {
+        pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
+                           mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                           P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr, 1,
+                           s_l13[warp >> 1], 1 + (warp >> 1), first ? 8 : 0, (h == 0 && P.iw_state) ? 9 : 0);
+        first = false;
+      }
+    } else {
+      // rank among the preparing threads: with H = 1 warps 1, 2, 3 (96 threads), otherwise the odd warps (64 threads)
+      const int n_role1 = H < kChainThreads / 64 ? H : kChainThreads / 64;
+      const int n_pre = kChainThreads - 32 * n_role1;
+      const int pw = (warp & 1) ? (warp >> 1) : (kChainThreads / 64 + (warp >> 1) - n_role1);   // odd warps first
+      const int p = pw * 32 + lane;
+      if (sigma_step && p == 0) iw_sigma_mode(P.iw_state, P.eps_psd, s_sigma);
+      for (int b = p - 32; b >= 0 && b < B; b += n_pre - 32)   // the first warp is busy with Sigma_meas
+        map_derived_bin(P.map_S_dir, P.map_N_dir, P.map_N_pos, P.map_sum_p, P.map_sum_ppT, B, b, P.eps_mass, P.eps_psd, mder);
+      if (p == 0) TR(10);
+      if (p == 32) TR(11);
+      if (sigma_step) {
+        asm volatile("bar.sync 10, %0;" ::"r"(n_pre) : "memory");
+        for (int idx = p; idx < B * H; idx += n_pre) {
+          const int h = idx / B, b = idx - h * B;
+          double* st = st0 + (size_t)h * P.stats_stride;
+          double Spsd[9];
+          sigma_p_with_meas(st, SL, b, s_sigma, P.eps_mass, P.eps_psd, Spsd);
+          for (int i = 0; i < 9; ++i) st[SL.Sigma_p() + b * 9 + i] = Spsd[i];
+        }
+      }
+      __threadfence_block();
+      if (p == 0) TR(12);
+      asm volatile("bar.arrive 8, %0;" ::"r"(kChainThreads) : "memory");
+      if ((warp & 1) && (warp >> 1) < H) {
+        for (int h = warp >> 1; h < H; h += kChainThreads / 64)
+          pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
+                             mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                             P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, nullptr, 2, s_l13[warp >> 1], 1 + (warp >> 1));
+        if (warp == 1 && P.iw_state) {
+          asm volatile("bar.sync 9, 64;" ::: "memory");
+          TR(15);
+          if (lane == 0) iw_update(P.iw_state, s_iw, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
+          TR(16);
+        }
+      }
+    }
     __syncthreads();
-    // 4. IW update from hypothesis 0's translation residuals
-    if (P.iw_state && tid == 0) iw_update(P.iw_state, s_iw, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
+    if (tid == 0) TR(17);
     // 5. map update (hypothesis 0's statistics, pose_update[s])
     if (P.pose_update) {
       double R[9];
@@ -477,7 +587,24 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     }
     __syncthreads();
   }
+  if (tid == 0) TR(18);
+  if (P.stage_out_dst) {
+    // map / IW / stats / evidence back to page-locked host memory, then the completion ticket (posted writes stay in order)
+    const double2* src = reinterpret_cast<const double2*>(P.stage_out_src);
+    double2* dst = reinterpret_cast<double2*>(P.stage_out_dst);
+    const int n2 = P.stage_out_doubles >> 1;
+    copy_batched(dst, src, n2, tid);
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(P.done_flag) = P.done_value;
+      TR(19);
+    }
+  }
 }
+#ifdef GCL_CHAIN_TRACE
+extern "C" int gcl_debug_chain_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_chain_trace, sizeof(long long) * 32); }
+#endif
 
 // ---- staged stream ----------------------------------------------------------------------------------------------------
 // workspace carve (doubles): [single-scan map-derived 16B][map_pre: S x 26B][mder: S x 16B][sigma: S x 16][tpart: S*H x 32]

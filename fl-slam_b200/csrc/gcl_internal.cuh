@@ -24,6 +24,8 @@ struct gcl_handle_s {
   int64_t launches = 0;
   std::string err;
   // resources of the *_host entry points (allocated on first use, grown on demand)
+  unsigned long long done_seq = 0;     // completion ticket of the single-launch evidence step (0 = the copy-engine path is in flight)
+  unsigned long long* done_flag = nullptr;   // page-locked word the chain kernel writes the ticket to
   cudaStream_t stream = nullptr;       // stage 2: chain step + D2H
   cudaStream_t stream1 = nullptr;      // stage 1: scan_moments + reduce_finalize
   cudaStream_t stream_copy = nullptr;  // H2D of the scans
@@ -45,7 +47,7 @@ struct gcl_handle_s {
   bool pin_val[8] = {false, false, false, false, false, false, false, false};
   int pin_next = 0;
   int stage2_slot = -1;                 // slot whose evidence step is enqueued and not yet collected
-  bool stage2_has_update = false, stage2_has_iw = false;
+  bool stage2_has_update = false, stage2_has_iw = false, stage2_single = false;
 };
 
 namespace gcl {
@@ -121,6 +123,13 @@ struct ChainParams {
   int n_scans, n_hyp, n_bins, use_sigma_meas;
   int chain_smem;           // single-launch chain: map-derived statistics live in dynamic shared memory
   double forgetting, iw_rho, iw_nu_weak_add, iw_nu_max, eps_psd, eps_mass;
+  // single-launch host staging (one scan, gcl_scan_evidence_begin_host): the kernel itself carries the small blocks across PCIe
+  // -- inputs out of page-locked host memory first, outputs back at the end, then a completion flag the host polls -- so that
+  // the evidence step is ONE enqueue instead of H2D + D2D + kernel + D2H + stream synchronisation.  All zero: not used.
+  const double* stage_in_src = nullptr; double* stage_in_dst = nullptr; int stage_in_doubles = 0;      // pinned host -> device
+  const double* stats_src = nullptr; int stats_doubles = 0;                                            // stage-1 records -> stats
+  const double* stage_out_src = nullptr; double* stage_out_dst = nullptr; int stage_out_doubles = 0;   // device -> pinned host
+  unsigned long long* done_flag = nullptr; unsigned long long done_value = 0;                          // pinned host
 };
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches);
 size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins);

@@ -34,16 +34,16 @@ def run2(n_rep):
     m = {k: np.zeros(v) for k, v in (("S_dir", (B, 3)), ("S_dir_scatter", (B, 3, 3)), ("N_dir", (B,)), ("N_pos", (B,)), ("sum_p", (B, 3)), ("sum_ppT", (B, 3, 3)))}
     iw_h = np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
     acc = [0.0, 0.0, 0.0]
-    sub = lambda k: pl.submit_scan_host(k % 2, pinned[k][0], pinned[k][1], pinned[k][2], scans[k].scan_start_time, scans[k].scan_end_time, xis[k][None])
+    sub = lambda k: pl.submit_scan_host(k % 4, pinned[k][0], pinned[k][1], pinned[k][2], scans[k].scan_start_time, scans[k].scan_end_time, xis[k][None])
     t_all = time.perf_counter()
     for _ in range(n_rep):
-        sub(0)
+        sub(0); sub(1)
         for k in range(S):
             t0 = time.perf_counter()
-            pl.evidence_begin_host(k % 2, poses[k][None], m, pose_update=poses[k], iw_state_host=iw_h, use_sigma_meas=True)
+            pl.evidence_begin_host(k % 4, poses[k][None], m, pose_update=poses[k], iw_state_host=iw_h, use_sigma_meas=True)
             t1 = time.perf_counter()
-            if k + 1 < S:
-                sub(k + 1)
+            if k + 2 < S:
+                sub(k + 2)
             t2 = time.perf_counter()
             pl.evidence_end_host()
             t3 = time.perf_counter()
