@@ -180,14 +180,15 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
                                    const double* map_N_dir, const double* map_N_pos, const double* map_derived,
                                    const double* pose, const double* R_hat_override, int B, double eps_psd, double eps,
                                    int do_rotation, int do_translation, double* ev, double* iw_out, int role = 0,
-                                   double* s_l13 = nullptr, int bar_id = 0, int pre_bar = 0, int iw_bar = 0) {
+                                   double* s_l13 = nullptr, int bar_id = 0, int pre_bar = 0, int iw_bar = 0, int iw_bar_count = 64) {
   // role 0: everything on this warp.  Roles 1 / 2 split one hypothesis over a PAIR of warps (the latency-critical single-scan
   // chain): role 2 computes the scan / map scatter metrics (two symmetric eigen problems) while role 1 runs the SVD chain;
   // they meet at named barrier `bar_id` (64 threads) where role 2 hands over the map eigenvalues through s_l13.
   // pre_bar (role 1, single-scan chain): the rotation part needs neither the bin covariances nor the map-derived statistics,
   // so it runs while other warps prepare those; this warp waits on named barrier `pre_bar` (whole CTA) only before the
-  // translation part.  iw_bar: the residual statistics are handed to the warp that runs the IW update (arrive, 64 threads)
-  // BEFORE this warp's lane 0 finishes the translation evidence, so the two run side by side.
+  // translation part.  iw_bar: once the residual statistics are written (and the map is no longer read) this warp arrives on
+  // named barrier `iw_bar`, BEFORE its lane 0 finishes the translation evidence: the IW update and, with one hypothesis, the
+  // map update of the other warps run side by side with that finish.
   const StatsLayout SL(B);
   const double* sN = st + SL.N();
   const double* s_dir = st + SL.s_dir();
@@ -318,11 +319,11 @@ __device__ void pose_evidence_warp(int lane, const double* st, const double* map
       for (int i = 0; i < 9; ++i) iw_out[i] = rr[i];
       iw_out[9] = ws;
     }
-    if (iw_bar) {
-      __threadfence_block();
-      __syncwarp();
-      asm volatile("bar.arrive %0, 64;" ::"r"(iw_bar) : "memory");
-    }
+  }
+  if (iw_bar) {   // this warp is done reading the map and has left the residual statistics: IW update / map update may start
+    __threadfence_block();
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(iw_bar), "r"(iw_bar_count) : "memory");
   }
   if (role == 1) TR(8);
   if (lane == 0) translation_finish(Lf, tw, NeffT, l1m, l3m, pose, eps_psd, eps, ev);
@@ -460,17 +461,18 @@ __device__ __forceinline__ void sigma_p_with_meas(const double* st, const StatsL
 
 // CTA-wide copy of n2 16-byte words, eight loads of a thread in flight before its first store (a dependent load / store pair
 // per iteration would pay the full L2 latency every time)
-__device__ __forceinline__ void copy_batched(double2* __restrict__ dst, const double2* __restrict__ src, int n2, int tid) {
-  for (int base = 0; base < n2; base += 8 * kChainThreads) {
+__device__ __forceinline__ void copy_batched(double2* __restrict__ dst, const double2* __restrict__ src, int n2, int tid,
+                                             int nthreads = kChainThreads) {
+  for (int base = 0; base < n2; base += 8 * nthreads) {
     double2 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int i = base + k * kChainThreads + tid;
+      const int i = base + k * nthreads + tid;
       v[k] = i < n2 ? src[i] : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int i = base + k * kChainThreads + tid;
+      const int i = base + k * nthreads + tid;
       if (i < n2) dst[i] = v[k];
     }
   }
@@ -529,14 +531,26 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     if (tid == 0) TR(1);
     const bool role1 = (warp & 1) == 0 && (warp >> 1) < H;
     const bool sigma_step = P.iw_state && P.use_sigma_meas;
+    // One hypothesis: warps 2 and 3 have no evidence role, so they also take the map update (as soon as warp 0 has read the map
+    // for the last time: barrier 9) and, when the kernel stages its own outputs, carry the finished blocks to the host while
+    // warp 0 is still busy -- statistics after step 1, the map after its update; warp 1 the IW state, warp 0 the evidence.
+    const bool solo = H == 1;
+    const bool solo_out = solo && P.stage_out_dst != nullptr;
+    const bool early_map = solo && P.pose_update != nullptr;
+    const int bar9 = 32 + (P.iw_state ? 32 : 0) + (early_map ? 64 : 0);   // 32: nobody waits, barrier not used
     if (role1) {
       bool first = true;
       for (int h = warp >> 1; h < H; h += kChainThreads / 64) {
         pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
                            mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
                            P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr, 1,
-                           s_l13[warp >> 1], 1 + (warp >> 1), first ? 8 : 0, (h == 0 && P.iw_state) ? 9 : 0);
+                           s_l13[warp >> 1], 1 + (warp >> 1), first ? 8 : 0, (h == 0 && bar9 > 32) ? 9 : 0, bar9);
         first = false;
+      }
+      if (solo_out) {   // the evidence record is complete (warp 1 wrote its part before the pair barrier)
+        __syncwarp();
+        copy_batched(reinterpret_cast<double2*>(P.stage_out_dst + P.out_off_evid), reinterpret_cast<const double2*>(P.evidence),
+                     GCL_EVID_DOUBLES >> 1, lane, 32);
       }
     } else {
       // rank among the preparing threads: with H = 1 warps 1, 2, 3 (96 threads), otherwise the odd warps (64 threads)
@@ -562,23 +576,48 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
       __threadfence_block();
       if (p == 0) TR(12);
       asm volatile("bar.arrive 8, %0;" ::"r"(kChainThreads) : "memory");
+      if (solo_out && sigma_step) asm volatile("bar.sync 10, %0;" ::"r"(n_pre) : "memory");   // every bin covariance is in place
+      if (solo && warp >= 2) {   // warps 2 and 3: no evidence role with one hypothesis
+        const int q = p - 32;      // rank among these 64 threads
+        if (solo_out) {
+          copy_batched(reinterpret_cast<double2*>(P.stage_out_dst + P.out_off_stats), reinterpret_cast<const double2*>(st0),
+                       P.stats_doubles >> 1, q, 64);
+        }
+        if (early_map) {
+          asm volatile("bar.sync 9, %0;" ::"r"(bar9) : "memory");
+          double R[9];
+          so3_exp(P.pose_update + (size_t)s * 6 + 3, R);
+          for (int b = q; b < B; b += 64)
+            map_update_bin(st0, R, P.pose_update + (size_t)s * 6, B, b, P.forgetting, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir,
+                           P.map_N_pos, P.map_sum_p, P.map_sum_ppT);
+          if (solo_out) {
+            __threadfence_block();
+            asm volatile("bar.sync 11, 64;" ::: "memory");
+            copy_batched(reinterpret_cast<double2*>(P.stage_out_dst), reinterpret_cast<const double2*>(P.stage_out_src), (26 * B) >> 1, q, 64);
+          }
+        }
+      }
       if ((warp & 1) && (warp >> 1) < H) {
         for (int h = warp >> 1; h < H; h += kChainThreads / 64)
           pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
                              mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
                              P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, nullptr, 2, s_l13[warp >> 1], 1 + (warp >> 1));
         if (warp == 1 && P.iw_state) {
-          asm volatile("bar.sync 9, 64;" ::: "memory");
+          asm volatile("bar.sync 9, %0;" ::"r"(bar9) : "memory");
           TR(15);
           if (lane == 0) iw_update(P.iw_state, s_iw, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd);
           TR(16);
+          if (solo_out) {
+            __syncwarp();
+            if (lane < 10) P.stage_out_dst[P.out_off_iw + lane] = P.iw_state[lane];
+          }
         }
       }
     }
     __syncthreads();
     if (tid == 0) TR(17);
-    // 5. map update (hypothesis 0's statistics, pose_update[s])
-    if (P.pose_update) {
+    // 5. map update (hypothesis 0's statistics, pose_update[s]) -- already done by warps 2, 3 when there is one hypothesis
+    if (P.pose_update && !early_map) {
       double R[9];
       so3_exp(P.pose_update + (size_t)s * 6 + 3, R);
       for (int b = tid; b < B; b += kChainThreads)
@@ -593,7 +632,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     const double2* src = reinterpret_cast<const double2*>(P.stage_out_src);
     double2* dst = reinterpret_cast<double2*>(P.stage_out_dst);
     const int n2 = P.stage_out_doubles >> 1;
-    copy_batched(dst, src, n2, tid);
+    if (P.n_hyp != 1) {
+      copy_batched(dst, src, n2, tid);
+    } else if (!P.pose_update) {
+      copy_batched(dst, src, (26 * B) >> 1, tid);   // the map was not updated: it rides along unchanged
+    }
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {

@@ -129,6 +129,7 @@ struct ChainParams {
   const double* stage_in_src = nullptr; double* stage_in_dst = nullptr; int stage_in_doubles = 0;      // pinned host -> device
   const double* stats_src = nullptr; int stats_doubles = 0;                                            // stage-1 records -> stats
   const double* stage_out_src = nullptr; double* stage_out_dst = nullptr; int stage_out_doubles = 0;   // device -> pinned host
+  int out_off_iw = 0, out_off_stats = 0, out_off_evid = 0;   // offsets (doubles) of the IW / stats / evidence blocks in the output
   unsigned long long* done_flag = nullptr; unsigned long long done_value = 0;                          // pinned host
 };
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches);

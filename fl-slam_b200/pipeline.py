@@ -146,6 +146,7 @@ class LidarEvidencePipeline:
         self._ptr_cache: Dict[int, Tuple[np.ndarray, int]] = {}
         self._inflight: Dict[int, tuple] = {}
         self._msg_layouts: Dict[tuple, tuple] = {}
+        self._map_checked: Optional[tuple] = None
 
     # ------------------------------------------------------------------------------------------------------------
     def manifest_entries(self, n_gpus: int = 1, shard_mode: str = "none") -> Dict[str, Any]:
@@ -339,20 +340,22 @@ class LidarEvidencePipeline:
     def submit_scan_host(self, slot: int, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body) -> int:
         """Stage 1 of the host call (gcl_scan_submit_host): asynchronous upload + moment pass of one scan under H twists.
         Returns H.  Page-locked inputs are read in place: keep them unchanged until ``evidence_host(slot, ...)`` returns."""
-        f = self._f64
-        pts, ts, w = f(points, (-1, 3)), f(timestamps, (-1,)), f(weights, (-1,))
-        n = pts.shape[0]
-        if ts.shape[0] != n or w.shape[0] != n:
+        c = self._c64
+        pts, ts, w = c(points, 0, 3), c(timestamps, 0, 1), c(weights, 0, 1)   # only sizes and addresses matter below
+        n = ts.size
+        if pts.size != 3 * n or w.size != n:
             raise ValueError("points, timestamps and weights must have the same length")
-        xi = f(xi_body, (-1, 6))
+        xi = c(xi_body, 0, 6)
+        if xi.ndim != 2:
+            xi = xi.reshape(-1, 6)
         bins_host = getattr(self, "_bins_host", None)
         if bins_host is None:
             bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
-        p = lambda a: a.ctypes.data
-        self._inflight[slot] = (pts, ts, w, xi, n)           # keep the arrays alive while the copy is in flight
-        _abi.check(_lib.gcl_scan_submit_host(self.handle, int(slot), p(pts), p(ts), p(w), n, self.n_points_cap, float(scan_start_time),
-                                             float(scan_end_time), p(xi), xi.shape[0], self._addr(self.origin), self._addr(bins_host), self.n_bins,
-                                             self.tau, PRECISIONS[self.precision], self.eps_psd, self.eps_mass), self.handle)
+        self._inflight[slot] = (pts, ts, w, xi, n)           # keep the arrays alive while the device reads them
+        _abi.check(_lib.gcl_scan_submit_host(self.handle, int(slot), pts.ctypes.data, ts.ctypes.data, w.ctypes.data, n, self.n_points_cap,
+                                             float(scan_start_time), float(scan_end_time), self._addr(xi), xi.shape[0], self._addr(self.origin),
+                                             self._addr(bins_host), self.n_bins, self.tau, PRECISIONS[self.precision], self.eps_psd,
+                                             self.eps_mass), self.handle)
         return xi.shape[0]
 
     def submit_scan_msg_host(self, slot: int, msg=None, *, data=None, fields=None, point_step: Optional[int] = None,
@@ -457,35 +460,45 @@ class LidarEvidencePipeline:
         poses = f(pose_pred, (-1, 6))
         if poses.shape[0] != H:
             raise ValueError("xi_body and pose_pred must have one row per hypothesis")
-        shapes = self._map_shapes()
-        if pose_update is not None:
-            for k, sh in shapes:   # in/out: the caller's arrays are written, so they must be usable as they are
-                a = map_stats_host[k]
-                if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == sh):
-                    raise ValueError(f"map_stats_host[{k!r}] must be a C-contiguous float64 array of shape {sh} for an in-place update")
-            m = map_stats_host
+        # the map arrays and the IW state usually are the SAME objects scan after scan (updated in place): their checks and
+        # addresses are remembered and re-used as long as every array is the very object that was checked
+        mc = self._map_checked
+        arrs = (map_stats_host["S_dir"], map_stats_host["S_dir_scatter"], map_stats_host["N_dir"], map_stats_host["N_pos"],
+                map_stats_host["sum_p"], map_stats_host["sum_ppT"], iw_state_host)
+        if mc is not None and mc[0][0] is arrs[0] and mc[0][1] is arrs[1] and mc[0][2] is arrs[2] and mc[0][3] is arrs[3] \
+                and mc[0][4] is arrs[4] and mc[0][5] is arrs[5] and mc[0][6] is arrs[6]:
+            ma = mc[1]
         else:
-            m = {k: f(map_stats_host[k], sh) for k, sh in shapes}
+            shapes = self._map_shapes()
+            conforming = all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == sh
+                             for a, (k, sh) in zip(arrs, shapes))
+            if pose_update is not None and not conforming:   # in/out: the caller's arrays are written, so they must be usable as they are
+                raise ValueError("map_stats_host arrays must be C-contiguous float64 arrays of shapes "
+                                 f"{dict(shapes)} for an in-place update")
+            if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
+                                                  and iw_state_host.shape == (10,) and iw_state_host.flags.c_contiguous):
+                raise ValueError("iw_state_host must be a C-contiguous float64 array of shape (10,)")
+            if conforming:
+                ma = tuple(None if a is None else a.ctypes.data for a in arrs)
+                self._map_checked = (arrs, ma)
+            else:                                             # read-only use of non-conforming arrays: converted copies
+                conv = tuple(f(a, sh) for a, (k, sh) in zip(arrs, shapes)) + (iw_state_host,)
+                ma = tuple(None if a is None else a.ctypes.data for a in conv)
+                arrs = conv
         p = self._addr
         pu = None if pose_update is None else f(pose_update, (6,))
-        if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
-                                              and iw_state_host.shape == (10,) and iw_state_host.flags.c_contiguous):
-            raise ValueError("iw_state_host must be a C-contiguous float64 array of shape (10,)")
-        _abi.check(_lib.gcl_scan_evidence_begin_host(self.handle, int(slot), p(poses), p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]),
-                                                     p(m["N_pos"]), p(m["sum_p"]), p(m["sum_ppT"]), p(pu), float(forgetting),
-                                                     p(iw_state_host), 1 if use_sigma_meas else 0), self.handle)
-        self._stage2 = (H, n, m, iw_state_host, ess_imu, chart_id, anchor_id, poses, pu)
+        _abi.check(_lib.gcl_scan_evidence_begin_host(self.handle, int(slot), poses.ctypes.data, ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], p(pu),
+                                                     float(forgetting), ma[6], 1 if use_sigma_meas else 0), self.handle)
+        self._stage2 = (H, n, arrs, ma, ess_imu, chart_id, anchor_id, poses, pu)
 
     def evidence_end_host(self) -> LidarScanEvidence:
         """Second half of stage 2 (gcl_scan_evidence_end_host): wait for the D2H, write the map / IW arrays back, return."""
-        H, n, m, iw_state_host, ess_imu, chart_id, anchor_id, _poses, _pu = self._stage2
+        H, n, _arrs, ma, ess_imu, chart_id, anchor_id, _poses, _pu = self._stage2
         self._stage2 = None
         stats = np.empty((H, self.srec), dtype=np.float64)
         evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
-        p = self._addr
-        _abi.check(_lib.gcl_scan_evidence_end_host(self.handle, p(m["S_dir"]), p(m["S_dir_scatter"]), p(m["N_dir"]), p(m["N_pos"]),
-                                                   p(m["sum_p"]), p(m["sum_ppT"]), p(iw_state_host), stats.ctypes.data, evid.ctypes.data),
-                   self.handle)
+        _abi.check(_lib.gcl_scan_evidence_end_host(self.handle, ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], ma[6], stats.ctypes.data,
+                                                   evid.ctypes.data), self.handle)
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
                                  stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
                                  n_points_cap=self.n_points_cap, ess_imu=ess_imu)

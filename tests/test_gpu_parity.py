@@ -757,3 +757,27 @@ def test_message_path_errors(g):
         pl.submit_scan_msg_host(0, data=bytes(8), fields=f3 + [("ring", 12, 4)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
     with pytest.raises(ValueError):
         pl.submit_scan_msg_host(0, data=bytes(16), fields=f3 + [("ring", 12, 9)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
+
+
+def test_pinned_buffers_reused_across_scans(g, O):
+    """Page-locked scan arrays are read IN PLACE by the device (one hypothesis: no copy at all).  The same buffers refilled with a
+    different scan must give that scan's statistics -- nothing of the previous contents may survive in a device cache."""
+    B, tau, n, cap = 48, g.synth.DEFAULT_TAU, 20000, 8192
+    bins = O.create_fibonacci_atlas(B)
+    bufs = [torch.empty(n, 3, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory(),
+            torch.empty(n, dtype=torch.float64).pin_memory()]
+    pts, ts, w = (b.numpy() for b in bufs)
+    pl = None
+    ms = O.empty_map_stats(B)
+    for seed in (11, 12, 13):
+        sc = g.synth.make_scan(n, seed=seed)
+        pts[:], ts[:], w[:] = sc.points, sc.timestamps, sc.weights
+        pl = pl or g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=sc.lidar_origin, bin_directions=bins)
+        ev = pl.process_scan_host(pts, ts, w, sc.scan_start_time, sc.scan_end_time, sc.xi_body[None], np.zeros((1, 6)), ms)
+        _, _, raw, fin = _oracle_sums(O, sc, cap, bins, tau)
+        sb = ev.scan_bins(0)
+        for name in ("N", "s_dir", "S_dir_scatter", "p_bar"):
+            assert rel_err(H(getattr(sb, name)), fin[name]) < 1e-9, (seed, name)
+    # the copying path (pageable arrays) gives the same bits
+    pageable = pl.process_scan_host(pts.copy(), ts.copy(), w.copy(), sc.scan_start_time, sc.scan_end_time, sc.xi_body[None], np.zeros((1, 6)), ms)
+    assert np.array_equal(H(pageable.stats), H(ev.stats))
