@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2]/[3] side measurements")
+    ap.add_argument("--no-overlap", action="store_true", help="one batch at a time (no pipelining of consecutive 200-scan batches)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=100, help="scans in the CPU-baseline sample (walked repeatedly for >= 12 s)")
     args = ap.parse_args()
@@ -225,14 +226,30 @@ def main():
     def stream_pass():
         # scan_moments + reduce_finalize for all 200 scans (independent of the map), then ONE chain launch that walks the
         # scans in order carrying map statistics (forgetting 0.99) and the LiDAR measurement-noise IW state on the device
-        pl.run_stream(res, xis, poses_dev, poses_dev, ms, iw_state=iw, use_sigma_meas=True, jobs_dev=jobs_dev, ctas=ctas)
+        # Consecutive batches are pipelined (overlap=True): the moment pass of batch k+1 does not depend on the map, so it runs on
+        # 147 SMs while the sequential chain of batch k keeps one SM busy; map and IW state still pass from batch to batch in order.
+        pl.run_stream(res, xis, poses_dev, poses_dev, ms, iw_state=iw, use_sigma_meas=True, jobs_dev=jobs_dev, ctas=ctas, overlap=overlap)
 
+    overlap = False
     launches0 = g._abi.launch_count(local_rank)
     stream_pass()                                   # warm-up (allocates work buffers, sets kernel attributes)
     torch.cuda.synchronize()
     launches_per_step = g._abi.launch_count(local_rank) - launches0
+    # the same K steps without pipelining (one batch at a time), for the record
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.warmup):
         stream_pass()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        stream_pass()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_per_step_serial = ev0.elapsed_time(ev1) / args.steps
+    overlap = not args.no_overlap
+    for _ in range(args.warmup):
+        stream_pass()
+    pl.join_stream()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -243,6 +260,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         stream_pass()
+    pl.join_stream()                                # the current stream waits for the last batch's chain
     ev1.record()
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
@@ -291,13 +309,17 @@ def main():
         p, t_, w_ = (torch.from_numpy(a).pin_memory() for a in (s.points, s.timestamps, s.weights))
         pinned.append((p.numpy(), t_.numpy(), w_.numpy(), p, t_, w_))
 
+    lat_blocking = []          # per-scan latency of the blocking call (SURVEY.md 8d asks for p50 / p99 on configs[1])
+
     def e2e_pass():
         m = {k: np.zeros(v) for k, v in (("S_dir", (N_BINS, 3)), ("S_dir_scatter", (N_BINS, 3, 3)), ("N_dir", (N_BINS,)),
                                          ("N_pos", (N_BINS,)), ("sum_p", (N_BINS, 3)), ("sum_ppT", (N_BINS, 3, 3)))}
         iw_h = np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
         for k in range(n_e2e):
+            t_a = time.perf_counter()
             pl.process_scan_host(pinned[k][0], pinned[k][1], pinned[k][2], scans[k].scan_start_time, scans[k].scan_end_time,
                                  xis[k][None], poses[k][None], m, pose_update=poses[k], iw_state_host=iw_h, use_sigma_meas=True)
+            lat_blocking.append(time.perf_counter() - t_a)
         return m
     def e2e_pass_pipelined():
         """Same work per scan, two-stage API: the upload + moment pass of scans k+1 and k+2 (which need only the scan and the IMU
@@ -358,16 +380,19 @@ def main():
         return dt
     n_rep = max(1, args.steps // 2)
     e2e_blocking_s = _time_e2e(e2e_pass)
+    lat = np.sort(np.array(lat_blocking[n_e2e:])) * 1e6          # the first pass is the warm-up
     e2e_s = _time_e2e(e2e_pass_pipelined)
     e2e_msg_s = _time_e2e(e2e_pass_messages)
     e2e_points = sum(s.points.shape[0] for s in scans[:n_e2e])
     rec_bytes = (38 * N_BINS + 24 + 640 + 26 * N_BINS + 10) * 8
     e2e = {"value": world * n_rep * e2e_points / e2e_s, "unit": "points/s",
-           "h2d_bytes_per_step": int(e2e_points * 40 + n_e2e * (N_BINS * 26 * 8 + N_BINS * 24 + 48 + 48 + 80 + 120)),
+           "h2d_bytes_per_step": int(sum(_alg_bytes(s.points.shape[0]) for s in scans[:n_e2e]) + n_e2e * (N_BINS * 26 * 8 + 48 + 48 + 80 + 120)),
            "d2h_bytes_per_step": int(n_e2e * rec_bytes), "scans_per_sec": world * n_rep * n_e2e / e2e_s,
            "us_per_scan": 1e6 * e2e_s / (n_rep * n_e2e),
            "blocking_call": {"value": world * n_rep * e2e_points / e2e_blocking_s, "unit": "points/s",
                              "us_per_scan": 1e6 * e2e_blocking_s / (n_rep * n_e2e),
+                             "latency_us": {"p50": float(lat[len(lat) // 2]), "p99": float(lat[min(len(lat) - 1, int(0.99 * len(lat)))]),
+                                            "max": float(lat[-1]), "n": int(len(lat))},
                              "note": "one gcl_lidar_scan_evidence_host call per scan, nothing overlapped"},
            "from_message": {"value": world * n_rep * e2e_points / e2e_msg_s, "unit": "points/s", "us_per_scan": 1e6 * e2e_msg_s / (n_rep * n_e2e),
                             "h2d_bytes_per_step": int(e2e_points * msgs[0][1]["point_step"] + n_e2e * (512 * 7 * 8 + N_BINS * 26 * 8 + N_BINS * 24 + 400)),
@@ -378,7 +403,10 @@ def main():
            "note": f"{n_e2e} scans per pass through the two-stage host API with pinned host arrays: gcl_scan_submit_host (H2D of "
                    "the scan, scan_moments, reduce_finalize; asynchronous) for scan k+2 is issued between "
                    "gcl_scan_evidence_begin_host (H2D of pose/map/IW, chain step incl. IW + map update, one D2H of "
-                   "map/IW/stats/evidence enqueued) and gcl_scan_evidence_end_host (sync, results out) of scan k; every scan's inputs cross PCIe and every scan's results are read back inside the timed region"}
+                   "map/IW/stats/evidence enqueued) and gcl_scan_evidence_end_host (sync, results out) of scan k; every scan's inputs cross PCIe and every scan's results are read back inside the timed region. "
+                   "Stage 1 reads the page-locked scan arrays in place (one hypothesis: zero-copy, the selected rows and every raw weight cross PCIe "
+                   "exactly once, inside scan_moments); stage 2 is ONE launch: the chain kernel pulls pose / map / IW out of page-locked memory, pushes "
+                   "map / IW / stats / evidence back and raises a ticket the host polls"}
 
     # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
     extra = {}
@@ -423,7 +451,10 @@ def main():
                            "tau": tau, "precision": args.precision, "layout": "ref_f64 (40 B/point)" if args.precision == "fp64" else "packed_f32 (20 B/point)",
                            "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (stream does not shard)",
                            "l2": "inputs total 240 MB > 126 MB L2; each scan is read once per step",
-                           "launches_per_step": int(launches_per_step), "iw": "LiDAR measurement-noise IW block adapted every scan (Sigma_meas into bin covariances)"},
+                           "launches_per_step": int(launches_per_step),
+                           "batches": "consecutive 200-scan batches pipelined (moment pass of batch k+1 overlaps the sequential chain of batch k)"
+                                      if overlap else "one 200-scan batch at a time",
+                           "ms_per_step_one_batch_at_a_time": ms_per_step_serial, "iw": "LiDAR measurement-noise IW block adapted every scan (Sigma_meas into bin covariances)"},
                 "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "extra": extra}
         print(json.dumps(line))

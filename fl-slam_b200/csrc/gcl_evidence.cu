@@ -6,7 +6,6 @@
 // metrics), :155-256 + :264-394 (Matrix Fisher), :413-499 + :502-671 (planar translation), :729-756 (22-D);
 // pkg/backend/operators/measurement_noise_iw_jax.py:37-127 (LiDAR measurement-noise inverse-Wishart block).
 // The 3x3 SVD / symmetric eigen / LU routines are in gcl_math.cuh.  All arithmetic is binary64.
-#define GCL_HEAVY __noinline__   // see gcl_math.cuh
 #include "gcl_internal.cuh"
 
 namespace gcl {

@@ -10,14 +10,6 @@ constexpr double kSmallAngle = 1e-7;  // pkg/common/geometry/se3_jax.py:32
 constexpr double kNearPi = 1e-7;      // pkg/common/geometry/se3_jax.py:36
 constexpr double kF64Eps = 2.220446049250313e-16;
 
-// The heavy 3x3 routines (Jacobi eigen / SVD, Rodrigues, log) are inlined by default.  A translation unit whose kernels run
-// them once or twice on a latency-critical path (gcl_evidence.cu) defines GCL_HEAVY as __noinline__ before including this
-// header: ONE copy of each routine stays hot in the instruction cache instead of a fresh straight-line copy per call site
-// (the single-scan chain kernel was 14.5 K instructions executed ~once each: instruction-fetch bound).
-#ifndef GCL_HEAVY
-#define GCL_HEAVY
-#endif
-
 __host__ __device__ inline void mat3_mul(const double* A, const double* B, double* C) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
@@ -42,7 +34,7 @@ __host__ __device__ inline double sigmoid64(double x) { return 1.0 / (1.0 + exp(
 
 // ---- SO(3) -----------------------------------------------------------------------------------------------
 // so3_exp, pkg/common/geometry/se3_jax.py:259-301.
-__host__ __device__ GCL_HEAVY inline void so3_exp(const double* w, double* R) {
+__host__ __device__ inline void so3_exp(const double* w, double* R) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = sqrt(th2);
   const bool small = th < kSmallAngle;
@@ -57,7 +49,7 @@ __host__ __device__ GCL_HEAVY inline void so3_exp(const double* w, double* R) {
 }
 
 // so3_log, pkg/common/geometry/se3_jax.py:304-366 (softmax-mixture axis near pi).
-__host__ __device__ GCL_HEAVY inline void so3_log(const double* R, double* w) {
+__host__ __device__ inline void so3_log(const double* R, double* w) {
   double c = 0.5 * (R[0] + R[4] + R[8] - 1.0);
   c = fmin(1.0, fmax(-1.0, c));
   const double th = acos(c);
@@ -90,7 +82,7 @@ __host__ __device__ GCL_HEAVY inline void so3_log(const double* R, double* w) {
 // A (row-major, symmetric part used) -> ascending eigenvalues `val`, eigenvectors as COLUMNS of V (row-major).
 // Matches LAPACK syevd on V diag(val) V^T to a few ulps of ||A|| (eigenvector signs are free; the rebuilt
 // matrix is not).  Replaces jnp.linalg.eigh at pkg/common/primitives.py:101 and matrix_fisher_evidence.py:104.
-__host__ __device__ GCL_HEAVY inline void sym_eig3(const double* Ain, double* val, double* V) {
+__host__ __device__ inline void sym_eig3(const double* Ain, double* val, double* V) {
   double a00 = Ain[0], a11 = Ain[4], a22 = Ain[8];
   double a01 = 0.5 * (Ain[1] + Ain[3]), a02 = 0.5 * (Ain[2] + Ain[6]), a12 = 0.5 * (Ain[5] + Ain[7]);
   double v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -135,7 +127,7 @@ __host__ __device__ GCL_HEAVY inline void sym_eig3(const double* Ain, double* va
 
 // domain_projection_psd_core, pkg/common/primitives.py:80-123.
 // cert = [projection_delta, sym_delta, eig_min, eig_max, cond, near_null_count]
-__host__ __device__ GCL_HEAVY inline void psd_project3(const double* M, double eps_psd, double* Mpsd, double* cert, double* vals_floored = nullptr) {
+__host__ __device__ inline void psd_project3(const double* M, double eps_psd, double* Mpsd, double* cert, double* vals_floored = nullptr) {
   double Ms[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) Ms[i * 3 + j] = 0.5 * (M[i * 3 + j] + M[j * 3 + i]);
@@ -183,7 +175,7 @@ __host__ __device__ inline double psd_project3_fast(const double* M, double eps_
 // H = U diag(s) V^T, s descending, U and V orthogonal (full matrices), as jnp.linalg.svd(H, full_matrices=True)
 // (matrix_fisher_evidence.py:215).  For a rank-deficient H the missing columns of U are completed orthonormally;
 // the reflection fix in the caller makes R_mf independent of that choice when s1 > s2.
-__host__ __device__ GCL_HEAVY inline void svd3(const double* H, double* U, double* s, double* V) {
+__host__ __device__ inline void svd3(const double* H, double* U, double* s, double* V) {
   double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int i = 0; i < 9; ++i) a[i] = H[i];
   for (int sweep = 0; sweep < 30; ++sweep) {

@@ -147,6 +147,7 @@ class LidarEvidencePipeline:
         self._inflight: Dict[int, tuple] = {}
         self._msg_layouts: Dict[tuple, tuple] = {}
         self._map_checked: Optional[tuple] = None
+        self._ov: Optional[Dict[str, Any]] = None          # streams / events of run_stream(overlap=True)
 
     # ------------------------------------------------------------------------------------------------------------
     def manifest_entries(self, n_gpus: int = 1, shard_mode: str = "none") -> Dict[str, Any]:
@@ -204,8 +205,8 @@ class LidarEvidencePipeline:
         stride = max(1, int(math.ceil(n_raw / cap))) if n_raw > 0 else 1
         return stride, (n_raw + stride - 1) // stride
 
-    def _buffers(self, n_jobs: int, ctas: int) -> Dict[str, torch.Tensor]:
-        key = (n_jobs, ctas)
+    def _buffers(self, n_jobs: int, ctas: int, slot: int = 0) -> Dict[str, torch.Tensor]:
+        key = (n_jobs, ctas, slot)
         b = self._bufs.get(key)
         if b is None:
             z = lambda *s: torch.empty(s, dtype=torch.float64, device=self.device)
@@ -267,22 +268,56 @@ class LidarEvidencePipeline:
     # ---- a stream of scans resident in HBM: three launches for the whole stream -------------------------------------------
     def run_stream(self, scans: Sequence[ResidentScan], xi_bodies, poses_pred: torch.Tensor, poses_update: Optional[torch.Tensor],
                    map_stats: ops.MapBinStats, iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False,
-                   forgetting: float = 0.99, jobs_dev: Optional[torch.Tensor] = None, ctas: Optional[int] = None) -> LidarScanEvidence:
+                   forgetting: float = 0.99, jobs_dev: Optional[torch.Tensor] = None, ctas: Optional[int] = None,
+                   overlap: bool = False) -> LidarScanEvidence:
         """scan_moments and reduce_finalize run for ALL scans at once (they do not depend on the map); one chain launch
-        then walks the scans in order.  Returns per-scan stats / evidence records (n_hyp = number of scans here)."""
+        then walks the scans in order.  Returns per-scan stats / evidence records (n_hyp = number of scans here).
+
+        ``overlap=True`` pipelines consecutive batches: the moment pass of this batch runs on an internal stream and only the
+        chain step (map + IW state carried from the previous batch) is ordered after the previous batch's chain, on a second,
+        high-priority internal stream -- the sequential chain keeps one SM busy while the next batch's moment pass fills the other
+        147.  Inputs must be ready on the current stream when the call is made; results alternate between two buffer sets and are
+        ordered on the current stream by ``join_stream()`` (they stay valid until the call after next)."""
         S = len(scans)
         xi = np.asarray(xi_bodies, dtype=np.float64).reshape(S, 6)
         max_sel = max(self.selected_rows(s.n_raw, self.n_points_cap)[1] for s in scans)
         ctas = self.plan_ctas(S, max_sel) if ctas is None else ctas
-        b = self._buffers(S, ctas)
         if jobs_dev is None:
             jobs_dev = self.jobs_to_device([self.make_job(scans[k], xi[k]) for k in range(S)])
-        self.launch_moments(jobs_dev, None, S, ctas, scans[0].layout, b["partials"])
-        self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, None, S, True, b["reduced"], b["stats"])
-        self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
-                          use_sigma_meas, forgetting)
+        if not overlap:
+            b = self._buffers(S, ctas)
+            self.launch_moments(jobs_dev, None, S, ctas, scans[0].layout, b["partials"])
+            self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, None, S, True, b["reduced"], b["stats"])
+            self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
+                              use_sigma_meas, forgetting)
+        else:
+            ov = self._ov
+            if ov is None:
+                ov = self._ov = {"s_mom": torch.cuda.Stream(device=self.device, priority=0), "s_chain": torch.cuda.Stream(device=self.device, priority=-1),
+                                 "free": [None, None], "turn": 0, "last": None}
+                cur = torch.cuda.current_stream(self.device)
+                ov["s_mom"].wait_stream(cur); ov["s_chain"].wait_stream(cur)     # everything enqueued so far comes first
+            i = ov["turn"] & 1
+            ov["turn"] += 1
+            b = self._buffers(S, ctas, slot=i)
+            if ov["free"][i] is not None:
+                ov["s_mom"].wait_event(ov["free"][i])                            # this buffer set was last read by the chain two calls ago
+            with torch.cuda.stream(ov["s_mom"]):
+                self.launch_moments(jobs_dev, None, S, ctas, scans[0].layout, b["partials"])
+                self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, None, S, True, b["reduced"], b["stats"])
+                ready = ov["s_mom"].record_event()
+            ov["s_chain"].wait_event(ready)
+            with torch.cuda.stream(ov["s_chain"]):
+                self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
+                                  use_sigma_meas, forgetting)
+                ov["free"][i] = ov["last"] = ov["s_chain"].record_event()
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=S, stats=b["stats"], evidence=b["evidence"], n_input=scans[0].n_raw,
                                  n_points_cap=self.n_points_cap)
+
+    def join_stream(self) -> None:
+        """Order the current stream after every batch submitted with ``run_stream(overlap=True)``."""
+        if self._ov is not None and self._ov["last"] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._ov["last"])
 
     # ---- one scan, H hypotheses, data already in HBM -------------------------------------------------------------------
     def run_resident(self, scan: ResidentScan, xi_bodies, poses_dev: torch.Tensor, map_stats: ops.MapBinStats,

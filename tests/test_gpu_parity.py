@@ -781,3 +781,31 @@ def test_pinned_buffers_reused_across_scans(g, O):
     # the copying path (pageable arrays) gives the same bits
     pageable = pl.process_scan_host(pts.copy(), ts.copy(), w.copy(), sc.scan_start_time, sc.scan_end_time, sc.xi_body[None], np.zeros((1, 6)), ms)
     assert np.array_equal(H(pageable.stats), H(ev.stats))
+
+
+def test_pipelined_batches_match_one_at_a_time(g, O):
+    """run_stream(overlap=True) -- moment pass of batch k+1 on one stream while the chain of batch k runs on another -- gives the
+    same bits as one batch at a time, with map and IW state carried through three consecutive batches."""
+    B, tau, cap, S = 48, g.synth.DEFAULT_TAU, 2048, 6
+    scans = [g.synth.make_scan(5000 + 13 * k, seed=700 + k) for k in range(S)]
+    poses = np.stack([np.array([0.01 * k, -0.005 * k, 0.0, 0.0, 0.0, 0.002 * k]) for k in range(S)])
+    out = {}
+    for mode in (False, True):
+        pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=scans[0].lidar_origin)
+        res = [pl.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
+        xis = np.stack([s.xi_body for s in scans])
+        pd = torch.from_numpy(poses).cuda()
+        ms, iw = g.create_empty_map_stats(B), pl.create_lidar_iw_state(1e-3)
+        torch.cuda.synchronize()
+        recs = []
+        for _ in range(3):
+            ev = pl.run_stream(res, xis, pd, pd, ms, iw_state=iw, use_sigma_meas=True, overlap=mode)
+            if mode:
+                pl.join_stream()
+            recs.append((H(ev.stats).copy(), H(ev.evidence).copy()))
+        torch.cuda.synchronize()
+        out[mode] = (recs, H(ms.S_dir).copy(), H(ms.sum_ppT).copy(), H(iw).copy())
+    for (sa, ea), (sb, eb) in zip(out[False][0], out[True][0]):
+        assert np.array_equal(sa, sb) and np.array_equal(ea, eb)
+    for a, b in zip(out[False][1:], out[True][1:]):
+        assert np.array_equal(a, b)
