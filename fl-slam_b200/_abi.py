@@ -73,6 +73,8 @@ def _load():
         "gcl_map_update": (i32, [vp, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, vp, vp]),
         "gcl_scan_chain": (i32, [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, f64,
                                  f64, f64, vp]),
+        "gcl_scan_chain_phase": (i32, [vp, vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, f64, f64, f64,
+                                       f64, f64, vp]),
         "gcl_scan_chain_workspace_doubles": (C.c_size_t, [i32, i32, i32]),
         "gcl_pointcloud2_ingest": (i32, [vp, vp, vp, i64, C.c_int32, vp, vp, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp]),
         "gcl_imu_preintegrate": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, i32, i32, vp, vp, vp]),

@@ -360,7 +360,18 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
                    double* map_derived, const double* pose_pred, const double* pose_update, double forgetting, double* iw_state,
                    int use_sigma_meas, double iw_rho, double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass,
                    double* evidence) {
+  return gcl_scan_chain_phase(h, stream, 0, stats, stats_stride, n_scans, n_hyp, n_bins, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT,
+                              map_derived, pose_pred, pose_update, forgetting, iw_state, use_sigma_meas, iw_rho, iw_nu_weak_add, iw_nu_max,
+                              eps_psd, eps_mass, evidence);
+}
+
+int gcl_scan_chain_phase(gcl_handle h, void* stream, int phase, double* stats, int64_t stats_stride, int n_scans, int n_hyp, int n_bins,
+                         double* mS_dir, double* mS_sc, double* mN_dir, double* mN_pos, double* msum_p, double* msum_ppT,
+                         double* map_derived, const double* pose_pred, const double* pose_update, double forgetting, double* iw_state,
+                         int use_sigma_meas, double iw_rho, double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass,
+                         double* evidence) {
   if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, phase >= 0 && phase <= 2, "phase must be 0 (all), 1 (map-dependent part) or 2 (IW-dependent part)");
   GCL_REQUIRE(h, n_scans >= 1 && n_hyp >= 1 && n_bins >= 1, "n_scans, n_hyp, n_bins must be >= 1");
   GCL_REQUIRE(h, stats && mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT && map_derived && pose_pred && evidence,
               "NULL pointer");
@@ -372,7 +383,7 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
   P.map_sum_ppT = msum_ppT; P.workspace = map_derived; P.pose_pred = pose_pred; P.pose_update = pose_update;
   P.iw_state = iw_state; P.evidence = evidence; P.n_scans = n_scans; P.n_hyp = n_hyp; P.n_bins = n_bins;
   P.use_sigma_meas = use_sigma_meas; P.forgetting = forgetting; P.iw_rho = iw_rho; P.iw_nu_weak_add = iw_nu_weak_add;
-  P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.chain_smem = 0;
+  P.iw_nu_max = iw_nu_max; P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.chain_smem = 0; P.phase = phase;
   cudaSetDevice(h->device);
   int l = 0;
   GCL_CUDA(h, launch_chain(P, (cudaStream_t)stream, &l));

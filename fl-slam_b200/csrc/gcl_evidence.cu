@@ -954,7 +954,11 @@ __global__ void __launch_bounds__(32) stream_translation_finish_kernel(const __g
 
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches) {
   *launches = 0;
+  // phase 0: everything.  Phases 1 / 2 split a staged stream for pipelining across batches: 1 = what depends only on the map of
+  // the previous batch (increments, map recurrence, map-derived statistics, rotation evidence, pre blocks), 2 = what depends on
+  // its IW state (the sequential measurement-noise core and the translation finish).  A short chain runs whole in phase 2.
   if (P.n_scans < kStagedMinScans) {
+    if (P.phase == 1) return cudaSuccess;
     ChainParams Q = P;
     const size_t smem = 16 * (size_t)P.n_bins * sizeof(double);
     Q.chain_smem = smem <= 40 * 1024;
@@ -963,13 +967,16 @@ cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launche
     return cudaGetLastError();
   }
   const int B = P.n_bins, S = P.n_scans;
-  if (P.pose_update) {
-    stream_increments_kernel<<<S, B < 128 ? ((B + 31) / 32) * 32 : 128, 0, stream>>>(P);
-    stream_map_recurrence_kernel<<<(26 * B + 127) / 128, 128, 0, stream>>>(P);
-    *launches += 2;
+  if (P.phase != 2) {
+    if (P.pose_update) {
+      stream_increments_kernel<<<S, B < 128 ? ((B + 31) / 32) * 32 : 128, 0, stream>>>(P);
+      stream_map_recurrence_kernel<<<(26 * B + 127) / 128, 128, 0, stream>>>(P);
+      *launches += 2;
+    }
+    stream_evidence_kernel<<<S, kChainThreads, 0, stream>>>(P);
+    *launches += 1;
   }
-  stream_evidence_kernel<<<S, kChainThreads, 0, stream>>>(P);
-  *launches += 1;
+  if (P.phase == 1) return cudaGetLastError();
   if (P.iw_state && P.use_sigma_meas) {
     const size_t smem = 2 * pre_block_doubles(B) * sizeof(double);
     const int use_smem = smem <= 200 * 1024;

@@ -122,6 +122,7 @@ struct ChainParams {
   double* evidence;         // (n_scans * n_hyp) records
   int n_scans, n_hyp, n_bins, use_sigma_meas;
   int chain_smem;           // single-launch chain: map-derived statistics live in dynamic shared memory
+  int phase = 0;            // staged stream: 0 = all, 1 = map-dependent part, 2 = IW-dependent part (launch_chain)
   double forgetting, iw_rho, iw_nu_weak_add, iw_nu_max, eps_psd, eps_mass;
   // single-launch host staging (one scan, gcl_scan_evidence_begin_host): the kernel itself carries the small blocks across PCIe
   // -- inputs out of page-locked host memory first, outputs back at the end, then a completion flag the host polls -- so that

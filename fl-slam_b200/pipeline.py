@@ -250,9 +250,10 @@ class LidarEvidencePipeline:
 
     def launch_chain(self, stats: torch.Tensor, n_scans: int, n_hyp: int, m: ops.MapBinStats, map_derived: torch.Tensor,
                      poses_pred: torch.Tensor, poses_update: Optional[torch.Tensor], evidence: torch.Tensor,
-                     iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False, forgetting: float = 0.99) -> None:
-        """The sequential part of a stream in one launch (gcl_scan_chain): map + IW state stay on the device."""
-        _abi.check(_lib.gcl_scan_chain(self.handle, ops._stream(), ops._ptr(stats), self.srec, n_scans, n_hyp, self.n_bins,
+                     iw_state: Optional[torch.Tensor] = None, use_sigma_meas: bool = False, forgetting: float = 0.99, phase: int = 0) -> None:
+        """The sequential part of a stream in one launch (gcl_scan_chain): map + IW state stay on the device.  ``phase`` 1 / 2:
+        the map-dependent and the IW-dependent half (gcl_scan_chain_phase)."""
+        _abi.check(_lib.gcl_scan_chain_phase(self.handle, ops._stream(), int(phase), ops._ptr(stats), self.srec, n_scans, n_hyp, self.n_bins,
                                        ops._ptr(m.S_dir), ops._ptr(m.S_dir_scatter), ops._ptr(m.N_dir), ops._ptr(m.N_pos),
                                        ops._ptr(m.sum_p), ops._ptr(m.sum_ppT), ops._ptr(map_derived), ops._ptr(poses_pred),
                                        ops._ptr(poses_update), float(forgetting), ops._ptr(iw_state), 1 if use_sigma_meas else 0,
@@ -305,11 +306,15 @@ class LidarEvidencePipeline:
             with torch.cuda.stream(ov["s_mom"]):
                 self.launch_moments(jobs_dev, None, S, ctas, scans[0].layout, b["partials"])
                 self.launch_finalize(b["partials"], ctas, self.rec, self.rec * ctas, jobs_dev, None, S, True, b["reduced"], b["stats"])
+                # the half of the chain that depends only on the map (left by the previous batch's phase 1, same stream)
+                self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
+                                  use_sigma_meas, forgetting, phase=1)
                 ready = ov["s_mom"].record_event()
             ov["s_chain"].wait_event(ready)
             with torch.cuda.stream(ov["s_chain"]):
+                # the half that depends on the IW state (left by the previous batch's phase 2, same stream)
                 self.launch_chain(b["stats"], S, 1, map_stats, b["map_derived"], poses_pred, poses_update, b["evidence"], iw_state,
-                                  use_sigma_meas, forgetting)
+                                  use_sigma_meas, forgetting, phase=2)
                 ov["free"][i] = ov["last"] = ov["s_chain"].record_event()
         return LidarScanEvidence(n_bins=self.n_bins, n_hyp=S, stats=b["stats"], evidence=b["evidence"], n_input=scans[0].n_raw,
                                  n_points_cap=self.n_points_cap)

@@ -239,6 +239,18 @@ int gcl_scan_chain(gcl_handle h, void* stream, double* stats, int64_t stats_stri
                    const double* pose_update, double forgetting, double* iw_state, int use_sigma_meas, double iw_rho,
                    double iw_nu_weak_add, double iw_nu_max, double eps_psd, double eps_mass, double* evidence);
 
+/* gcl_scan_chain in two halves, for pipelining consecutive batches of one stream on two CUDA streams: phase 1 launches what
+ * depends only on the MAP left by the previous batch (world-frame increments, map recurrence, map-derived statistics, rotation
+ * evidence), phase 2 what depends on its IW state (the sequential measurement-noise core, translation finish).  Phase 1 of batch
+ * k+1 may run while phase 2 of batch k is still walking its scans (separate stats / workspace / evidence buffers per batch);
+ * phase 0 = both, i.e. gcl_scan_chain.  A chain shorter than 4 scans runs whole in phase 2. */
+int gcl_scan_chain_phase(gcl_handle h, void* stream, int phase, double* stats, int64_t stats_stride_doubles, int n_scans,
+                         int n_hyp, int n_bins, double* map_S_dir, double* map_S_dir_scatter, double* map_N_dir,
+                         double* map_N_pos, double* map_sum_p, double* map_sum_ppT, double* workspace,
+                         const double* pose_pred, const double* pose_update, double forgetting, double* iw_state,
+                         int use_sigma_meas, double iw_rho, double iw_nu_weak_add, double iw_nu_max, double eps_psd,
+                         double eps_mass, double* evidence);
+
 /* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,
                         const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,
