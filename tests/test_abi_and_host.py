@@ -135,3 +135,57 @@ def test_launch_planning_without_a_gpu(g):
     assert lib.gcl_plan_ctas_per_job(None, 1, 0, 48, 0) >= 1
     w = [lib.gcl_scan_chain_workspace_doubles(s, h, b) for s, h, b in ((1, 1, 48), (200, 1, 48), (200, 4, 48), (200, 4, 256))]
     assert w == sorted(w) and w[0] >= 16 * 48
+
+
+# ---- message path: host-side pieces (the device side is covered by the gpu tests) -------------------------------------------
+@pytest.mark.parametrize("time_field,step", [("time_f32", 22), ("t_f64", 26), ("t_u32ns", 22), (None, 18)])
+def test_synthetic_pointcloud2_parses_back_with_the_oracle(g, time_field, step):
+    """synth.make_pointcloud2 writes the VLP-16 message layout the reference parser reads (backend_node.py:377-468): the oracle's
+    restatement of that parser recovers points (to float32 rounding), ring, weights and the per-point times."""
+    from oracle import gc_oracle as O
+    sc = g.synth.make_scan(3000, seed=5, with_times=time_field is not None)
+    R, t = g.synth.rotation_from_rotvec(np.array([0.02, -0.01, 0.3])), sc.lidar_origin
+    base = sc.scan_start_time - (0.5 if time_field == "t_u32ns" else 12.25)
+    m = g.synth.make_pointcloud2(sc, R, t, time_field=time_field, time_base=base, header_stamp_sec=12.0)
+    assert m["point_step"] == step and m["data"].size == 3000 * step
+    par = O.parse_pointcloud2_vlp16(m["data"], m["fields"], m["point_step"], m["n_points"], header_stamp=(12.0, 0))
+    assert np.max(np.abs(O.lidar_points_to_base(par["points"], R, t) - sc.points)) < 5e-6
+    assert np.array_equal(par["ring"], sc.ring)
+    np.testing.assert_allclose(par["weights"], sc.weights, rtol=0, atol=2e-6)   # the window sees float32 coordinates
+    if time_field is None:
+        assert np.all(par["timestamps"] == 12.0)
+    else:
+        np.testing.assert_allclose(par["timestamps"], sc.timestamps - base, rtol=0, atol=2e-6)
+
+
+def test_scan_time_bounds_rule():
+    """pkg/backend/backend_node.py:1776-1786."""
+    from oracle import gc_oracle as O
+    assert O.scan_time_bounds(np.array([5.0, 5.0, 5.0]), 7.0) == (5.0, 7.0)                 # no per-point spread: [min, stamp]
+    assert O.scan_time_bounds(np.array([5.0, 5.0 + 5e-10]), 4.0) == (5.0, 4.0)              # below the 1e-9 threshold, even backwards
+    assert O.scan_time_bounds(np.array([5.0, 5.1]), 5.05) == (5.0, 5.1)                     # stamp inside
+    assert O.scan_time_bounds(np.array([5.0, 5.1]), 4.9) == (4.9, 5.1)                      # stamp before
+    assert O.scan_time_bounds(np.array([5.0, 5.1]), 5.3) == (5.0, 5.3)                      # stamp after
+
+
+def test_message_submit_argument_checks_need_no_gpu(g):
+    """The layout / argument checks of submit_scan_msg_host run before anything touches the device."""
+    pl = object.__new__(g.LidarEvidencePipeline)
+    pl._msg_layouts = {}
+    f3 = [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)]
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(16), fields=f3 + [("ring", 12, 4)], point_step=16, n_points=1)          # neither twist nor IMU
+    with pytest.raises(RuntimeError):
+        pl.submit_scan_msg_host(0, data=bytes(12), fields=f3, point_step=12, n_points=1, xi_body=np.zeros((1, 6)))    # no ring field
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(16), fields=f3 + [("ring", 12, 9)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
+    with pytest.raises(ValueError):
+        pl.submit_scan_msg_host(0, data=bytes(8), fields=f3 + [("ring", 12, 4)], point_step=16, n_points=1, xi_body=np.zeros((1, 6)))
+    c = g.LidarEvidencePipeline._c64
+    a = np.zeros((4, 3))
+    assert c(a, 12) is a and c(a, 0, 3) is a
+    assert c([[1, 2, 3]], 3).dtype == np.float64
+    with pytest.raises(ValueError):
+        c(a, 9)
+    with pytest.raises(ValueError):
+        c(np.zeros(7), 0, 3)
