@@ -537,10 +537,17 @@ static bool is_pinned(gcl_handle h, const void* p) {
   return v;
 }
 
-int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
+static bool is_pinned_now(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess) return a.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return false;
+}
+
+static int submit_arrays(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
                          const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1, const double* xi_host,
                          int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
-                         double eps_psd, double eps_mass) {
+                         double eps_psd, double eps_mass, bool latency_call) {
   if (!h) return GCL_ERR_ARG;
   GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
   GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
@@ -582,8 +589,13 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   // out of host memory (unified addressing; each value is read exactly once, prefetched a tile ahead with cp.async).  With
   // stride 4 that is 0.54 MB over PCIe instead of 1.2 MB through the copy engine, and three cudaMemcpyAsync calls plus the
   // copy-stream event hand-off less on the host.  GCL_HOST_ZERO_COPY=0 restores the copies.
+  // For the copy engine a stale "page-locked" answer from the cache is harmless; a kernel reading the array is not, so the
+  // zero-copy decision asks the driver afresh (~2 us per array).  That is worth it where the latency of stage 1 counts -- the
+  // blocking call: 121 -> 105 us -- and not in the two-stage form, whose stage 1 is hidden behind the previous scan's evidence
+  // step (there it cost 6 us per scan of host time for nothing), so only the blocking entry takes this route.
   static const bool zero_copy_ok = !(getenv("GCL_HOST_ZERO_COPY") && atoi(getenv("GCL_HOST_ZERO_COPY")) == 0);
-  const bool zero_copy = direct && n_hyp == 1 && zero_copy_ok && !g_ht.on;
+  const bool zero_copy = latency_call && direct && n_hyp == 1 && zero_copy_ok && !g_ht.on && is_pinned_now(points_host) &&
+                         is_pinned_now(timestamps_host) && is_pinned_now(weights_host);
   if (!direct && n > 0) {
     memcpy(hb + o_pts, points_host, n * 24);
     memcpy(hb + o_ts, timestamps_host, n * 8);
@@ -642,6 +654,14 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   S.n_hyp = n_hyp; S.n_bins = n_bins; S.d_stats = d_stats; S.pending = true;
   S.eps_psd = eps_psd; S.eps_mass = eps_mass;
   return GCL_OK;
+}
+
+int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
+                         const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1, const double* xi_host,
+                         int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
+                         double eps_psd, double eps_mass) {
+  return submit_arrays(h, slot_index, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
+                       bins_host, n_bins, tau, precision, eps_psd, eps_mass, false);
 }
 
 // Stage 1 from the MESSAGE: the raw PointCloud2 bytes (point_step bytes per point, 22 for the Kimera VLP-16 layout against 40
@@ -992,8 +1012,8 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
   GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
   GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
-  int rc = gcl_scan_submit_host(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
-                                bins_host, n_bins, tau, precision, eps_psd, eps_mass);
+  int rc = submit_arrays(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
+                         bins_host, n_bins, tau, precision, eps_psd, eps_mass, true);
   if (rc != GCL_OK) return rc;
   return gcl_scan_evidence_host(h, 0, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host, forgetting,
                                 iw_state_host, use_sigma_meas, stats_host, evidence_host);

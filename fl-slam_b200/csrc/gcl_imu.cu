@@ -54,6 +54,11 @@ __global__ void __launch_bounds__(kImuThreads) imu_preintegrate_kernel(const __g
   so3_exp(P.rotvec_start + h * 3, R_start);
 
   // ---- pass 1: product of this thread's per-sample rotations, sum of weights --------------------------------------------
+  // (with at most kKeep samples per thread -- 512 samples: 2 -- the window weight and the sample rotation are kept in registers
+  // for pass 2 instead of being evaluated again: two exponentials and a Rodrigues formula per sample)
+  constexpr int kKeep = 2;
+  const bool keep = C <= kKeep;
+  double k_dte[kKeep] = {0, 0}, k_dR[kKeep][9];
   double Pm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ess = 0.0;
   for (int i = i0; i < i1; ++i) {
     const double w = imu_weight(P, i);
@@ -66,6 +71,15 @@ __global__ void __launch_bounds__(kImuThreads) imu_preintegrate_kernel(const __g
     mat3_mul(Pm, dR, T);
     for (int k = 0; k < 9; ++k) Pm[k] = T[k];
     ess += w;
+    if (keep) {
+#pragma unroll
+      for (int j = 0; j < kKeep; ++j)
+        if (i - i0 == j) {
+          k_dte[j] = dte;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) k_dR[j][k] = dR[k];
+        }
+    }
   }
   // ---- inclusive scan of the thread products (earlier threads multiply from the LEFT): warp scan, then warp totals --------
   double Q[9];
@@ -104,9 +118,14 @@ __global__ void __launch_bounds__(kImuThreads) imu_preintegrate_kernel(const __g
   // ---- pass 2: accelerations in the world frame, local velocity / position integrals, weighted means ---------------------
   double v[3] = {0, 0, 0}, p[3] = {0, 0, 0}, Tl = 0.0, s_ab[3] = {0, 0, 0}, s_awn[3] = {0, 0, 0}, s_aw[3] = {0, 0, 0};
   for (int i = i0; i < i1; ++i) {
-    const double w = imu_weight(P, i);
-    const double dt = (i + 1 < M) ? fmax(P.stamps[i + 1] - P.stamps[i], 0.0) : 0.0;
-    const double dte = w * dt;
+    double dte;
+    if (keep) {
+      dte = (i - i0 == 0) ? k_dte[0] : k_dte[1];
+    } else {
+      const double w = imu_weight(P, i);
+      const double dt = (i + 1 < M) ? fmax(P.stamps[i + 1] - P.stamps[i], 0.0) : 0.0;
+      dte = w * dt;
+    }
     const double ab[3] = {P.accel[i * 3] - ba[0], P.accel[i * 3 + 1] - ba[1], P.accel[i * 3 + 2] - ba[2]};
     double awn[3], aw[3];
     for (int r = 0; r < 3; ++r) {
@@ -120,9 +139,14 @@ __global__ void __launch_bounds__(kImuThreads) imu_preintegrate_kernel(const __g
       v[r] = v[r] + aw[r] * dte;
     }
     if (i + 1 < i1) {
-      const double om[3] = {(P.gyro[i * 3] - bg[0]) * dte, (P.gyro[i * 3 + 1] - bg[1]) * dte, (P.gyro[i * 3 + 2] - bg[2]) * dte};
       double dR[9], T[9];
-      so3_exp(om, dR);
+      if (keep) {   // only the first kept sample can have a successor in this chunk
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dR[k] = k_dR[0][k];
+      } else {
+        const double om[3] = {(P.gyro[i * 3] - bg[0]) * dte, (P.gyro[i * 3 + 1] - bg[1]) * dte, (P.gyro[i * 3 + 2] - bg[2]) * dte};
+        so3_exp(om, dR);
+      }
       mat3_mul(Rc, dR, T);
       for (int k = 0; k < 9; ++k) Rc[k] = T[k];
     }

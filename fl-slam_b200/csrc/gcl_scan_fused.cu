@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   const double cscale_d = Num<T>::kScale / P.tau;
   const T cscale = (T)cscale_d;
 
-  // --- zero this CTA's record; atlas (pre-scaled) and exp table to shared --------------------------------------------------
-  for (int i = tid; i < GCL_NM * B + GCL_NCERT; i += kNT) part[i] = 0.0;
+  // --- atlas (pre-scaled) and exp table to shared (the CTA's record is written, not accumulated, by its first flush) ----------
+  bool flushed = false;
   {
     const int nb = TA * BA;  // padded bin count of phase A
     constexpr int V = Num<T>::kVec;
@@ -360,15 +360,26 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   if (stride > 1 && hi > lo) {
     const int64_t rlo = lo * stride;
     const int64_t rhi = (hi >= n_sel_total) ? n_raw : hi * stride;
-    // four loads in flight per thread; the partial sums are combined in a fixed order
+    // eight loads in flight per thread (this is a latency-bound prologue: ~24 loads per thread on the stream workload, and a
+    // load -> add pair per iteration would pay the DRAM latency every time); the partial sums are combined in a fixed order
     double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     int64_t r = rlo + tid;
     if (P.layout == GCL_LAYOUT_REF_F64) {
       const double* w = static_cast<const double*>(J.weights);
+      for (; r + 7 * kNT < rhi; r += 8 * kNT) {
+        const double a0 = w[r], a1 = w[r + kNT], a2 = w[r + 2 * kNT], a3 = w[r + 3 * kNT];
+        const double a4 = w[r + 4 * kNT], a5 = w[r + 5 * kNT], a6 = w[r + 6 * kNT], a7 = w[r + 7 * kNT];
+        p0 += a0; p1 += a1; p2 += a2; p3 += a3; p0 += a4; p1 += a5; p2 += a6; p3 += a7;
+      }
       for (; r + 3 * kNT < rhi; r += 4 * kNT) { p0 += w[r]; p1 += w[r + kNT]; p2 += w[r + 2 * kNT]; p3 += w[r + 3 * kNT]; }
       for (; r < rhi; r += kNT) p0 += w[r];
     } else {
       const float* w = static_cast<const float*>(J.weights);
+      for (; r + 7 * kNT < rhi; r += 8 * kNT) {
+        const float a0 = w[r], a1 = w[r + kNT], a2 = w[r + 2 * kNT], a3 = w[r + 3 * kNT];
+        const float a4 = w[r + 4 * kNT], a5 = w[r + 5 * kNT], a6 = w[r + 6 * kNT], a7 = w[r + 7 * kNT];
+        p0 += (double)a0; p1 += (double)a1; p2 += (double)a2; p3 += (double)a3; p0 += (double)a4; p1 += (double)a5; p2 += (double)a6; p3 += (double)a7;
+      }
       for (; r + 3 * kNT < rhi; r += 4 * kNT) { p0 += (double)w[r]; p1 += (double)w[r + kNT]; p2 += (double)w[r + 2 * kNT]; p3 += (double)w[r + 3 * kNT]; }
       for (; r < rhi; r += kNT) p0 += (double)w[r];
     }
@@ -394,11 +405,12 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
         if (k < GCL_NM && b < B) {
           double s = 0.0;
           for (int sl = 0; sl < PS; ++sl) s += (double)s_stage[((size_t)sl * kKC + kc) * Bp + b];
-          part[(size_t)k * B + b] += s;
+          if (flushed) part[(size_t)k * B + b] += s; else part[(size_t)k * B + b] = s;   // no read-modify-write the first time
         }
       }
       __syncthreads();
     }
+    flushed = true;
     acc.zero();
   };
 
@@ -540,6 +552,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   }
   __syncthreads();
   if (pts_since_flush > 0) flush();
+  if (!flushed)   // a CTA without rows: its record is all zeros
+    for (int i = tid; i < GCL_NM * B; i += kNT) part[i] = 0.0;
 
   // --- certificate scalars of this CTA -------------------------------------------------------------------------
 #pragma unroll

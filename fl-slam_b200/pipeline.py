@@ -500,8 +500,18 @@ class LidarEvidencePipeline:
         poses = f(pose_pred, (-1, 6))
         if poses.shape[0] != H:
             raise ValueError("xi_body and pose_pred must have one row per hypothesis")
-        # the map arrays and the IW state usually are the SAME objects scan after scan (updated in place): their checks and
-        # addresses are remembered and re-used as long as every array is the very object that was checked
+        arrs, ma = self._map_args(map_stats_host, iw_state_host, pose_update is not None)
+        p = self._addr
+        pu = None if pose_update is None else f(pose_update, (6,))
+        _abi.check(_lib.gcl_scan_evidence_begin_host(self.handle, int(slot), poses.ctypes.data, ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], p(pu),
+                                                     float(forgetting), ma[6], 1 if use_sigma_meas else 0), self.handle)
+        self._stage2 = (H, n, arrs, ma, ess_imu, chart_id, anchor_id, poses, pu)
+
+    def _map_args(self, map_stats_host: Dict[str, np.ndarray], iw_state_host: Optional[np.ndarray], in_place: bool):
+        """The six map arrays + the IW state as (arrays, addresses).  They usually are the SAME objects scan after scan (updated
+        in place): their checks and addresses are remembered and re-used as long as every array is the very object that was
+        checked."""
+        f = self._f64
         mc = self._map_checked
         arrs = (map_stats_host["S_dir"], map_stats_host["S_dir_scatter"], map_stats_host["N_dir"], map_stats_host["N_pos"],
                 map_stats_host["sum_p"], map_stats_host["sum_ppT"], iw_state_host)
@@ -512,7 +522,7 @@ class LidarEvidencePipeline:
             shapes = self._map_shapes()
             conforming = all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == sh
                              for a, (k, sh) in zip(arrs, shapes))
-            if pose_update is not None and not conforming:   # in/out: the caller's arrays are written, so they must be usable as they are
+            if in_place and not conforming:   # in/out: the caller's arrays are written, so they must be usable as they are
                 raise ValueError("map_stats_host arrays must be C-contiguous float64 arrays of shapes "
                                  f"{dict(shapes)} for an in-place update")
             if iw_state_host is not None and not (isinstance(iw_state_host, np.ndarray) and iw_state_host.dtype == np.float64
@@ -525,11 +535,7 @@ class LidarEvidencePipeline:
                 conv = tuple(f(a, sh) for a, (k, sh) in zip(arrs, shapes)) + (iw_state_host,)
                 ma = tuple(None if a is None else a.ctypes.data for a in conv)
                 arrs = conv
-        p = self._addr
-        pu = None if pose_update is None else f(pose_update, (6,))
-        _abi.check(_lib.gcl_scan_evidence_begin_host(self.handle, int(slot), poses.ctypes.data, ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], p(pu),
-                                                     float(forgetting), ma[6], 1 if use_sigma_meas else 0), self.handle)
-        self._stage2 = (H, n, arrs, ma, ess_imu, chart_id, anchor_id, poses, pu)
+        return arrs, ma
 
     def evidence_end_host(self) -> LidarScanEvidence:
         """Second half of stage 2 (gcl_scan_evidence_end_host): wait for the D2H, write the map / IW arrays back, return."""
@@ -557,10 +563,29 @@ class LidarEvidencePipeline:
         poses = np.asarray(pose_pred, dtype=np.float64).reshape(-1, 6)
         if poses.shape[0] != xi.shape[0]:
             raise ValueError("xi_body and pose_pred must have one row per hypothesis")
-        self.submit_scan_host(0, points, timestamps, weights, scan_start_time, scan_end_time, xi)
-        return self.evidence_host(0, poses, map_stats_host, ess_imu=ess_imu, chart_id=chart_id, anchor_id=anchor_id,
-                                  pose_update=pose_update, forgetting=forgetting, iw_state_host=iw_state_host,
-                                  use_sigma_meas=use_sigma_meas)
+        c = self._c64
+        pts, ts, w = c(points, 0, 3), c(timestamps, 0, 1), c(weights, 0, 1)
+        n = ts.size
+        if pts.size != 3 * n or w.size != n:
+            raise ValueError("points, timestamps and weights must have the same length")
+        xi, poses = np.ascontiguousarray(xi), np.ascontiguousarray(poses)
+        H = xi.shape[0]
+        arrs, ma = self._map_args(map_stats_host, iw_state_host, pose_update is not None)
+        pu = None if pose_update is None else self._f64(pose_update, (6,))
+        bins_host = getattr(self, "_bins_host", None)
+        if bins_host is None:
+            bins_host = self._bins_host = np.ascontiguousarray(self.bin_dirs.detach().cpu().numpy())
+        stats = np.empty((H, self.srec), dtype=np.float64)
+        evid = np.empty((H, _abi.GCL_EVID_DOUBLES), dtype=np.float64)
+        ad = self._addr
+        _abi.check(_lib.gcl_lidar_scan_evidence_host(
+            self.handle, pts.ctypes.data, ts.ctypes.data, w.ctypes.data, n, self.n_points_cap, float(scan_start_time), float(scan_end_time),
+            xi.ctypes.data, poses.ctypes.data, H, ad(self.origin), ad(bins_host), self.n_bins, self.tau, PRECISIONS[self.precision],
+            ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], ad(pu), float(forgetting), ma[6], 1 if use_sigma_meas else 0, self.eps_psd,
+            self.eps_mass, stats.ctypes.data, evid.ctypes.data), self.handle)
+        return LidarScanEvidence(n_bins=self.n_bins, n_hyp=H, stats=torch.from_numpy(stats), evidence=torch.from_numpy(evid),
+                                 stats_host=stats, evidence_host=evid, chart_id=chart_id, anchor_id=anchor_id, n_input=n,
+                                 n_points_cap=self.n_points_cap, ess_imu=ess_imu)
 
 
 def lidar_scan_evidence(points, timestamps, weights, *, scan_start_time: float, scan_end_time: float, xi_body, belief_pred,
