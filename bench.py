@@ -199,6 +199,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout, where the one JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
     tau = synth.DEFAULT_TAU
     peak_gbs, peak_src = load_peaks()

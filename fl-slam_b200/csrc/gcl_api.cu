@@ -68,9 +68,9 @@ void gcl_destroy(gcl_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-  if (h->stream1) { cudaStreamSynchronize(h->stream1); cudaStreamDestroy(h->stream1); }
   if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
   for (int i = 0; i < GCL_HOST_SLOTS; ++i) {
+    if (h->slot[i].stream1) { cudaStreamSynchronize(h->slot[i].stream1); cudaStreamDestroy(h->slot[i].stream1); }
     if (h->slot[i].ev_copy) cudaEventDestroy(h->slot[i].ev_copy);
     if (h->slot[i].ev_stage1) cudaEventDestroy(h->slot[i].ev_stage1);
     if (h->slot[i].d_buf) cudaFree(h->slot[i].d_buf);
@@ -481,9 +481,9 @@ static int grow(gcl_handle h, void** d, size_t* dcap, void** hp, size_t* hcap, s
 static int ensure_streams(gcl_handle h) {
   if (h->stream) return GCL_OK;
   GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream1, cudaStreamNonBlocking));
   GCL_CUDA(h, cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
   for (int i = 0; i < GCL_HOST_SLOTS; ++i) {
+    GCL_CUDA(h, cudaStreamCreateWithFlags(&h->slot[i].stream1, cudaStreamNonBlocking));
     GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_copy, cudaEventDisableTiming));
     GCL_CUDA(h, cudaEventCreateWithFlags(&h->slot[i].ev_stage1, cudaEventDisableTiming));
   }
@@ -498,7 +498,11 @@ struct HostTiming {
   void start() { if (on) t = std::chrono::steady_clock::now(); }
   void mark(int i, gcl_handle h, bool sync = true) {
     if (!on) return;
-    if (sync) { cudaStreamSynchronize(h->stream_copy); cudaStreamSynchronize(h->stream1); cudaStreamSynchronize(h->stream); }
+    if (sync) {
+      cudaStreamSynchronize(h->stream_copy);
+      for (int i = 0; i < GCL_HOST_SLOTS; ++i) cudaStreamSynchronize(h->slot[i].stream1);
+      cudaStreamSynchronize(h->stream);
+    }
     const auto now = std::chrono::steady_clock::now();
     acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
     t = now;
@@ -561,7 +565,7 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
   if (rc != GCL_OK) return rc;
   gcl_handle_s::Slot& S = h->slot[slot_index];
   if (S.pending) {  // a scan that was submitted and never collected is dropped
-    cudaStreamSynchronize(h->stream1);
+    cudaStreamSynchronize(S.stream1);
     S.pending = false;
   }
   const size_t B = n_bins, H = n_hyp, n = (size_t)n_raw;
@@ -617,7 +621,7 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
     j.scan_start_time = t0; j.scan_end_time = t1;
     for (int k = 0; k < 6; ++k) j.xi_body[k] = xi_host[i * 6 + k];
   }
-  cudaStream_t sc = h->stream_copy, s1 = h->stream1;
+  cudaStream_t sc = h->stream_copy, s1 = S.stream1;
   if (zero_copy) {
     if (!atlas_same) GCL_CUDA(h, cudaMemcpyAsync(db + o_bins, hb + o_bins, B * 24, cudaMemcpyHostToDevice, s1));
   } else if (direct) {
@@ -703,7 +707,7 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
   int rc = ensure_streams(h);
   if (rc != GCL_OK) return rc;
   gcl_handle_s::Slot& S = h->slot[slot_index];
-  if (S.pending) { cudaStreamSynchronize(h->stream1); S.pending = false; }
+  if (S.pending) { cudaStreamSynchronize(S.stream1); S.pending = false; }
   const size_t B = n_bins, H = n_hyp, n = (size_t)n_points, M = imu ? (size_t)imu_samples : 0;
   int64_t stride = (n_points + cap - 1) / cap; if (stride < 1) stride = 1;
   const int64_t n_sel = (n_points + stride - 1) / stride;
@@ -750,7 +754,7 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
     memcpy(himu + 7 * M, rotvec_start_host, H * 24); memcpy(himu + 7 * M + 3 * H, gyro_bias_host, H * 24);
     memcpy(himu + 7 * M + 6 * H, accel_bias_host, H * 24);
   }
-  cudaStream_t sc = h->stream_copy, s1 = h->stream1;
+  cudaStream_t sc = h->stream_copy, s1 = S.stream1;
   const bool direct = n > 0 && is_pinned(h, msg_host);
   if (direct) {
     GCL_CUDA(h, cudaMemcpyAsync(db, hb, o_msg, cudaMemcpyHostToDevice, sc));

@@ -27,7 +27,6 @@ struct gcl_handle_s {
   unsigned long long done_seq = 0;     // completion ticket of the single-launch evidence step (0 = the copy-engine path is in flight)
   unsigned long long* done_flag = nullptr;   // page-locked word the chain kernel writes the ticket to
   cudaStream_t stream = nullptr;       // stage 2: chain step + D2H
-  cudaStream_t stream1 = nullptr;      // stage 1: scan_moments + reduce_finalize
   cudaStream_t stream_copy = nullptr;  // H2D of the scans
   void* d_buf = nullptr; size_t d_bytes = 0;   // stage-2 block
   void* h_buf = nullptr; size_t h_bytes = 0;
@@ -35,6 +34,7 @@ struct gcl_handle_s {
     void* d_buf = nullptr; size_t d_bytes = 0;
     void* h_buf = nullptr; size_t h_bytes = 0;
     cudaEvent_t ev_copy = nullptr, ev_stage1 = nullptr;
+    cudaStream_t stream1 = nullptr;     // stage 1 of this slot (its own stream: the stage-1 chains of scans in flight overlap)
     double* d_stats = nullptr;
     int n_hyp = 0, n_bins = 0;
     double eps_psd = 0, eps_mass = 0;
