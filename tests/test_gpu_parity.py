@@ -809,3 +809,41 @@ def test_pipelined_batches_match_one_at_a_time(g, O):
         assert np.array_equal(sa, sb) and np.array_equal(ea, eb)
     for a, b in zip(out[False][1:], out[True][1:]):
         assert np.array_equal(a, b)
+
+
+def test_message_path_hypothesis_batch_and_empty_message(g, O):
+    """Three hypotheses (start orientation and biases differ) from one message + IMU buffer: per-hypothesis twist and bin statistics
+    against the oracle; then an EMPTY message through the same entry (bounds = [stamp, stamp], all-zero statistics, no fault)."""
+    B, tau, n, cap = 48, g.synth.DEFAULT_TAU, 9000, 4096
+    sc, msg, R_bl, t_bl, par, pts_base, t0, t1 = _msg_case(g, O, "time_f32", n, seed=321)
+    bins = O.create_fibonacci_atlas(B)
+    imu = g.synth.make_imu_buffer(t0, t1, 300, seed=7)          # not a multiple of the CTA width
+    rv = np.array([[0.01, -0.02, 0.4], [0.3, 0.1, -0.2], [0.0, 0.0, 0.0]])
+    bg = np.array([[1e-3, -2e-3, 5e-4], [0.0, 0.0, 0.0], [2e-3, 2e-3, -1e-3]])
+    ba = np.array([[0.02, 0.01, -0.03], [0.0, 0.0, 0.0], [-0.05, 0.02, 0.01]])
+    grav = np.array([0.0, 0.0, -9.81])
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=sc.lidar_origin, bin_directions=bins)
+    ms = O.empty_map_stats(B)
+    pl.submit_scan_msg_host(2, data=msg["data"], fields=msg["fields"], point_step=msg["point_step"], n_points=n,
+                            header_stamp_sec=msg["header_stamp_sec"], R_base_lidar=R_bl, t_base_lidar=t_bl,
+                            imu=dict(stamps=imu["stamps"], gyro=imu["gyro"], accel=imu["accel"], sigma=0.02, rotvec_start_WB=rv, gyro_bias=bg,
+                                     accel_bias=ba, gravity_W=grav, deskew_rotation_only=True))
+    ev = pl.evidence_host(2, np.zeros((3, 6)), ms)
+    info = pl.msg_info_host(2, n_hyp=3)
+    pb = O.point_budget_resample(pts_base, par["timestamps"], par["weights"], par["ring"], par["tag"], cap)
+    for h in range(3):
+        io = O.imu_deskew_twist(imu["stamps"], imu["gyro"], imu["accel"], t0, t1, 0.02, rv[h], bg[h], ba[h], grav, rotation_only=True)
+        np.testing.assert_allclose(info["xi_body"][h], io["xi_body"], rtol=0, atol=1e-11)
+        assert np.all(info["xi_body"][h][:3] == 0.0)
+        dk = O.deskew_constant_twist(pb["points"], pb["timestamps"], pb["weights"], t0, t1, io["xi_body"])
+        fin = O.scan_bin_finalize(O.fused_scan_raw_sums(dk["points"], dk["weights"], bins, tau, sc.lidar_origin))
+        sb = ev.scan_bins(h)
+        for name in ("N", "s_dir", "S_dir_scatter", "p_bar"):
+            assert rel_err(H(getattr(sb, name)), fin[name]) < 1e-9, (h, name)
+    # empty message
+    pl.submit_scan_msg_host(3, data=np.zeros(0, np.uint8), fields=msg["fields"], point_step=msg["point_step"], n_points=0,
+                            header_stamp_sec=5.5, xi_body=np.zeros((1, 6)))
+    ev0 = pl.evidence_host(3, np.zeros((1, 6)), ms)
+    i0 = pl.msg_info_host(3)
+    assert (i0["scan_start_time"], i0["scan_end_time"], i0["n_points"], i0["n_selected"]) == (5.5, 5.5, 0, 0)
+    assert float(H(ev0.scan_bins(0).N).sum()) == 0.0 and np.all(np.isfinite(H(ev0.evidence)))
