@@ -486,9 +486,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
   __shared__ double s_l13[kChainThreads / 64][2];
   extern __shared__ __align__(16) double s_mder_dyn[];
   double* mder = P.chain_smem ? s_mder_dyn : P.workspace;   // map-derived statistics stay on chip when they fit
+  // poses that travel as kernel arguments (host call, few hypotheses): read straight out of the parameter block
+  const double* pose_pred = P.pose_inline_n ? P.pose_inline : P.pose_pred;
+  const double* pose_update = P.pose_inline_n ? (P.pose_inline_update ? P.pose_inline + (size_t)H * 6 : nullptr) : P.pose_update;
   if (tid == 0) TR(0);
-  if (P.stage_in_src) {
-    // pose / map / IW out of page-locked host memory (16-byte loads, all of a thread's loads in flight before its first store:
+  if (P.stats_src) {
+    // pose / map / IW out of page-locked host memory (nothing at all when the poses came as arguments and the device still holds
+    // the map and the IW state the previous call left -- see gcl_scan_evidence_begin_host) (16-byte loads, all of a thread's loads in flight before its first store:
     // a PCIe read takes ~1.5 us), and the stage-1 records into the working copy that the chain step rewrites
     const double2* src = reinterpret_cast<const double2*>(P.stage_in_src);
     double2* dst = reinterpret_cast<double2*>(P.stage_in_dst);
@@ -535,13 +539,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     // warp 0 is still busy -- statistics after step 1, the map after its update; warp 1 the IW state, warp 0 the evidence.
     const bool solo = H == 1;
     const bool solo_out = solo && P.stage_out_dst != nullptr;
-    const bool early_map = solo && P.pose_update != nullptr;
+    const bool early_map = solo && pose_update != nullptr;
     const int bar9 = 32 + (P.iw_state ? 32 : 0) + (early_map ? 64 : 0);   // 32: nobody waits, barrier not used
     if (role1) {
       bool first = true;
       for (int h = warp >> 1; h < H; h += kChainThreads / 64) {
         pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
-                           mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                           mder, pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
                            P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, (h == 0 && P.iw_state) ? s_iw : nullptr, 1,
                            s_l13[warp >> 1], 1 + (warp >> 1), first ? 8 : 0, (h == 0 && bar9 > 32) ? 9 : 0, bar9);
         first = false;
@@ -585,9 +589,9 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
         if (early_map) {
           asm volatile("bar.sync 9, %0;" ::"r"(bar9) : "memory");
           double R[9];
-          so3_exp(P.pose_update + (size_t)s * 6 + 3, R);
+          so3_exp(pose_update + (size_t)s * 6 + 3, R);
           for (int b = q; b < B; b += 64)
-            map_update_bin(st0, R, P.pose_update + (size_t)s * 6, B, b, P.forgetting, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir,
+            map_update_bin(st0, R, pose_update + (size_t)s * 6, B, b, P.forgetting, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir,
                            P.map_N_pos, P.map_sum_p, P.map_sum_ppT);
           if (solo_out) {
             __threadfence_block();
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
       if ((warp & 1) && (warp >> 1) < H) {
         for (int h = warp >> 1; h < H; h += kChainThreads / 64)
           pose_evidence_warp(lane, st0 + (size_t)h * P.stats_stride, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir, P.map_N_pos,
-                             mder, P.pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
+                             mder, pose_pred + ((size_t)s * H + h) * 6, nullptr, B, P.eps_psd, P.eps_mass, 1, 1,
                              P.evidence + ((size_t)s * H + h) * GCL_EVID_DOUBLES, nullptr, 2, s_l13[warp >> 1], 1 + (warp >> 1));
         if (warp == 1 && P.iw_state) {
           asm volatile("bar.sync 9, %0;" ::"r"(bar9) : "memory");
@@ -616,11 +620,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     __syncthreads();
     if (tid == 0) TR(17);
     // 5. map update (hypothesis 0's statistics, pose_update[s]) -- already done by warps 2, 3 when there is one hypothesis
-    if (P.pose_update && !early_map) {
+    if (pose_update && !early_map) {
       double R[9];
-      so3_exp(P.pose_update + (size_t)s * 6 + 3, R);
+      so3_exp(pose_update + (size_t)s * 6 + 3, R);
       for (int b = tid; b < B; b += kChainThreads)
-        map_update_bin(st0, R, P.pose_update + (size_t)s * 6, B, b, P.forgetting, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir,
+        map_update_bin(st0, R, pose_update + (size_t)s * 6, B, b, P.forgetting, P.map_S_dir, P.map_S_dir_scatter, P.map_N_dir,
                        P.map_N_pos, P.map_sum_p, P.map_sum_ppT);
     }
     __syncthreads();
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const __grid_const
     const int n2 = P.stage_out_doubles >> 1;
     if (P.n_hyp != 1) {
       copy_batched(dst, src, n2, tid);
-    } else if (!P.pose_update) {
+    } else if (!pose_update) {
       copy_batched(dst, src, (26 * B) >> 1, tid);   // the map was not updated: it rides along unchanged
     }
     __threadfence_system();

@@ -25,6 +25,9 @@ struct gcl_handle_s {
   std::string err;
   // resources of the *_host entry points (allocated on first use, grown on demand)
   unsigned long long done_seq = 0;     // completion ticket of the single-launch evidence step (0 = the copy-engine path is in flight)
+  std::string map_shadow;              // map (26 B doubles) + IW state (10) exactly as the last single-launch step left them on the DEVICE
+  int map_shadow_bins = 0;             // 0 = the device copy is not known to match anything
+  size_t map_shadow_off = 0;           // where in the stage-2 block that map lives
   unsigned long long* done_flag = nullptr;   // page-locked word the chain kernel writes the ticket to
   cudaStream_t stream = nullptr;       // stage 2: chain step + D2H
   cudaStream_t stream_copy = nullptr;  // H2D of the scans
@@ -131,6 +134,8 @@ struct ChainParams {
   const double* stats_src = nullptr; int stats_doubles = 0;                                            // stage-1 records -> stats
   const double* stage_out_src = nullptr; double* stage_out_dst = nullptr; int stage_out_doubles = 0;   // device -> pinned host
   int out_off_iw = 0, out_off_stats = 0, out_off_evid = 0;   // offsets (doubles) of the IW / stats / evidence blocks in the output
+  double pose_inline[30] = {0};   // pose_pred (n_hyp x 6) [+ pose_update (6)] by value: no PCIe read for them (n_hyp <= 4)
+  int pose_inline_n = 0, pose_inline_update = 0;
   unsigned long long* done_flag = nullptr; unsigned long long done_value = 0;                          // pinned host
 };
 cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launches);

@@ -847,3 +847,37 @@ def test_message_path_hypothesis_batch_and_empty_message(g, O):
     i0 = pl.msg_info_host(3)
     assert (i0["scan_start_time"], i0["scan_end_time"], i0["n_points"], i0["n_selected"]) == (5.5, 5.5, 0, 0)
     assert float(H(ev0.scan_bins(0).N).sum()) == 0.0 and np.all(np.isfinite(H(ev0.evidence)))
+
+
+def test_host_calls_carry_map_and_iw_against_oracle_with_host_side_edit(g, O):
+    """The evidence step fetches the map / IW state from the host only when they differ from what the device already holds (the
+    usual case: the caller hands back what it was given).  Five scans against the oracle's sequential loop, with the caller
+    EDITING the map and the IW state on the host after the third scan: the edit must be picked up."""
+    S, B, cap, tau = 5, 48, 4096, 0.1
+    scans = [g.synth.make_scan(7000 + 53 * k, seed=910 + k, t0=g.synth.T0_EPOCH + 0.1 * k) for k in range(S)]
+    poses = np.stack([np.array([0.04 * k, -0.01 * k, 0.0, 0.0, 0.0, 0.008 * k]) for k in range(S)])
+    bins = O.create_fibonacci_atlas(B)
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=scans[0].lidar_origin, bin_directions=bins)
+    m = O.empty_map_stats(B)
+    iw = np.concatenate([[4.5], (1e-3 * 0.5 * np.eye(3)).reshape(-1)])
+    iw_o = {"nu": 4.5, "Psi": 1e-3 * 0.5 * np.eye(3)}
+    ms_o = None
+    EVo = g._abi.EV
+    for k in range(S):
+        if k == 3:   # host-side edit between two calls
+            for a in m.values():
+                a *= 0.5
+            iw[1:] *= 2.0
+            ms_o = {kk: 0.5 * v for kk, v in ms_o.items()}
+            iw_o = {"nu": iw_o["nu"], "Psi": 2.0 * iw_o["Psi"]}
+        ev = pl.process_scan_host(scans[k].points, scans[k].timestamps, scans[k].weights, scans[k].scan_start_time, scans[k].scan_end_time,
+                                  scans[k].xi_body[None], poses[k][None], m, pose_update=poses[k], iw_state_host=iw, use_sigma_meas=True)
+        outs, ms_o, iw_o = O.scan_stream([scans[k]], poses[k][None], poses[k][None], n_points_cap=cap, bin_directions=bins, tau=tau,
+                                         lidar_origin=scans[0].lidar_origin, iw_state=iw_o, use_sigma_meas=True, map_stats=ms_o)
+        e = ev.evidence_host[0]
+        assert np.linalg.norm(e[EVo["R_MF"]:EVo["R_MF"] + 9].reshape(3, 3) - outs[0]["matrix_fisher"]["R_mf"]) / math.sqrt(2.0) < 1e-8
+        if k > 0:
+            np.testing.assert_allclose(e[EVo["T_WLS"]:EVo["T_WLS"] + 3], outs[0]["planar_translation"]["t_wls"], rtol=1e-8, atol=1e-10)
+        for kk in m:
+            assert rel_err(m[kk], ms_o[kk]) < 1e-9, (k, kk)
+        assert abs(iw[0] - iw_o["nu"]) < 1e-9 * iw_o["nu"] and rel_err(iw[1:].reshape(3, 3), iw_o["Psi"]) < 1e-8, k
