@@ -66,6 +66,11 @@ int gcl_create(int device, gcl_handle* out) {
 
 void gcl_destroy(gcl_handle h) {
   if (!h) return;
+  if (h->worker.joinable()) {
+    { std::lock_guard<std::mutex> lk(h->mu); h->stop = true; }
+    h->cv_task.notify_all();
+    h->worker.join();
+  }
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->stream_copy) { cudaStreamSynchronize(h->stream_copy); cudaStreamDestroy(h->stream_copy); }
@@ -84,7 +89,7 @@ void gcl_destroy(gcl_handle h) {
 
 const char* gcl_last_error(gcl_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int gcl_device_sm_count(gcl_handle h) { return h ? h->sm_count : 0; }
-int64_t gcl_launch_count(gcl_handle h) { return h ? h->launches : 0; }
+int64_t gcl_launch_count(gcl_handle h) { return h ? h->launches.load() : (int64_t)0; }
 
 size_t gcl_partial_record_doubles(int n_bins) { return (size_t)GCL_NM * n_bins + GCL_NCERT; }
 size_t gcl_stats_record_doubles(int n_bins) { return (size_t)StatsLayout(n_bins).total(); }
@@ -660,14 +665,6 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
   return GCL_OK;
 }
 
-int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
-                         const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1, const double* xi_host,
-                         int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
-                         double eps_psd, double eps_mass) {
-  return submit_arrays(h, slot_index, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
-                       bins_host, n_bins, tau, precision, eps_psd, eps_mass, false);
-}
-
 // Stage 1 from the MESSAGE: the raw PointCloud2 bytes (point_step bytes per point, 22 for the Kimera VLP-16 layout against 40
 // bytes of parsed float64) and, optionally, the IMU buffer cross PCIe; everything between the message and the bin statistics
 // runs on the device without a host round trip:
@@ -675,7 +672,7 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
 //   deskew twist into the jobs] -> decode + range weights + base-frame transform into COMPACT rows (only the rows
 //   PointBudgetResample keeps; every raw weight) -> scan_moments -> reduce_finalize -> D2H of the info record.
 // The reference does this with a NumPy parse on the host, five H2D copies, one D2H sync for the bounds and a 512-step lax.scan.
-int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_host, int64_t n_points, int32_t point_step,
+static int submit_msg_impl(gcl_handle h, int slot_index, const uint8_t* msg_host, int64_t n_points, int32_t point_step,
                              const int32_t* off, const int32_t* dt, double header_stamp, const double* R_host,
                              const double* t_host, int32_t cap, const double* xi_host, const double* imu_stamps_host,
                              const double* imu_gyro_host, const double* imu_accel_host, int imu_samples, double imu_sigma,
@@ -813,11 +810,152 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
   return GCL_OK;
 }
 
+// ---- the submit thread ----------------------------------------------------------------------------------------------------------
+static int run_task(gcl_handle h, int slot) {
+  const gcl_submit_task& T = h->slot[slot].task;
+  if (T.kind == 1)
+    return submit_arrays(h, slot, T.points, T.timestamps, T.weights, T.n, T.cap, T.t0, T.t1, T.xi.data(), T.n_hyp, T.origin,
+                         T.bins.data(), T.n_bins, T.tau, T.precision, T.eps_psd, T.eps_mass, false);
+  return submit_msg_impl(h, slot, T.msg, T.n, T.point_step, T.off, T.dt, T.header_stamp, T.has_T ? T.R : nullptr, T.has_T ? T.t : nullptr,
+                         T.cap, T.has_xi ? T.xi.data() : nullptr, T.imu_stamps, T.imu_gyro, T.imu_accel, T.imu_samples, T.imu_sigma,
+                         T.has_xi ? nullptr : T.rotvec.data(), T.has_xi ? nullptr : T.bg.data(), T.has_xi ? nullptr : T.ba.data(),
+                         T.has_xi ? nullptr : T.gravity, T.rotation_only, T.n_hyp, T.origin, T.bins.data(), T.n_bins, T.tau, T.precision,
+                         T.eps_psd, T.eps_mass);
+}
+
+static void submit_thread_main(gcl_handle h) {
+  cudaSetDevice(h->device);
+  std::unique_lock<std::mutex> lk(h->mu);
+  for (;;) {
+    h->cv_task.wait(lk, [&] { return h->stop || !h->queue.empty(); });
+    if (h->queue.empty()) return;   // stop requested and nothing left to do
+    const int slot = h->queue.front();
+    h->queue.pop_front();
+    lk.unlock();
+    const int rc = run_task(h, slot);
+    lk.lock();
+    gcl_handle_s::Slot& S = h->slot[slot];
+    S.task_rc = rc;
+    if (rc != GCL_OK) S.task_err = h->err;
+    S.busy = false;
+    h->cv_done.notify_all();
+  }
+}
+
+static bool use_submit_thread(gcl_handle h) {
+  if (h->async_mode < 0) {
+    const char* e = getenv("GCL_HOST_ASYNC");
+    h->async_mode = (e ? atoi(e) != 0 : true) && !g_ht.on;   // the per-stage timing mode serialises everything
+  }
+  return h->async_mode == 1;
+}
+
+// wait until the submit thread has finished enqueuing the task of `slot` (if any); surfaces its error
+static int wait_slot(gcl_handle h, int slot) {
+  gcl_handle_s::Slot& S = h->slot[slot];
+  std::unique_lock<std::mutex> lk(h->mu);
+  h->cv_done.wait(lk, [&] { return !S.busy; });
+  const int rc = S.task_rc;
+  if (rc != GCL_OK) { h->err = S.task_err; S.task_rc = GCL_OK; }
+  return rc;
+}
+
+// hand the filled task of `slot` to the submit thread (started on first use)
+static int post_task(gcl_handle h, int slot) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->worker.joinable()) h->worker = std::thread(submit_thread_main, h);
+  h->slot[slot].busy = true;
+  h->queue.push_back(slot);
+  h->cv_task.notify_one();
+  return GCL_OK;
+}
+
+int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host, const double* timestamps_host,
+                         const double* weights_host, int64_t n_raw, int32_t cap, double t0, double t1, const double* xi_host,
+                         int n_hyp, const double* origin_host, const double* bins_host, int n_bins, double tau, int precision,
+                         double eps_psd, double eps_mass) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
+  GCL_REQUIRE(h, n_raw >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_raw >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
+  GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
+  GCL_REQUIRE(h, xi_host && origin_host && bins_host, "NULL pointer");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  int rc = wait_slot(h, slot_index);   // an earlier submission to this slot goes first (its error, if any, is reported here)
+  if (rc != GCL_OK) return rc;
+  if (!use_submit_thread(h))
+    return submit_arrays(h, slot_index, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
+                         bins_host, n_bins, tau, precision, eps_psd, eps_mass, false);
+  gcl_submit_task& T = h->slot[slot_index].task;
+  T.kind = 1;
+  T.points = points_host; T.timestamps = timestamps_host; T.weights = weights_host; T.n = n_raw; T.cap = cap; T.t0 = t0; T.t1 = t1;
+  T.xi.assign(xi_host, xi_host + (size_t)n_hyp * 6);
+  T.bins.assign(bins_host, bins_host + (size_t)n_bins * 3);
+  T.n_hyp = n_hyp; T.n_bins = n_bins; T.precision = precision; T.tau = tau; T.eps_psd = eps_psd; T.eps_mass = eps_mass;
+  for (int k = 0; k < 3; ++k) T.origin[k] = origin_host[k];
+  return post_task(h, slot_index);
+}
+
+int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_host, int64_t n_points, int32_t point_step,
+                             const int32_t* off, const int32_t* dt, double header_stamp, const double* R_host,
+                             const double* t_host, int32_t cap, const double* xi_host, const double* imu_stamps_host,
+                             const double* imu_gyro_host, const double* imu_accel_host, int imu_samples, double imu_sigma,
+                             const double* rotvec_start_host, const double* gyro_bias_host, const double* accel_bias_host,
+                             const double* gravity_host, int rotation_only, int n_hyp, const double* origin_host,
+                             const double* bins_host, int n_bins, double tau, int precision, double eps_psd, double eps_mass) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
+  GCL_REQUIRE(h, n_points >= 0 && cap >= 1 && n_hyp >= 1 && n_hyp <= 4096, "n_points >= 0, cap >= 1, 1 <= n_hyp <= 4096 required");
+  GCL_REQUIRE(h, point_step >= 1 && point_step <= 512, "1 <= point_step <= 512 required");
+  GCL_REQUIRE(h, n_bins >= 1 && n_bins <= GCL_MAX_BINS && tau > 0.0, "1 <= n_bins <= 1024 and tau > 0 required");
+  GCL_REQUIRE(h, off && dt && origin_host && bins_host && (n_points == 0 || msg_host), "NULL pointer");
+  GCL_REQUIRE(h, (R_host == nullptr) == (t_host == nullptr), "R_base_lidar and t_base_lidar go together");
+  GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  const bool imu = imu_stamps_host != nullptr;
+  GCL_REQUIRE(h, imu != (xi_host != nullptr), "exactly one of xi_body_host and the IMU buffer must be given");
+  GCL_REQUIRE(h, !imu || (imu_gyro_host && imu_accel_host && rotvec_start_host && gyro_bias_host && accel_bias_host && gravity_host
+                          && imu_samples >= 1), "incomplete IMU buffer");
+  static const int width[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+  for (int k = 0; k < 5; ++k) {
+    const bool optional = (k == 4) && off[k] < 0;
+    GCL_REQUIRE(h, optional || (dt[k] >= 1 && dt[k] <= 8), "Unsupported PointField datatype");   // backend_node.py:374
+    GCL_REQUIRE(h, optional || (off[k] >= 0 && off[k] + width[dt[k]] <= point_step), "field does not fit in point_step");
+  }
+  int rc = wait_slot(h, slot_index);
+  if (rc != GCL_OK) return rc;
+  if (!use_submit_thread(h))
+    return submit_msg_impl(h, slot_index, msg_host, n_points, point_step, off, dt, header_stamp, R_host, t_host, cap, xi_host,
+                           imu_stamps_host, imu_gyro_host, imu_accel_host, imu_samples, imu_sigma, rotvec_start_host, gyro_bias_host,
+                           accel_bias_host, gravity_host, rotation_only, n_hyp, origin_host, bins_host, n_bins, tau, precision, eps_psd,
+                           eps_mass);
+  gcl_submit_task& T = h->slot[slot_index].task;
+  T.kind = 2;
+  T.msg = msg_host; T.n = n_points; T.point_step = point_step; T.cap = cap; T.header_stamp = header_stamp;
+  for (int k = 0; k < 5; ++k) { T.off[k] = off[k]; T.dt[k] = dt[k]; }
+  T.has_T = R_host != nullptr;
+  if (R_host) { for (int k = 0; k < 9; ++k) T.R[k] = R_host[k]; for (int k = 0; k < 3; ++k) T.t[k] = t_host[k]; }
+  T.has_xi = xi_host != nullptr;
+  if (xi_host) T.xi.assign(xi_host, xi_host + (size_t)n_hyp * 6);
+  T.imu_stamps = imu_stamps_host; T.imu_gyro = imu_gyro_host; T.imu_accel = imu_accel_host; T.imu_samples = imu_samples;
+  T.imu_sigma = imu_sigma; T.rotation_only = rotation_only;
+  if (imu) {
+    T.rotvec.assign(rotvec_start_host, rotvec_start_host + (size_t)n_hyp * 3);
+    T.bg.assign(gyro_bias_host, gyro_bias_host + (size_t)n_hyp * 3);
+    T.ba.assign(accel_bias_host, accel_bias_host + (size_t)n_hyp * 3);
+    for (int k = 0; k < 3; ++k) T.gravity[k] = gravity_host[k];
+  }
+  T.bins.assign(bins_host, bins_host + (size_t)n_bins * 3);
+  T.n_hyp = n_hyp; T.n_bins = n_bins; T.precision = precision; T.tau = tau; T.eps_psd = eps_psd; T.eps_mass = eps_mass;
+  for (int k = 0; k < 3; ++k) T.origin[k] = origin_host[k];
+  return post_task(h, slot_index);
+}
+
 // the info record of the last gcl_scan_submit_msg_host on `slot`: waits for stage 1 of that slot only
 int gcl_scan_msg_info_host(gcl_handle h, int slot_index, double* info_host, int64_t n_doubles) {
   if (!h) return GCL_ERR_ARG;
   GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
   gcl_handle_s::Slot& S = h->slot[slot_index];
+  { const int rcw = wait_slot(h, slot_index); if (rcw != GCL_OK) return rcw; }
   GCL_REQUIRE(h, S.info_doubles > 0 && S.h_buf, "no message was submitted to this slot");
   GCL_REQUIRE(h, info_host && n_doubles >= (int64_t)S.info_doubles, "info buffer too small (GCL_MSG_INFO_HEADER + n_hyp * GCL_IMU_DOUBLES doubles)");
   cudaSetDevice(h->device);
@@ -834,6 +972,7 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   if (!h) return GCL_ERR_ARG;
   GCL_REQUIRE(h, slot_index >= 0 && slot_index < GCL_HOST_SLOTS, "slot must be in [0, GCL_HOST_SLOTS)");
   gcl_handle_s::Slot& S = h->slot[slot_index];
+  { const int rcw = wait_slot(h, slot_index); if (rcw != GCL_OK) return rcw; }   // the submit thread is done with this slot
   GCL_REQUIRE(h, S.pending, "no scan was submitted to this slot");
   GCL_REQUIRE(h, h->stage2_slot < 0, "an evidence step is already in flight: call gcl_scan_evidence_end_host first");
   GCL_REQUIRE(h, pose_host, "NULL pointer");
@@ -1040,8 +1179,10 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   GCL_REQUIRE(h, mS_dir && mS_sc && mN_dir && mN_pos && msum_p && msum_ppT, "NULL map statistics");
   GCL_REQUIRE(h, !pose_update_host || (forgetting > 0.0 && forgetting <= 1.0), "forgetting factor must be in (0, 1]");
   GCL_REQUIRE(h, !use_sigma_meas || iw_state_host, "use_sigma_meas needs iw_state_host");
-  int rc = submit_arrays(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
-                         bins_host, n_bins, tau, precision, eps_psd, eps_mass, true);
+  int rc = wait_slot(h, 0);
+  if (rc != GCL_OK) return rc;
+  rc = submit_arrays(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
+                     bins_host, n_bins, tau, precision, eps_psd, eps_mass, true);   // blocking call: no hop to the submit thread
   if (rc != GCL_OK) return rc;
   return gcl_scan_evidence_host(h, 0, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host, forgetting,
                                 iw_state_host, use_sigma_meas, stats_host, evidence_host);

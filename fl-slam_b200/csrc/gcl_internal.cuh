@@ -3,7 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/gcl_b200.h"
 #include "gcl_math.cuh"
@@ -18,10 +24,33 @@
 #define GCL_USE_FFMA2 1  // packed fp32 FMA (fma.rn.f32x2, sm_100+); 0 = two scalar FFMAs (for A/B timing)
 #endif
 
+// One stage-1 submission, as handed to the submit thread: small arrays by value, the big ones (scan arrays, message bytes, IMU
+// samples) by pointer -- the caller keeps those valid and unchanged until the matching evidence call has returned.
+struct gcl_submit_task {
+  int kind = 0;                           // 1 = parsed arrays (gcl_scan_submit_host), 2 = message (gcl_scan_submit_msg_host)
+  const double *points = nullptr, *timestamps = nullptr, *weights = nullptr;
+  int64_t n = 0; int32_t cap = 0; double t0 = 0, t1 = 0;
+  const uint8_t* msg = nullptr; int32_t point_step = 0; int32_t off[5] = {0, 0, 0, 0, 0}, dt[5] = {0, 0, 0, 0, 0};
+  double header_stamp = 0; bool has_T = false; double R[9] = {0}, t[3] = {0};
+  bool has_xi = false; const double *imu_stamps = nullptr, *imu_gyro = nullptr, *imu_accel = nullptr;
+  int imu_samples = 0; double imu_sigma = 0, gravity[3] = {0, 0, 0}; int rotation_only = 0;
+  std::vector<double> xi, rotvec, bg, ba, bins;
+  int n_hyp = 0, n_bins = 0, precision = 0; double origin[3] = {0, 0, 0}, tau = 0, eps_psd = 0, eps_mass = 0;
+};
+
 struct gcl_handle_s {
   int device = 0;
   int sm_count = 148;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
+  // submit thread: stage 1 of the two-stage host entry points is enqueued from a second host thread.  The ten-odd CUDA calls of a
+  // submission cost 25-45 us of host time; the caller's thread meanwhile runs the evidence step of the previous scan, which
+  // since it became one launch plus a polled ticket needs almost no driver time of its own.
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv_task, cv_done;
+  std::deque<int> queue;                 // slots with a task waiting
+  bool stop = false;
+  int async_mode = -1;                   // -1 = not decided yet (GCL_HOST_ASYNC, default 1)
   std::string err;
   // resources of the *_host entry points (allocated on first use, grown on demand)
   unsigned long long done_seq = 0;     // completion ticket of the single-launch evidence step (0 = the copy-engine path is in flight)
@@ -45,6 +74,8 @@ struct gcl_handle_s {
     std::string atlas_copy;             // bytes of the atlas this slot holds on the device
     int atlas_bins = 0; void* atlas_dev = nullptr;
     size_t info_off = 0, info_doubles = 0;   // info record of the last gcl_scan_submit_msg_host (pinned block)
+    gcl_submit_task task;                    // the submission in flight on the submit thread (busy = not yet enqueued)
+    bool busy = false; int task_rc = 0; std::string task_err;
   } slot[GCL_HOST_SLOTS];
   const void* pin_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool pin_val[8] = {false, false, false, false, false, false, false, false};

@@ -322,7 +322,12 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
  *                           at once.  Page-locked input arrays are read in place and must stay untouched until the matching
  *                           gcl_scan_evidence_host returns.  slot is in [0, GCL_HOST_SLOTS).
  *   gcl_scan_evidence_host  waits on the GPU for stage 1 of `slot`, runs the chain step, ONE D2H of map / IW / stats /
- *                           evidence, synchronises.  Arguments as in gcl_lidar_scan_evidence_host. */
+ *                           evidence, synchronises.  Arguments as in gcl_lidar_scan_evidence_host.
+ * The CUDA calls of a submission (gcl_scan_submit_host, gcl_scan_submit_msg_host) are issued from a submit thread owned by the
+ * handle: arguments are checked and the small arrays copied before the call returns, errors of the thread surface at the next
+ * call on the same slot, and the caller's thread spends ~1 us in the call.  The scan arrays / message bytes / IMU samples are
+ * read later: keep them valid and unchanged until the matching evidence call has returned.  GCL_HOST_ASYNC=0 issues everything
+ * from the caller's thread instead. */
 int gcl_scan_submit_host(gcl_handle h, int slot, const double* points_host, const double* timestamps_host,
                          const double* weights_host, int64_t n_raw, int32_t n_points_cap, double scan_start_time,
                          double scan_end_time, const double* xi_body_host, int n_hyp, const double* lidar_origin_host,
