@@ -388,7 +388,7 @@ def main():
     e2e_points = sum(s.points.shape[0] for s in scans[:n_e2e])
     rec_bytes = (38 * N_BINS + 24 + 640 + 26 * N_BINS + 10) * 8
     e2e = {"value": world * n_rep * e2e_points / e2e_s, "unit": "points/s",
-           "h2d_bytes_per_step": int(e2e_points * 40 + n_e2e * (N_BINS * 26 * 8 + 48 + 48 + 80 + 120)),
+           "h2d_bytes_per_step": int(sum(_alg_bytes(s.points.shape[0]) for s in scans[:n_e2e]) + n_e2e * (48 + 48 + 120)),
            "d2h_bytes_per_step": int(n_e2e * rec_bytes), "scans_per_sec": world * n_rep * n_e2e / e2e_s,
            "us_per_scan": 1e6 * e2e_s / (n_rep * n_e2e),
            "blocking_call": {"value": world * n_rep * e2e_points / e2e_blocking_s, "unit": "points/s",
@@ -406,9 +406,10 @@ def main():
                    "the scan, scan_moments, reduce_finalize; asynchronous) for scan k+2 is issued between "
                    "gcl_scan_evidence_begin_host (H2D of pose/map/IW, chain step incl. IW + map update, one D2H of "
                    "map/IW/stats/evidence enqueued) and gcl_scan_evidence_end_host (sync, results out) of scan k; every scan's inputs cross PCIe and every scan's results are read back inside the timed region. "
-                   "Stage 1 copies the page-locked scan arrays with the copy engine (the blocking call instead lets scan_moments read them in place: "
-                   "zero-copy, selected rows and raw weights cross PCIe once); stage 2 is ONE launch: the chain kernel pulls pose / map / IW out of "
-                   "page-locked memory, pushes map / IW / stats / evidence back and raises a ticket the host polls"}
+                   "Stage 1 is issued by the handle's submit thread and reads the page-locked scan arrays in place (zero-copy: scan_moments pulls the "
+                   "selected rows and every raw weight across PCIe once, which is what h2d_bytes_per_step counts); stage 2 is ONE launch: poses as "
+                   "kernel arguments, map / IW fetched only when they differ from what the device already holds (here they never do: the arrays "
+                   "handed back are the ones the previous step wrote), map / IW / stats / evidence pushed back by the kernel, then a ticket the host polls"}
 
     # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
     extra = {}

@@ -600,8 +600,9 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
   // copy-stream event hand-off less on the host.  GCL_HOST_ZERO_COPY=0 restores the copies.
   // For the copy engine a stale "page-locked" answer from the cache is harmless; a kernel reading the array is not, so the
   // zero-copy decision asks the driver afresh (~2 us per array).  That is worth it where the latency of stage 1 counts -- the
-  // blocking call: 121 -> 105 us -- and not in the two-stage form, whose stage 1 is hidden behind the previous scan's evidence
-  // step (there it cost 6 us per scan of host time for nothing), so only the blocking entry takes this route.
+  // blocking call: 121 -> 105 us -- and where the queries do not cost the caller's thread: submissions issued by the submit
+  // thread (52 -> 50 us per scan: 0.54 MB instead of 1.2 MB competing with the evidence step's outputs for PCIe).  On the
+  // caller's thread in the two-stage form (GCL_HOST_ASYNC=0) they cost 6 us per scan for nothing, so that route copies.
   static const bool zero_copy_ok = !(getenv("GCL_HOST_ZERO_COPY") && atoi(getenv("GCL_HOST_ZERO_COPY")) == 0);
   const bool zero_copy = latency_call && direct && n_hyp == 1 && zero_copy_ok && !g_ht.on && is_pinned_now(points_host) &&
                          is_pinned_now(timestamps_host) && is_pinned_now(weights_host);
@@ -815,7 +816,7 @@ static int run_task(gcl_handle h, int slot) {
   const gcl_submit_task& T = h->slot[slot].task;
   if (T.kind == 1)
     return submit_arrays(h, slot, T.points, T.timestamps, T.weights, T.n, T.cap, T.t0, T.t1, T.xi.data(), T.n_hyp, T.origin,
-                         T.bins.data(), T.n_bins, T.tau, T.precision, T.eps_psd, T.eps_mass, false);
+                         T.bins.data(), T.n_bins, T.tau, T.precision, T.eps_psd, T.eps_mass, true);   // zero-copy: the driver queries cost this thread, not the caller
   return submit_msg_impl(h, slot, T.msg, T.n, T.point_step, T.off, T.dt, T.header_stamp, T.has_T ? T.R : nullptr, T.has_T ? T.t : nullptr,
                          T.cap, T.has_xi ? T.xi.data() : nullptr, T.imu_stamps, T.imu_gyro, T.imu_accel, T.imu_samples, T.imu_sigma,
                          T.has_xi ? nullptr : T.rotvec.data(), T.has_xi ? nullptr : T.bg.data(), T.has_xi ? nullptr : T.ba.data(),
