@@ -1000,7 +1000,9 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   }
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
   unsigned char* db = static_cast<unsigned char*>(h->d_buf);
-  cudaStream_t st = h->stream;
+  // the blocking call runs stage 2 on the slot's own stage-1 stream: plain stream order instead of a cross-stream event wait
+  cudaStream_t st = h->stage2_on_slot_stream ? S.stream1 : h->stream;
+  h->stage2_stream = st;
   // small blocks (one or a few hypotheses): ONE launch, the chain kernel stages its own inputs and outputs across PCIe and the
   // host polls a ticket; large blocks (many hypotheses) go through the copy engine
   static const bool single_launch_ok = !(getenv("GCL_HOST_SINGLE_LAUNCH") && atoi(getenv("GCL_HOST_SINGLE_LAUNCH")) == 0);
@@ -1012,7 +1014,7 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   if (pose_update_host) memcpy(hb + o_pupd, pose_update_host, 48);
   if (iw_state_host) memcpy(hb + o_iw, iw_state_host, 80);
   if (!single) GCL_CUDA(h, cudaMemcpyAsync(db + o_pose, hb + o_pose, (o_iw + 80) - o_pose, cudaMemcpyHostToDevice, st));
-  GCL_CUDA(h, cudaStreamWaitEvent(st, S.ev_stage1, 0));
+  if (st != S.stream1) GCL_CUDA(h, cudaStreamWaitEvent(st, S.ev_stage1, 0));
   double* dm = reinterpret_cast<double*>(db + o_map);
   double* d_stats = reinterpret_cast<double*>(db + o_stats);
   double* d_evid = reinterpret_cast<double*>(db + o_evid);
@@ -1101,7 +1103,7 @@ int gcl_scan_evidence_end_host(gcl_handle h, double* mS_dir, double* mS_sc, doub
   const size_t o_iw = al(o_map + B * 26 * 8), o_stats = al(o_iw + 80);
   const size_t o_evid = al(o_stats + H * srec * 8);
   unsigned char* hb = static_cast<unsigned char*>(h->h_buf);
-  cudaStream_t st = h->stream;
+  cudaStream_t st = h->stage2_stream ? h->stage2_stream : h->stream;
   std::chrono::steady_clock::time_point tr_a;
   if (g_s2.on && h->stage2_single) { tr_a = std::chrono::steady_clock::now(); g_s2.acc[1] += Stage2Trace::us(g_s2.t1, tr_a); }
   if (h->stage2_single) {
@@ -1185,8 +1187,11 @@ int gcl_lidar_scan_evidence_host(gcl_handle h, const double* points_host, const 
   rc = submit_arrays(h, 0, points_host, timestamps_host, weights_host, n_raw, cap, t0, t1, xi_host, n_hyp, origin_host,
                      bins_host, n_bins, tau, precision, eps_psd, eps_mass, true);   // blocking call: no hop to the submit thread
   if (rc != GCL_OK) return rc;
-  return gcl_scan_evidence_host(h, 0, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host, forgetting,
-                                iw_state_host, use_sigma_meas, stats_host, evidence_host);
+  h->stage2_on_slot_stream = true;
+  rc = gcl_scan_evidence_host(h, 0, pose_host, mS_dir, mS_sc, mN_dir, mN_pos, msum_p, msum_ppT, pose_update_host, forgetting,
+                              iw_state_host, use_sigma_meas, stats_host, evidence_host);
+  h->stage2_on_slot_stream = false;
+  return rc;
 }
 
 }  // extern "C"

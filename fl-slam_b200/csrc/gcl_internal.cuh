@@ -81,7 +81,8 @@ struct gcl_handle_s {
   bool pin_val[8] = {false, false, false, false, false, false, false, false};
   int pin_next = 0;
   int stage2_slot = -1;                 // slot whose evidence step is enqueued and not yet collected
-  bool stage2_has_update = false, stage2_has_iw = false, stage2_single = false;
+  bool stage2_has_update = false, stage2_has_iw = false, stage2_single = false, stage2_on_slot_stream = false;
+  cudaStream_t stage2_stream = nullptr;   // the stream the evidence step in flight was enqueued on
 };
 
 namespace gcl {
