@@ -310,6 +310,7 @@ def main():
     for s in scans[:n_e2e]:
         p, t_, w_ = (torch.from_numpy(a).pin_memory() for a in (s.points, s.timestamps, s.weights))
         pinned.append((p.numpy(), t_.numpy(), w_.numpy(), p, t_, w_))
+        pl.register_pinned(*pinned[-1][:3])     # a ring of page-locked receive buffers, registered once
 
     lat_blocking = []          # per-scan latency of the blocking call (SURVEY.md 8d asks for p50 / p99 on configs[1])
 

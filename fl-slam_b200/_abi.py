@@ -83,6 +83,8 @@ def _load():
         "gcl_scan_submit_msg_host": (i32, [vp, i32, vp, i64, C.c_int32, vp, vp, f64, vp, vp, C.c_int32, vp, vp, vp, vp, i32, f64, vp, vp, vp,
                                            vp, i32, i32, vp, vp, i32, f64, i32, f64, f64]),
         "gcl_scan_msg_info_host": (i32, [vp, i32, vp, i64]),
+        "gcl_host_register": (i32, [vp, vp, sz]),
+        "gcl_host_unregister": (i32, [vp, vp]),
         "gcl_scan_evidence_begin_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32]),
         "gcl_scan_evidence_end_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gcl_scan_evidence_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp, i32, vp, vp]),

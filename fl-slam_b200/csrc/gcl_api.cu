@@ -546,6 +546,16 @@ static bool is_pinned(gcl_handle h, const void* p) {
   return v;
 }
 
+// Ranges registered with gcl_host_register: the caller vouches that they stay page-locked until unregistered, so the zero-copy
+// decision needs no driver query for arrays inside them.
+static bool in_registered(gcl_handle h, const void* p, size_t bytes) {
+  const char* c = static_cast<const char*>(p);
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (const auto& r : h->pinned_ranges)
+    if (c >= r.first && c + bytes <= r.first + r.second) return true;
+  return false;
+}
+
 static bool is_pinned_now(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) == cudaSuccess) return a.type == cudaMemoryTypeHost;
@@ -604,8 +614,10 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
   // thread (52 -> 50 us per scan: 0.54 MB instead of 1.2 MB competing with the evidence step's outputs for PCIe).  On the
   // caller's thread in the two-stage form (GCL_HOST_ASYNC=0) they cost 6 us per scan for nothing, so that route copies.
   static const bool zero_copy_ok = !(getenv("GCL_HOST_ZERO_COPY") && atoi(getenv("GCL_HOST_ZERO_COPY")) == 0);
-  const bool zero_copy = latency_call && direct && n_hyp == 1 && zero_copy_ok && !g_ht.on && is_pinned_now(points_host) &&
-                         is_pinned_now(timestamps_host) && is_pinned_now(weights_host);
+  const bool zero_copy = latency_call && direct && n_hyp == 1 && zero_copy_ok && !g_ht.on &&
+                         (in_registered(h, points_host, n * 24) || is_pinned_now(points_host)) &&
+                         (in_registered(h, timestamps_host, n * 8) || is_pinned_now(timestamps_host)) &&
+                         (in_registered(h, weights_host, n * 8) || is_pinned_now(weights_host));
   if (!direct && n > 0) {
     memcpy(hb + o_pts, points_host, n * 24);
     memcpy(hb + o_ts, timestamps_host, n * 8);
@@ -1157,6 +1169,31 @@ int gcl_scan_evidence_end_host(gcl_handle h, double* mS_dir, double* mS_sc, doub
     }
   }
   return GCL_OK;
+}
+
+int gcl_host_register(gcl_handle h, const void* ptr, size_t bytes) {
+  if (!h) return GCL_ERR_ARG;
+  GCL_REQUIRE(h, ptr && bytes > 0, "NULL pointer or empty range");
+  cudaSetDevice(h->device);
+  GCL_REQUIRE(h, is_pinned_now(ptr) && is_pinned_now(static_cast<const char*>(ptr) + bytes - 1),
+              "the range is not page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (auto& r : h->pinned_ranges)
+    if (r.first == static_cast<const char*>(ptr)) { r.second = bytes; return GCL_OK; }
+  h->pinned_ranges.emplace_back(static_cast<const char*>(ptr), bytes);
+  return GCL_OK;
+}
+
+int gcl_host_unregister(gcl_handle h, const void* ptr) {
+  if (!h) return GCL_ERR_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (size_t i = 0; i < h->pinned_ranges.size(); ++i)
+    if (h->pinned_ranges[i].first == static_cast<const char*>(ptr)) {
+      h->pinned_ranges.erase(h->pinned_ranges.begin() + i);
+      return GCL_OK;
+    }
+  h->err = "gcl_host_unregister: range not registered";
+  return GCL_ERR_ARG;
 }
 
 int gcl_scan_evidence_host(gcl_handle h, int slot_index, const double* pose_host, double* mS_dir, double* mS_sc, double* mN_dir,

@@ -83,6 +83,7 @@ struct gcl_handle_s {
   int stage2_slot = -1;                 // slot whose evidence step is enqueued and not yet collected
   bool stage2_has_update = false, stage2_has_iw = false, stage2_single = false, stage2_on_slot_stream = false;
   cudaStream_t stage2_stream = nullptr;   // the stream the evidence step in flight was enqueued on
+  std::vector<std::pair<const char*, size_t>> pinned_ranges;   // gcl_host_register: ranges the caller vouches for as page-locked
 };
 
 namespace gcl {

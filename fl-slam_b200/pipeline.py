@@ -377,6 +377,16 @@ class LidarEvidencePipeline:
         self._ptr_cache[id(a)] = (a, addr)   # holding `a` keeps id(a) from being reused by another object
         return addr
 
+    def register_pinned(self, *arrays: np.ndarray) -> None:
+        """Vouch for page-locked arrays that carry scans call after call (gcl_host_register): the calls that read them in place
+        then skip their per-call driver query.  Raises ValueError for pageable memory."""
+        for a in arrays:
+            _abi.check(_lib.gcl_host_register(self.handle, a.ctypes.data, a.nbytes), self.handle)
+
+    def unregister_pinned(self, *arrays: np.ndarray) -> None:
+        for a in arrays:
+            _abi.check(_lib.gcl_host_unregister(self.handle, a.ctypes.data), self.handle)
+
     def submit_scan_host(self, slot: int, points, timestamps, weights, scan_start_time: float, scan_end_time: float, xi_body) -> int:
         """Stage 1 of the host call (gcl_scan_submit_host): asynchronous upload + moment pass of one scan under H twists.
         Returns H.  Page-locked inputs are read in place: keep them unchanged until ``evidence_host(slot, ...)`` returns."""

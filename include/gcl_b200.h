@@ -361,6 +361,13 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot, const uint8_t* msg_data_hos
                              int n_bins, double tau, int precision, double eps_psd, double eps_mass);
 int gcl_scan_msg_info_host(gcl_handle h, int slot, double* info_host, int64_t n_doubles);
 
+/* Page-locked scan buffers that are used scan after scan (a ring of receive buffers) can be registered once: the caller vouches
+ * that [ptr, ptr + bytes) stays page-locked until gcl_host_unregister, and the entry points that read scan arrays in place
+ * (zero-copy) skip their per-call driver query (~2 us per array) for arrays inside a registered range.  Registration itself
+ * checks the range with the driver and fails for pageable memory. */
+int gcl_host_register(gcl_handle h, const void* ptr, size_t bytes);
+int gcl_host_unregister(gcl_handle h, const void* ptr);
+
 /* gcl_scan_evidence_host in two halves, so that the caller can issue the next scan's gcl_scan_submit_host while the GPU runs
  * this scan's chain step: _begin enqueues everything (H2D of pose / map / IW, chain step, the one D2H) and returns; _end
  * waits for the D2H and hands out the results (map / IW arrays are written only if the step carried an update / an IW state).

@@ -769,10 +769,14 @@ def test_pinned_buffers_reused_across_scans(g, O):
     pts, ts, w = (b.numpy() for b in bufs)
     pl = None
     ms = O.empty_map_stats(B)
-    for seed in (11, 12, 13):
+    for seed in (11, 12, 13, 14):
         sc = g.synth.make_scan(n, seed=seed)
         pts[:], ts[:], w[:] = sc.points, sc.timestamps, sc.weights
         pl = pl or g.LidarEvidencePipeline(n_bins=B, tau=tau, precision="fp64", n_points_cap=cap, lidar_origin=sc.lidar_origin, bin_directions=bins)
+        if seed == 13:   # from here on the buffers are registered: no per-call driver query
+            pl.register_pinned(pts, ts, w)
+            with pytest.raises(ValueError):
+                pl.register_pinned(np.zeros(16))          # pageable memory is refused
         ev = pl.process_scan_host(pts, ts, w, sc.scan_start_time, sc.scan_end_time, sc.xi_body[None], np.zeros((1, 6)), ms)
         _, _, raw, fin = _oracle_sums(O, sc, cap, bins, tau)
         sb = ev.scan_bins(0)
@@ -781,6 +785,7 @@ def test_pinned_buffers_reused_across_scans(g, O):
     # the copying path (pageable arrays) gives the same bits
     pageable = pl.process_scan_host(pts.copy(), ts.copy(), w.copy(), sc.scan_start_time, sc.scan_end_time, sc.xi_body[None], np.zeros((1, 6)), ms)
     assert np.array_equal(H(pageable.stats), H(ev.stats))
+    pl.unregister_pinned(pts, ts, w)
 
 
 def test_pipelined_batches_match_one_at_a_time(g, O):
