@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""A/B timing of scan_moments alone on the named workloads (the kernel variant is chosen by the environment:
-GCL_K1_WS=0 two-phase kernel, GCL_K1_WS=1 warp-specialised kernel; GCL_K1_TP caps the tile of the latter).
+"""Timing of scan_moments alone on the named workloads (best of 3 x 30 launches, CUDA events) -- the harness used for A/B runs of
+kernel variants (build the variant, run this, compare; GCL_K1_G forces the bins-per-thread tile).
 
-    GCL_K1_WS=0 python tools/ab_k1.py; GCL_K1_WS=1 python tools/ab_k1.py
+    python tools/ab_k1.py [stream] [1M] [single] [hyp] [16M]
 """
 import json
 import os
@@ -64,7 +64,7 @@ def single(precision, n, bins, cap=None, iters=30):
     return {"us": us, "ctas": ctas, "Gpairs_per_s": n_sel * bins / us * 1e-3}
 
 
-out = {"GCL_K1_WS": os.environ.get("GCL_K1_WS"), "GCL_K1_TP": os.environ.get("GCL_K1_TP")}
+out = {"GCL_K1_G": os.environ.get("GCL_K1_G")}
 only = sys.argv[1:] or ["stream", "1M", "single", "hyp", "16M"]
 for prec in ("fp64", "fp32c"):
     if "stream" in only:

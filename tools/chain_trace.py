@@ -1,3 +1,6 @@
+"""clock64 trace of the single-scan chain kernel (stage 2 of the host call): needs the trace build,
+    make -C fl-slam_b200/csrc EXTRA=-DGCL_CHAIN_TRACE   (touch gcl_evidence.cu first),
+which adds gcl_debug_chain_trace; prints the phase marks in microseconds from kernel start (profiles/r1_chain_kernel_single_scan_trace.md)."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
