@@ -403,8 +403,8 @@ __device__ __forceinline__ double softplus64(double x) {
 // IW mode Sigma = PSD(Psi / (nu + p + 1)), p = 3   (measurement_noise_iw_jax.py:37-57)
 __device__ inline void iw_sigma_mode(const double* iw /* [nu, Psi(9)] */, double eps_psd, double* Sigma) {
   double S[9];
-  const double den = iw[0] + 3.0 + 1.0;
-  for (int i = 0; i < 9; ++i) S[i] = iw[1 + i] / den;
+  const double inv = 1.0 / (iw[0] + 3.0 + 1.0);   // one reciprocal (nine divisions were 0.4 us of the sequential stream core per scan)
+  for (int i = 0; i < 9; ++i) S[i] = iw[1 + i] * inv;
   psd_project3_fast(S, eps_psd, Sigma);
 }
 
@@ -654,7 +654,7 @@ extern "C" int gcl_debug_chain_trace(long long* out) { return (int)cudaMemcpyFro
 
 // ---- staged stream ----------------------------------------------------------------------------------------------------
 // workspace carve (doubles): [single-scan map-derived 16B][map_pre: S x 26B][mder: S x 16B][sigma: S x 16][tpart: S*H x 32]
-//                           [pre: S x (32 + 16B)]
+//                           [pre: S x (32 + 17B, rounded up to even)]
 struct StreamWs {
   double *map_pre, *mder, *sigma, *tpart, *pre;
   __host__ __device__ StreamWs(double* ws, int S, int B, int H) {
@@ -665,7 +665,10 @@ struct StreamWs {
     pre = tpart + (size_t)S * H * 32;
   }
 };
-__host__ __device__ inline size_t pre_block_doubles(int B) { return 32 + 16 * (size_t)B; }
+// 16 values per bin at a pitch of 17 doubles: the sequential core reads "its" bin with one lane per bin, and a pitch of 16
+// doubles (128 bytes) put all 32 lanes on the same shared-memory bank (every LDS.64 a 32-way conflict: 1.1 of its 2.9 us per scan)
+constexpr int kPrePitch = 17;
+__host__ __device__ inline size_t pre_block_doubles(int B) { return (32 + kPrePitch * (size_t)B + 1) & ~(size_t)1; }
 size_t chain_workspace_doubles(int n_scans, int n_hyp, int n_bins) {
   return 16 * (size_t)n_bins + (size_t)n_scans * (26 * (size_t)n_bins + 16 * (size_t)n_bins + 16) + (size_t)n_scans * n_hyp * 32 +
          (size_t)n_scans * pre_block_doubles(n_bins);
@@ -797,7 +800,7 @@ __global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __
     As[0] = a; As[1] = bb; As[2] = c; As[3] = bb; As[4] = d; As[5] = e2; As[6] = c; As[7] = e2; As[8] = f;
     mat3_mul(R, As, RA);
     mat3_mul_nt(RA, R, RAR);
-    double* q = pre + 32 + 16 * (size_t)b;
+    double* q = pre + 32 + kPrePitch * (size_t)b;
     for (int i = 0; i < 9; ++i) q[i] = mder[7 * B + b * 9 + i] + RAR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
     q[9] = N * invN;
     for (int i = 0; i < 3; ++i) q[10 + i] = mder[4 * B + b * 3 + i] - (R[i * 3] * pb[0] + R[i * 3 + 1] * pb[1] + R[i * 3 + 2] * pb[2]);
@@ -809,7 +812,7 @@ __global__ void __launch_bounds__(kChainThreads) stream_evidence_kernel(const __
   if (warp == 0) {
     double acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = lane; b < B; b += 32) {
-      const double* q = pre + 32 + 16 * (size_t)b;
+      const double* q = pre + 32 + kPrePitch * (size_t)b;
       const double w = q[13];
       for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) acc[i * 3 + j] += w * q[10 + i] * q[10 + j];
@@ -869,6 +872,12 @@ __global__ void __launch_bounds__(32 * (1 + kSeqHelpers)) stream_sigma_chain_ker
   double iw[10];
   for (int i = 0; i < 10; ++i) iw[i] = P.iw_state[i];
   double nu_h = iw[0];
+#ifdef GCL_CHAIN_TRACE
+  long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tr_t = clock64();
+#define SQ(i) do { const long long n_ = clock64(); tr_acc[i] += n_ - tr_t; tr_t = n_; } while (0)
+#else
+#define SQ(i) do { } while (0)
+#endif
   for (int s = 0; s < S; ++s) {
     if (warp >= 1) {
       if (hl == 0) { nu_h = iw_nu_next(nu_h, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max); s_nu[(s + 1) & 1] = nu_h; }
@@ -881,10 +890,9 @@ __global__ void __launch_bounds__(32 * (1 + kSeqHelpers)) stream_sigma_chain_ker
       for (int i = 0; i < 9; ++i) R[i] = in[i];
       mat3_mul(R, sigma, RS);
       mat3_mul_nt(RS, R, Sc);   // S = R Sigma_meas R^T
+      SQ(0);
       double Lf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hf[3] = {0, 0, 0};
-      for (int b = lane; b < B; b += 32) {
-        const double* q = in + 32 + 16 * (size_t)b;
-        double Sg[9], Si[9];
+      auto bin_matrix = [&](int b, const double* q, double* Sg) {
         if (q[14] != 0.0) {
           for (int i = 0; i < 9; ++i) Sg[i] = q[i] + q[9] * Sc[i];
         } else {   // full route for this bin
@@ -896,26 +904,52 @@ __global__ void __launch_bounds__(32 * (1 + kSeqHelpers)) stream_sigma_chain_ker
           mat3_mul_nt(T1, R, RSR);
           for (int i = 0; i < 9; ++i) Sg[i] = md[7 * B + b * 9 + i] + RSR[i] + ((i % 4 == 0) ? P.eps_mass : 0.0);
         }
-        mat3_inv_adj(Sg, Si);
-        const double wb = q[13];
-        for (int i = 0; i < 9; ++i) { Si[i] *= wb; Lf[i] += Si[i]; }
-        for (int i = 0; i < 3; ++i) hf[i] += Si[i * 3] * q[10] + Si[i * 3 + 1] * q[11] + Si[i * 3 + 2] * q[12];
+      };
+      // two bins of a lane at a time: their inverses (a division each, the longest dependent chain of the loop) overlap; the
+      // sums still take the lane's bins in increasing order
+      for (int b0 = lane; b0 < B; b0 += 64) {
+        const int b1 = b0 + 32;
+        const bool two = b1 < B;
+        const double* q0 = in + 32 + kPrePitch * (size_t)b0;
+        const double* q1 = in + 32 + kPrePitch * (size_t)(two ? b1 : b0);
+        double Sg0[9], Sg1[9], Si0[9], Si1[9];
+        bin_matrix(b0, q0, Sg0);
+        bin_matrix(two ? b1 : b0, q1, Sg1);
+        mat3_inv_adj(Sg0, Si0);
+        mat3_inv_adj(Sg1, Si1);
+        const double wb0 = q0[13], wb1 = two ? q1[13] : 0.0;
+        for (int i = 0; i < 9; ++i) { Si0[i] *= wb0; Lf[i] += Si0[i]; }
+        for (int i = 0; i < 3; ++i) hf[i] += Si0[i * 3] * q0[10] + Si0[i * 3 + 1] * q0[11] + Si0[i * 3 + 2] * q0[12];
+        if (two) {
+          for (int i = 0; i < 9; ++i) { Si1[i] *= wb1; Lf[i] += Si1[i]; }
+          for (int i = 0; i < 3; ++i) hf[i] += Si1[i * 3] * q1[10] + Si1[i * 3 + 1] * q1[11] + Si1[i * 3 + 2] * q1[12];
+        }
       }
+      SQ(1);
       for (int i = 0; i < 9; ++i) Lf[i] = warp_sum(Lf[i]);
       for (int i = 0; i < 3; ++i) hf[i] = warp_sum(hf[i]);
+      SQ(2);
       double tw[3], rr_w[10];
       translation_solve(Lf, hf, P.eps_mass, tw);
       const double* Swtt = in + 9; const double* Swt = in + 18; const double Sw = in[21];
       for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) rr_w[i * 3 + j] = Swtt[i * 3 + j] - Swt[i] * tw[j] - tw[i] * Swt[j] + Sw * tw[i] * tw[j];
       rr_w[9] = Sw;
+      SQ(3);
       double* tp = W.tpart + ((size_t)s * H) * 32;
       if (lane < 9) { tp[lane] = Lf[lane]; W.sigma[(size_t)s * 16 + lane] = sigma[lane]; }
       if (lane == 0) { tp[9] = tw[0]; tp[10] = tw[1]; tp[11] = tw[2]; tp[12] = Sw; }
+      SQ(4);
       iw_update(iw, rr_w, P.iw_rho, P.iw_nu_weak_add, P.iw_nu_max, P.eps_mass, P.eps_psd, false);  // identical on every lane
+      SQ(5);
     }
     __syncthreads();
+    if (warp == 0) SQ(6);
   }
+#ifdef GCL_CHAIN_TRACE
+  if (tid == 0) for (int i = 0; i < 7; ++i) g_chain_trace[20 + i] = tr_acc[i];
+#endif
+#undef SQ
   if (tid == 0) {
     P.iw_state[0] = s_nu[S & 1];
     for (int i = 1; i < 10; ++i) P.iw_state[i] = iw[i];
