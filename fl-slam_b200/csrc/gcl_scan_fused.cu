@@ -278,6 +278,14 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   return p;
 }
 
+#ifdef GCL_K1_TRACE
+__device__ long long g_k1_trace[16];
+#define K1T(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 7) { const long long n_ = clock64(); k1_acc[i] += n_ - k1_t; k1_t = n_; } } while (0)
+extern "C" int gcl_debug_k1_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_k1_trace, sizeof(long long) * 16); }
+#else
+#define K1T(i) do { } while (0)
+#endif
+
 template <typename T, int G, int MINB>
 __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,6 +294,9 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   __shared__ double s_cert[kNT * GCL_NCERT];
 
   const int tid = threadIdx.x;
+#ifdef GCL_K1_TRACE
+  long long k1_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, k1_t = clock64();
+#endif
   // the job record is read all through the kernel (array pointers at every prefetch, times and twist at every front end): keep
   // it in shared memory instead of going back to global memory for every field
   __shared__ gcl_job s_job;
@@ -351,9 +362,12 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 
   const TimeConst tconst = time_const(J);
   // per-thread certificate partials live in shared memory (they are touched once per tile; registers are for the tile)
-  double* my_cert = s_cert + (size_t)tid * GCL_NCERT;
+  // scalar k of thread t lives at s_cert[k * kNT + t]: consecutive lanes, consecutive words (thread-major rows of 8 doubles put
+  // the 32 lanes of a warp on two banks: every one of the ~10 accesses per point was a 16-way conflict)
+  double* my_cert = s_cert + tid;
+#define CERT(k) my_cert[(k) * kNT]
 #pragma unroll
-  for (int k = 0; k < GCL_NCERT; ++k) my_cert[k] = 0.0;
+  for (int k = 0; k < GCL_NCERT; ++k) CERT(k) = 0.0;
   double c_wraw = 0;
 
   // --- sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69) ------------------
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       for (; r < rhi; r += kNT) p0 += (double)w[r];
     }
     c_wraw = (p0 + p1) + (p2 + p3);
-    my_cert[GCL_CS_SUM_W_RAW] = c_wraw;
+    CERT(GCL_CS_SUM_W_RAW) = c_wraw;
   }
 
   // fixed-order cross-slice reduction, kKC moments at a time, carried in fp64 in this CTA's record
@@ -433,6 +447,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     }
   };
   prefetch_tile(lo);
+  K1T(0);   // prologue: job record, atlas, exp table, raw-weight sum
 
   int pts_since_flush = 0;
   const int flush_points = (sizeof(T) == 4) ? 512 * PS : (1 << 30);  // per-thread chain length ~512 in fp32
@@ -478,8 +493,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       }
       const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
       const double w_desk = w_sel * w_time;
-      my_cert[GCL_CS_SUM_W_SEL] += w_sel; my_cert[GCL_CS_SUM_W_SEL_SQ] += w_sel * w_sel; my_cert[GCL_CS_SUM_W_DESKEW] += w_desk;
-      my_cert[GCL_CS_ROWS] += 1.0;
+      CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
+      CERT(GCL_CS_ROWS) += 1.0;
       wq = (T)(w_desk * lam);
       // Shift = the largest possible logit (|d.b| <= 1) when that cannot underflow, else the true row maximum
       // (jax.nn.softmax, binning.py:69).
@@ -488,6 +503,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       sd[0] = d0; sd[1] = d1; sd[2] = d2; sd[3] = offv;
     }
     __syncthreads();
+    K1T(1);   // wait for the rows + front end
     prefetch_tile(tile0 + TP);  // next tile's raw rows stream in while this tile is processed
     // ======================================= phase A ===========================================================
     if (pi < count) {
@@ -498,6 +514,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       zp[0] = Z; zp[1] = S1; zp[2] = xmax;
     }
     __syncthreads();
+    K1T(2);   // phase A
     // ======================================= scale =============================================================
     if (tid < count) {
       T Z = 0, S1 = 0, xmax = (T)-1.0e30;
@@ -509,13 +526,14 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       const double Zd = (double)Z;
       if (sizeof(T) == 4) {
         const float invZ = 1.f / (float)Z;
-        my_cert[GCL_CS_SUM_ENTROPY] += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
+        CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
         const double mr = (double)(fast_exp2((float)xmax) * invZ);
-        if (mr > my_cert[GCL_CS_MAX_RESP]) my_cert[GCL_CS_MAX_RESP] = mr;
+        if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
       } else {
-        my_cert[GCL_CS_SUM_ENTROPY] += log(Zd) - Num<T>::kToNat * (double)S1 / Zd - (double)B * C.eps_mass;
-        const double mr = (double)exp_of_max(xmax, s_tab) / Zd;
-        if (mr > my_cert[GCL_CS_MAX_RESP]) my_cert[GCL_CS_MAX_RESP] = mr;
+        const double rZ = 1.0 / Zd;
+        CERT(GCL_CS_SUM_ENTROPY) += log(Zd) - Num<T>::kToNat * (double)S1 * rZ - (double)B * C.eps_mass;
+        const double mr = (double)exp_of_max(xmax, s_tab) * rZ;
+        if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
       }
       const T w = wq / Z;
       T f[kRowPitch];
@@ -537,12 +555,14 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       }
     }
     __syncthreads();
+    K1T(3);   // scale
     // ======================================= phase B ===========================================================
     {
       const T* ebase = s_etile + (size_t)binlane * VB;
 #pragma unroll 2
       for (int pt = slice; pt < count; pt += PS) acc.step(ebase + (size_t)pt * EP, L, s_rows + (size_t)pt * kRowPitch);
     }
+    K1T(4);   // phase B (this thread's share; the next barrier is charged to the front end of the next tile)
     pts_since_flush += count;
     if (pts_since_flush >= flush_points) {
       __syncthreads();
@@ -551,14 +571,16 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     }
   }
   __syncthreads();
+  K1T(5);   // tail barrier
   if (pts_since_flush > 0) flush();
+  K1T(6);   // flush
   if (!flushed)   // a CTA without rows: its record is all zeros
     for (int i = tid; i < GCL_NM * B; i += kNT) part[i] = 0.0;
 
   // --- certificate scalars of this CTA -------------------------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < GCL_NCERT; ++k) {
-    double v = my_cert[k];
+    double v = CERT(k);
     for (int o = 16; o > 0; o >>= 1) {
       const double other = __shfl_xor_sync(0xffffffffu, v, o);
       v = (k == GCL_CS_MAX_RESP) ? fmax(v, other) : v + other;
@@ -573,6 +595,12 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     for (int w = 1; w < kNT / 32; ++w) v = (src == GCL_CS_MAX_RESP) ? fmax(v, s_red[w][src]) : v + s_red[w][src];
     part[(size_t)GCL_NM * B + tid] = v;
   }
+#undef CERT
+#ifdef GCL_K1_TRACE
+  K1T(7);   // certificate reduction
+  if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 7)
+    for (int i = 0; i < 8; ++i) g_k1_trace[i] = k1_acc[i];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
