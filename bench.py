@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_moments launch of this workload, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
-TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.094720e6 + 7.802112e6, "fp32c": None}
+TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.095488e6 + 8.889856e6, "fp32c": None}
 TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch; the "
                   "stride-4 gather of 24-byte rows touches every 32-byte sector, hence ~2.3x the algorithmic bytes)")
 
