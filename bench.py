@@ -165,10 +165,30 @@ def run_reference(args, rank):
                              "sample": f"{n_sample} scans/step x {args.steps} steps of the configs[1] stream; NumPy float64 "
                                        f"restatement of the reference (JAX unavailable); os.cpu_count()={os.cpu_count()}"},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Only the one JSON line may reach stdout (NCCL, for one, prints its version banner there under torchrun): keep a private
+    copy of the descriptor for that line and point descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -199,8 +219,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout, where the one JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
     tau = synth.DEFAULT_TAU
     peak_gbs, peak_src = load_peaks()
@@ -461,7 +479,7 @@ def main():
                            "ms_per_step_one_batch_at_a_time": ms_per_step_serial, "iw": "LiDAR measurement-noise IW block adapted every scan (Sigma_meas into bin covariances)"},
                 "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "extra": extra}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
