@@ -307,6 +307,38 @@ def run_pointcloud2():
     np.savez_compressed(os.path.join(HERE, "ref_pointcloud2.npz"), **out)
 
 
+def run_time_bounds():
+    """Scan time bounds (pkg/backend/backend_node.py:1776-1786): the statements are inline in a ROS node method, so they are cut out
+    of the reference source as TEXT (from the `time_bounds = jnp.array(` line to the line before `dt_raw = (`), dedented and
+    executed unmodified on `timestamps` / `stamp_sec` with NumPy standing in for jnp."""
+    import textwrap
+    path = "/root/reference/fl_ws/src/fl_slam_poc/fl_slam_poc/backend/backend_node.py"
+    lines = open(path).read().split("\n")
+    a = next(i for i, l in enumerate(lines) if l.strip().startswith("time_bounds = jnp.array("))
+    b = next(i for i in range(a, len(lines)) if lines[i].strip().startswith("dt_raw = ("))
+    code = textwrap.dedent("\n".join(lines[a:b]))
+    assert "scan_start_time" in code and "scan_end_time" in code and "1e-9" in code
+    rng = np.random.default_rng(77)
+    cases = []
+    for k in range(12):
+        base = [0.0, 12.25, 1.7e9][k % 3]
+        if k % 4 == 3:
+            ts = np.full(50, base + 0.05)                              # no per-point spread
+        elif k == 5:
+            ts = base + np.array([0.0, 4e-10, 9e-10])                  # spread below the 1e-9 threshold
+        else:
+            ts = base + np.sort(rng.uniform(0.0, 0.1, 200))
+        for stamp in (base - 0.3, base + 0.04, base + 0.7):
+            cases.append((ts, float(stamp)))
+    out = {"n_cases": len(cases)}
+    for i, (ts, stamp) in enumerate(cases):
+        ns = {"jnp": np, "timestamps": ts, "stamp_sec": stamp, "record_device_to_host": lambda *a_, **k_: None}
+        exec(code, ns)
+        out[f"ts_{i}"] = ts
+        out[f"io_{i}"] = np.array([stamp, ns["scan_start_time"], ns["scan_end_time"]])
+    np.savez_compressed(os.path.join(HERE, "ref_time_bounds.npz"), **out)
+
+
 def main():
     ref = _jaxshim.load_reference("/root/reference", n_bins=48, tau=0.1)
     synth = _load_synth()
@@ -327,6 +359,7 @@ def main():
     run_pieces(ref)
     run_imu(ref)
     run_pointcloud2()
+    run_time_bounds()
     print("wrote goldens to", HERE)
 
 

@@ -303,3 +303,13 @@ def test_pointcloud2_parse_matches_reference(name):
     np.testing.assert_allclose(out["weights"], z[f"{name}_w"], rtol=1e-15, atol=0)
     np.testing.assert_allclose(O.lidar_points_to_base(out["points"], z["R_base_lidar"], z["t_base_lidar"]), z[f"{name}_points_base"],
                                rtol=1e-15, atol=1e-15)
+
+
+def test_scan_time_bounds_against_reference_source():
+    """O.scan_time_bounds against the reference's own statements (backend_node.py:1776-1786), cut out of the source as text and
+    executed by tests/golden/generate_goldens.py::run_time_bounds: bit-exact on every case (spread, no spread, spread below the
+    1e-9 threshold; header stamp before / inside / after the scan; epoch-scale and small time bases)."""
+    z = np.load(os.path.join(GOLDEN, "ref_time_bounds.npz"))
+    for i in range(int(z["n_cases"])):
+        stamp, t0, t1 = z[f"io_{i}"]
+        assert O.scan_time_bounds(z[f"ts_{i}"], float(stamp)) == (float(t0), float(t1)), i
