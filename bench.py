@@ -4,15 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp64|fp32c] [--no-extra] [--no-cpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Default workload = BASELINE.json configs[1]: a Kimera-jackal-shaped synthetic scan stream (200 scans of ~30k points,
-cap 8192 => stride 4 / 7500 selected rows, 48 bins, 1 hypothesis) with the map bin statistics carried from scan to scan
-(forgetting 0.99) and the LiDAR measurement-noise IW block adapted every scan.  One "step" = one pass over the whole stream
-(seven launches).  `value` = raw points per second with the scans resident in HBM; `e2e` = the same stream through the
-reference-facing host calls (pinned host buffers; every scan's H2D, kernels and D2H inside the timed region).  `roofline` is for the dominant kernel, scan_moments.
-`extra` carries the 1M-point x 256-bin cloud (configs[3]) -- the configuration the HBM target is quoted on -- and
-the 64-hypothesis batch (configs[2]).  At N > 1 the stream workload runs as N independent replicas (scan k+1 depends on
-scan k's map: it does not shard); configs[3] shards by points with one all-gather of the per-bin moment
-buffer, configs[2] shards by hypothesis.
+Headline workload = BASELINE.json configs[3], the configuration the north star's HBM / scaling target is quoted on: one dense
+synthetic cloud of 1 048 576 points (n_points_cap = n => stride 1), 256 bins, 1 hypothesis, through resample -> deskew -> soft
+assign -> moment match -> Matrix Fisher -> planar translation.  One "step" = 64 scans; the cloud is rotated through enough
+copies that no scan re-reads an L2-resident input.  At N > 1 the POINTS are sharded over the ranks (strong scaling) with one
+exchange of the per-bin record per scan through the fused NVLink kernel (csrc/gcl_exchange.cu); the sharded result is compared
+with the unsharded one and bit for bit across ranks inside the run (`parity`).  `value` = points per second with the inputs
+resident in HBM (fp64 arithmetic; the fp32c mode is in `extra`); `e2e` = the same scans with every scan's rows crossing PCIe from
+page-locked host arrays and every scan's records read back; `roofline` is for the dominant kernel, scan_moments.
+`extra` carries the same cloud in fp32c mode, the configs[1] scan stream (200 scans x ~30k points, map + IW state carried; at
+N > 1 it runs as N independent replicas: scan k+1 needs scan k's map) with its per-scan host-call latencies, and
+the configs[2] 64-hypothesis batch sharded by hypothesis.
 """
 from __future__ import annotations
 
@@ -30,10 +32,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48
+N_SCANS, PTS_PER_SCAN, CAP, N_BINS = 200, 30000, 8192, 48          # configs[1] (side measurement)
+HEAD_POINTS, HEAD_BINS, SCANS_PER_STEP = 1 << 20, 256, 64           # configs[3] (headline)
+REF_SAMPLE_POINTS = 1 << 16                                         # points of the same cloud one reference-arm step processes
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_moments launch of this workload, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
 TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.095488e6 + 8.889856e6, "fp32c": None}
+# the same for one launch of the headline workload (1M x 256, one GPU); filled from profiles/r2_*.md once captured
+HEAD_TRAFFIC_BYTES_PER_LAUNCH = {"fp64": None, "fp32c": None}
+HEAD_TRAFFIC_SOURCE = "profiles/ (ncu --set full capture of one scan_moments launch of the 1M x 256 cloud); None = not captured for this build"
 TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch; the "
                   "stride-4 gather of 24-byte rows touches every 32-byte sector, hence ~2.3x the algorithmic bytes)")
 
@@ -112,22 +119,65 @@ def make_stream(n_scans, seed0=1234 + 2):
     return scans, np.stack(poses)
 
 
-def cpu_stream_rate(n_sample, tau, min_seconds=0.0):
-    """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the SAME stream workload:
-    resample, deskew, soft assign, moment match, Matrix Fisher, planar translation, IW update, map update per scan.
-    The n_sample-scan stream is walked repeatedly until min_seconds of CPU work have been timed."""
+def head_config(tau, precision="fp64"):
+    """The `config` both arms print (the reference arm times a bounded sample of the same cloud; it says so in cpu_baseline)."""
+    return {"workload": f"configs[3]: dense synthetic cloud, {HEAD_POINTS} points/scan, {HEAD_BINS} bins, 1 hypothesis, n_points_cap = n "
+                        "(stride 1); resample -> deskew -> soft assign -> moment match -> Matrix Fisher -> planar translation",
+            "n_points": HEAD_POINTS, "n_bins": HEAD_BINS, "n_hyp": 1, "tau": tau, "precision": precision}
+
+
+def _load_by_path(name, rel):
+    """A module of the package loaded by file path: the reference arm must not import the package (whose __init__ loads the CUDA
+    library)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, rel))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _synth():
+    return sys.modules.get("fl_slam_b200.synth") or sys.modules.get("_gcl_synth") or _load_by_path("_gcl_synth", "fl-slam_b200/synth.py")
+
+
+def cpu_head_rate(n_sample, tau, min_seconds=0.0, return_result=False):
+    """The NumPy restatement of the reference (JAX unavailable) on a bounded sample of the SAME cloud: the first n_sample points
+    of the 1M-point cloud (a contiguous arc of the sweep) against all 256 bins -- resample, deskew, soft assign, moment match
+    (chunked so that no (N, B) array exceeds 64 M elements), finalisation, Matrix Fisher, planar translation."""
     from oracle import gc_oracle as O
-    scans, poses = make_stream(n_sample)
-    bins = O.create_fibonacci_atlas(N_BINS)
-    pts = sum(s.points.shape[0] for s in scans)
-    dt, passes = 0.0, 0
+    synth = _synth()
+    sc = synth.make_scan(HEAD_POINTS, seed=1234 + 4, dense=True)
+    pts, ts, w = sc.points[:n_sample], sc.timestamps[:n_sample], sc.weights[:n_sample]
+    bins = O.create_fibonacci_atlas(HEAD_BINS)
+    dt, passes, out = 0.0, 0, None
     while passes == 0 or dt < min_seconds:
         t0 = time.perf_counter()
-        O.scan_stream(scans, poses, poses, n_points_cap=CAP, bin_directions=bins, tau=tau, lidar_origin=scans[0].lidar_origin,
-                      iw_state=O.iw_lidar_init(1e-3), use_sigma_meas=True)
+        pb = O.point_budget_resample(pts, ts, w, sc.ring[:n_sample], sc.tag[:n_sample], n_sample)
+        dk = O.deskew_constant_twist(pb["points"], pb["timestamps"], pb["weights"], sc.scan_start_time, sc.scan_end_time, sc.xi_body)
+        raw = O.fused_scan_raw_sums(dk["points"], dk["weights"], bins, tau, sc.lidar_origin)
+        fin = O.scan_bin_finalize(raw)
+        Rs, tstar = synth.known_map_transform(4)
+        ms = synth.map_stats_from_scan_sums(raw, Rs, tstar, seed=4)
+        md = O.compute_map_derived_stats(ms["S_dir"], ms["N_dir"], ms["N_pos"], ms["sum_p"], ms["sum_ppT"])
+        mf = O.matrix_fisher_rotation_evidence(np.zeros(6), fin["s_dir"], fin["S_dir_scatter"], fin["N"], ms["S_dir"], ms["S_dir_scatter"], ms["N_dir"])
+        pt = O.planar_translation_evidence(np.zeros(6), fin["p_bar"], fin["Sigma_p"], fin["N"], md["centroid"], md["Sigma_c"], ms["N_pos"],
+                                           ms["S_dir_scatter"], ms["N_dir"], mf["R_mf"])
         dt += time.perf_counter() - t0
         passes += 1
-    return passes * pts / dt, passes * n_sample / dt, dt
+        out = (sc, raw, fin, ms, mf, pt)
+    rate = passes * n_sample / dt
+    return (rate, dt, passes, out) if return_result else (rate, dt, passes)
+
+
+def cpu_single_thread_rate(n_sample, tau):
+    """The same sample with BLAS / OpenMP pools limited to one thread (SURVEY.md 8d asks for both figures)."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None
+    with threadpool_limits(limits=1):
+        return cpu_head_rate(n_sample, tau)[0]
 
 
 def blas_threads():
@@ -139,32 +189,33 @@ def blas_threads():
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path = the NumPy restatement (the JAX
-    implementation cannot run here), all host threads NumPy/BLAS will use, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path = the NumPy restatement (the JAX implementation cannot
+    run here: no JAX, no network), all host threads NumPy/BLAS will use, one bounded sample of the headline cloud per step.  Imports
+    nothing of the package: the CUDA library is never loaded into this process."""
     if rank != 0:
         return
-    from fl_slam_b200 import synth
+    synth = _synth()
     tau = synth.DEFAULT_TAU
-    n_sample = 100
-    for _ in range(args.warmup):
-        cpu_stream_rate(10, tau)
-    t_all, pts_all, scans_all = 0.0, 0.0, 0.0
+    for _ in range(max(1, args.warmup)):
+        cpu_head_rate(REF_SAMPLE_POINTS // 8, tau)
+    t_all, pts_all = 0.0, 0.0
     for _ in range(args.steps):
-        pps, sps, dt = cpu_stream_rate(n_sample, tau, min_seconds=3.0)
-        t_all += dt; pts_all += pps * dt; scans_all += sps * dt
+        rate, dt, passes = cpu_head_rate(REF_SAMPLE_POINTS, tau)
+        t_all += dt; pts_all += passes * REF_SAMPLE_POINTS
     value = pts_all / t_all
+    single = cpu_single_thread_rate(REF_SAMPLE_POINTS // 4, tau)
     cores = blas_threads()
     line = {"impl": "reference", "metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value,
             "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[1] scan stream, bounded sample of {n_sample} scans per step (~30k points, cap {CAP}, "
-                                   f"{N_BINS} bins, 1 hypothesis, map carried)", "tau": tau},
-            "scans_per_sec": scans_all / t_all,
-            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_sample} scans/step x {args.steps} steps of the configs[1] stream; NumPy float64 "
-                                       f"restatement of the reference (JAX unavailable); os.cpu_count()={os.cpu_count()}"},
-            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": head_config(tau),
+            "scans_per_sec": value / HEAD_POINTS,
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "single_thread_value": single,
+                             "sample": f"the first {REF_SAMPLE_POINTS} points of the same {HEAD_POINTS}-point cloud against all {HEAD_BINS} bins per step, "
+                                       f"{args.steps} steps; NumPy float64 restatement of the reference operators (JAX unavailable); "
+                                       f"os.cpu_count()={os.cpu_count()}, BLAS threads={cores}"},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "loaded_native_libraries": [m for m in ("fl_slam_b200", "fl_slam_b200._abi") if m in sys.modules]}
     emit(line)
 
 
@@ -187,42 +238,13 @@ def emit(line):
     out.flush()
 
 
-def main():
-    claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2]/[3] side measurements")
-    ap.add_argument("--no-overlap", action="store_true", help="one batch at a time (no pipelining of consecutive 200-scan batches)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline (profiling runs)")
-    ap.add_argument("--cpu-sample", type=int, default=100, help="scans in the CPU-baseline sample (walked repeatedly for >= 12 s)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-
+def bench_stream(args, g, synth, dev, rank, world, local_rank, tau, peak_gbs, peak_src, precision):
+    """BASELINE.json configs[1] (side measurement; headline of round 1): the 200-scan stream with map + IW state carried, one
+    replica per rank, and the per-scan host calls (pinned host buffers) with their latencies."""
     import torch
     import torch.distributed as dist
-
-    import fl_slam_b200 as g
-    from fl_slam_b200 import synth
-    from fl_slam_b200 import sharding
-
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    tau = synth.DEFAULT_TAU
-    peak_gbs, peak_src = load_peaks()
-
+    args = argparse.Namespace(**vars(args))
+    args.precision = precision
     # ---------------------------------------------------------------- workload: configs[1] scan stream (replica per rank)
     scans, poses = make_stream(N_SCANS, seed0=1234 + 2 + 1000 * rank)
     pl = g.LidarEvidencePipeline(n_bins=N_BINS, tau=tau, precision=args.precision, n_points_cap=CAP,
@@ -273,8 +295,6 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
@@ -320,8 +340,6 @@ def main():
                         "clock (DESIGN.md section 4).  The other large launch of a step is the sequential measurement-noise core "
                         "(stream_sigma_chain_kernel, one warp walking the 200 scans, ~2.6 us per scan: latency-bound by construction); "
                         "the remaining five launches take ~0.1 ms together (profiles/r1_launches_bench_stream_fp64.csv)"}
-    roofline["traffic"] = TRAFFIC_BYTES_PER_LAUNCH.get(args.precision)
-
     # ---------------------------------------------------------------- e2e: the reference-facing host call, pinned buffers
     n_e2e = min(N_SCANS, 50)
     pinned = []
@@ -430,55 +448,140 @@ def main():
                    "kernel arguments, map / IW fetched only when they differ from what the device already holds (here they never do: the arrays "
                    "handed back are the ones the previous step wrote), map / IW / stats / evidence pushed back by the kernel, then a ticket the host polls"}
 
-    # ---------------------------------------------------------------- side measurements: configs[3] and configs[2]
-    extra = {}
-    if not args.no_extra and args.precision == "fp64":
-        # the same stream in fp32c mode (packed 20 B/point layout, <= 1e-5 on the moments): side figure
-        pl32 = g.LidarEvidencePipeline(n_bins=N_BINS, tau=tau, precision="fp32c", n_points_cap=CAP, lidar_origin=scans[0].lidar_origin)
-        res32 = [pl32.upload_scan(s.points, s.timestamps, s.weights, s.scan_start_time, s.scan_end_time) for s in scans]
-        jobs32 = pl32.jobs_to_device([pl32.make_job(res32[k], xis[k]) for k in range(N_SCANS)])
-        ms32, iw32 = g.create_empty_map_stats(N_BINS), pl32.create_lidar_iw_state(1e-3)
-        ctas32 = pl32.plan_ctas(N_SCANS, max_sel)
-        b32 = pl32._buffers(N_SCANS, ctas32)
-        step32 = _time(lambda: pl32.run_stream(res32, xis, poses_dev, poses_dev, ms32, iw_state=iw32, use_sigma_meas=True, jobs_dev=jobs32, ctas=ctas32), n=max(args.steps, 20))
-        k132 = _time(lambda: pl32.launch_moments(jobs32, None, N_SCANS, ctas32, res32[0].layout, b32["partials"]))
-        extra["stream_fp32c"] = {"ms_per_step": step32, "points_per_sec": world * total_points / (step32 * 1e-3), "scan_moments_ms": k132,
-                                 "pairs_per_sec": pairs / (k132 * 1e-3), "layout": "packed_f32 (20 B/point)"}
-        del pl32, res32
-    if not args.no_extra:
-        extra["cfg4_1Mx256"] = sharding.bench_points_sharded(g, n_points=1 << 20, n_bins=256, tau=tau, steps=max(args.steps, 10),
-                                                            warmup=args.warmup, rank=rank, world=world, peak_gbs=peak_gbs)
-        extra["cfg3_64hyp"] = sharding.bench_hypothesis_sharded(g, n_points=30000, cap=32768, n_bins=48, n_hyp=64, tau=tau,
-                                                               steps=max(args.steps, 10), warmup=args.warmup, rank=rank, world=world)
 
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        pps, sps, dt = cpu_stream_rate(args.cpu_sample, tau, min_seconds=12.0)
-        cpu = {"value": pps, "unit": "points/s", "cores": blas_threads(), "kind": "port", "scans_per_sec": sps,
-               "sample": f"first {args.cpu_sample} scans of the same stream, walked repeatedly for {dt:.1f} s; NumPy float64 restatement of the "
-                         f"reference operators (JAX unavailable); os.cpu_count()={os.cpu_count()}"}
+    roofline["traffic"] = TRAFFIC_BYTES_PER_LAUNCH.get(precision)
+    ceiling = pair_ceiling(precision, 1965.0)
+    roofline["compute_ceiling_pairs_per_sec_at_1965MHz"] = ceiling
+    roofline["compute_frac_at_1965MHz"] = roofline["pairs_per_sec"] / ceiling
+    out = {"workload": f"configs[1]: scan stream, {N_SCANS} scans x ~{PTS_PER_SCAN} points, cap {CAP} (stride 4, 7500 rows), {N_BINS} bins, "
+                       "1 hypothesis, map statistics carried (forgetting 0.99), LiDAR measurement-noise IW block adapted every scan",
+           "precision": precision, "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (a stream does not shard)",
+           "points_per_sec": value, "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "ms_per_step": ms_per_step,
+           "ms_per_step_one_batch_at_a_time": ms_per_step_serial, "launches_per_step": int(launches_per_step),
+           "processed_rows_per_sec": value * 7500.0 / PTS_PER_SCAN, "roofline": roofline, "e2e": e2e}
+    del res, pinned, msgs
+    return out
 
-    clocks = sampler.stop()   # sampled over the timed stream passes, the per-kernel timing loops, e2e and the side measurements
+
+def main():
+    claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32c"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the fp32c / configs[1] / configs[2] side measurements")
+    ap.add_argument("--no-overlap", action="store_true", help="stream side measurement: one batch at a time")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: fused NVLink exchange kernel, or the NCCL all-gather route")
+    ap.add_argument("--scans-per-step", type=int, default=SCANS_PER_STEP)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fl_slam_b200 as g
+    from fl_slam_b200 import synth
+    from fl_slam_b200 import sharding
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tau = synth.DEFAULT_TAU
+    peak_gbs, peak_src = load_peaks()
+
+    # ---------------------------------------------------------------- headline: configs[3], points sharded over the ranks
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    head = sharding.bench_points_sharded(g, n_points=HEAD_POINTS, n_bins=HEAD_BINS, tau=tau, steps=args.steps, warmup=args.warmup, rank=rank,
+                                         world=world, peak_gbs=peak_gbs, precision=args.precision, scans_per_step=args.scans_per_step,
+                                         exchange=args.exchange, with_e2e=not args.no_e2e)
+    clocks = sampler.stop()
+    roofline = head.pop("roofline")
+    roofline["peak_source"] = peak_src
+    roofline["traffic"] = HEAD_TRAFFIC_BYTES_PER_LAUNCH.get(args.precision) if world == 1 else None
+    roofline["traffic_source"] = HEAD_TRAFFIC_SOURCE
     ceiling = pair_ceiling(args.precision, clocks.get("sm_mhz") or 1965.0)
+    roofline["pairs_per_sec"] = head["pairs_per_sec"] / world       # per GPU, like achieved
     roofline["compute_ceiling_pairs_per_sec"] = ceiling
     roofline["compute_frac"] = roofline["pairs_per_sec"] / ceiling
+    roofline["note"] = ("scan_moments is bound by FMA-pipe issue, not by HBM (DESIGN.md section 4): compute_frac = pairs/s over the FMA-issue "
+                        "ceiling of its own instruction mix at the sampled SM clock; frac is the HBM fraction the north star asks for")
+    e2e = head.pop("e2e", None)
+    parity = head.pop("parity")
+
+    # ---------------------------------------------------------------- side measurements
+    extra = {}
+    if not args.no_extra:
+        other = "fp32c" if args.precision == "fp64" else "fp64"
+        o = sharding.bench_points_sharded(g, n_points=HEAD_POINTS, n_bins=HEAD_BINS, tau=tau, steps=max(3, args.steps // 2), warmup=args.warmup,
+                                          rank=rank, world=world, peak_gbs=peak_gbs, precision=other, scans_per_step=args.scans_per_step,
+                                          exchange=args.exchange, with_e2e=not args.no_e2e)
+        o["roofline"]["compute_frac"] = (o["pairs_per_sec"] / world) / pair_ceiling(other, clocks.get("sm_mhz") or 1965.0)
+        extra[f"cfg4_1Mx256_{other}"] = o
+        if world > 1 and args.exchange == "peer":
+            n = sharding.bench_points_sharded(g, n_points=HEAD_POINTS, n_bins=HEAD_BINS, tau=tau, steps=max(3, args.steps // 2), warmup=args.warmup,
+                                              rank=rank, world=world, peak_gbs=peak_gbs, precision=args.precision,
+                                              scans_per_step=args.scans_per_step, exchange="nccl", with_e2e=False)
+            extra["cfg4_1Mx256_nccl_all_gather_route"] = {k: n[k] for k in ("ms_per_scan", "scan_moments_ms", "rest_of_scan_ms", "points_per_sec", "parity")}
+        extra["cfg3_64hyp"] = sharding.bench_hypothesis_sharded(g, n_points=30000, cap=32768, n_bins=48, n_hyp=64, tau=tau,
+                                                               steps=max(3, args.steps // 2), warmup=args.warmup, rank=rank, world=world)
+        extra["cfg3_64hyp_fp32c"] = sharding.bench_hypothesis_sharded(g, n_points=30000, cap=32768, n_bins=48, n_hyp=64, tau=tau,
+                                                                     steps=max(3, args.steps // 2), warmup=args.warmup, rank=rank, world=world,
+                                                                     precision="fp32c")
+        extra["cfg2_stream"] = bench_stream(args, g, synth, dev, rank, world, local_rank, tau, peak_gbs, peak_src, "fp64")
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only) + parity of the GPU path on its sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_s = REF_SAMPLE_POINTS
+        rate, dt, passes, (sc_s, raw_s, fin_s, ms_s, mf_s, pt_s) = cpu_head_rate(n_s, tau, min_seconds=12.0, return_result=True)
+        single = cpu_single_thread_rate(n_s // 4, tau)
+        pl_s = g.LidarEvidencePipeline(n_bins=HEAD_BINS, tau=tau, precision=args.precision, n_points_cap=n_s, lidar_origin=sc_s.lidar_origin)
+        ev_s = pl_s.process_scan_host(sc_s.points[:n_s], sc_s.timestamps[:n_s], sc_s.weights[:n_s], sc_s.scan_start_time, sc_s.scan_end_time,
+                                      sc_s.xi_body[None], np.zeros((1, 6)), ms_s)
+        sb = ev_s.scan_bins(0)
+        def _r(a, b):
+            a, b = np.asarray(a.cpu().numpy() if hasattr(a, "cpu") else a), np.asarray(b)
+            return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+        chk = {"N": _r(sb.N, fin_s["N"]), "s_dir": _r(sb.s_dir, fin_s["s_dir"]), "S_dir_scatter": _r(sb.S_dir_scatter, fin_s["S_dir_scatter"]),
+               "p_bar": _r(sb.p_bar, fin_s["p_bar"]), "Sigma_p": _r(sb.Sigma_p, fin_s["Sigma_p"]),
+               "R_mf_rad": float(np.linalg.norm(ev_s.evidence[0, :9].cpu().numpy().reshape(3, 3) - mf_s["R_mf"]) / np.sqrt(2.0)),
+               "t_wls": _r(ev_s.evidence[0, 71:74], pt_s["t_wls"])}
+        cpu = {"value": rate, "unit": "points/s", "cores": blas_threads(), "kind": "port", "single_thread_value": single,
+               "sample": f"the first {n_s} points of the same {HEAD_POINTS}-point cloud against all {HEAD_BINS} bins, walked {passes} times in {dt:.1f} s; "
+                         f"NumPy float64 restatement of the reference operators (JAX unavailable); os.cpu_count()={os.cpu_count()}",
+               "gpu_vs_oracle_on_sample_max_rel": chk}
+        parity["vs_oracle_on_cpu_sample"] = chk
+
     if rank == 0:
-        line = {"metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": value, "unit": "points/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32 (fp64 carry)",
-                "data": "synthetic",
-                "config": {"workload": f"configs[1]: scan stream, {N_SCANS} scans x ~{PTS_PER_SCAN} points, cap {CAP} (stride 4, "
-                                       f"7500 rows), {N_BINS} bins, 1 hypothesis, map statistics carried (forgetting 0.99)",
-                           "tau": tau, "precision": args.precision, "layout": "ref_f64 (40 B/point)" if args.precision == "fp64" else "packed_f32 (20 B/point)",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (stream does not shard)",
-                           "l2": "inputs total 240 MB > 126 MB L2; each scan is read once per step",
-                           "launches_per_step": int(launches_per_step),
-                           "batches": "consecutive 200-scan batches pipelined (moment pass of batch k+1 overlaps the sequential chain of batch k)"
-                                      if overlap else "one 200-scan batch at a time",
-                           "ms_per_step_one_batch_at_a_time": ms_per_step_serial, "iw": "LiDAR measurement-noise IW block adapted every scan (Sigma_meas into bin covariances)"},
-                "scans_per_sec": world * N_SCANS / (ms_per_step * 1e-3), "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "extra": extra}
+        cfg = head_config(tau, args.precision)
+        line = {"metric": "points/sec deskew+soft-assign+moment-match (whole evidence chain)", "value": head["points_per_sec"], "unit": "points/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32 (fp64 carry)",
+                "data": "synthetic", "config": cfg,
+                "details": {"layout": "ref_f64 (40 B/point)" if args.precision == "fp64" else "packed_f32 (20 B/point)",
+                            "parallelism": "1 GPU" if world == 1 else f"points sharded over {world} GPUs, one fused NVLink exchange of the "
+                                           f"{(19 * HEAD_BINS + 8) * 8} B per-bin record per scan ({head['exchange']})",
+                            "step": f"{head['scans_per_step']} scans", "l2": f"{head['input_copies_rotated']} copies of the input rotated "
+                                    "(> 2 x the 126 MB L2 per rank): no scan re-reads an L2-resident cloud",
+                            "timed_region_ms": head["ms_per_step"] * args.steps, **{k: head[k] for k in (
+                                "ms_per_scan", "ms_per_scan_median", "ms_per_scan_best", "scan_moments_ms", "rest_of_scan_ms", "launches_per_scan",
+                                "ctas_per_rank", "rows_per_rank")}},
+                "scans_per_sec": head["scans_per_sec"], "pairs_per_sec": head["pairs_per_sec"],
+                "processed_rows_per_sec": head["points_per_sec"], "gpu_launches": int(head["launches_per_step"] * args.steps),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "clocks": clocks, "extra": extra}
         emit(line)
     if world > 1:
         dist.barrier()

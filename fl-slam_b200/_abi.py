@@ -16,6 +16,7 @@ GCL_F64, GCL_F32C = 0, 1
 GCL_LAYOUT_REF_F64, GCL_LAYOUT_PACKED_F32 = 0, 1
 GCL_NM, GCL_NCERT, GCL_STATS_SCALARS, GCL_EVID_DOUBLES, GCL_MAX_BINS = 19, 8, 24, 640, 1024
 GCL_MSG_INFO_HEADER = 8
+GCL_MAX_RANKS, GCL_EXCHANGE_HANDLE_BYTES = 8, 64
 
 # scalar tail of a stats record (enum GCL_SS_* in the header)
 SS = dict(TOTAL_MASS_IN=0, TOTAL_MASS_SEL=1, MASS_SCALE=2, PB_ESS=3, N_SELECTED=4, STRIDE=5, DESKEW_RETAINED=6,
@@ -79,6 +80,15 @@ def _load():
         "gcl_pointcloud2_ingest": (i32, [vp, vp, vp, i64, C.c_int32, vp, vp, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp, f64, vp]),
         "gcl_imu_preintegrate": (i32, [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
         "gcl_pack_points_f32": (i32, [vp, vp, vp, vp, vp, i64, f64, vp, vp]),
+        "gcl_exchange_create": (i32, [vp, i32, i32, sz, C.POINTER(vp), vp]),
+        "gcl_exchange_connect": (i32, [vp, vp, vp]),
+        "gcl_exchange_disconnect": (i32, [vp, vp]),
+        "gcl_exchange_destroy": (None, [vp, vp]),
+        "gcl_exchange_last_error": (C.c_char_p, [vp]),
+        "gcl_exchange_error_flag": (i32, [vp]),
+        "gcl_sharded_reduce_finalize": (i32, [vp, vp, vp, vp, i32, i64, i64, vp, pj, i32, i32, vp, f64, C.POINTER(f64), f64, f64, vp, vp]),
+        "gcl_exchange_all_gather": (i32, [vp, vp, vp, vp, sz, vp]),
+        "gcl_exchange_gathered": (vp, [vp, i32]),
         "gcl_scan_submit_host": (i32, [vp, i32, vp, vp, vp, i64, C.c_int32, f64, f64, vp, i32, vp, vp, i32, f64, i32, f64, f64]),
         "gcl_scan_submit_msg_host": (i32, [vp, i32, vp, i64, C.c_int32, vp, vp, f64, vp, vp, C.c_int32, vp, vp, vp, vp, i32, f64, vp, vp, vp,
                                            vp, i32, i32, vp, vp, i32, f64, i32, f64, f64]),

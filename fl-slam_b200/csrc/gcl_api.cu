@@ -11,16 +11,21 @@ using namespace gcl;
 
 static std::string g_create_error;
 
+// The submit thread and the caller's thread both run argument checks and CUDA calls on one handle: each writes its OWN error
+// string (the thread's text reaches the caller through Slot::task_err at the next call on the slot).
+static thread_local bool t_submit_thread = false;
+static inline std::string& err_of(gcl_handle h) { return t_submit_thread ? h->err_submit : h->err; }
+
 #define GCL_REQUIRE(h, cond, msg)                  \
   do {                                             \
     if (!(cond)) {                                 \
-      (h)->err = std::string(__func__) + ": " + (msg); \
+      err_of(h) = std::string(__func__) + ": " + (msg); \
       return GCL_ERR_ARG;                          \
     }                                              \
   } while (0)
 
 static int cuda_fail(gcl_handle h, const char* fn, cudaError_t e) {
-  h->err = std::string(fn) + ": CUDA error: " + cudaGetErrorString(e);
+  err_of(h) = std::string(fn) + ": CUDA error: " + cudaGetErrorString(e);
   return GCL_ERR_CUDA;
 }
 #define GCL_CUDA(h, expr)                                   \
@@ -597,8 +602,12 @@ static int submit_arrays(gcl_handle h, int slot_index, const double* points_host
   const size_t o_ts = al(o_pts + n * 24), o_w = al(o_ts + n * 8), in_end = al(o_w + n * 8);
   const size_t o_parts = in_end, o_red = al(o_parts + H * ctas * rec * 8), o_stats = al(o_red + H * rec * 8);
   const size_t d_end = al(o_stats + H * srec * 8);
+  const size_t d_bytes_before = S.d_bytes;
   rc = grow(h, &S.d_buf, &S.d_bytes, &S.h_buf, &S.h_bytes, d_end, in_end);
   if (rc != GCL_OK) return rc;
+  if (S.d_bytes != d_bytes_before) {   // the device block was reallocated (possibly at the same address): its atlas is gone
+    S.atlas_bins = 0; S.atlas_dev = nullptr; S.atlas_copy.clear();
+  }
   unsigned char* hb = static_cast<unsigned char*>(S.h_buf);
   unsigned char* db = static_cast<unsigned char*>(S.d_buf);
   // Scan arrays that already live in page-locked memory are copied straight from the caller's buffers (they must stay
@@ -837,6 +846,7 @@ static int run_task(gcl_handle h, int slot) {
 }
 
 static void submit_thread_main(gcl_handle h) {
+  t_submit_thread = true;
   cudaSetDevice(h->device);
   std::unique_lock<std::mutex> lk(h->mu);
   for (;;) {
@@ -849,7 +859,7 @@ static void submit_thread_main(gcl_handle h) {
     lk.lock();
     gcl_handle_s::Slot& S = h->slot[slot];
     S.task_rc = rc;
-    if (rc != GCL_OK) S.task_err = h->err;
+    if (rc != GCL_OK) S.task_err = h->err_submit;
     S.busy = false;
     h->cv_done.notify_all();
   }
@@ -894,6 +904,7 @@ int gcl_scan_submit_host(gcl_handle h, int slot_index, const double* points_host
   GCL_REQUIRE(h, n_raw == 0 || (points_host && timestamps_host && weights_host), "NULL scan arrays");
   GCL_REQUIRE(h, xi_host && origin_host && bins_host, "NULL pointer");
   GCL_REQUIRE(h, precision == GCL_F64 || precision == GCL_F32C, "unknown precision mode");
+  GCL_REQUIRE(h, h->stage2_slot != slot_index, "the evidence step of this slot is in flight: call gcl_scan_evidence_end_host first");
   int rc = wait_slot(h, slot_index);   // an earlier submission to this slot goes first (its error, if any, is reported here)
   if (rc != GCL_OK) return rc;
   if (!use_submit_thread(h))
@@ -934,6 +945,7 @@ int gcl_scan_submit_msg_host(gcl_handle h, int slot_index, const uint8_t* msg_ho
     GCL_REQUIRE(h, optional || (dt[k] >= 1 && dt[k] <= 8), "Unsupported PointField datatype");   // backend_node.py:374
     GCL_REQUIRE(h, optional || (off[k] >= 0 && off[k] + width[dt[k]] <= point_step), "field does not fit in point_step");
   }
+  GCL_REQUIRE(h, h->stage2_slot != slot_index, "the evidence step of this slot is in flight: call gcl_scan_evidence_end_host first");
   int rc = wait_slot(h, slot_index);
   if (rc != GCL_OK) return rc;
   if (!use_submit_thread(h))
@@ -1002,10 +1014,10 @@ int gcl_scan_evidence_begin_host(gcl_handle h, int slot_index, const double* pos
   const size_t o_iw = al(o_map + B * 26 * 8), o_stats = al(o_iw + 80);
   const size_t o_evid = al(o_stats + H * srec * 8), io_end = al(o_evid + H * GCL_EVID_DOUBLES * 8);
   const size_t d_end = al(io_end + B * 16 * 8);
-  const void* d_before = h->d_buf;
+  const size_t d_bytes_before = h->d_bytes;
   int rc = grow(h, &h->d_buf, &h->d_bytes, &h->h_buf, &h->h_bytes, d_end, io_end);
   if (rc != GCL_OK) return rc;
-  if (h->d_buf != d_before) h->map_shadow_bins = 0;   // a new device block holds nothing yet
+  if (h->d_bytes != d_bytes_before) h->map_shadow_bins = 0;   // a new device block (even at the old address) holds nothing yet
   if (!h->done_flag) {
     GCL_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->done_flag), 64));
     *h->done_flag = 0;

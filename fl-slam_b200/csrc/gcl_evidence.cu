@@ -1032,12 +1032,8 @@ cudaError_t launch_chain(const ChainParams& P, cudaStream_t stream, int* launche
   if (P.iw_state && P.use_sigma_meas) {
     const size_t smem = 2 * pre_block_doubles(B) * sizeof(double);
     const int use_smem = smem <= 200 * 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(stream_sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return e;
-      attr_done = true;
-    }
+    static std::atomic<uint64_t> optin{0};
+    if (cudaError_t e = optin_dynamic_smem(stream_sigma_chain_kernel, 200 * 1024, optin)) return e;
     stream_sigma_chain_kernel<<<1, 32 * (1 + kSeqHelpers), use_smem ? smem : 0, stream>>>(P, use_smem);
     stream_translation_finish_kernel<<<S * P.n_hyp, 32, 0, stream>>>(P);
     *launches += 2;

@@ -184,12 +184,8 @@ cudaError_t launch_ingest_decode(const IngestParams& P, cudaStream_t stream, int
   if (P.n_points <= 0) return cudaSuccess;
   const int grid = (int)((P.n_points + kIngestThreads - 1) / kIngestThreads);
   const size_t smem = (size_t)kIngestThreads * P.point_step;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> optin{0};
+  if (cudaError_t e = optin_dynamic_smem(ingest_kernel, 200 * 1024, optin)) return e;
   ingest_kernel<<<grid, kIngestThreads, smem, stream>>>(P);
   *launches += 1;
   return cudaGetLastError();

@@ -51,7 +51,8 @@ struct gcl_handle_s {
   std::deque<int> queue;                 // slots with a task waiting
   bool stop = false;
   int async_mode = -1;                   // -1 = not decided yet (GCL_HOST_ASYNC, default 1)
-  std::string err;
+  std::string err;                       // error text of calls made on the caller's thread
+  std::string err_submit;                // ... and of the submit thread (handed over through Slot::task_err)
   // resources of the *_host entry points (allocated on first use, grown on demand)
   unsigned long long done_seq = 0;     // completion ticket of the single-launch evidence step (0 = the copy-engine path is in flight)
   std::string map_shadow;              // map (26 B doubles) + IW state (10) exactly as the last single-launch step left them on the DEVICE
@@ -87,6 +88,21 @@ struct gcl_handle_s {
 };
 
 namespace gcl {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies PER DEVICE, and one process may hold handles on several devices
+// (and enqueue from the caller's and the submit thread at once): one bit per device ordinal, set atomically after the opt-in.
+template <typename K>
+inline cudaError_t optin_dynamic_smem(K kern, int bytes, std::atomic<uint64_t>& done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  done_mask.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
+}
 
 struct ScanConst {
   double origin[3];
@@ -134,6 +150,10 @@ struct FinalizeParams {
   double* stats;
 };
 cudaError_t launch_reduce_finalize(const FinalizeParams& P, int n_jobs, cudaStream_t stream, int* launches);
+constexpr int kFinThreads = 512;
+constexpr int kRedSmem = 5120;   // doubles of the reduced record kept in shared memory (19 * 256 + 8 fits)
+struct FinalizeShared { double buf[kFinThreads / 32]; double pad[2]; double redrec[kRedSmem]; };
+
 
 struct EvidenceParams {
   const double* stats;

@@ -642,12 +642,8 @@ int plan_fused_tile(int n_bins, int precision, int G, int L, int minb) {
 template <typename T, int G, int MINB>
 static cudaError_t launch_fused_one(const ScanParams& P, dim3 grid, size_t smem, cudaStream_t stream) {
   auto kern = scan_moments_fused_kernel<T, G, MINB>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> optin{0};  // per instantiation, one bit per device
+  if (cudaError_t e = optin_dynamic_smem(kern, 204 * 1024, optin)) return e;
   kern<<<grid, kNT, smem, stream>>>(P);
   return cudaGetLastError();
 }

@@ -146,12 +146,8 @@ void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_ou
 template <int G>
 static cudaError_t launch_mm(const ScanParams& P, int ctas, size_t smem, cudaStream_t stream) {
   auto kern = moments_from_resp_kernel<G>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> optin{0};
+  if (cudaError_t e = optin_dynamic_smem(kern, 200 * 1024, optin)) return e;
   kern<<<ctas, kMmThreads, smem, stream>>>(P);
   return cudaGetLastError();
 }

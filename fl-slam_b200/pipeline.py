@@ -278,7 +278,8 @@ class LidarEvidencePipeline:
         chain step (map + IW state carried from the previous batch) is ordered after the previous batch's chain, on a second,
         high-priority internal stream -- the sequential chain keeps one SM busy while the next batch's moment pass fills the other
         147.  Inputs must be ready on the current stream when the call is made; results alternate between two buffer sets and are
-        ordered on the current stream by ``join_stream()`` (they stay valid until the call after next)."""
+        ordered on the current stream by ``join_stream()`` (they stay valid until the call after next).  Inputs produced on the
+        current stream before the call are ordered before the batch (the internal streams wait for it at every call)."""
         S = len(scans)
         xi = np.asarray(xi_bodies, dtype=np.float64).reshape(S, 6)
         max_sel = max(self.selected_rows(s.n_raw, self.n_points_cap)[1] for s in scans)
@@ -295,12 +296,20 @@ class LidarEvidencePipeline:
             ov = self._ov
             if ov is None:
                 ov = self._ov = {"s_mom": torch.cuda.Stream(device=self.device, priority=0), "s_chain": torch.cuda.Stream(device=self.device, priority=-1),
-                                 "free": [None, None], "turn": 0, "last": None}
-                cur = torch.cuda.current_stream(self.device)
-                ov["s_mom"].wait_stream(cur); ov["s_chain"].wait_stream(cur)     # everything enqueued so far comes first
+                                 "free": [None, None], "turn": 0, "last": None, "keep": [None, None]}
+            # EVERY call: what the caller enqueued on the current stream so far (uploads of scans, poses, map edits, the jobs
+            # array built above) comes before this batch on both internal streams
+            cur = torch.cuda.current_stream(self.device)
+            ov["s_mom"].wait_stream(cur); ov["s_chain"].wait_stream(cur)
             i = ov["turn"] & 1
             ov["turn"] += 1
             b = self._buffers(S, ctas, slot=i)
+            # caller tensors read by the internal streams stay referenced until this buffer set comes round again (two calls
+            # later, after its chain has been waited for): the caching allocator cannot hand their memory out in between
+            ov["keep"][i] = (jobs_dev, poses_pred, poses_update, iw_state, list(scans))
+            for t in (jobs_dev, poses_pred, poses_update, iw_state):
+                if t is not None:
+                    t.record_stream(ov["s_mom"]); t.record_stream(ov["s_chain"])
             if ov["free"][i] is not None:
                 ov["s_mom"].wait_event(ov["free"][i])                            # this buffer set was last read by the chain two calls ago
             with torch.cuda.stream(ov["s_mom"]):

@@ -251,6 +251,44 @@ int gcl_scan_chain_phase(gcl_handle h, void* stream, int phase, double* stats, i
                          int use_sigma_meas, double iw_rho, double iw_nu_weak_add, double iw_nu_max, double eps_psd,
                          double eps_mass, double* evidence);
 
+/* ---- multi-GPU: the one exchange step of the point-sharded path, over NVLink peer memory ---------------- */
+/* The reference runs on one GPU in one process and has no collective; every raw bin sum of
+ * scan_bin_moment_match is linear in the points (archive/legacy_operators/binning.py:166-173), so one scan's points can be
+ * sharded over the GPUs of a node (one process per GPU) with ONE exchange of the per-bin record per job.
+ *   gcl_exchange_create   allocates this rank's exchange block (two parities x world slots of slot_bytes, flag words) and
+ *                         returns its CUDA IPC handle (GCL_EXCHANGE_HANDLE_BYTES bytes) for the caller to all-gather by any
+ *                         means (torch.distributed in the Python layer);
+ *   gcl_exchange_connect  maps the peers' blocks (all_handles: world x GCL_EXCHANGE_HANDLE_BYTES, rank-major);
+ *   gcl_sharded_reduce_finalize
+ *                         = gcl_reduce_finalize(finalize 0) + all-gather + gcl_reduce_finalize(finalize 1) in ONE launch: each
+ *                         CTA sums this rank's partial records in a fixed order and stores the result straight into every
+ *                         peer's block over NVLink; the last CTA publishes the step number in the peers' flag words, waits for
+ *                         theirs, and runs the per-bin finalisation over the gathered records in rank order (bit-identical
+ *                         statistics on every rank).  Collective: every rank must call it, in the same order, once per step.
+ *                         A peer that never arrives trips a time limit (GCL_EXCHANGE_TIMEOUT_S, default 2 s): the kernel
+ *                         returns without finalising and gcl_exchange_error_flag() becomes non-zero.
+ *   gcl_exchange_all_gather
+ *                         the same publish / wait protocol for a small device buffer (hypothesis-sharded evidence records):
+ *                         src (bytes) lands in slot [rank] of every rank; dst (world x bytes) may be NULL, in which case the
+ *                         data are read in place through gcl_exchange_gathered(x, src_rank). */
+#define GCL_MAX_RANKS 8
+#define GCL_EXCHANGE_HANDLE_BYTES 64
+typedef struct gcl_exchange_s* gcl_exchange;
+int gcl_exchange_create(gcl_handle h, int world, int rank, size_t slot_bytes, gcl_exchange* out,
+                        unsigned char* ipc_handle_out /* GCL_EXCHANGE_HANDLE_BYTES */);
+int gcl_exchange_connect(gcl_handle h, gcl_exchange x, const unsigned char* all_handles);
+int gcl_exchange_disconnect(gcl_handle h, gcl_exchange x); /* unmap the peers' blocks; barrier; then gcl_exchange_destroy */
+void gcl_exchange_destroy(gcl_handle h, gcl_exchange x);
+const char* gcl_exchange_last_error(gcl_exchange x);
+int gcl_exchange_error_flag(gcl_exchange x); /* synchronous read of the device-side error word: 0 = no time-out so far */
+int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, const double* parts, int n_parts,
+                                int64_t part_stride_doubles, int64_t job_stride_doubles, const gcl_job* jobs_dev,
+                                const gcl_job* job_by_value_host, int n_jobs, int n_bins, const double* bin_dirs, double tau,
+                                const double* lidar_origin_host, double eps_psd, double eps_mass,
+                                double* reduced /* [n_jobs][record]: the combined record */, double* stats);
+int gcl_exchange_all_gather(gcl_handle h, gcl_exchange x, void* stream, const void* src, size_t bytes, void* dst);
+const void* gcl_exchange_gathered(gcl_exchange x, int src_rank);
+
 /* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,
                         const double* weights, int64_t n, double scan_start_time, void* packed_xyzt /* float4[n] */,
