@@ -131,6 +131,8 @@ struct ScanParams {
 void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_out);
 int fused_ctas_per_sm(int n_bins, int precision);
 cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_job, int precision, cudaStream_t stream);
+bool tc_path_supported(int n_bins, int precision, int fixed_shift);
+cudaError_t launch_scan_moments_tc(ScanParams& P, int n_jobs, int ctas_per_job, cudaStream_t stream);
 cudaError_t launch_moments_from_resp(const ScanParams& P, int ctas, int G, cudaStream_t stream);
 
 struct FinalizeParams {

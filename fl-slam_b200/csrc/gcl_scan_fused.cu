@@ -655,6 +655,8 @@ int fused_ctas_per_sm(int n_bins, int precision) {
 }
 
 cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_job, int precision, cudaStream_t stream) {
+  // fp32c, up to 256 bins, fixed softmax shift: the tensor-core kernel (gcl_scan_tc.cu); GCL_K1_TC=0 keeps everything on the CUDA cores
+  if (tc_path_supported(P.n_bins, precision, P.fixed_shift)) return launch_scan_moments_tc(P, n_jobs, ctas_per_job, stream);
   int G, L, M;
   plan_fused_bins(P.n_bins, precision, &G, &L, &M);
   const int TP = plan_fused_tile(P.n_bins, precision, G, L, M);
