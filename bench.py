@@ -577,7 +577,8 @@ def main():
                             "step": f"{head['scans_per_step']} scans", "l2": f"{head['input_copies_rotated']} copies of the input rotated "
                                     "(> 2 x the 126 MB L2 per rank): no scan re-reads an L2-resident cloud",
                             "timed_region_ms": head["ms_per_step"] * args.steps, **{k: head[k] for k in (
-                                "ms_per_scan", "ms_per_scan_median", "ms_per_scan_best", "scan_moments_ms", "rest_of_scan_ms", "launches_per_scan",
+                                "ms_per_scan", "ms_per_scan_median", "ms_per_scan_best", "ms_per_scan_one_at_a_time", "pipelining", "scan_moments_ms",
+                                "rest_of_scan_ms", "launches_per_scan",
                                 "ctas_per_rank", "rows_per_rank")}},
                 "scans_per_sec": head["scans_per_sec"], "pairs_per_sec": head["pairs_per_sec"],
                 "processed_rows_per_sec": head["points_per_sec"], "gpu_launches": int(head["launches_per_step"] * args.steps),

@@ -86,6 +86,7 @@ def _load():
         "gcl_exchange_destroy": (None, [vp, vp]),
         "gcl_exchange_last_error": (C.c_char_p, [vp]),
         "gcl_exchange_error_flag": (i32, [vp]),
+        "gcl_exchange_set_max_ctas": (i32, [vp, i32]),
         "gcl_sharded_reduce_finalize": (i32, [vp, vp, vp, vp, i32, i64, i64, vp, pj, i32, i32, vp, f64, C.POINTER(f64), f64, f64, vp, vp]),
         "gcl_exchange_all_gather": (i32, [vp, vp, vp, vp, sz, vp]),
         "gcl_exchange_gathered": (vp, [vp, i32]),

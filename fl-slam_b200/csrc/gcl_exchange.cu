@@ -80,34 +80,39 @@ __global__ void __launch_bounds__(kFinThreads) sharded_reduce_finalize_kernel(co
   const int tid = threadIdx.x, el = tid & (kXEl - 1), sub = tid >> 7;
   const int job = blockIdx.y;
   const int rec = P.nmom * P.n_bins + GCL_NCERT;
-  const int e = blockIdx.x * kXEl + el;
   const int parity = (int)(X.step & 1);
-  // ---- fixed-order sum of this rank's partials: thread (el, sub) takes the sub-th quarter of the partials -------------------------
-  double s = 0.0;
-  const bool is_max = (e == P.nmom * P.n_bins + GCL_CS_MAX_RESP);
-  if (e < rec) {
-    const int q = (P.n_parts + 3) >> 2;
-    const int p_lo = sub * q, p_hi = min(P.n_parts, p_lo + q);
-    const double* src = P.parts + (size_t)job * P.job_stride + e;
-    for (int p0 = p_lo; p0 < p_hi; p0 += 8) {
-      double v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (p0 + j < p_hi) ? __ldcg(src + (size_t)(p0 + j) * P.part_stride) : 0.0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (p0 + j < p_hi) s = is_max ? fmax(s, v[j]) : s + v[j];
-    }
-  }
   double* s_part = sh.redrec;                     // [4][kXEl]
-  s_part[sub * kXEl + el] = s;
-  __syncthreads();
-  if (e < rec) {
-    const double a = s_part[el], b = s_part[kXEl + el], c = s_part[2 * kXEl + el], d = s_part[3 * kXEl + el];
-    const double tot = is_max ? fmax(fmax(a, b), fmax(c, d)) : ((a + b) + (c + d));
-    // this rank's record goes into slot [parity][rank] of EVERY rank's block (its own included); thread (el, sub) serves
-    // peers sub, sub + 4
-    for (int r = sub; r < X.world; r += 4)
-      reinterpret_cast<double*>(slot_of(X, r, parity, X.rank))[(size_t)job * rec + e] = tot;
+  // ---- fixed-order sum of this rank's partials: thread (el, sub) takes the sub-th quarter of the partials; a CTA walks the
+  //      chunks blockIdx.x, blockIdx.x + gridDim.x, ... of the record (few CTAs when the launch shares the GPU with the next
+  //      scan's moment pass) ---------------------------------------------------------------------------------------------------------
+  for (int chunk = blockIdx.x; chunk * kXEl < rec; chunk += gridDim.x) {
+    const int e = chunk * kXEl + el;
+    double s = 0.0;
+    const bool is_max = (e == P.nmom * P.n_bins + GCL_CS_MAX_RESP);
+    if (e < rec) {
+      const int q = (P.n_parts + 3) >> 2;
+      const int p_lo = sub * q, p_hi = min(P.n_parts, p_lo + q);
+      const double* src = P.parts + (size_t)job * P.job_stride + e;
+      for (int p0 = p_lo; p0 < p_hi; p0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (p0 + j < p_hi) ? __ldcg(src + (size_t)(p0 + j) * P.part_stride) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (p0 + j < p_hi) s = is_max ? fmax(s, v[j]) : s + v[j];
+      }
+    }
+    s_part[sub * kXEl + el] = s;
+    __syncthreads();
+    if (e < rec) {
+      const double a = s_part[el], b = s_part[kXEl + el], c = s_part[2 * kXEl + el], d = s_part[3 * kXEl + el];
+      const double tot = is_max ? fmax(fmax(a, b), fmax(c, d)) : ((a + b) + (c + d));
+      // this rank's record goes into slot [parity][rank] of EVERY rank's block (its own included); thread (el, sub) serves
+      // peers sub, sub + 4
+      for (int r = sub; r < X.world; r += 4)
+        reinterpret_cast<double*>(slot_of(X, r, parity, X.rank))[(size_t)job * rec + e] = tot;
+    }
+    __syncthreads();
   }
   __threadfence_system();
   __syncthreads();
@@ -179,6 +184,7 @@ struct gcl_exchange_s {
   unsigned long long step = 0;
   double timeout_seconds = 2.0;
   int clock_khz = 1965000;
+  int max_ctas = 0;            // 0 = one CTA per 128 record elements; > 0: at most this many CTAs (gcl_exchange_set_max_ctas)
   std::string err;
 };
 
@@ -266,6 +272,12 @@ void gcl_exchange_destroy(gcl_handle h, gcl_exchange x) {
   delete x;
 }
 
+int gcl_exchange_set_max_ctas(gcl_exchange x, int max_ctas) {
+  if (!x || max_ctas < 0) return GCL_ERR_ARG;
+  x->max_ctas = max_ctas;
+  return GCL_OK;
+}
+
 int gcl_exchange_error_flag(gcl_exchange x) {
   if (!x) return -1;
   int v = 0;
@@ -298,7 +310,12 @@ int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, cons
   cudaSetDevice(x->device);
   x->step += 1;
   const ExchangeDev X = dev_view(x);
-  const dim3 grid((unsigned)((rec + kXEl - 1) / kXEl), (unsigned)n_jobs);
+  unsigned chunks = (unsigned)((rec + kXEl - 1) / kXEl);
+  if (x->max_ctas > 0 && chunks * (unsigned)n_jobs > (unsigned)x->max_ctas) {
+    chunks = (unsigned)x->max_ctas / (unsigned)n_jobs;
+    if (chunks < 1) chunks = 1;
+  }
+  const dim3 grid(chunks, (unsigned)n_jobs);
   sharded_reduce_finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(P, X);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { x->err = std::string("gcl_sharded_reduce_finalize: ") + cudaGetErrorString(e); return GCL_ERR_CUDA; }

@@ -16,7 +16,7 @@
 //       Phi_rem E_head (rows 32q + 8 + j);  2 x kind::f16 (K = 16) add  Phi E_rem  onto the head rows.  The dropped term
 //       Phi_rem E_rem is 2^-22 relative.  (The tensor core truncates tf32 operands -- tools/microbench/umma_probe.cu -- so the
 //       heads are cut with a mask and the remainders are exact.)
-// Every 16 sub-tiles (512 points) the accumulation moves to the other half of tensor memory and the finished half is drained
+// Every 8 sub-tiles (256 points) the accumulation moves to the other half of tensor memory and the finished half is drained
 // (tcgen05.ld.16x256b puts head row and remainder row of one moment in the same thread) into fp64 accumulators that live in
 // registers for the whole kernel: each (moment, bin) has one owner thread, so there is no shared-memory record, no atomics, and the
 // partial record is written once at the end.  Two shared-memory stages: the tensor core works on sub-tile t while the CTA computes
@@ -30,11 +30,15 @@
 
 namespace gcl {
 
-constexpr int kTcNT = 256;       // threads per CTA
+constexpr int kTcProd = 256;     // producer threads: front end, phase A, scale, drains (8 warps)
+constexpr int kTcNT = 288;       // + one warp whose lane 0 issues the MMAs (a tcgen05.mma issue blocks its thread while the queue is
+                                 // full -- measured 830 cycles per sub-tile -- so it must not be a thread the others wait for)
 constexpr int kTcMacro = 256;    // points per front-end pass
 constexpr int kTcSub = 32;       // points per MMA sub-tile
-constexpr int kTcGroup = 16;     // sub-tiles accumulated in one half of tensor memory (512 points: 96 fp32 accumulations)
-constexpr int kTcIssuer = 224;   // the thread that issues the MMAs (warp 7, lane 0; warp 0 carries the certificates)
+constexpr int kTcGroupLog2 = 3;  // 2^3 = 8 sub-tiles (256 points, 48 instructions) accumulate in one half of tensor memory between drains:
+                                 // the fp32 accumulation of the tensor core truncates, and the bias grows with the number of products an
+                                 // accumulator has absorbed (16 sub-tiles: 6.8e-6 of the largest entry against the fp64 kernel; 8: half that)
+constexpr int kTcGroupMask = (1 << kTcGroupLog2) - 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sw128(uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); }
@@ -77,11 +81,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // {lo -
   return r;
 }
 
-// shared-memory plan (dynamic part; host and device agree through this)
+// shared-memory plan of the dynamic part: two operand stages + the raw-row staging (host and device agree through this)
 struct TcPlan {
   int n_pad;                                   // bins rounded up to what the MMA shape needs (48, 128, 256)
   uint32_t o_a32, o_ehi, o_a16, o_elo, stage;  // inside one stage
-  uint32_t o_pt, o_atlas, o_z2, o_in, total;
+  uint32_t o_in, total;
 };
 __host__ __device__ inline TcPlan tc_plan(int nrep) {
   TcPlan p;
@@ -92,41 +96,69 @@ __host__ __device__ inline TcPlan tc_plan(int nrep) {
   p.o_elo = p.o_a16 + 8192;
   p.stage = p.o_elo + (uint32_t)p.n_pad * 64;
   p.stage = (p.stage + 1023u) & ~1023u;
-  p.o_pt = 2 * p.stage;
-  p.o_atlas = p.o_pt + kTcMacro * 32;
-  p.o_z2 = p.o_atlas + 256 * 16;
-  p.o_in = p.o_z2 + 3 * 8 * kTcSub * 4;
+  p.o_in = 2 * p.stage;
   p.total = p.o_in + kTcMacro * 40 + 1024;     // + slack for the manual 1024-byte alignment of the base
   return p;
 }
+__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kTcProd) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory"); }
+
+#ifdef GCL_K1_TRACE
+__device__ long long g_tc_trace[2][12];
+#define TCT(i) do { if ((tid == 0 || tid == 64) && blockIdx.x == 1 && blockIdx.y == 0) { const long long n_ = clock64(); tc_acc[i] += n_ - tc_t; tc_t = n_; } } while (0)
+extern "C" int gcl_debug_tc_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 24); }
+#else
+#define TCT(i) do { } while (0)
+#endif
 
 template <int NREP>
 __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ unsigned char smem_raw_tc[];
+  // small arrays are STATIC shared memory: distinct objects, so the compiler may move their loads across the operand-tile stores
+  // (with everything carved out of one dynamic array every atlas load waited for the previous bin's stores: phase A ran at a
+  // quarter of its issue rate)
+  __shared__ float4 s_atlas[256];                  // [bin]: log2(e)/tau * direction
+  __shared__ float4 s_dq[kTcMacro / 4][4];         // [quad of points][dx, dy, dz, shift]: one float4 = that component of 4 consecutive points
+  __shared__ float4 s_pw[kTcMacro];                // [point]: {p0, p1, p2, w}
   __shared__ double s_red[kTcNT / 32][GCL_NCERT];
   __shared__ double s_cert[kTcNT * GCL_NCERT];
   __shared__ gcl_job s_job;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) uint64_t s_bar[4];      // stage 0, stage 1, drain of tensor-memory half 0, half 1
+  __shared__ __align__(8) uint64_t s_bar[6];      // operands ready (stage 0, 1), stage consumed (0, 1), tensor-memory half complete (0, 1)
   constexpr int NPAD = 16 * NREP;
   const TcPlan pl = tc_plan(NREP);
   const int B = P.n_bins;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef GCL_K1_TRACE
+  long long tc_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc_t = clock64();
+#endif
   unsigned char* smem = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);   // swizzled tiles need 1024-byte alignment
 
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
   // operand tiles start as zeros: rows that are never written (unused moments, bins beyond n_bins, points beyond a partial tile)
   for (uint32_t i = tid; i < 2 * pl.stage / 16; i += kTcNT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  constexpr uint32_t kCols = (2 * NPAD <= 32) ? 32u : (2 * NPAD <= 64) ? 64u : (2 * NPAD <= 128) ? 128u : (2 * NPAD <= 256) ? 256u : 512u;
   if (warp == 0) {
-    constexpr uint32_t cols = (2 * NPAD <= 32) ? 32u : (2 * NPAD <= 64) ? 64u : (2 * NPAD <= 128) ? 128u : (2 * NPAD <= 256) ? 256u : 512u;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+    mbar_init(smem_u32(&s_bar[0]), kTcProd); mbar_init(smem_u32(&s_bar[1]), kTcProd);     // every producer thread arrives
+    for (int i = 2; i < 6; ++i) mbar_init(smem_u32(&s_bar[i]), 1);                         // tcgen05.commit arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const double cscale_d = 1.4426950408889634 / P.tau;                // logits in octaves
+  const float cscale = (float)cscale_d;
+  for (int b = tid; b < 256; b += kTcNT)
+    s_atlas[b] = (b < B) ? make_float4((float)(P.bin_dirs[b * 3] * cscale_d), (float)(P.bin_dirs[b * 3 + 1] * cscale_d),
+                                       (float)(P.bin_dirs[b * 3 + 2] * cscale_d), 0.f)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  double* my_cert = s_cert + tid;
+#define CERT(k) my_cert[(k) * kTcNT]
+#pragma unroll
+  for (int k = 0; k < GCL_NCERT; ++k) CERT(k) = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the zero fill, before the first MMA reads the tiles
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -148,23 +180,8 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
   const int64_t lo = lo0 < sel_end ? lo0 : sel_end;
   const int64_t hi = (lo + rpc < sel_end) ? lo + rpc : sel_end;
   double* part = P.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * P.rec_doubles;
-
-  float4* s_pt = reinterpret_cast<float4*>(smem + pl.o_pt);          // [point][2]: {d0, d1, d2, shift} {p0, p1, p2, w}
-  float4* s_atlas = reinterpret_cast<float4*>(smem + pl.o_atlas);    // [bin]: log2(e)/tau * direction
-  float* s_z2 = reinterpret_cast<float*>(smem + pl.o_z2);            // [3][8 warps][32 points]: partial Z, sum e x, max x
+  const int n_sub_total = (int)(((hi - lo) / kTcMacro) * (kTcMacro / kTcSub) + (((hi - lo) % kTcMacro) + kTcSub - 1) / kTcSub);
   double* s_in = reinterpret_cast<double*>(smem + pl.o_in);
-
-  const double cscale_d = 1.4426950408889634 / P.tau;                // logits in octaves
-  const float cscale = (float)cscale_d;
-  for (int b = tid; b < 256; b += kTcNT)
-    s_atlas[b] = (b < B) ? make_float4((float)(P.bin_dirs[b * 3] * cscale_d), (float)(P.bin_dirs[b * 3 + 1] * cscale_d),
-                                       (float)(P.bin_dirs[b * 3 + 2] * cscale_d), 0.f)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-
-  double* my_cert = s_cert + tid;
-#define CERT(k) my_cert[(k) * kTcNT]
-#pragma unroll
-  for (int k = 0; k < GCL_NCERT; ++k) CERT(k) = 0.0;
 
   // --- sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69) ---------------------------------------
   if (stride > 1 && hi > lo) {
@@ -183,201 +200,22 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
     }
     CERT(GCL_CS_SUM_W_RAW) = (p0 + p1) + (p2 + p3);
   }
+  TCT(0);   // prologue
 
-  // --- ownership of the fp64 accumulators: warp = (quarter of the tensor-memory lanes, half of the bins); inside the 16x256b fragment
-  //     thread t holds moment row t/4 (head) and t/4 + 8 (remainder) for the two bins 2(t%4), 2(t%4) + 1 of every 8-column block
-  const int quarter = warp & 3, half = warp >> 2;
-  const int kq = lane >> 2, cpair = lane & 3;
-  const int my_moment = 5 * quarter + kq;
-  const bool owns = kq < (quarter < 3 ? 5 : 4);
-  double acc[NREP][2];
-#pragma unroll
-  for (int r = 0; r < NREP; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
-
-  uint32_t par_stage[2] = {0u, 0u}, par_drain[2] = {0u, 0u};
-  int drained = 0;
-  auto drain = [&](int g) {
-    const int buf = g & 1;
-    mbar_wait(smem_u32(&s_bar[2 + buf]), par_drain[buf]);
-    par_drain[buf] ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(buf * NPAD + half * (NPAD / 2));
-    uint32_t v[NREP][4];
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) tmem_ld_16x256b(taddr + 8 * r, v[r]);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      acc[r][0] += (double)__uint_as_float(v[r][0]) + (double)__uint_as_float(v[r][2]);
-      acc[r][1] += (double)__uint_as_float(v[r][1]) + (double)__uint_as_float(v[r][3]);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  // raw rows of the macro tile [t0, t0 + 256) -> s_in, asynchronously (one row per thread)
-  auto prefetch_tile = [&](int64_t t0) {
-    const int64_t srow = t0 + tid;
-    if (srow >= hi) return;
-    const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
-    const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;
-    if (P.layout == GCL_LAYOUT_REF_F64) {
-      const double* pts = static_cast<const double*>(J.points) + rp * 3;
-      double* dst = s_in + (size_t)tid * 5;
-      cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
-      cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
-      cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
-    } else {
-      float* base = reinterpret_cast<float*>(s_in);
-      cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + rp);
-      cp_async4(base + (size_t)kTcMacro * 4 + tid, static_cast<const float*>(J.weights) + r);
-    }
-  };
-  prefetch_tile(lo);
-
-  float xi32[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
-  const uint32_t idesc32 = umma_idesc(2, NPAD), idesc16 = umma_idesc(1, NPAD);
-  const int q4 = tid & 7, slice = tid >> 3;       // phase A: 4 consecutive points x the bins slice, slice + 32, ...
-
-  int T = 0;                                      // sub-tiles issued so far
-  for (int64_t tile0 = lo; tile0 < hi; tile0 += kTcMacro) {
-    const int count = (int)((hi - tile0 < kTcMacro) ? hi - tile0 : kTcMacro);
-    cp_async_wait_all();
-    __syncthreads();          // raw rows landed; the previous macro tile's last scale step has read s_pt
-    // ======================================= front: one point per thread =======================================================
-    {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tid < count) {
-        const int64_t srow = tile0 + tid;
-        double w_sel;
-        PointOut32 o;
-        if (P.layout == GCL_LAYOUT_REF_F64) {
-          const double* in = s_in + (size_t)tid * 5;
-          w_sel = in[4];
-          point_front32(J, C, xi32, (float)in[0], (float)in[1], (float)in[2], (float)(in[3] - J.scan_start_time), o);
-        } else {
-          const float* base = reinterpret_cast<const float*>(s_in);
-          const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)tid * 4);
-          w_sel = (double)base[(size_t)kTcMacro * 4 + tid];
-          point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
-        }
-        const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
-        const double w_desk = w_sel * (double)o.w_time;
-        CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
-        CERT(GCL_CS_ROWS) += 1.0;
-        a = make_float4(o.d[0], o.d[1], o.d[2], -cscale);          // fixed shift: the largest possible logit (|d.b| <= 1)
-        b = make_float4(o.p0[0], o.p0[1], o.p0[2], (float)(w_desk * lam));
-      }
-      s_pt[2 * tid] = a; s_pt[2 * tid + 1] = b;
-    }
-    __syncthreads();
-    prefetch_tile(tile0 + kTcMacro);
-    const int n_sub = (count + kTcSub - 1) / kTcSub;
-    for (int st = 0; st < n_sub; ++st, ++T) {
-      const int stage = T & 1;
-      unsigned char* sb = smem + (size_t)stage * pl.stage;
-      if (T >= 2) { mbar_wait(smem_u32(&s_bar[stage]), par_stage[stage]); par_stage[stage] ^= 1u; }   // sub-tile T - 2 is through the tensor core
-      if (drained < (T >> 4) && (T & 15) >= 2) drain(drained++);
-      // ===================================== phase A: exponentials of 4 points x this thread's bins ===============================
-      {
-        const float4* pp = s_pt + 2 * (st * kTcSub + 4 * q4);
-        const float4 a0 = pp[0], a1 = pp[2], a2 = pp[4], a3 = pp[6];
-        const float2 dx01 = make_float2(a0.x, a1.x), dy01 = make_float2(a0.y, a1.y), dz01 = make_float2(a0.z, a1.z), sh01 = make_float2(a0.w, a1.w);
-        const float2 dx23 = make_float2(a2.x, a3.x), dy23 = make_float2(a2.y, a3.y), dz23 = make_float2(a2.z, a3.z), sh23 = make_float2(a2.w, a3.w);
-        float2 Z01 = make_float2(0.f, 0.f), Z23 = Z01, S01 = Z01, S23 = Z01;
-        float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;
-        unsigned char* ehi = sb + pl.o_ehi;
-        unsigned char* elo = sb + pl.o_elo;
-#pragma unroll 2
-        for (int b = slice; b < B; b += 32) {
-          const float4 bb = s_atlas[b];
-          const float2 bx = make_float2(bb.x, bb.x), by = make_float2(bb.y, bb.y), bz = make_float2(bb.z, bb.z);
-          const float2 x01 = ffma2(dx01, bx, ffma2(dy01, by, ffma2(dz01, bz, sh01)));
-          const float2 x23 = ffma2(dx23, bx, ffma2(dy23, by, ffma2(dz23, bz, sh23)));
-          const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-          const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
-          const uint32_t h0 = __float_as_uint(e01.x) & 0xFFFFE000u, h1 = __float_as_uint(e01.y) & 0xFFFFE000u;
-          const uint32_t h2 = __float_as_uint(e23.x) & 0xFFFFE000u, h3 = __float_as_uint(e23.y) & 0xFFFFE000u;
-          const float2 l01 = fadd2(e01, make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
-          const float2 l23 = fadd2(e23, make_float2(-__uint_as_float(h2), -__uint_as_float(h3)));
-          Z01 = fadd2(Z01, e01); Z23 = fadd2(Z23, e23);
-          S01 = ffma2(e01, x01, S01); S23 = ffma2(e23, x23, S23);
-          m0 = fmaxf(m0, x01.x); m1 = fmaxf(m1, x01.y); m2 = fmaxf(m2, x23.x); m3 = fmaxf(m3, x23.y);
-          const uint32_t row = (uint32_t)b;
-          *reinterpret_cast<uint4*>(ehi + sw128((row >> 3) * 1024u + (row & 7u) * 128u + (uint32_t)q4 * 16u)) = make_uint4(h0, h1, h2, h3);
-          *reinterpret_cast<uint2*>(elo + sw64((row >> 3) * 512u + (row & 7u) * 64u + (uint32_t)q4 * 8u)) =
-              make_uint2(pack_bf16x2(l01.x, l01.y), pack_bf16x2(l23.x, l23.y));
-        }
-        // the four slices of a warp: lanes q4 + 8 j
-        float z[4] = {Z01.x, Z01.y, Z23.x, Z23.y}, s1[4] = {S01.x, S01.y, S23.x, S23.y}, mx[4] = {m0, m1, m2, m3};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          z[i] += __shfl_xor_sync(0xffffffffu, z[i], 8); z[i] += __shfl_xor_sync(0xffffffffu, z[i], 16);
-          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 8); s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 16);
-          mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 8)); mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 16));
-        }
-        if (lane < 8) {
-          float4* zz = reinterpret_cast<float4*>(s_z2);
-          zz[(0 * 8 + warp) * 8 + q4] = make_float4(z[0], z[1], z[2], z[3]);
-          zz[(1 * 8 + warp) * 8 + q4] = make_float4(s1[0], s1[1], s1[2], s1[3]);
-          zz[(2 * 8 + warp) * 8 + q4] = make_float4(mx[0], mx[1], mx[2], mx[3]);
-        }
-      }
-      __syncthreads();
-      // ===================================== scale: Z_i, certificate partials, the Phi tile ==========================================
-      {
-        const int p = lane;                                   // point of the sub-tile; warp u writes moments u, u + 8, u + 16
-        float Z = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) Z += s_z2[(0 * 8 + w) * kTcSub + p];
-        const float4 a = s_pt[2 * (st * kTcSub + p)], bq = s_pt[2 * (st * kTcSub + p) + 1];
-        const float invZ = 1.f / Z;
-        const float wn = bq.w * invZ;
-        if (warp == 0 && st * kTcSub + p < count) {
-          float S1 = 0.f, xmax = -3.0e38f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) { S1 += s_z2[(1 * 8 + w) * kTcSub + p]; xmax = fmaxf(xmax, s_z2[(2 * 8 + w) * kTcSub + p]); }
-          // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in octaves
-          CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf(Z) - 0.6931471805599453f * S1 * invZ) - (double)B * C.eps_mass;
-          const double mr = (double)(fast_exp2(xmax) * invZ);
-          if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
-        }
-        unsigned char* a32 = sb + pl.o_a32;
-        unsigned char* a16 = sb + pl.o_a16;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int k = warp + 8 * j;                       // warp-uniform
-          if (k < GCL_NM) {
-            float v;
-            const float wd0 = wn * a.x, wd1 = wn * a.y, wd2 = wn * a.z, wp0 = wn * bq.x, wp1 = wn * bq.y, wp2 = wn * bq.z;
-            switch (k) {
-              case 0: v = wn; break;
-              case 1: v = wd0; break;        case 2: v = wd1; break;        case 3: v = wd2; break;
-              case 4: v = wd0 * a.x; break;  case 5: v = wd0 * a.y; break;  case 6: v = wd0 * a.z; break;
-              case 7: v = wd1 * a.y; break;  case 8: v = wd1 * a.z; break;  case 9: v = wd2 * a.z; break;
-              case 10: v = wp0; break;       case 11: v = wp1; break;       case 12: v = wp2; break;
-              case 13: v = wp0 * bq.x; break; case 14: v = wp0 * bq.y; break; case 15: v = wp0 * bq.z; break;
-              case 16: v = wp1 * bq.y; break; case 17: v = wp1 * bq.z; break; default: v = wp2 * bq.z; break;
-            }
-            const uint32_t hbits = __float_as_uint(v) & 0xFFFFE000u;
-            const float rem = v - __uint_as_float(hbits);
-            const uint32_t row = (uint32_t)(32 * (k / 5) + (k % 5));
-            *reinterpret_cast<uint32_t*>(a32 + sw128((row >> 3) * 1024u + (row & 7u) * 128u + (uint32_t)p * 4u)) = hbits;
-            *reinterpret_cast<float*>(a32 + sw128(((row + 8) >> 3) * 1024u + ((row + 8) & 7u) * 128u + (uint32_t)p * 4u)) = rem;
-            const uint32_t pk = pack_bf16x2(v, 0.f);
-            *reinterpret_cast<unsigned short*>(a16 + sw64((row >> 3) * 512u + (row & 7u) * 64u + (uint32_t)p * 2u)) = (unsigned short)(pk & 0xFFFFu);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.shared -> visible to the tensor core's async proxy
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == kTcIssuer) {
+  if (warp == kTcProd / 32) {
+    // ================================= the MMA warp: lane 0 feeds the tensor core, sub-tile after sub-tile ================================
+    if (lane == 0) {
+      const uint32_t idesc32 = umma_idesc(2, NPAD), idesc16 = umma_idesc(1, NPAD);
+      uint32_t par_full[2] = {0u, 0u};
+      for (int T = 0; T < n_sub_total; ++T) {
+        const int stage = T & 1;
+        mbar_wait(smem_u32(&s_bar[stage]), par_full[stage]);           // the producers have written (and fenced) both operand tiles
+        par_full[stage] ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem + (uint32_t)(((T >> 4) & 1) * NPAD);
-        const uint32_t s0 = smem_u32(sb);
-        uint32_t accf = (T & 15) ? 1u : 0u;                            // first instruction of a group overwrites its half
+        const uint32_t d = tmem + (uint32_t)(((T >> kTcGroupLog2) & 1) * NPAD);
+        const uint32_t s0 = smem_u32(smem + (size_t)stage * pl.stage);
+        uint32_t accf = (T & kTcGroupMask) ? 1u : 0u;                  // first instruction of a group overwrites its half
+#if !defined(GCL_TC_DEBUG) || GCL_TC_DEBUG < 1     // debug builds: 1 = no MMAs (commits only), 2 = also no phase-A bin loop, 3 = also no scale stores
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           mma_tf32(d, umma_desc(s0 + pl.o_a32 + kb * 32, 1024, 2), umma_desc(s0 + pl.o_ehi + kb * 32, 1024, 2), idesc32, accf);
@@ -386,22 +224,263 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           mma_bf16(d, umma_desc(s0 + pl.o_a16 + j * 32, 512, 4), umma_desc(s0 + pl.o_elo + j * 32, 512, 4), idesc16, 1u);
-        umma_commit(smem_u32(&s_bar[stage]));
-        if ((T & 15) == 15) umma_commit(smem_u32(&s_bar[2 + ((T >> 4) & 1)]));
+#endif
+        umma_commit(smem_u32(&s_bar[2 + stage]));
+        if ((T & kTcGroupMask) == kTcGroupMask || T == n_sub_total - 1) umma_commit(smem_u32(&s_bar[4 + ((T >> kTcGroupLog2) & 1)]));
       }
     }
-  }
-  // --- tail: the last (partial) group, then whatever has not been drained yet ---------------------------------------------------------
-  if (tid == kTcIssuer && (T & 15) != 0) umma_commit(smem_u32(&s_bar[2 + ((T >> 4) & 1)]));
-  const int groups = (T + 15) >> 4;
-  while (drained < groups) drain(drained++);
-
-  if (owns) {
+    __syncwarp();
+  } else {
+    // ================================= the producers ===========================================================================================
+    // ownership of the fp64 accumulators: warp = (quarter of the tensor-memory lanes, half of the bins); inside the 16x256b fragment
+    // thread t holds moment row t/4 (head) and t/4 + 8 (remainder) for the two bins 2(t%4), 2(t%4) + 1 of every 8-column block
+    const int quarter = warp & 3, half = warp >> 2;
+    const int kq = lane >> 2, cpair = lane & 3;
+    const int my_moment = 5 * quarter + kq;
+    const bool owns = kq < (quarter < 3 ? 5 : 4);
+    double acc[NREP][2];
 #pragma unroll
-    for (int r = 0; r < NREP; ++r) {
-      const int b0 = half * (NPAD / 2) + 8 * r + 2 * cpair;
-      if (b0 < B) part[(size_t)my_moment * B + b0] = acc[r][0];
-      if (b0 + 1 < B) part[(size_t)my_moment * B + b0 + 1] = acc[r][1];
+    for (int r = 0; r < NREP; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
+
+    uint32_t par_empty[2] = {0u, 0u}, par_drain[2] = {0u, 0u};
+    int drained = 0;
+    auto drain = [&](int g) {
+      const int buf = g & 1;
+      mbar_wait(smem_u32(&s_bar[4 + buf]), par_drain[buf]);
+      par_drain[buf] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(buf * NPAD + half * (NPAD / 2));
+      uint32_t v[NREP][4];
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) tmem_ld_16x256b(taddr + 8 * r, v[r]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        acc[r][0] += (double)(__uint_as_float(v[r][0]) + __uint_as_float(v[r][2]));     // head row + remainder row (2^-11 of it)
+        acc[r][1] += (double)(__uint_as_float(v[r][1]) + __uint_as_float(v[r][3]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    // raw rows of the macro tile [t0, t0 + 256) -> s_in, asynchronously (one row per producer thread)
+    auto prefetch_tile = [&](int64_t t0) {
+      const int64_t srow = t0 + tid;
+      if (srow >= hi) return;
+      const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
+      const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;
+      if (P.layout == GCL_LAYOUT_REF_F64) {
+        const double* pts = static_cast<const double*>(J.points) + rp * 3;
+        double* dst = s_in + (size_t)tid * 5;
+        cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
+        cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
+        cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
+      } else {
+        float* base = reinterpret_cast<float*>(s_in);
+        cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + rp);
+        cp_async4(base + (size_t)kTcMacro * 4 + tid, static_cast<const float*>(J.weights) + r);
+      }
+    };
+    prefetch_tile(lo);
+
+    float xi32[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
+    // phase A: WARP = one quad of points (4 consecutive points of the sub-tile), LANE = the bins lane, lane + 32, ...: a warp carries its
+    // quad from the exponentials through the normaliser to the scaled rows without meeting the other warps (no CTA barrier inside a
+    // sub-tile; the hand-off to the MMA warp is the mbarrier).  The lane's atlas entries never change: they live in registers.
+    constexpr int NJ = (NPAD + 31) / 32;
+    float abx[NJ], aby[NJ], abz[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const float4 bb = s_atlas[lane + 32 * j]; abx[j] = bb.x; aby[j] = bb.y; abz[j] = bb.z; }
+    const uint32_t off_hi0 = sw128((uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)warp * 16u);
+    const uint32_t off_lo0 = sw64((uint32_t)(lane >> 3) * 512u + (uint32_t)(lane & 7) * 64u + (uint32_t)warp * 8u);
+    const float* s_dq_f = reinterpret_cast<const float*>(&s_dq[0][0]);
+    // scale: lane = (point of the quad, moment group): point (lane >> 2) & 3, moments g, g + 8, g + 16 with g = (lane & 3) + 4 (lane >> 4)
+    const int sc_pt = (lane >> 2) & 3, sc_g = (lane & 3) + 4 * (lane >> 4);
+
+    int T = 0;                                      // sub-tiles handed to the MMA warp so far
+    for (int64_t tile0 = lo; tile0 < hi; tile0 += kTcMacro) {
+      const int count = (int)((hi - tile0 < kTcMacro) ? hi - tile0 : kTcMacro);
+      cp_async_wait_all();
+      bar_producers();          // raw rows landed; every warp is done with the previous macro tile's s_dq / s_pw
+      // ======================================= front: one point per thread =======================================================
+      {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, sh = 0.f;
+        float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < count) {
+          const int64_t srow = tile0 + tid;
+          double w_sel;
+          PointOut32 o;
+          if (P.layout == GCL_LAYOUT_REF_F64) {
+            const double* in = s_in + (size_t)tid * 5;
+            w_sel = in[4];
+            point_front32(J, C, xi32, (float)in[0], (float)in[1], (float)in[2], (float)(in[3] - J.scan_start_time), o);
+          } else {
+            const float* base = reinterpret_cast<const float*>(s_in);
+            const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)tid * 4);
+            w_sel = (double)base[(size_t)kTcMacro * 4 + tid];
+            point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
+          }
+          const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
+          const double w_desk = w_sel * (double)o.w_time;
+          CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
+          CERT(GCL_CS_ROWS) += 1.0;
+          d0 = o.d[0]; d1 = o.d[1]; d2 = o.d[2]; sh = -cscale;        // fixed shift: the largest possible logit (|d.b| <= 1)
+          pw = make_float4(o.p0[0], o.p0[1], o.p0[2], (float)(w_desk * lam));
+        }
+        float* dq = reinterpret_cast<float*>(&s_dq[0][0]) + (size_t)(tid >> 2) * 16 + (tid & 3);
+        dq[0] = d0; dq[4] = d1; dq[8] = d2; dq[12] = sh;
+        s_pw[tid] = pw;
+      }
+      bar_producers();
+      prefetch_tile(tile0 + kTcMacro);
+      TCT(1);   // row wait + front end
+      const int n_sub = (count + kTcSub - 1) / kTcSub;
+      for (int st = 0; st < n_sub; ++st, ++T) {
+        const int stage = T & 1;
+        unsigned char* sb = smem + (size_t)stage * pl.stage;
+        if (T >= 2) { mbar_wait(smem_u32(&s_bar[2 + stage]), par_empty[stage]); par_empty[stage] ^= 1u; }   // sub-tile T - 2 is through the tensor core
+        TCT(2);   // stage wait
+        if (drained < (T >> kTcGroupLog2) && (T & kTcGroupMask) >= 2) drain(drained++);
+        TCT(3);   // drain
+        // ===================================== phase A: exponentials of this warp's 4 points x this lane's bins ===========================
+        const int quad = st * (kTcSub / 4) + warp;
+        const float4 DX = s_dq[quad][0], DY = s_dq[quad][1], DZ = s_dq[quad][2], SH = s_dq[quad][3];
+        const float2 dx01 = make_float2(DX.x, DX.y), dx23 = make_float2(DX.z, DX.w), dy01 = make_float2(DY.x, DY.y), dy23 = make_float2(DY.z, DY.w);
+        const float2 dz01 = make_float2(DZ.x, DZ.y), dz23 = make_float2(DZ.z, DZ.w), sh01 = make_float2(SH.x, SH.y), sh23 = make_float2(SH.z, SH.w);
+        float2 Z01 = make_float2(0.f, 0.f), Z23 = Z01, S01 = Z01, S23 = Z01;
+        float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;
+        {
+          unsigned char* ehi = sb + pl.o_ehi + off_hi0;
+          unsigned char* elo = sb + pl.o_elo + off_lo0;
+#if defined(GCL_TC_DEBUG) && GCL_TC_DEBUG >= 2
+#pragma unroll
+          for (int j = 0; j < 0; ++j) {
+#else
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+#endif
+            if (lane + 32 * j < B) {
+              const float2 bx = make_float2(abx[j], abx[j]), by = make_float2(aby[j], aby[j]), bz = make_float2(abz[j], abz[j]);
+              const float2 x01 = ffma2(dx01, bx, ffma2(dy01, by, ffma2(dz01, bz, sh01)));
+              const float2 x23 = ffma2(dx23, bx, ffma2(dy23, by, ffma2(dz23, bz, sh23)));
+              const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+              const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+              const uint32_t h0 = __float_as_uint(e01.x) & 0xFFFFE000u, h1 = __float_as_uint(e01.y) & 0xFFFFE000u;
+              const uint32_t h2 = __float_as_uint(e23.x) & 0xFFFFE000u, h3 = __float_as_uint(e23.y) & 0xFFFFE000u;
+              const float2 l01 = fadd2(e01, make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
+              const float2 l23 = fadd2(e23, make_float2(-__uint_as_float(h2), -__uint_as_float(h3)));
+              Z01 = fadd2(Z01, e01); Z23 = fadd2(Z23, e23);
+              S01 = ffma2(e01, x01, S01); S23 = ffma2(e23, x23, S23);
+              m0 = fmaxf(m0, x01.x); m1 = fmaxf(m1, x01.y); m2 = fmaxf(m2, x23.x); m3 = fmaxf(m3, x23.y);
+              *reinterpret_cast<uint4*>(ehi + j * 4096) = make_uint4(h0, h1, h2, h3);
+              *reinterpret_cast<uint2*>(elo + j * 2048) = make_uint2(pack_bf16x2(l01.x, l01.y), pack_bf16x2(l23.x, l23.y));
+            }
+          }
+        }
+        // ---- sums over the 32 lanes (= all bins) of {Z0..3, S0..3} and max of {m0..3}: reduce-scatter (each step halves what a lane
+        //      carries), 15 shuffles instead of 60: afterwards lane l holds v[(l >> 2) & 7] (Z of point l >> 2 for l < 16, S of point
+        //      (l >> 2) & 3 for l >= 16) and the maximum of point (l >> 3) & 3
+        float sumv, maxv;
+        {
+          float v[8] = {Z01.x, Z01.y, Z23.x, Z23.y, S01.x, S01.y, S23.x, S23.y};
+          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+          float w4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                         // keep v[i] (lanes < 16) or v[4 + i] (lanes >= 16)
+            const float keep = b4 ? v[4 + i] : v[i], give = b4 ? v[i] : v[4 + i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+          }
+          float w2[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = b3 ? w4[2 + i] : w4[i], give = b3 ? w4[i] : w4[2 + i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+          }
+          {
+            const float keep = b2 ? w2[1] : w2[0], give = b2 ? w2[0] : w2[1];
+            sumv = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+          }
+          sumv += __shfl_xor_sync(0xffffffffu, sumv, 2);
+          sumv += __shfl_xor_sync(0xffffffffu, sumv, 1);
+          float u2[2];
+          {
+            const float k0 = b4 ? m2 : m0, g0 = b4 ? m0 : m2, k1 = b4 ? m3 : m1, g1 = b4 ? m1 : m3;
+            u2[0] = fmaxf(k0, __shfl_xor_sync(0xffffffffu, g0, 16));
+            u2[1] = fmaxf(k1, __shfl_xor_sync(0xffffffffu, g1, 16));
+          }
+          {
+            const float keep = b3 ? u2[1] : u2[0], give = b3 ? u2[0] : u2[1];
+            maxv = fmaxf(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+          }
+          maxv = fmaxf(maxv, __shfl_xor_sync(0xffffffffu, maxv, 4));
+          maxv = fmaxf(maxv, __shfl_xor_sync(0xffffffffu, maxv, 2));
+          maxv = fmaxf(maxv, __shfl_xor_sync(0xffffffffu, maxv, 1));
+        }
+        TCT(4);   // phase A
+        // ===================================== scale: Z_i, certificate partials, the Phi tile ==========================================
+        {
+          // v index held by lane l: bit4 -> +4 (S instead of Z), bit3 -> +2, bit2 -> +1: lanes 0..15 hold Z of point (l >> 2),
+          // lanes 16..31 hold S of point (l >> 2) & 3; the maximum of point p sits in the lanes with (bit4, bit3) = (p >> 1, p & 1)
+          const float Zp = __shfl_sync(0xffffffffu, sumv, sc_pt << 2);
+          const int p = 4 * warp + sc_pt;                       // point of the sub-tile
+          const float4 bq = s_pw[st * kTcSub + p];
+          const float* dqp = s_dq_f + (size_t)quad * 16 + sc_pt;
+          const float a_x = dqp[0], a_y = dqp[4], a_z = dqp[8];
+          const float invZ = __frcp_rn(Zp);
+          const float wn = bq.w * invZ;
+          const float xmax = __shfl_sync(0xffffffffu, maxv, ((sc_pt >> 1) << 4) | ((sc_pt & 1) << 3));
+          if (lane >= 16 && (lane & 3) == 0 && st * kTcSub + p < count) {      // one lane per point holds its S
+            // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in octaves
+            CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf(Zp) - 0.6931471805599453f * sumv * invZ) - (double)B * C.eps_mass;
+            const double mr = (double)(fast_exp2(xmax) * invZ);
+            if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
+          }
+          unsigned char* a32 = sb + pl.o_a32;
+          unsigned char* a16 = sb + pl.o_a16;
+          const float wd0 = wn * a_x, wd1 = wn * a_y, wd2 = wn * a_z, wp0 = wn * bq.x, wp1 = wn * bq.y, wp2 = wn * bq.z;
+          // moments sc_g, sc_g + 8, sc_g + 16 by selection (no branches: 8 lane groups, 3 rounds)
+          const float r0[8] = {wn, wd0, wd1, wd2, wd0 * a_x, wd0 * a_y, wd0 * a_z, wd1 * a_y};
+          const float r1[8] = {wd1 * a_z, wd2 * a_z, wp0, wp1, wp2, wp0 * bq.x, wp0 * bq.y, wp0 * bq.z};
+          const float r2[8] = {wp1 * bq.y, wp1 * bq.z, wp2 * bq.z, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float vv[3] = {r0[0], r1[0], r2[0]};
+#pragma unroll
+          for (int i = 1; i < 8; ++i) { if (sc_g == i) { vv[0] = r0[i]; vv[1] = r1[i]; vv[2] = r2[i]; } }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int k = sc_g + 8 * j;
+#if defined(GCL_TC_DEBUG) && GCL_TC_DEBUG >= 3
+            if (k < 0) {
+#else
+            if (k < GCL_NM) {
+#endif
+              const float v = vv[j];
+              const uint32_t hbits = __float_as_uint(v) & 0xFFFFE000u;
+              const float rem = v - __uint_as_float(hbits);
+              const uint32_t row = (uint32_t)(32 * (k / 5) + (k % 5));
+              *reinterpret_cast<uint32_t*>(a32 + sw128((row >> 3) * 1024u + (row & 7u) * 128u + (uint32_t)p * 4u)) = hbits;
+              *reinterpret_cast<float*>(a32 + sw128(((row + 8) >> 3) * 1024u + ((row + 8) & 7u) * 128u + (uint32_t)p * 4u)) = rem;
+              const uint32_t pk = pack_bf16x2(v, 0.f);
+              *reinterpret_cast<unsigned short*>(a16 + sw64((row >> 3) * 512u + (row & 7u) * 64u + (uint32_t)p * 2u)) = (unsigned short)(pk & 0xFFFFu);
+            }
+          }
+        }
+        TCT(6);   // scale
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this thread's st.shared -> visible to the tensor core's async proxy
+        mbar_arrive(smem_u32(&s_bar[stage]));                            // ... and handed to the MMA warp (256 arrivals complete the phase)
+        TCT(7);   // proxy fence + arrive
+      }
+    }
+    // --- whatever has not been drained yet (the MMA warp commits the last, possibly partial, group itself) ---------------------------------
+    const int groups = (T + kTcGroupMask) >> kTcGroupLog2;
+    while (drained < groups) drain(drained++);
+    if (owns) {
+#pragma unroll
+      for (int r = 0; r < NREP; ++r) {
+        const int b0 = half * (NPAD / 2) + 8 * r + 2 * cpair;
+        if (b0 < B) part[(size_t)my_moment * B + b0] = acc[r][0];
+        if (b0 + 1 < B) part[(size_t)my_moment * B + b0 + 1] = acc[r][1];
+      }
     }
   }
 
@@ -424,10 +503,12 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
     part[(size_t)GCL_NM * B + tid] = v;
   }
 #undef CERT
-  if (warp == 0) {
-    constexpr uint32_t cols = (2 * NPAD <= 32) ? 32u : (2 * NPAD <= 64) ? 64u : (2 * NPAD <= 128) ? 128u : (2 * NPAD <= 256) ? 256u : 512u;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(cols) : "memory");
-  }
+#ifdef GCL_K1_TRACE
+  TCT(11);  // tail: last drains, write-out, certificates
+  if ((tid == 0 || tid == 64) && blockIdx.x == 1 && blockIdx.y == 0)
+    for (int i = 0; i < 12; ++i) g_tc_trace[tid == 0 ? 0 : 1][i] = tc_acc[i];
+#endif
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kCols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------

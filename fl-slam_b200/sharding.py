@@ -185,6 +185,64 @@ class PointShardedEvidence:
         return LidarScanEvidence(n_bins=pl.n_bins, n_hyp=H, stats=buf["stats"], evidence=buf["evidence"], n_input=n_raw_total,
                                  n_points_cap=pl.n_points_cap)
 
+    # ---- consecutive scans pipelined: the exchange + evidence step of scan k under the moment pass of scan k + 1 -------------------
+    def run_overlapped(self, scan, n_raw_total: int, xi_bodies, poses_dev, map_stats, reserve_sms: int = 8):
+        """Same result as ``run``; the moment pass goes on one internal stream with ``reserve_sms`` SMs left free, the fused exchange +
+        finalisation (grid capped to the free SMs) and the evidence step on a second, high-priority stream -- so the O(B), single-CTA
+        tail of scan k (~50 us, latency-bound) runs beside the moment pass of scan k + 1 instead of after it.  Results alternate between
+        two buffer sets (valid until the call after next); ``join_overlapped()`` orders the caller's stream after everything submitted."""
+        from .pipeline import LidarScanEvidence
+        from . import _abi, operators as ops
+        pl = self.pl
+        if self.px is None:
+            raise ValueError("run_overlapped needs the peer exchange (exchange='peer')")
+        xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
+        H = xi.shape[0]
+        _, n_sel, (b, e), _ = self.plan(n_raw_total)
+        sms = int(_abi.lib.gcl_device_sm_count(pl.handle))
+        ctas = max(1, min(pl.plan_ctas(H, max(1, e - b)), (sms - reserve_sms) // max(1, H)))
+        ov = getattr(self, "_ov", None)
+        if ov is None:
+            ov = self._ov = {"s_k1": torch.cuda.Stream(device=pl.device, priority=0), "s_rest": torch.cuda.Stream(device=pl.device, priority=-1),
+                             "free": [None, None], "turn": 0, "last": None, "keep": [None, None]}
+            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, max(1, reserve_sms))
+        cur = torch.cuda.current_stream(pl.device)
+        ov["s_k1"].wait_stream(cur); ov["s_rest"].wait_stream(cur)     # what the caller enqueued so far (uploads, poses, map) comes first
+        i = ov["turn"] & 1
+        ov["turn"] += 1
+        buf = pl._buffers(H, ctas, slot=i)
+        jobs = [pl.make_job(scan, xi[h], n_raw_total=n_raw_total, sel_range=(b, e)) for h in range(H)]
+        job, jobs_dev = (jobs[0], None) if H == 1 else (None, pl.jobs_to_device(jobs))
+        ov["keep"][i] = (jobs_dev, poses_dev, scan)
+        if ov["free"][i] is not None:
+            ov["s_k1"].wait_event(ov["free"][i])                       # the tail that read this buffer set two scans ago is done
+        with torch.cuda.stream(ov["s_k1"]):
+            pl.launch_moments(jobs_dev, job, H, ctas, scan.layout, buf["partials"])
+            ready = ov["s_k1"].record_event()
+        ov["s_rest"].wait_event(ready)
+        with torch.cuda.stream(ov["s_rest"]):
+            self.px._check(_abi.lib.gcl_sharded_reduce_finalize(
+                pl.handle, self.px.x, ops._stream(), ops._ptr(buf["partials"]), ctas, pl.rec, pl.rec * ctas,
+                None if jobs_dev is None else C.c_void_p(jobs_dev.data_ptr()), None if job is None else C.byref(job), H, pl.n_bins,
+                ops._ptr(pl.bin_dirs), pl.tau, pl._origin_c, pl.eps_psd, pl.eps_mass, ops._ptr(buf["reduced"]), ops._ptr(buf["stats"])))
+            pl.launch_chain(buf["stats"], 1, H, map_stats, buf["map_derived"], poses_dev, None, buf["evidence"])
+            ov["free"][i] = ov["last"] = ov["s_rest"].record_event()
+        return LidarScanEvidence(n_bins=pl.n_bins, n_hyp=H, stats=buf["stats"], evidence=buf["evidence"], n_input=n_raw_total,
+                                 n_points_cap=pl.n_points_cap)
+
+    def join_overlapped(self) -> None:
+        ov = getattr(self, "_ov", None)
+        if ov is not None and ov["last"] is not None:
+            torch.cuda.current_stream(self.pl.device).wait_event(ov["last"])
+
+    def end_overlapped(self) -> None:
+        """Back to one scan at a time (the exchange kernel's grid is no longer capped)."""
+        from . import _abi
+        self.join_overlapped()
+        if self.px is not None:
+            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, 0)
+        self._ov = None
+
     # ---- the same scan from HOST memory: this rank's shard crosses PCIe inside the call --------------------------------------
     def host_stage(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float):
         """Page-locked copies of this rank's raw rows + two device staging shards (so that the upload of scan k + 1 can run on a
@@ -289,11 +347,15 @@ def _bits_identical_across_ranks(t: torch.Tensor, world: int) -> bool:
 
 def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, warmup: int, rank: int, world: int,
                          peak_gbs: float, precision: str = "fp64", scans_per_step: int = 64, exchange: str = "peer",
-                         with_e2e: bool = True) -> Dict[str, object]:
+                         with_e2e: bool = True, reserve_sms: Optional[int] = None) -> Dict[str, object]:
     """BASELINE.json configs[3]: one dense cloud of n_points, sharded by points over the ranks (strong scaling).  One "step" =
     `scans_per_step` scans (each: scan_moments on this rank's rows, the fused NVLink exchange + finalisation, the evidence step);
     several copies of the input are rotated so that consecutive scans never re-read an L2-resident cloud."""
     from . import synth
+    if reserve_sms is None:
+        # SMs left to the exchange + evidence tail of the previous scan: enough that the tail (latency-bound, ~50-70 us) finishes
+        # under the moment pass of the next scan, which shrinks with the number of ranks
+        reserve_sms = {1: 2, 2: 2, 4: 4}.get(world, 6)
     sc = synth.make_scan(n_points, seed=1234 + 4, dense=True)
     pl = g.LidarEvidencePipeline(n_bins=n_bins, tau=tau, precision=precision, n_points_cap=n_points, lidar_origin=sc.lidar_origin)
     sh = PointShardedEvidence(pl, rank, world, exchange=exchange)
@@ -317,8 +379,22 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
     ms = g.MapBinStats.from_arrays(synth.map_stats_from_scan_sums(raw, rs[0], rs[1], seed=4))
 
     it = [0]
+    overlapped = sh.px is not None and reserve_sms > 0
+    ctas_run = max(1, min(ctas, int(g._abi.lib.gcl_device_sm_count(pl.handle)) - reserve_sms)) if overlapped else ctas
 
     def step(_k):
+        # consecutive scans are pipelined: the exchange + evidence tail of scan k (three small launches' worth of latency on a few SMs)
+        # runs under the moment pass of scan k + 1
+        for _ in range(scans_per_step):
+            if overlapped:
+                sh.run_overlapped(shards[it[0] % n_copies], n_points, xi, poses, ms, reserve_sms=reserve_sms)
+            else:
+                sh.run(shards[it[0] % n_copies], n_points, xi, poses, ms, ctas=ctas)
+            it[0] += 1
+        if overlapped:
+            sh.join_overlapped()
+
+    def step_serial(_k):
         for _ in range(scans_per_step):
             sh.run(shards[it[0] % n_copies], n_points, xi, poses, ms, ctas=ctas)
             it[0] += 1
@@ -328,13 +404,16 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
             scan = shards[it[0] % n_copies]
             it[0] += 1
             job = pl.make_job(scan, sc.xi_body, n_raw_total=n_points, sel_range=(b, e))
-            pl.launch_moments(None, job, 1, ctas, scan.layout, pl._buffers(1, ctas)["partials"])
+            pl.launch_moments(None, job, 1, ctas_run, scan.layout, pl._buffers(1, ctas_run)["partials"])
 
     l0 = g._abi.launch_count(pl.device_index)
     step(0)
     torch.cuda.synchronize()
     launches_per_step = g._abi.launch_count(pl.device_index) - l0
     ms_step, per = _time_steps(step, steps, warmup, world)
+    if overlapped:
+        sh.end_overlapped()
+    ms_serial_step, _ = _time_steps(step_serial, max(2, steps // 2), 1, world)
     ms_k1_step, _ = _time_steps(k1_step, max(2, steps // 2), 1, world)
     ms_scan, ms_k1 = ms_step / scans_per_step, ms_k1_step / scans_per_step
     shard_bytes = (e - b) * bpp                                   # algorithmic bytes of one scan_moments launch on this rank
@@ -361,7 +440,10 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
         "scans_per_step": scans_per_step, "ms_per_step": ms_step, "ms_per_scan": ms_scan, "ms_per_scan_median": float(per[len(per) // 2]),
         "ms_per_scan_best": float(per[0]), "points_per_sec": n_points / (ms_scan * 1e-3), "scans_per_sec": 1e3 / ms_scan,
         "scan_moments_ms": ms_k1, "rest_of_scan_ms": ms_scan - ms_k1, "pairs_per_sec": n_points * n_bins / (ms_k1 * 1e-3),
-        "launches_per_step": int(launches_per_step), "launches_per_scan": launches_per_step / scans_per_step, "ctas_per_rank": ctas,
+        "ms_per_scan_one_at_a_time": ms_serial_step / scans_per_step,
+        "pipelining": (f"consecutive scans pipelined on two streams: scan_moments on {ctas_run} CTAs, the exchange + evidence tail of the previous "
+                       f"scan on the {reserve_sms} SMs left free") if overlapped else "none (one scan at a time)",
+        "launches_per_step": int(launches_per_step), "launches_per_scan": launches_per_step / scans_per_step, "ctas_per_rank": ctas_run,
         "rows_per_rank": int(e - b), "input_copies_rotated": n_copies,
         "roofline": {"bound": "hbm", "kernel": "scan_moments_fused_kernel", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                      "ms_per_launch": ms_k1, "algorithmic_bytes_per_launch": float(shard_bytes), "bytes_per_point": bpp,

@@ -281,6 +281,10 @@ int gcl_exchange_disconnect(gcl_handle h, gcl_exchange x); /* unmap the peers' b
 void gcl_exchange_destroy(gcl_handle h, gcl_exchange x);
 const char* gcl_exchange_last_error(gcl_exchange x);
 int gcl_exchange_error_flag(gcl_exchange x); /* synchronous read of the device-side error word: 0 = no time-out so far */
+/* Cap the grid of gcl_sharded_reduce_finalize (0 = one CTA per 128 record elements).  A caller that overlaps the exchange of scan k
+ * with the moment pass of scan k + 1 leaves a few SMs free for it (gcl_scan_moments with ctas_per_job < SM count) and caps the
+ * exchange kernel's grid to that number, so that its CTAs do not queue behind the moment pass. */
+int gcl_exchange_set_max_ctas(gcl_exchange x, int max_ctas);
 int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, const double* parts, int n_parts,
                                 int64_t part_stride_doubles, int64_t job_stride_doubles, const gcl_job* jobs_dev,
                                 const gcl_job* job_by_value_host, int n_jobs, int n_bins, const double* bin_dirs, double tau,
