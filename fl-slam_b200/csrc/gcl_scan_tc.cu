@@ -288,16 +288,25 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
     // phase A: WARP = one quad of points (4 consecutive points of the sub-tile), LANE = the bins lane, lane + 32, ...: a warp carries its
     // quad from the exponentials through the normaliser to the scaled rows without meeting the other warps (no CTA barrier inside a
     // sub-tile; the hand-off to the MMA warp is the mbarrier).  The lane's atlas entries never change: they live in registers.
+    // The softmax shift is the same for every point (fixed shift -1/tau): it is folded into the bin's constants, and a bin beyond
+    // n_bins gets -1e30 instead, which makes its exponential exactly 0 -- so the bin loop has no branches (only its two stores are
+    // predicated) and the compiler interleaves the 8 x 4 independent exponential chains of a lane.
     constexpr int NJ = (NPAD + 31) / 32;
-    float abx[NJ], aby[NJ], abz[NJ];
+    float abx[NJ], aby[NJ], abz[NJ], ash[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { const float4 bb = s_atlas[lane + 32 * j]; abx[j] = bb.x; aby[j] = bb.y; abz[j] = bb.z; }
+    for (int j = 0; j < NJ; ++j) {
+      const float4 bb = s_atlas[lane + 32 * j];
+      abx[j] = bb.x; aby[j] = bb.y; abz[j] = bb.z; ash[j] = (lane + 32 * j < B) ? -cscale : -1.0e30f;
+    }
     const uint32_t off_hi0 = sw128((uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)warp * 16u);
     const uint32_t off_lo0 = sw64((uint32_t)(lane >> 3) * 512u + (uint32_t)(lane & 7) * 64u + (uint32_t)warp * 8u);
     const float* s_dq_f = reinterpret_cast<const float*>(&s_dq[0][0]);
     // scale: lane = (point of the quad, moment group): point (lane >> 2) & 3, moments g, g + 8, g + 16 with g = (lane & 3) + 4 (lane >> 4)
     const int sc_pt = (lane >> 2) & 3, sc_g = (lane & 3) + 4 * (lane >> 4);
 
+    double ent_acc = 0.0;                           // certificate partials of the scale step stay in registers
+    float mr_acc = 0.f;
+    const double ent_eps = (double)B * C.eps_mass;
     int T = 0;                                      // sub-tiles handed to the MMA warp so far
     for (int64_t tile0 = lo; tile0 < hi; tile0 += kTcMacro) {
       const int count = (int)((hi - tile0 < kTcMacro) ? hi - tile0 : kTcMacro);
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
       bar_producers();          // raw rows landed; every warp is done with the previous macro tile's s_dq / s_pw
       // ======================================= front: one point per thread =======================================================
       {
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, sh = 0.f;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
         float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < count) {
           const int64_t srow = tile0 + tid;
@@ -325,11 +334,11 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
           const double w_desk = w_sel * (double)o.w_time;
           CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
           CERT(GCL_CS_ROWS) += 1.0;
-          d0 = o.d[0]; d1 = o.d[1]; d2 = o.d[2]; sh = -cscale;        // fixed shift: the largest possible logit (|d.b| <= 1)
+          d0 = o.d[0]; d1 = o.d[1]; d2 = o.d[2];
           pw = make_float4(o.p0[0], o.p0[1], o.p0[2], (float)(w_desk * lam));
         }
         float* dq = reinterpret_cast<float*>(&s_dq[0][0]) + (size_t)(tid >> 2) * 16 + (tid & 3);
-        dq[0] = d0; dq[4] = d1; dq[8] = d2; dq[12] = sh;
+        dq[0] = d0; dq[4] = d1; dq[8] = d2;
         s_pw[tid] = pw;
       }
       bar_producers();
@@ -345,9 +354,9 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
         TCT(3);   // drain
         // ===================================== phase A: exponentials of this warp's 4 points x this lane's bins ===========================
         const int quad = st * (kTcSub / 4) + warp;
-        const float4 DX = s_dq[quad][0], DY = s_dq[quad][1], DZ = s_dq[quad][2], SH = s_dq[quad][3];
+        const float4 DX = s_dq[quad][0], DY = s_dq[quad][1], DZ = s_dq[quad][2];
         const float2 dx01 = make_float2(DX.x, DX.y), dx23 = make_float2(DX.z, DX.w), dy01 = make_float2(DY.x, DY.y), dy23 = make_float2(DY.z, DY.w);
-        const float2 dz01 = make_float2(DZ.x, DZ.y), dz23 = make_float2(DZ.z, DZ.w), sh01 = make_float2(SH.x, SH.y), sh23 = make_float2(SH.z, SH.w);
+        const float2 dz01 = make_float2(DZ.x, DZ.y), dz23 = make_float2(DZ.z, DZ.w);
         float2 Z01 = make_float2(0.f, 0.f), Z23 = Z01, S01 = Z01, S23 = Z01;
         float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;
         {
@@ -360,19 +369,20 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
 #endif
-            if (lane + 32 * j < B) {
-              const float2 bx = make_float2(abx[j], abx[j]), by = make_float2(aby[j], aby[j]), bz = make_float2(abz[j], abz[j]);
-              const float2 x01 = ffma2(dx01, bx, ffma2(dy01, by, ffma2(dz01, bz, sh01)));
-              const float2 x23 = ffma2(dx23, bx, ffma2(dy23, by, ffma2(dz23, bz, sh23)));
-              const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
-              const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
-              const uint32_t h0 = __float_as_uint(e01.x) & 0xFFFFE000u, h1 = __float_as_uint(e01.y) & 0xFFFFE000u;
-              const uint32_t h2 = __float_as_uint(e23.x) & 0xFFFFE000u, h3 = __float_as_uint(e23.y) & 0xFFFFE000u;
-              const float2 l01 = fadd2(e01, make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
-              const float2 l23 = fadd2(e23, make_float2(-__uint_as_float(h2), -__uint_as_float(h3)));
-              Z01 = fadd2(Z01, e01); Z23 = fadd2(Z23, e23);
-              S01 = ffma2(e01, x01, S01); S23 = ffma2(e23, x23, S23);
-              m0 = fmaxf(m0, x01.x); m1 = fmaxf(m1, x01.y); m2 = fmaxf(m2, x23.x); m3 = fmaxf(m3, x23.y);
+            const float2 bx = make_float2(abx[j], abx[j]), by = make_float2(aby[j], aby[j]), bz = make_float2(abz[j], abz[j]);
+            const float2 sh = make_float2(ash[j], ash[j]);
+            const float2 x01 = ffma2(dx01, bx, ffma2(dy01, by, ffma2(dz01, bz, sh)));
+            const float2 x23 = ffma2(dx23, bx, ffma2(dy23, by, ffma2(dz23, bz, sh)));
+            const float2 e01 = make_float2(fast_exp2(x01.x), fast_exp2(x01.y));
+            const float2 e23 = make_float2(fast_exp2(x23.x), fast_exp2(x23.y));
+            const uint32_t h0 = __float_as_uint(e01.x) & 0xFFFFE000u, h1 = __float_as_uint(e01.y) & 0xFFFFE000u;
+            const uint32_t h2 = __float_as_uint(e23.x) & 0xFFFFE000u, h3 = __float_as_uint(e23.y) & 0xFFFFE000u;
+            const float2 l01 = fadd2(e01, make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
+            const float2 l23 = fadd2(e23, make_float2(-__uint_as_float(h2), -__uint_as_float(h3)));
+            Z01 = fadd2(Z01, e01); Z23 = fadd2(Z23, e23);
+            S01 = ffma2(e01, x01, S01); S23 = ffma2(e23, x23, S23);        // a masked bin adds 0 * -1e30 = -0
+            m0 = fmaxf(m0, x01.x); m1 = fmaxf(m1, x01.y); m2 = fmaxf(m2, x23.x); m3 = fmaxf(m3, x23.y);
+            if (NPAD % 32 == 0 || j < NJ - 1 || lane + 32 * j < NPAD) {     // only the last step of a 48-row tile has rows to skip
               *reinterpret_cast<uint4*>(ehi + j * 4096) = make_uint4(h0, h1, h2, h3);
               *reinterpret_cast<uint2*>(elo + j * 2048) = make_uint2(pack_bf16x2(l01.x, l01.y), pack_bf16x2(l23.x, l23.y));
             }
@@ -430,11 +440,13 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
           const float invZ = __frcp_rn(Zp);
           const float wn = bq.w * invZ;
           const float xmax = __shfl_sync(0xffffffffu, maxv, ((sc_pt >> 1) << 4) | ((sc_pt & 1) << 3));
-          if (lane >= 16 && (lane & 3) == 0 && st * kTcSub + p < count) {      // one lane per point holds its S
+          {
+            // one lane per point holds its S (lanes 16, 20, 24, 28); no branch: the other lanes add 0 / keep their maximum
             // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in octaves
-            CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf(Zp) - 0.6931471805599453f * sumv * invZ) - (double)B * C.eps_mass;
-            const double mr = (double)(fast_exp2(xmax) * invZ);
-            if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
+            const bool mine = lane >= 16 && (lane & 3) == 0 && st * kTcSub + p < count;
+            const float h = __logf(Zp) - 0.6931471805599453f * sumv * invZ;
+            ent_acc += mine ? (double)h - ent_eps : 0.0;
+            mr_acc = fmaxf(mr_acc, mine ? fast_exp2(xmax) * invZ : 0.f);
           }
           unsigned char* a32 = sb + pl.o_a32;
           unsigned char* a16 = sb + pl.o_a16;
@@ -471,6 +483,8 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
         TCT(7);   // proxy fence + arrive
       }
     }
+    CERT(GCL_CS_SUM_ENTROPY) = ent_acc;
+    CERT(GCL_CS_MAX_RESP) = (double)mr_acc;
     // --- whatever has not been drained yet (the MMA warp commits the last, possibly partial, group itself) ---------------------------------
     const int groups = (T + kTcGroupMask) >> kTcGroupLog2;
     while (drained < groups) drain(drained++);
