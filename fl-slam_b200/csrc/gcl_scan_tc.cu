@@ -30,10 +30,13 @@
 
 namespace gcl {
 
-constexpr int kTcProd = 256;     // producer threads: front end, phase A, scale, drains (8 warps)
-constexpr int kTcNT = 288;       // + one warp whose lane 0 issues the MMAs (a tcgen05.mma issue blocks its thread while the queue is
+constexpr int kTcTeam = 256;     // threads of one producer team (8 warps = the 8 quads of a sub-tile)
+constexpr int kTcProd = 512;     // two teams: team t takes the sub-tiles t, t + 2, ... and owns shared-memory stage t.  Everything a warp does
+                                 // per sub-tile is a chain of dependent latencies (shuffles, reciprocal, fences, barrier round trips): with one
+                                 // team (2 warps per scheduler) a sub-tile cost ~1900 cycles before its first exponential
+constexpr int kTcNT = 544;       // + one warp whose lane 0 issues the MMAs (a tcgen05.mma issue blocks its thread while the queue is
                                  // full -- measured 830 cycles per sub-tile -- so it must not be a thread the others wait for)
-constexpr int kTcMacro = 256;    // points per front-end pass
+constexpr int kTcMacroMax = 512; // points per front-end pass: 512 (packed 20-byte rows) or 256 (40-byte float64 rows: same staging bytes)
 constexpr int kTcSub = 32;       // points per MMA sub-tile
 constexpr int kTcGroupLog2 = 3;  // 2^3 = 8 sub-tiles (256 points, 48 instructions) accumulate in one half of tensor memory between drains:
                                  // the fp32 accumulation of the tensor core truncates, and the bias grows with the number of products an
@@ -81,11 +84,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // {lo -
   return r;
 }
 
-// shared-memory plan of the dynamic part: two operand stages + the raw-row staging (host and device agree through this)
+// shared-memory plan of the dynamic part: two operand stages, the fp64 record, the raw-row staging (host and device agree through this)
 struct TcPlan {
   int n_pad;                                   // bins rounded up to what the MMA shape needs (48, 128, 256)
   uint32_t o_a32, o_ehi, o_a16, o_elo, stage;  // inside one stage
-  uint32_t o_in, total;
+  uint32_t o_rec, o_in, total;
 };
 __host__ __device__ inline TcPlan tc_plan(int nrep) {
   TcPlan p;
@@ -96,8 +99,9 @@ __host__ __device__ inline TcPlan tc_plan(int nrep) {
   p.o_elo = p.o_a16 + 8192;
   p.stage = p.o_elo + (uint32_t)p.n_pad * 64;
   p.stage = (p.stage + 1023u) & ~1023u;
-  p.o_in = 2 * p.stage;
-  p.total = p.o_in + kTcMacro * 40 + 1024;     // + slack for the manual 1024-byte alignment of the base
+  p.o_rec = 2 * p.stage;                                    // [19][n_pad] doubles: this CTA's sums, carried in fp64
+  p.o_in = p.o_rec + (uint32_t)GCL_NM * p.n_pad * 8;
+  p.total = p.o_in + kTcMacroMax * 20 + 1024;               // 512 packed rows = 256 float64 rows; + slack for the 1024-byte alignment
   return p;
 }
 __device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kTcProd) : "memory"); }
@@ -118,10 +122,9 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
   // (with everything carved out of one dynamic array every atlas load waited for the previous bin's stores: phase A ran at a
   // quarter of its issue rate)
   __shared__ float4 s_atlas[256];                  // [bin]: log2(e)/tau * direction
-  __shared__ float4 s_dq[kTcMacro / 4][4];         // [quad of points][dx, dy, dz, shift]: one float4 = that component of 4 consecutive points
-  __shared__ float4 s_pw[kTcMacro];                // [point]: {p0, p1, p2, w}
+  __shared__ float4 s_dq[kTcMacroMax / 4][3];      // [quad of points][dx, dy, dz]: one float4 = that component of 4 consecutive points
+  __shared__ float4 s_pw[kTcMacroMax];             // [point]: {p0, p1, p2, w}
   __shared__ double s_red[kTcNT / 32][GCL_NCERT];
-  __shared__ double s_cert[kTcNT * GCL_NCERT];
   __shared__ gcl_job s_job;
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar[6];      // operands ready (stage 0, 1), stage consumed (0, 1), tensor-memory half complete (0, 1)
@@ -136,15 +139,16 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
 
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
-  // operand tiles start as zeros: rows that are never written (unused moments, bins beyond n_bins, points beyond a partial tile)
-  for (uint32_t i = tid; i < 2 * pl.stage / 16; i += kTcNT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // operand tiles and the fp64 record start as zeros (tile rows that are never written: unused moments, bins beyond n_bins, points
+  // beyond a partial tile)
+  for (uint32_t i = tid; i < pl.o_in / 16; i += kTcNT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   constexpr uint32_t kCols = (2 * NPAD <= 32) ? 32u : (2 * NPAD <= 64) ? 64u : (2 * NPAD <= 128) ? 128u : (2 * NPAD <= 256) ? 256u : 512u;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&s_bar[0]), kTcProd); mbar_init(smem_u32(&s_bar[1]), kTcProd);     // every producer thread arrives
+    mbar_init(smem_u32(&s_bar[0]), kTcTeam); mbar_init(smem_u32(&s_bar[1]), kTcTeam);     // every thread of the stage's team arrives
     for (int i = 2; i < 6; ++i) mbar_init(smem_u32(&s_bar[i]), 1);                         // tcgen05.commit arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,10 +158,9 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
     s_atlas[b] = (b < B) ? make_float4((float)(P.bin_dirs[b * 3] * cscale_d), (float)(P.bin_dirs[b * 3 + 1] * cscale_d),
                                        (float)(P.bin_dirs[b * 3 + 2] * cscale_d), 0.f)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
-  double* my_cert = s_cert + tid;
-#define CERT(k) my_cert[(k) * kTcNT]
-#pragma unroll
-  for (int k = 0; k < GCL_NCERT; ++k) CERT(k) = 0.0;
+  // per-thread certificate partials (registers): raw weights, selected weights, their squares, deskewed weights, rows, entropy, max r
+  double c_wraw = 0.0, c_wsel = 0.0, c_wsel2 = 0.0, c_wdesk = 0.0, c_rows = 0.0, ent_acc = 0.0;
+  float mr_acc = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the zero fill, before the first MMA reads the tiles
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -180,8 +183,10 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
   const int64_t lo = lo0 < sel_end ? lo0 : sel_end;
   const int64_t hi = (lo + rpc < sel_end) ? lo + rpc : sel_end;
   double* part = P.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * P.rec_doubles;
-  const int n_sub_total = (int)(((hi - lo) / kTcMacro) * (kTcMacro / kTcSub) + (((hi - lo) % kTcMacro) + kTcSub - 1) / kTcSub);
+  const int macro = (P.layout == GCL_LAYOUT_REF_F64) ? 256 : 512;   // points per front-end pass (one raw-row staging buffer of 10 KB)
+  const int n_sub_total = (int)(((hi - lo) / macro) * (macro / kTcSub) + (((hi - lo) % macro) + kTcSub - 1) / kTcSub);
   double* s_in = reinterpret_cast<double*>(smem + pl.o_in);
+  double* s_rec = reinterpret_cast<double*>(smem + pl.o_rec);        // [moment][NPAD]
 
   // --- sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69) ---------------------------------------
   if (stride > 1 && hi > lo) {
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
       for (; r + 3 * kTcNT < rhi; r += 4 * kTcNT) { p0 += (double)w[r]; p1 += (double)w[r + kTcNT]; p2 += (double)w[r + 2 * kTcNT]; p3 += (double)w[r + 3 * kTcNT]; }
       for (; r < rhi; r += kTcNT) p0 += (double)w[r];
     }
-    CERT(GCL_CS_SUM_W_RAW) = (p0 + p1) + (p2 + p3);
+    c_wraw = (p0 + p1) + (p2 + p3);
   }
   TCT(0);   // prologue
 
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
       uint32_t par_full[2] = {0u, 0u};
       for (int T = 0; T < n_sub_total; ++T) {
         const int stage = T & 1;
-        mbar_wait(smem_u32(&s_bar[stage]), par_full[stage]);           // the producers have written (and fenced) both operand tiles
+        mbar_wait(smem_u32(&s_bar[stage]), par_full[stage]);           // the stage's team has written (and fenced) both operand tiles
         par_full[stage] ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem + (uint32_t)(((T >> kTcGroupLog2) & 1) * NPAD);
@@ -231,41 +236,48 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
     }
     __syncwarp();
   } else {
-    // ================================= the producers ===========================================================================================
-    // ownership of the fp64 accumulators: warp = (quarter of the tensor-memory lanes, half of the bins); inside the 16x256b fragment
-    // thread t holds moment row t/4 (head) and t/4 + 8 (remainder) for the two bins 2(t%4), 2(t%4) + 1 of every 8-column block
-    const int quarter = warp & 3, half = warp >> 2;
+    // ================================= the producers: two teams of 8 warps ===================================================================
+    const int team = warp >> 3, wq = warp & 7;       // team t = sub-tiles t, t + 2, ... = stage t; wq = this warp's quad of the sub-tile
+    // ownership of the fp64 sums: warp = (quarter of the tensor-memory lanes, part of the bins); inside the 16x256b fragment thread t
+    // holds moment row t/4 (head) and t/4 + 8 (remainder) for the two bins 2(t%4), 2(t%4) + 1 of every 8-column block
+    constexpr int PARTS = (NPAD % 32 == 0) ? 4 : 2;  // a 48-bin record splits in 2 x 24 columns (warps 8..15 own nothing then)
+    constexpr int REPS = NPAD / (8 * PARTS);
+    const int quarter = warp & 3, bpart = warp >> 2;
     const int kq = lane >> 2, cpair = lane & 3;
     const int my_moment = 5 * quarter + kq;
-    const bool owns = kq < (quarter < 3 ? 5 : 4);
-    double acc[NREP][2];
-#pragma unroll
-    for (int r = 0; r < NREP; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
+    const bool owns = kq < (quarter < 3 ? 5 : 4) && bpart < PARTS;
 
-    uint32_t par_empty[2] = {0u, 0u}, par_drain[2] = {0u, 0u};
+    uint32_t par_empty = 0u, par_drain[2] = {0u, 0u};
     int drained = 0;
     auto drain = [&](int g) {
       const int buf = g & 1;
       mbar_wait(smem_u32(&s_bar[4 + buf]), par_drain[buf]);
       par_drain[buf] ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(buf * NPAD + half * (NPAD / 2));
-      uint32_t v[NREP][4];
+      if (bpart < PARTS) {                                   // warp-uniform
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(buf * NPAD + bpart * (NPAD / PARTS));
+        uint32_t v[REPS][4];
 #pragma unroll
-      for (int r = 0; r < NREP; ++r) tmem_ld_16x256b(taddr + 8 * r, v[r]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int r = 0; r < REPS; ++r) tmem_ld_16x256b(taddr + 8 * r, v[r]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (owns) {
+          double* rec = s_rec + (size_t)my_moment * NPAD + bpart * (NPAD / PARTS) + 2 * cpair;
 #pragma unroll
-      for (int r = 0; r < NREP; ++r) {
-        acc[r][0] += (double)(__uint_as_float(v[r][0]) + __uint_as_float(v[r][2]));     // head row + remainder row (2^-11 of it)
-        acc[r][1] += (double)(__uint_as_float(v[r][1]) + __uint_as_float(v[r][3]));
+          for (int r = 0; r < REPS; ++r) {
+            double2 a = *reinterpret_cast<double2*>(rec + 8 * r);
+            a.x += (double)(__uint_as_float(v[r][0]) + __uint_as_float(v[r][2]));     // head row + remainder row (2^-11 of it)
+            a.y += (double)(__uint_as_float(v[r][1]) + __uint_as_float(v[r][3]));
+            *reinterpret_cast<double2*>(rec + 8 * r) = a;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    // raw rows of the macro tile [t0, t0 + 256) -> s_in, asynchronously (one row per producer thread)
+    // raw rows of the macro tile [t0, t0 + macro) -> s_in, asynchronously (one row per thread)
     auto prefetch_tile = [&](int64_t t0) {
       const int64_t srow = t0 + tid;
-      if (srow >= hi) return;
+      if (tid >= macro || srow >= hi) return;
       const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
       const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;
       if (P.layout == GCL_LAYOUT_REF_F64) {
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
       } else {
         float* base = reinterpret_cast<float*>(s_in);
         cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + rp);
-        cp_async4(base + (size_t)kTcMacro * 4 + tid, static_cast<const float*>(J.weights) + r);
+        cp_async4(base + (size_t)kTcMacroMax * 4 + tid, static_cast<const float*>(J.weights) + r);
       }
     };
     prefetch_tile(lo);
@@ -298,22 +310,23 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
       const float4 bb = s_atlas[lane + 32 * j];
       abx[j] = bb.x; aby[j] = bb.y; abz[j] = bb.z; ash[j] = (lane + 32 * j < B) ? -cscale : -1.0e30f;
     }
-    const uint32_t off_hi0 = sw128((uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)warp * 16u);
-    const uint32_t off_lo0 = sw64((uint32_t)(lane >> 3) * 512u + (uint32_t)(lane & 7) * 64u + (uint32_t)warp * 8u);
+    const uint32_t off_hi0 = sw128((uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)wq * 16u);
+    const uint32_t off_lo0 = sw64((uint32_t)(lane >> 3) * 512u + (uint32_t)(lane & 7) * 64u + (uint32_t)wq * 8u);
     const float* s_dq_f = reinterpret_cast<const float*>(&s_dq[0][0]);
     // scale: lane = (point of the quad, moment group): point (lane >> 2) & 3, moments g, g + 8, g + 16 with g = (lane & 3) + 4 (lane >> 4)
     const int sc_pt = (lane >> 2) & 3, sc_g = (lane & 3) + 4 * (lane >> 4);
-
-    double ent_acc = 0.0;                           // certificate partials of the scale step stay in registers
-    float mr_acc = 0.f;
     const double ent_eps = (double)B * C.eps_mass;
-    int T = 0;                                      // sub-tiles handed to the MMA warp so far
-    for (int64_t tile0 = lo; tile0 < hi; tile0 += kTcMacro) {
-      const int count = (int)((hi - tile0 < kTcMacro) ? hi - tile0 : kTcMacro);
+    unsigned char* const sb = smem + (size_t)team * pl.stage;          // this team's stage
+    const uint32_t bar_full = smem_u32(&s_bar[team]), bar_empty = smem_u32(&s_bar[2 + team]);
+
+    int T0 = 0;                                     // sub-tile index of the macro tile's first sub-tile (always even)
+    int my_subs = 0;                                // sub-tiles this team has handed over so far
+    for (int64_t tile0 = lo; tile0 < hi; tile0 += macro) {
+      const int count = (int)((hi - tile0 < macro) ? hi - tile0 : macro);
       cp_async_wait_all();
       bar_producers();          // raw rows landed; every warp is done with the previous macro tile's s_dq / s_pw
       // ======================================= front: one point per thread =======================================================
-      {
+      if (tid < macro) {
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
         float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < count) {
@@ -327,33 +340,31 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
           } else {
             const float* base = reinterpret_cast<const float*>(s_in);
             const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)tid * 4);
-            w_sel = (double)base[(size_t)kTcMacro * 4 + tid];
+            w_sel = (double)base[(size_t)kTcMacroMax * 4 + tid];
             point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
           }
           const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
           const double w_desk = w_sel * (double)o.w_time;
-          CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
-          CERT(GCL_CS_ROWS) += 1.0;
+          c_wsel += w_sel; c_wsel2 += w_sel * w_sel; c_wdesk += w_desk; c_rows += 1.0;
           d0 = o.d[0]; d1 = o.d[1]; d2 = o.d[2];
           pw = make_float4(o.p0[0], o.p0[1], o.p0[2], (float)(w_desk * lam));
         }
-        float* dq = reinterpret_cast<float*>(&s_dq[0][0]) + (size_t)(tid >> 2) * 16 + (tid & 3);
+        float* dq = reinterpret_cast<float*>(&s_dq[0][0]) + (size_t)(tid >> 2) * 12 + (tid & 3);
         dq[0] = d0; dq[4] = d1; dq[8] = d2;
         s_pw[tid] = pw;
       }
       bar_producers();
-      prefetch_tile(tile0 + kTcMacro);
+      prefetch_tile(tile0 + macro);
       TCT(1);   // row wait + front end
       const int n_sub = (count + kTcSub - 1) / kTcSub;
-      for (int st = 0; st < n_sub; ++st, ++T) {
-        const int stage = T & 1;
-        unsigned char* sb = smem + (size_t)stage * pl.stage;
-        if (T >= 2) { mbar_wait(smem_u32(&s_bar[2 + stage]), par_empty[stage]); par_empty[stage] ^= 1u; }   // sub-tile T - 2 is through the tensor core
+      for (int st = team; st < n_sub; st += 2, ++my_subs) {
+        const int T = T0 + st;
+        if (my_subs >= 1) { mbar_wait(bar_empty, par_empty); par_empty ^= 1u; }   // this team's previous sub-tile is through the tensor core
         TCT(2);   // stage wait
         if (drained < (T >> kTcGroupLog2) && (T & kTcGroupMask) >= 2) drain(drained++);
         TCT(3);   // drain
         // ===================================== phase A: exponentials of this warp's 4 points x this lane's bins ===========================
-        const int quad = st * (kTcSub / 4) + warp;
+        const int quad = st * (kTcSub / 4) + wq;
         const float4 DX = s_dq[quad][0], DY = s_dq[quad][1], DZ = s_dq[quad][2];
         const float2 dx01 = make_float2(DX.x, DX.y), dx23 = make_float2(DX.z, DX.w), dy01 = make_float2(DY.x, DY.y), dy23 = make_float2(DY.z, DY.w);
         const float2 dz01 = make_float2(DZ.x, DZ.y), dz23 = make_float2(DZ.z, DZ.w);
@@ -433,9 +444,9 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
           // v index held by lane l: bit4 -> +4 (S instead of Z), bit3 -> +2, bit2 -> +1: lanes 0..15 hold Z of point (l >> 2),
           // lanes 16..31 hold S of point (l >> 2) & 3; the maximum of point p sits in the lanes with (bit4, bit3) = (p >> 1, p & 1)
           const float Zp = __shfl_sync(0xffffffffu, sumv, sc_pt << 2);
-          const int p = 4 * warp + sc_pt;                       // point of the sub-tile
+          const int p = 4 * wq + sc_pt;                         // point of the sub-tile
           const float4 bq = s_pw[st * kTcSub + p];
-          const float* dqp = s_dq_f + (size_t)quad * 16 + sc_pt;
+          const float* dqp = s_dq_f + (size_t)quad * 12 + sc_pt;
           const float a_x = dqp[0], a_y = dqp[4], a_z = dqp[8];
           const float invZ = __frcp_rn(Zp);
           const float wn = bq.w * invZ;
@@ -479,29 +490,21 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
         }
         TCT(6);   // scale
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this thread's st.shared -> visible to the tensor core's async proxy
-        mbar_arrive(smem_u32(&s_bar[stage]));                            // ... and handed to the MMA warp (256 arrivals complete the phase)
+        mbar_arrive(bar_full);                                           // ... and handed to the MMA warp (the team's 256 arrivals complete the phase)
         TCT(7);   // proxy fence + arrive
       }
+      T0 += n_sub;
     }
-    CERT(GCL_CS_SUM_ENTROPY) = ent_acc;
-    CERT(GCL_CS_MAX_RESP) = (double)mr_acc;
     // --- whatever has not been drained yet (the MMA warp commits the last, possibly partial, group itself) ---------------------------------
-    const int groups = (T + kTcGroupMask) >> kTcGroupLog2;
+    const int groups = (T0 + kTcGroupMask) >> kTcGroupLog2;
     while (drained < groups) drain(drained++);
-    if (owns) {
-#pragma unroll
-      for (int r = 0; r < NREP; ++r) {
-        const int b0 = half * (NPAD / 2) + 8 * r + 2 * cpair;
-        if (b0 < B) part[(size_t)my_moment * B + b0] = acc[r][0];
-        if (b0 + 1 < B) part[(size_t)my_moment * B + b0 + 1] = acc[r][1];
-      }
-    }
   }
 
-  // --- certificate scalars of this CTA (as in scan_moments_fused_kernel) -----------------------------------------------------------------
+  // --- the fp64 record of this CTA -> its partial record; certificate scalars (as in scan_moments_fused_kernel) ----------------------------
+  double cert[GCL_NCERT] = {c_wraw, c_wsel, c_wsel2, c_wdesk, ent_acc, (double)mr_acc, c_rows, 0.0};
 #pragma unroll
   for (int k = 0; k < GCL_NCERT; ++k) {
-    double v = CERT(k);
+    double v = cert[k];
     for (int o = 16; o > 0; o >>= 1) {
       const double other = __shfl_xor_sync(0xffffffffu, v, o);
       v = (k == GCL_CS_MAX_RESP) ? fmax(v, other) : v + other;
@@ -510,13 +513,16 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  for (int i = tid; i < GCL_NM * B; i += kTcNT) {
+    const int k = i / B, b = i - k * B;
+    part[i] = s_rec[(size_t)k * NPAD + b];
+  }
   if (tid < GCL_NCERT) {
     const int src = (tid == GCL_CS_SUM_W_RAW && stride == 1) ? GCL_CS_SUM_W_SEL : tid;
     double v = s_red[0][src];
     for (int w = 1; w < kTcNT / 32; ++w) v = (src == GCL_CS_MAX_RESP) ? fmax(v, s_red[w][src]) : v + s_red[w][src];
     part[(size_t)GCL_NM * B + tid] = v;
   }
-#undef CERT
 #ifdef GCL_K1_TRACE
   TCT(11);  // tail: last drains, write-out, certificates
   if ((tid == 0 || tid == 64) && blockIdx.x == 1 && blockIdx.y == 0)
