@@ -39,8 +39,9 @@ REF_SAMPLE_POINTS = 1 << 16                                         # points of 
 # capture summarised in profiles/ (None until captured)
 TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.095488e6 + 8.889856e6, "fp32c": None}
 # the same for one launch of the headline workload (1M x 256, one GPU); filled from profiles/r2_*.md once captured
-HEAD_TRAFFIC_BYTES_PER_LAUNCH = {"fp64": None, "fp32c": None}
-HEAD_TRAFFIC_SOURCE = "profiles/ (ncu --set full capture of one scan_moments launch of the 1M x 256 cloud); None = not captured for this build"
+HEAD_TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 42047488, "fp32c": 21088512}   # dram__bytes_read.sum + dram__bytes_write.sum
+HEAD_TRAFFIC_SOURCE = ("profiles/r2_scan_moments_fp64_1Mx256.md, r2_scan_moments_fp32c_1Mx256.md (ncu --set full capture of one scan_moments launch of this "
+                       "workload: 1.003x / 1.006x the algorithmic bytes)")
 TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch; the "
                   "stride-4 gather of 24-byte rows touches every 32-byte sector, hence ~2.3x the algorithmic bytes)")
 

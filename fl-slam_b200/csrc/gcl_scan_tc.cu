@@ -533,8 +533,12 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 bool tc_path_supported(int n_bins, int precision, int fixed_shift) {
-  static const bool enabled = !(getenv("GCL_K1_TC") && atoi(getenv("GCL_K1_TC")) == 0);
-  return enabled && precision == GCL_F32C && n_bins >= 1 && n_bins <= 256 && (fixed_shift & 1);
+  // GCL_K1_TC: 0 = never, 2 = whenever the kernel can (any bin count up to 256), default = where it wins.  The instruction stream of the
+  // tensor core costs the same ~21-24 cycles per point at 48, 128 and 256 bins (profiles/r2_umma_probe.md), the CUDA-core sums scale with
+  // the bins: measured cross-over between 128 bins (CUDA cores 191 us, tensor cores 213 us per 1 M points) and 256 (370 / 300 us)
+  static const int mode = getenv("GCL_K1_TC") ? atoi(getenv("GCL_K1_TC")) : 1;
+  if (mode == 0 || precision != GCL_F32C || n_bins < 1 || n_bins > 256 || !(fixed_shift & 1)) return false;
+  return mode == 2 || n_bins > 128;
 }
 
 template <int NREP>

@@ -1,0 +1,26 @@
+"""The tensor-core fp32c kernel at EVERY bin count it supports (48-, 128- and 256-column variants).
+
+By default the library routes fp32c scans to the tensor-core kernel only where it is the faster one (more than 128 bins, see
+tc_path_supported in csrc/gcl_scan_tc.cu); the switch GCL_K1_TC is read once per process, so the fp32c parity cases are re-run here
+in a child process with GCL_K1_TC=2 (tensor cores wherever the kernel can) and with GCL_K1_TC=0 (CUDA cores everywhere).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("mode", ["2", "0"])
+def test_fp32c_parity_with_the_kernel_choice_forced(mode):
+    pytest.importorskip("torch")
+    env = dict(os.environ, GCL_K1_TC=mode)
+    sel = "fp32c and (fused_moments_vs_oracle or fused_pipeline_against_reference_goldens or bit_reproducible or degenerate_scans)"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-k", sel,
+                        "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

@@ -25,7 +25,15 @@ WANT = [
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe % of peak"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe % of peak"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe cycles active %"),
+    ("sm__ops_path_tensor_src_tf32_dst_fp32.avg.pct_of_peak_sustained_elapsed", "tensor ops tf32 % of peak"),
+    ("sm__ops_path_tensor_src_bf16_dst_fp32.avg.pct_of_peak_sustained_elapsed", "tensor ops bf16 % of peak"),
+    ("smsp__sass_inst_executed_op_utcmma.sum", "UTCMMA instructions"),
+    ("smsp__sass_inst_executed_op_tmem_ldt.sum", "LDTM instructions"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts of the tensor core (operand reads) % of peak"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts (LSU)"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts (all)"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "smem load bank conflicts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "smem store bank conflicts"),
     ("smsp__sass_inst_executed_op_local_st.sum", "local (spill) stores"),

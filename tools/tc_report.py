@@ -84,7 +84,7 @@ if __name__ == "__main__":
         measure()
         sys.exit(0)
     rows = {}
-    for label, val in (("tensor-core kernel", "1"), ("CUDA-core kernel (GCL_K1_TC=0)", "0")):
+    for label, val in (("tensor-core kernel (GCL_K1_TC=2: every bin count)", "2"), ("CUDA-core kernel (GCL_K1_TC=0)", "0")):
         env = dict(os.environ, GCL_K1_TC=val)
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=900)
         line = [l for l in p.stdout.splitlines() if l.startswith("TCREPORT ")]
