@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fl_slam_b200 as g  # noqa: E402
 
-names = ["prologue", "row wait + front", "stage wait", "drain", "phase A", "barrier A", "scale", "proxy fence + arrive", "-", "-", "-", "tail"]
+names = ["prologue", "row wait + front", "stage wait", "drain", "phase A", "reduction", "scale", "proxy fence + arrive", "-", "-", "-", "tail"]
 for n, bins, cap in ((1 << 20, 256, 1 << 20), (1 << 20, 48, 1 << 20)):
     sc = g.synth.make_scan(n, seed=1238, dense=True)
     pl = g.LidarEvidencePipeline(n_bins=bins, tau=g.synth.DEFAULT_TAU, precision="fp32c", n_points_cap=cap, lidar_origin=sc.lidar_origin)
@@ -24,7 +24,7 @@ for n, bins, cap in ((1 << 20, 256, 1 << 20), (1 << 20, 48, 1 << 20)):
     g._abi.lib.gcl_debug_tc_trace.restype = C.c_int
     rc = g._abi.lib.gcl_debug_tc_trace(out)
     rows = n // ctas
-    for who, off in (("thread 0", 0), ("thread 64", 12)):
+    for who, off in (("thread 0 (team 0)", 0), ("thread 256 (team 1)", 12)):
         v = [out[off + i] for i in range(12)]
         tot = sum(v)
         print(f"{n} x {bins}, {who}: total {tot} cycles for ~{rows} rows = {tot / rows:.1f} per point, {tot / (rows / 32):.0f} per sub-tile")
