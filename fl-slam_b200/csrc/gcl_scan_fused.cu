@@ -268,7 +268,7 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
   off = (off + 15) & ~(size_t)15;
   p.o_rows = off; off += (size_t)TP * kRowPitch * tsz;
-  p.o_in = off;   off += (size_t)TP * 5 * 8;
+  p.o_in = off;   off += (size_t)(TP + 2) * 5 * 8;                 // raw rows of a tile (+ 2: a bulk copy starts at an even row)
   p.o_etile = off;
   size_t et = (size_t)TP * p.EP * tsz;
   const size_t stage = (size_t)(kNT / L) * kKC * (size_t)(G * L) * tsz;
@@ -300,8 +300,13 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   // the job record is read all through the kernel (array pointers at every prefetch, times and twist at every front end): keep
   // it in shared memory instead of going back to global memory for every field
   __shared__ gcl_job s_job;
+  __shared__ __align__(8) uint64_t s_mbar;          // completion of the bulk copies of a tile's raw rows
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const gcl_job& J = s_job;
   const ScanConst& C = P.c;
@@ -315,7 +320,10 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   const int64_t sel_begin = J.sel_begin;
   const int64_t sel_end = (J.sel_end < 0 || J.sel_end > n_sel_total) ? n_sel_total : J.sel_end;
   const int64_t rows = sel_end > sel_begin ? sel_end - sel_begin : 0;
-  const int64_t rpc = (rows + gridDim.x - 1) / gridDim.x;
+  // rows per CTA; even for contiguous float64 rows, so that every CTA of a job that starts at an even row starts at one too (16-byte
+  // aligned bulk copies of 24-byte and 8-byte rows)
+  const int64_t rpc0 = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t rpc = (P.layout == GCL_LAYOUT_REF_F64 && stride == 1) ? ((rpc0 + 1) & ~(int64_t)1) : rpc0;
   const int64_t lo0 = sel_begin + (int64_t)blockIdx.x * rpc;
   const int64_t lo = lo0 < sel_end ? lo0 : sel_end;
   const int64_t hi = (lo + rpc < sel_end) ? lo + rpc : sel_end;
@@ -428,8 +436,27 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     acc.zero();
   };
 
-  // raw rows of tile [t0, t0 + TP) -> s_in, asynchronously (one row per thread of the front group)
+  // raw rows of tile [t0, t0 + TP) -> s_in, asynchronously.  Contiguous float64 rows (no PointBudget stride: the dense clouds) go as three
+  // bulk copies issued by one thread -- points, timestamps, weights, an even number of rows from the CTA's even first row (16-byte
+  // alignment), arrays of rows in shared memory, completion counted by an mbarrier.  Everything else (strided gather, packed rows,
+  // unaligned arrays or an odd first row, the job's very last tile when its row count is odd) takes one row per thread with cp.async.
+  const bool bulk_cta = P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
+                        ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0;
+  auto tile_is_bulk = [&](int64_t t0) -> bool {      // only the last tile of a CTA can fail this: the parity of the barrier is the tile index's
+    return bulk_cta && t0 < hi && t0 + ((((hi - t0 < TP) ? hi - t0 : TP) + 1) & ~(int64_t)1) <= sel_end;
+  };
   auto prefetch_tile = [&](int64_t t0) {
+    if (tile_is_bulk(t0)) {
+      if (tid == 0) {
+        const uint32_t n = (uint32_t)((((hi - t0 < TP) ? hi - t0 : TP) + 1) & ~(int64_t)1);   // even number of rows
+        const uint32_t mb = smem_u32(&s_mbar);
+        mbar_arrive_expect_tx(mb, n * 40u);
+        bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, n * 24u, mb);
+        bulk_copy_g2s(s_in + (size_t)(TP + 2) * 3, static_cast<const double*>(J.timestamps) + t0, n * 8u, mb);
+        bulk_copy_g2s(s_in + (size_t)(TP + 2) * 4, static_cast<const double*>(J.weights) + t0, n * 8u, mb);
+      }
+      return;
+    }
     const int64_t srow = t0 + tid;
     if (tid >= TP || srow >= hi) return;
     const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
@@ -454,7 +481,9 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 
   for (int64_t tile0 = lo; tile0 < hi; tile0 += TP) {
     const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
-    cp_async_wait_all();
+    const bool from_bulk = tile_is_bulk(tile0);
+    if (from_bulk) mbar_wait(smem_u32(&s_mbar), (uint32_t)(((tile0 - lo) / TP) & 1));
+    else cp_async_wait_all();
     __syncthreads();  // raw rows landed; previous tile's phase B (e-tile, rows) is finished
     // ======================================= front =============================================================
     T q0 = 0, q1 = 0, q2 = 0, d0 = 0, d1 = 0, d2 = 0, wq = 0;
@@ -465,9 +494,14 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       const int64_t srow = tile0 + tid;   // selected-row index; raw index = srow * stride (PointBudget gather)
       double w_sel, w_time;
       if (P.layout == GCL_LAYOUT_REF_F64) {
-        const double* in = s_in + (size_t)tid * 5;  // {x, y, z, t, w}
-        const double px = in[0], py = in[1], pz = in[2], tt = in[3];
-        w_sel = in[4];
+        double px, py, pz, tt;
+        if (from_bulk) {                            // arrays of rows
+          px = s_in[(size_t)tid * 3]; py = s_in[(size_t)tid * 3 + 1]; pz = s_in[(size_t)tid * 3 + 2];
+          tt = s_in[(size_t)(TP + 2) * 3 + tid]; w_sel = s_in[(size_t)(TP + 2) * 4 + tid];
+        } else {
+          const double* in = s_in + (size_t)tid * 5;  // {x, y, z, t, w}
+          px = in[0]; py = in[1]; pz = in[2]; tt = in[3]; w_sel = in[4];
+        }
         if (sizeof(T) == 8) {
           PointOut64 o;
           point_front64_fast(J, C, tconst, s_tab, px, py, pz, tt, o);

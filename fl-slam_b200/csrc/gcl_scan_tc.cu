@@ -15,7 +15,9 @@
 //   B = E tile, n_pad bins x 64: head = bf16(e) (round to nearest), remainder = bf16(e - head): 16-17 significant bits of e.  One lane
 //       owns a bin row and writes the 16 bytes of its warp's quad with ONE conflict-free 128-bit store.
 //   A = Phi^T, 128 rows x 64: row 32 q + 8 c + j holds part c (0, 1, 2 = three bf16 pieces, 24 bits together) of moment 5 q + j, written
-//       twice per quad (against the head and against the remainder of e); all other rows stay zero.
+//       twice per quad (against the head and against the remainder of e); all other rows stay zero.  (Two parts only -- 16-17 bits, like
+//       e -- were measured: 244 -> 238 us per 1 M x 256 launch, but kappa of the small "exact_fit" golden scan moves to 1.09e-5 of the
+//       reference, over the 1e-5 bar: bins that a handful of points dominate see the element-wise error of Phi.  Three parts stay.)
 //   D = 128 x n_pad fp32 in tensor memory: 4 x tcgen05.mma kind::f16 (K = 16 each) per sub-tile; rows 32 q + {j, 8 + j, 16 + j} are the
 //       three parts of moment 5 q + j and are added when the accumulators are drained.
 // The first layout (head of e as tf32 + remainder as bf16 in two tiles, 6 instructions per sub-tile) moved 6 bytes per (point, bin) pair
@@ -52,7 +54,6 @@ constexpr int kTcGroupMask = (1 << kTcGroupLog2) - 1;
 constexpr int kTcRecPad = 8;     // the fp64 record's row pitch is n_pad + 8 doubles: moment rows k, k + 1 fall in different halves of the
                                  // 128-byte bank window, so the 128-bit read-modify-writes of a drain are conflict free
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t sw128(uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); }
 // shared-memory matrix descriptor (K-major): start address, leading byte offset 16, stride between 8-row groups, version 1, layout
 // (2 = SWIZZLE_128B)
@@ -71,14 +72,6 @@ __device__ __forceinline__ void mma_bf16(uint32_t d, uint64_t a, uint64_t b, uin
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n"
-               :: "r"(mbar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory"); }
 // 16 lanes x 256 bits: thread t receives (lane t/4, columns 2(t%4), 2(t%4)+1) in r0, r1 and (lane t/4 + 8, same columns) in r2, r3
 __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
@@ -538,12 +531,13 @@ __global__ void __launch_bounds__(kTcNT, 1) scan_moments_tc_kernel(const __grid_
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 bool tc_path_supported(int n_bins, int precision, int fixed_shift) {
-  // GCL_K1_TC: 0 = never, 2 = whenever the kernel can (any bin count up to 256), default = where it wins.  The instruction stream of the
-  // tensor core costs the same ~21-24 cycles per point at 48, 128 and 256 bins (profiles/r2_umma_probe.md), the CUDA-core sums scale with
-  // the bins: measured cross-over between 128 bins (CUDA cores 191 us, tensor cores 213 us per 1 M points) and 256 (370 / 300 us)
+  // GCL_K1_TC: 0 = never, 2 = whenever the kernel can (any bin count up to 256), default = where it wins.  The tensor-core kernel's cost
+  // per point hardly depends on the bins (the instruction stream of the tensor core, the normaliser reduction and the Phi rows are per
+  // point), the CUDA-core sums scale with them.  Measured per 1 M points (tools/tc_report.py): 256 bins 244 us against 369 us on the CUDA
+  // cores, 128 bins 179 / 191 us, 48 bins (200 scans x 7500 rows) 267 / 218 us -- the cross-over is just below 128 bins.
   static const int mode = getenv("GCL_K1_TC") ? atoi(getenv("GCL_K1_TC")) : 1;
   if (mode == 0 || precision != GCL_F32C || n_bins < 1 || n_bins > 256 || !(fixed_shift & 1)) return false;
-  return mode == 2 || n_bins > 128;
+  return mode == 2 || n_bins >= 128;
 }
 
 template <int NREP>
