@@ -23,6 +23,10 @@
 #include "gcl_internal.cuh"
 #include "gcl_point.cuh"
 
+#ifndef GCL_BULK_ON
+#define GCL_BULK_ON 1   // 0: every tile takes the per-thread cp.async path (A/B builds)
+#endif
+
 namespace gcl {
 
 constexpr int kNT = 256;       // threads per CTA
@@ -268,7 +272,7 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
   off = (off + 15) & ~(size_t)15;
   p.o_rows = off; off += (size_t)TP * kRowPitch * tsz;
-  p.o_in = off;   off += (size_t)(TP + 2) * 5 * 8;                 // raw rows of a tile (+ 2: a bulk copy starts at an even row)
+  p.o_in = off;   off += (size_t)TP * 5 * 8;
   p.o_etile = off;
   size_t et = (size_t)TP * p.EP * tsz;
   const size_t stage = (size_t)(kNT / L) * kKC * (size_t)(G * L) * tsz;
@@ -301,6 +305,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   // it in shared memory instead of going back to global memory for every field
   __shared__ gcl_job s_job;
   __shared__ __align__(8) uint64_t s_mbar;          // completion of the bulk copies of a tile's raw rows
+  __shared__ long long s_bulk_lo;                   // first row of this CTA when its full tiles go by bulk copy, else -1 (kept in shared memory:
+                                                    // the <double, 4> variant has no register to spare across phase B)
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
   if (tid == 0) {
@@ -437,23 +443,24 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   };
 
   // raw rows of tile [t0, t0 + TP) -> s_in, asynchronously.  Contiguous float64 rows (no PointBudget stride: the dense clouds) go as three
-  // bulk copies issued by one thread -- points, timestamps, weights, an even number of rows from the CTA's even first row (16-byte
-  // alignment), arrays of rows in shared memory, completion counted by an mbarrier.  Everything else (strided gather, packed rows,
-  // unaligned arrays or an odd first row, the job's very last tile when its row count is odd) takes one row per thread with cp.async.
-  const bool bulk_cta = P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
-                        ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0;
-  auto tile_is_bulk = [&](int64_t t0) -> bool {      // only the last tile of a CTA can fail this: the parity of the barrier is the tile index's
-    return bulk_cta && t0 < hi && t0 + ((((hi - t0 < TP) ? hi - t0 : TP) + 1) & ~(int64_t)1) <= sel_end;
-  };
+  // bulk copies issued by one thread -- points, timestamps, weights of a full tile from the CTA's even first row (16-byte alignment),
+  // arrays of rows in shared memory, completion counted by an mbarrier.  Everything else (strided gather, packed rows, unaligned arrays
+  // or an odd first row, a CTA's last partial tile) takes one row per thread with cp.async.
+  if (tid == 0)
+    s_bulk_lo = (GCL_BULK_ON && P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
+                 ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0)
+                    ? (long long)lo : -1ll;
+  __syncthreads();
+  // full tiles only: a CTA's last, partial tile takes the per-thread path (so the barrier's phase parity is the tile index's)
+  auto tile_is_bulk = [&](int64_t t0) -> bool { return t0 + TP <= hi && s_bulk_lo >= 0; };
   auto prefetch_tile = [&](int64_t t0) {
     if (tile_is_bulk(t0)) {
       if (tid == 0) {
-        const uint32_t n = (uint32_t)((((hi - t0 < TP) ? hi - t0 : TP) + 1) & ~(int64_t)1);   // even number of rows
         const uint32_t mb = smem_u32(&s_mbar);
-        mbar_arrive_expect_tx(mb, n * 40u);
-        bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, n * 24u, mb);
-        bulk_copy_g2s(s_in + (size_t)(TP + 2) * 3, static_cast<const double*>(J.timestamps) + t0, n * 8u, mb);
-        bulk_copy_g2s(s_in + (size_t)(TP + 2) * 4, static_cast<const double*>(J.weights) + t0, n * 8u, mb);
+        mbar_arrive_expect_tx(mb, (uint32_t)TP * 40u);
+        bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, (uint32_t)TP * 24u, mb);
+        bulk_copy_g2s(s_in + (size_t)TP * 3, static_cast<const double*>(J.timestamps) + t0, (uint32_t)TP * 8u, mb);
+        bulk_copy_g2s(s_in + (size_t)TP * 4, static_cast<const double*>(J.weights) + t0, (uint32_t)TP * 8u, mb);
       }
       return;
     }
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   for (int64_t tile0 = lo; tile0 < hi; tile0 += TP) {
     const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
     const bool from_bulk = tile_is_bulk(tile0);
-    if (from_bulk) mbar_wait(smem_u32(&s_mbar), (uint32_t)(((tile0 - lo) / TP) & 1));
+    if (from_bulk) mbar_wait(smem_u32(&s_mbar), (uint32_t)(((tile0 - s_bulk_lo) >> (__ffs(TP) - 1)) & 1));
     else cp_async_wait_all();
     __syncthreads();  // raw rows landed; previous tile's phase B (e-tile, rows) is finished
     // ======================================= front =============================================================
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
         double px, py, pz, tt;
         if (from_bulk) {                            // arrays of rows
           px = s_in[(size_t)tid * 3]; py = s_in[(size_t)tid * 3 + 1]; pz = s_in[(size_t)tid * 3 + 2];
-          tt = s_in[(size_t)(TP + 2) * 3 + tid]; w_sel = s_in[(size_t)(TP + 2) * 4 + tid];
+          tt = s_in[(size_t)TP * 3 + tid]; w_sel = s_in[(size_t)TP * 4 + tid];
         } else {
           const double* in = s_in + (size_t)tid * 5;  // {x, y, z, t, w}
           px = in[0]; py = in[1]; pz = in[2]; tt = in[3]; w_sel = in[4];
