@@ -122,7 +122,8 @@ def make_stream(n_scans, seed0=1234 + 2):
 
 def head_config(tau, precision="fp64"):
     """The `config` both arms print (the reference arm times a bounded sample of the same cloud; it says so in cpu_baseline)."""
-    return {"workload": f"configs[3]: dense synthetic cloud, {HEAD_POINTS} points/scan, {HEAD_BINS} bins, 1 hypothesis, n_points_cap = n "
+    label = "configs[3]" if (HEAD_POINTS, HEAD_BINS) == (1 << 20, 256) else "configs[4]" if (HEAD_POINTS, HEAD_BINS) == (1 << 24, 1024) else "custom"
+    return {"workload": f"{label}: dense synthetic cloud, {HEAD_POINTS} points/scan, {HEAD_BINS} bins, 1 hypothesis, n_points_cap = n "
                         "(stride 1); resample -> deskew -> soft assign -> moment match -> Matrix Fisher -> planar translation",
             "n_points": HEAD_POINTS, "n_bins": HEAD_BINS, "n_hyp": 1, "tau": tau, "precision": precision}
 
@@ -478,7 +479,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: fused NVLink exchange kernel, or the NCCL all-gather route")
     ap.add_argument("--scans-per-step", type=int, default=SCANS_PER_STEP)
+    ap.add_argument("--head-points", type=int, default=HEAD_POINTS, help="points per scan of the sharded cloud (default = configs[3]; "
+                    "16777216 with --head-bins 1024 = configs[4], the extreme sweep)")
+    ap.add_argument("--head-bins", type=int, default=HEAD_BINS)
     args = ap.parse_args()
+    global HEAD_POINTS, HEAD_BINS
+    custom_head = (args.head_points, args.head_bins) != (HEAD_POINTS, HEAD_BINS)
+    HEAD_POINTS, HEAD_BINS = args.head_points, args.head_bins
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -511,7 +518,7 @@ def main():
     clocks = sampler.stop()
     roofline = head.pop("roofline")
     roofline["peak_source"] = peak_src
-    roofline["traffic"] = HEAD_TRAFFIC_BYTES_PER_LAUNCH.get(args.precision) if world == 1 else None
+    roofline["traffic"] = HEAD_TRAFFIC_BYTES_PER_LAUNCH.get(args.precision) if world == 1 and not custom_head else None
     roofline["traffic_source"] = HEAD_TRAFFIC_SOURCE
     ceiling = pair_ceiling(args.precision, clocks.get("sm_mhz") or 1965.0)
     roofline["pairs_per_sec"] = head["pairs_per_sec"] / world       # per GPU, like achieved
@@ -530,6 +537,9 @@ def main():
                                           rank=rank, world=world, peak_gbs=peak_gbs, precision=other, scans_per_step=args.scans_per_step,
                                           exchange=args.exchange, with_e2e=not args.no_e2e)
         o["roofline"]["compute_frac"] = (o["pairs_per_sec"] / world) / pair_ceiling(other, clocks.get("sm_mhz") or 1965.0)
+        o["roofline"]["compute_frac_note"] = ("pairs/s over the FMA-issue ceiling of the CUDA-core instruction mix (24 lane operations per pair); the "
+                                              "tensor-core kernel moves 19 of them to tcgen05 and is bound by the issue slots of what remains "
+                                              "(DESIGN.md, K1-TC)") if other == "fp32c" else "pairs/s over the FP64 FMA-issue ceiling (34 lane operations per pair)"
         extra[f"cfg4_1Mx256_{other}"] = o
         if world > 1 and args.exchange == "peer":
             n = sharding.bench_points_sharded(g, n_points=HEAD_POINTS, n_bins=HEAD_BINS, tau=tau, steps=max(3, args.steps // 2), warmup=args.warmup,

@@ -20,6 +20,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Dict, Optional, Tuple
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -434,6 +436,9 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
     err_flag = sh.px.error_flag() if sh.px is not None else 0
     del full
 
+    tc_mode = int(os.environ.get("GCL_K1_TC", "1"))
+    on_tc = precision == "fp32c" and n_bins <= 256 and tc_mode != 0 and (tc_mode == 2 or n_bins >= 128)     # tc_path_supported (gcl_scan_tc.cu)
+    k1_name = "scan_moments_tc_kernel (tcgen05)" if on_tc else "scan_moments_fused_kernel"
     out: Dict[str, object] = {
         "n_points": n_points, "n_bins": n_bins, "tau": tau, "precision": precision, "scaling": "strong",
         "sharding": "points" if world > 1 else "none", "exchange": sh.exchange if world > 1 else "none (1 rank: same fused kernel, no peers)",
@@ -445,7 +450,7 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
                        f"scan on the {reserve_sms} SMs left free") if overlapped else "none (one scan at a time)",
         "launches_per_step": int(launches_per_step), "launches_per_scan": launches_per_step / scans_per_step, "ctas_per_rank": ctas_run,
         "rows_per_rank": int(e - b), "input_copies_rotated": n_copies,
-        "roofline": {"bound": "hbm", "kernel": "scan_moments_fused_kernel", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+        "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                      "ms_per_launch": ms_k1, "algorithmic_bytes_per_launch": float(shard_bytes), "bytes_per_point": bpp,
                      "share_of_step": ms_k1 / ms_scan, "launches_per_step": scans_per_step, "per": "GPU (each rank's launch covers its own rows)"},
         "parity": {"vs_unsharded_max_rel": parity, "vs_unsharded_R_mf_rad": parity_rot, "vs_unsharded_t_wls_rel": parity_t,
