@@ -466,6 +466,7 @@ def bench_stream(args, g, synth, dev, rank, world, local_rank, tau, peak_gbs, pe
 
 
 def main():
+    global HEAD_POINTS, HEAD_BINS
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -483,7 +484,6 @@ def main():
                     "16777216 with --head-bins 1024 = configs[4], the extreme sweep)")
     ap.add_argument("--head-bins", type=int, default=HEAD_BINS)
     args = ap.parse_args()
-    global HEAD_POINTS, HEAD_BINS
     custom_head = (args.head_points, args.head_bins) != (HEAD_POINTS, HEAD_BINS)
     HEAD_POINTS, HEAD_BINS = args.head_points, args.head_bins
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

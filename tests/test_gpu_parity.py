@@ -194,8 +194,10 @@ def test_fused_pipeline_against_reference_goldens(g, ref_certs, name, precision,
     sb = ev.scan_bins(0)
     for k in ("N", "s_dir", "S_dir_scatter", "p_bar", "kappa_scan"):
         assert rel_err(H(getattr(sb, k)), gz["mm_" + k]) < tol, k
-    # Sigma_p = E[pp^T] - p_bar p_bar^T cancels a few digits; in fp32c it inherits the fp32 input rounding
-    assert rel_err(H(sb.Sigma_p), gz["mm_Sigma_p"]) < (1e-9 if precision == "fp64" else 2e-4)
+    # Sigma_p = E[pp^T] - p_bar p_bar^T cancels a few digits; in fp32c it inherits the fp32 input rounding.  The fp32c bars of the derived
+    # quantities below are ~5x what the worst golden achieves on either kernel (profiles/r2_fp32c_error_table.md: Sigma_p 2.0e-6,
+    # R_mf 9.9e-8 rad, L_rot 1.4e-7, t_wls 4.8e-6, L_trans 8.3e-6, L22 4.4e-6)
+    assert rel_err(H(sb.Sigma_p), gz["mm_Sigma_p"]) < (1e-9 if precision == "fp64" else 1e-5)
     certs = dict((n, (r, c, e)) for n, r, c, e in ev.certificates(0))
     ctol = 1e-9 if precision == "fp64" else 1e-5
     pb = cj["point_budget"]["cert"]
@@ -214,12 +216,12 @@ def test_fused_pipeline_against_reference_goldens(g, ref_certs, name, precision,
     for h in range(ev.n_hyp):
         _, mf, cmf, emf = ev.certificates(h)[4]
         _, pt, cpt, ept = ev.certificates(h)[5]
-        gtol = 1e-8 if precision == "fp64" else 1e-4
+        gtol = 1e-8 if precision == "fp64" else 1e-6
         assert geodesic(H(mf.R_mf), gz["hyp_R_mf"][h]) < gtol
-        assert rel_err(H(mf.L_rot), gz["hyp_L_rot"][h]) < 10 * tol
-        assert rel_err(H(pt.L_trans), gz["hyp_L_trans"][h]) < (1e-8 if precision == "fp64" else 5e-3)
-        assert rel_err(H(pt.t_wls), gz["hyp_t_wls"][h]) < (1e-8 if precision == "fp64" else 5e-3)
-        assert rel_err(H(ev.L_lidar(h)), gz["hyp_L22"][h]) < (1e-8 if precision == "fp64" else 5e-3)
+        assert rel_err(H(mf.L_rot), gz["hyp_L_rot"][h]) < (10 * tol if precision == "fp64" else tol)
+        assert rel_err(H(pt.L_trans), gz["hyp_L_trans"][h]) < (1e-8 if precision == "fp64" else 5e-5)
+        assert rel_err(H(pt.t_wls), gz["hyp_t_wls"][h]) < (1e-8 if precision == "fp64" else 5e-5)
+        assert rel_err(H(ev.L_lidar(h)), gz["hyp_L22"][h]) < (1e-8 if precision == "fp64" else 5e-5)
         assert cmf.approximation_triggers == ["MatrixFisherRotationEvidence"] and cpt.approximation_triggers == ["PlanarTranslationEvidence"]
 
 
