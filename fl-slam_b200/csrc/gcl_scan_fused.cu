@@ -284,7 +284,7 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
 
 #ifdef GCL_K1_TRACE
 __device__ long long g_k1_trace[16];
-#define K1T(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 7) { const long long n_ = clock64(); k1_acc[i] += n_ - k1_t; k1_t = n_; } } while (0)
+#define K1T(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && (blockIdx.y == 7 || gridDim.y == 1)) { const long long n_ = clock64(); k1_acc[i] += n_ - k1_t; k1_t = n_; } } while (0)
 extern "C" int gcl_debug_k1_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_k1_trace, sizeof(long long) * 16); }
 #else
 #define K1T(i) do { } while (0)
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   // it in shared memory instead of going back to global memory for every field
   __shared__ gcl_job s_job;
   __shared__ __align__(8) uint64_t s_mbar;          // completion of the bulk copies of a tile's raw rows
-  __shared__ long long s_bulk_lo;                   // first row of this CTA when its full tiles go by bulk copy, else -1 (kept in shared memory:
-                                                    // the <double, 4> variant has no register to spare across phase B)
+  __shared__ int s_lo32;                            // low word of this CTA's first row, and whether its full tiles go by bulk copy (kept in
+  __shared__ int s_bulk_on;                         // shared memory: the <double, 4> variant has no register to spare across phase B)
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
   if (tid == 0) {
@@ -442,28 +442,30 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     acc.zero();
   };
 
-  // raw rows of tile [t0, t0 + TP) -> s_in, asynchronously.  Contiguous float64 rows (no PointBudget stride: the dense clouds) go as three
-  // bulk copies issued by one thread -- points, timestamps, weights of a full tile from the CTA's even first row (16-byte alignment),
-  // arrays of rows in shared memory, completion counted by an mbarrier.  Everything else (strided gather, packed rows, unaligned arrays
-  // or an odd first row, a CTA's last partial tile) takes one row per thread with cp.async.
-  if (tid == 0)
-    s_bulk_lo = (GCL_BULK_ON && P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
-                 ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0)
-                    ? (long long)lo : -1ll;
+  // raw rows of tile [t0, t0 + TP) -> the tile's staging buffer, asynchronously.  Contiguous float64 rows (no PointBudget stride: the dense
+  // clouds) go as three bulk copies (TMA engine) issued by ONE thread -- points, timestamps, weights of a full tile from the CTA's even
+  // first row (16-byte alignment), arrays of rows in shared memory, completion counted by an mbarrier.  Issuing them costs that thread's
+  // warp ~400 cycles, so the thread is lane 0 of the LAST warp and the moment is the start of the previous tile's scale step, when only
+  // the first warps have work (measured with the issue on thread 0 after the front end: +2.3 % on the 1 M x 256 launch).  Everything
+  // else (strided gather, packed rows, unaligned arrays or an odd first row, a CTA's last partial tile) takes one row per thread with
+  // cp.async, after the front end.
+  if (tid == 0) {
+    s_lo32 = (int)lo;
+    s_bulk_on = (GCL_BULK_ON && P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
+                 ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0) ? 1 : 0;
+  }
   __syncthreads();
   // full tiles only: a CTA's last, partial tile takes the per-thread path (so the barrier's phase parity is the tile index's)
-  auto tile_is_bulk = [&](int64_t t0) -> bool { return t0 + TP <= hi && s_bulk_lo >= 0; };
-  auto prefetch_tile = [&](int64_t t0) {
-    if (tile_is_bulk(t0)) {
-      if (tid == 0) {
-        const uint32_t mb = smem_u32(&s_mbar);
-        mbar_arrive_expect_tx(mb, (uint32_t)TP * 40u);
-        bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, (uint32_t)TP * 24u, mb);
-        bulk_copy_g2s(s_in + (size_t)TP * 3, static_cast<const double*>(J.timestamps) + t0, (uint32_t)TP * 8u, mb);
-        bulk_copy_g2s(s_in + (size_t)TP * 4, static_cast<const double*>(J.weights) + t0, (uint32_t)TP * 8u, mb);
-      }
-      return;
-    }
+  auto tile_is_bulk = [&](int64_t t0) -> bool { return t0 + TP <= hi && s_bulk_on; };
+  auto prefetch_bulk = [&](int64_t t0) {            // one thread
+    const uint32_t mb = smem_u32(&s_mbar);
+    mbar_arrive_expect_tx(mb, (uint32_t)TP * 40u);
+    bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, (uint32_t)TP * 24u, mb);
+    bulk_copy_g2s(s_in + (size_t)TP * 3, static_cast<const double*>(J.timestamps) + t0, (uint32_t)TP * 8u, mb);
+    bulk_copy_g2s(s_in + (size_t)TP * 4, static_cast<const double*>(J.weights) + t0, (uint32_t)TP * 8u, mb);
+  };
+  auto prefetch_tile = [&](int64_t t0) {            // the per-thread path (all threads call it)
+    if (tile_is_bulk(t0)) return;
     const int64_t srow = t0 + tid;
     if (tid >= TP || srow >= hi) return;
     const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       cp_async4(base + (size_t)TP * 4 + tid, static_cast<const float*>(J.weights) + r);
     }
   };
-  prefetch_tile(lo);
+  if (tile_is_bulk(lo)) { if (tid == kNT - 32) prefetch_bulk(lo); } else prefetch_tile(lo);
   K1T(0);   // prologue: job record, atlas, exp table, raw-weight sum
 
   int pts_since_flush = 0;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   for (int64_t tile0 = lo; tile0 < hi; tile0 += TP) {
     const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
     const bool from_bulk = tile_is_bulk(tile0);
-    if (from_bulk) mbar_wait(smem_u32(&s_mbar), (uint32_t)(((tile0 - s_bulk_lo) >> (__ffs(TP) - 1)) & 1));
+    if (from_bulk) { if (tid < TP) mbar_wait(smem_u32(&s_mbar), (uint32_t)((((int)tile0 - s_lo32) >> (__ffs(TP) - 1)) & 1)); }   // only the front-end threads read the rows
     else cp_async_wait_all();
     __syncthreads();  // raw rows landed; previous tile's phase B (e-tile, rows) is finished
     // ======================================= front =============================================================
@@ -557,6 +559,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     __syncthreads();
     K1T(2);   // phase A
     // ======================================= scale =============================================================
+    if (tid == kNT - 32 && tile_is_bulk(tile0 + TP)) prefetch_bulk(tile0 + TP);   // the staging buffer is free since the front end; this warp idles here
     if (tid < count) {
       T Z = 0, S1 = 0, xmax = (T)-1.0e30;
       for (int a = 0; a < TA; ++a) {
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 #undef CERT
 #ifdef GCL_K1_TRACE
   K1T(7);   // certificate reduction
-  if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 7)
+  if (threadIdx.x == 0 && blockIdx.x == 1 && (blockIdx.y == 7 || gridDim.y == 1))
     for (int i = 0; i < 8; ++i) g_k1_trace[i] = k1_acc[i];
 #endif
 }

@@ -518,13 +518,61 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
             px.all_gather(ev.evidence, gathered)
         return ev
 
-    def step(_k):
+    def step_serial(_k):
         for _ in range(batches_per_step):
             one(it[0])
             it[0] += 1
 
+    # consecutive batches pipelined, as the point-sharded scans are: the moment pass of batch k + 1 (one internal stream, a few SMs left
+    # free) runs beside the O(B) tail of batch k -- reduce_finalize (one CTA per hypothesis), map-derived statistics, pose evidence, the
+    # gather of the records -- on a second, high-priority stream.  Two buffer sets alternate.
+    from . import _abi
+    Hl = hi - lo
+    sms = int(_abi.lib.gcl_device_sm_count(pl.handle))
+    reserve = 8
+    _, n_sel = pl.selected_rows(res[0].n_raw, cap)
+    ctas_p = max(1, min(pl.plan_ctas(Hl, n_sel), (sms - reserve) // max(1, Hl)))
+    s_k1, s_rest = torch.cuda.Stream(device=pl.device, priority=0), torch.cuda.Stream(device=pl.device, priority=-1)
+    gathered2 = [gathered, torch.empty_like(gathered)] if gathered is not None else [None, None]
+    ov = {"free": [None, None], "turn": 0, "last": None}
+
+    def one_pipelined(i):
+        slot = ov["turn"] & 1
+        ov["turn"] += 1
+        buf = pl._buffers(Hl, ctas_p, slot=slot)
+        jd = jobs_dev[i % n_rot]
+        if ov["free"][slot] is not None:
+            s_k1.wait_event(ov["free"][slot])                 # the tail that read this buffer set two batches ago is done
+        with torch.cuda.stream(s_k1):
+            pl.launch_moments(jd, None, Hl, ctas_p, res[i % n_rot].layout, buf["partials"])
+            ready = s_k1.record_event()
+        s_rest.wait_event(ready)
+        with torch.cuda.stream(s_rest):
+            pl.launch_finalize(buf["partials"], ctas_p, pl.rec, pl.rec * ctas_p, jd, None, Hl, True, buf["reduced"], buf["stats"])
+            pl.launch_chain(buf["stats"], 1, Hl, ms, buf["map_derived"], poses_dev, None, buf["evidence"])
+            if px is not None:
+                px.all_gather(buf["evidence"], gathered2[slot])
+            ov["free"][slot] = ov["last"] = s_rest.record_event()
+        return buf
+
+    def step(_k):
+        cur = torch.cuda.current_stream(pl.device)
+        s_k1.wait_stream(cur); s_rest.wait_stream(cur)
+        for _ in range(batches_per_step):
+            one_pipelined(it[0])
+            it[0] += 1
+        cur.wait_event(ov["last"])
+
     ms_step, per = _time_steps(step, steps, warmup, world)
+    ms_serial_step, _ = _time_steps(step_serial, max(2, steps // 2), 1, world)
     ms_batch = ms_step / batches_per_step
+    # the pipelined batch equals the batch run on one stream, bit for bit (same kernels, same grids per job are NOT guaranteed: the CTA
+    # count per job differs when SMs are reserved, which regroups the fp64 additions -- so compare to 1e-12, not bitwise)
+    torch.cuda.synchronize()
+    bufp = one_pipelined(0)
+    torch.cuda.current_stream(pl.device).wait_event(ov["last"])
+    torch.cuda.synchronize()
+    ev_p = bufp["evidence"].clone()
     # parity: hypothesis h of the batch against the same hypothesis run alone; gathered records bit-identical on every rank
     ev = one(0)
     torch.cuda.synchronize()
@@ -533,8 +581,13 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
         single = pl.run_resident(res[0], xis[h:h + 1], poses_dev[h - lo:h - lo + 1], ms)
         worst = max(worst, float((single.evidence[0] - ev.evidence[h - lo]).abs().max() / max(1e-300, float(single.evidence[0].abs().max()))))
     identical = _bits_identical_across_ranks(gathered.reshape(-1), world) if gathered is not None else True
+    pipe_vs_serial = float((ev_p - ev.evidence).abs().max() / max(1e-300, float(ev.evidence.abs().max())))
     out = {"n_points": n_points, "n_points_cap": cap, "n_bins": n_bins, "n_hyp": n_hyp, "precision": precision,
            "sharding": "hypotheses" if world > 1 else "none", "ms_per_batch": ms_batch, "batches_per_step": batches_per_step,
+           "ms_per_batch_one_at_a_time": ms_serial_step / batches_per_step,
+           "pipelining": f"consecutive batches pipelined on two streams: scan_moments on {ctas_p} CTAs per hypothesis x {Hl} hypotheses, the "
+                         f"finalise + evidence + gather tail of the previous batch on the {reserve} SMs left free; pipelined vs one-at-a-time "
+                         f"evidence max rel {pipe_vs_serial:.1e}",
            "hypothesis_scans_per_sec": n_hyp / (ms_batch * 1e-3), "points_per_sec": n_hyp * n_points / (ms_batch * 1e-3),
            "result_gather": "peer exchange (one launch, NVLink stores + flags)" if px is not None else "none",
            "parity": {"batch_vs_single_hypothesis_max_rel": worst, "gathered_bit_identical_across_ranks": bool(identical),
