@@ -10,7 +10,8 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libgcl_b200.so")
+# GCL_LIB: another build of the same library (A/B runs of kernel variants, trace builds); never a different implementation
+LIB_PATH = os.environ.get("GCL_LIB") or os.path.join(_PKG_DIR, "libgcl_b200.so")
 
 GCL_F64, GCL_F32C = 0, 1
 GCL_LAYOUT_REF_F64, GCL_LAYOUT_PACKED_F32 = 0, 1

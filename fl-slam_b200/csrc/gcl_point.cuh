@@ -69,10 +69,12 @@ __device__ __forceinline__ float expo(float x) { return fast_exp2(x); }
 __device__ __forceinline__ double expo(double x) { return exp(x); }
 
 // ---- fp64 exp for arguments in units of 1/128 octave ---------------------------------------------------------------------
-// 2^(t/128) = 2^k * T[j] * exp(r ln2/128), n = rint(t) = 128 k + j, r = t - n in [-1/2, 1/2].  T[j] = 2^(j/128) lives in
-// shared memory; the degree-4 polynomial has a truncation error of 1.2e-15 relative (the parity bar for the moments is
-// 1e-9).  GUARD: arguments below 2^-1000 return 0 and arguments above 2^1015 are clamped; without it the caller guarantees
-// |t| < 128000 (fixed softmax shift with 2/tau <= 600).
+// 2^(t/128) = 2^k * T[j] * exp(r ln2/128), n = rint(t) = 128 k + j, r = t - n in [-1/2, 1/2].  T lives in shared memory with
+// kExpTab = 1024 entries, T[i] = 2^(i/1024) (the bin loop of scan_moments works in 1/1024 octaves with a shorter polynomial); this
+// routine reads every eighth entry.  The degree-4 polynomial has a truncation error of 1.2e-15 relative (the parity bar for the
+// moments is 1e-9).  GUARD: arguments below 2^-1000 return 0 and arguments above 2^1015 are clamped; without it the caller
+// guarantees |t| < 128000 (fixed softmax shift with 2/tau <= 600).
+constexpr int kExpTabLog2 = 10, kExpTab = 1 << kExpTabLog2;
 template <bool GUARD>
 __device__ __forceinline__ double exp2_128(double t, const double* __restrict__ tab) {
   const double magic = 6755399441055744.0;  // 2^52 + 2^51
@@ -85,7 +87,7 @@ __device__ __forceinline__ double exp2_128(double t, const double* __restrict__ 
   p = fma(p, r, 1.4662262387640423e-05);
   p = fma(p, r, 0.0054152123481245725);
   p = fma(p, r, 1.0);
-  const double y = tab[n & 127] * p;
+  const double y = tab[(n & 127) << (kExpTabLog2 - 7)] * p;
   const double z = __hiloint2double(__double2hiint(y) + ((n >> 7) << 20), __double2loint(y));
   if (GUARD) return (t < -128000.0) ? 0.0 : z;
   return z;

@@ -19,10 +19,15 @@
 //   flush     per-thread partials are combined across point slices in a FIXED order and carried in fp64 in this CTA's
 //             record (no atomics => bit-reproducible).  fp32 mode flushes at least every ~512 accumulated points per
 //             thread so that fp32 chains stay short ("fp32c").
-// The contraction depth of the similarity is 3, so tensor cores are not used (BASELINE.json north_star).
+// The similarity dot has contraction depth 3 (no tensor-core shape), but phase B is a dense contraction over the POINTS: in fp32c
+// mode with 128..256 bins it runs on the tensor cores (gcl_scan_tc.cu); this file is the CUDA-core kernel: the fp64 parity mode, and
+// fp32c outside that range.
 #include "gcl_internal.cuh"
 #include "gcl_point.cuh"
 
+#ifndef GCL_A_NG4
+#define GCL_A_NG4 2     // fp64, G = 4: groups of two bins in flight per thread in phase A (registers: the 76-double tile stays live)
+#endif
 #ifndef GCL_BULK_ON
 #define GCL_BULK_ON 1   // 0: every tile takes the per-thread cp.async path (A/B builds)
 #endif
@@ -41,8 +46,8 @@ template <> struct Num<float> {
   static constexpr int kVec = 4;                                // bins per phase-A step
 };
 template <> struct Num<double> {
-  static constexpr double kScale = 184.6649652337873;           // logits in 1/128 octaves
-  static constexpr double kToNat = 0.0054152123481245725;
+  static constexpr double kScale = 1477.3197218702985;          // logits in 1/1024 octaves (kExpTab entries, gcl_point.cuh)
+  static constexpr double kToNat = 6.769015435155716e-04;
   static constexpr int kEpMod = 4, kEpRem = 2;                  // e-tile pitch = 2 (mod 4) doubles
   static constexpr int kVec = 2;
 };
@@ -161,7 +166,7 @@ __device__ __forceinline__ void phase_a_groups(const float4* __restrict__ p, int
     m = fmaxf(fmaxf(m, fmaxf(s0[g].x, s0[g].y)), fmaxf(s1[g].x, s1[g].y));
   }
 }
-template <int NGB>
+template <int NGB, bool LOWGUARD /* fp64 only: ex2.approx underflows to zero by itself */>
 __device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, const double*, int b0, int b1, int B, float d0,
                                              float d1, float d2, float off, float* __restrict__ erow, float& Z, float& S1, float& xmax) {
   const float2 dx = make_float2(d0, d0), dy = make_float2(d1, d1), dz = make_float2(d2, d2), o2 = make_float2(off, off);
@@ -176,12 +181,17 @@ __device__ __forceinline__ void phase_a_bins(const float* __restrict__ atlas, co
   Z = Z2.x + Z2.y; S1 = S2.x + S2.y; xmax = m;
 }
 // fp64 atlas: per group of 2 bins three double2 {bx0,bx1} {by0,by1} {bz0,bz1}.  NG groups (2 NG bins) at a time, written
-// stage by stage: the exp is a chain of ~13 dependent FP64 operations, and with two warps per scheduler the FP64 pipe only
+// stage by stage: the exp is a chain of ~12 dependent FP64 operations, and with two warps per scheduler the FP64 pipe only
 // fills when each warp carries 2 NG independent chains (measured: one group in flight ran phase A at 2.5x its FP64 bound).
-template <int NG, bool TAIL>
+// Logits come in units of 1/1024 octave: 2^(x/1024) = 2^k T[j] exp(r ln2/1024), n = rint(x) = 1024 k + j, |r| <= 1/2, so a
+// degree-3 polynomial is enough (truncation 5.5e-16 relative) -- 12 FP64-pipe operations per pair with the normaliser and the entropy
+// sum (14 with the 128-entry table and degree 4).  The row maximum is taken over the EXPONENTIALS as 64-bit integers (they are
+// positive doubles: same order), on the integer pipe; a double-precision max costs the FP64 pipe a DSETP per pair and the
+// scheduler four more issue slots of selects and moves.
+template <int NG, bool TAIL, bool LOWGUARD>
 __device__ __forceinline__ void phase_a_groups(const double2* __restrict__ p, const double* __restrict__ tab, int b, int B, double d0,
                                                double d1, double d2, double off, double* __restrict__ erow, double& z, double& s1,
-                                               double& m) {
+                                               unsigned long long& m) {
   constexpr int N = 2 * NG;
   const double magic = 6755399441055744.0;  // 2^52 + 2^51
   double x[N], tm[N], r[N], q[N], e[N];
@@ -191,23 +201,25 @@ __device__ __forceinline__ void phase_a_groups(const double2* __restrict__ p, co
     x[2 * g] = fma(d0, ax.x, fma(d1, ay.x, fma(d2, az.x, off)));
     x[2 * g + 1] = fma(d0, ax.y, fma(d1, ay.y, fma(d2, az.y, off)));
   }
+  if (LOWGUARD) {   // row-maximum shift (tiny tau): logits reach far below 2^-1022, where the exponent arithmetic below would wrap
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = fmax(x[k], -1.0e6);   // 2^-976 against a row maximum of 1
+  }
 #pragma unroll
   for (int k = 0; k < N; ++k) tm[k] = x[k] + magic;
 #pragma unroll
   for (int k = 0; k < N; ++k) r[k] = x[k] - (tm[k] - magic);
 #pragma unroll
-  for (int k = 0; k < N; ++k) q[k] = fma(3.583032305400251e-11, r[k], 2.6466421444330967e-08);
+  for (int k = 0; k < N; ++k) q[k] = fma(5.169222938345892e-11, r[k], 2.2909784980688163e-07);
 #pragma unroll
-  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 1.4662262387640423e-05);
-#pragma unroll
-  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 0.0054152123481245725);
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 6.769015435155716e-04);
 #pragma unroll
   for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 1.0);
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const int n = __double2loint(tm[k]);
-    const double y = tab[n & 127] * q[k];
-    e[k] = __hiloint2double(__double2hiint(y) + ((n >> 7) << 20), __double2loint(y));
+    const double y = tab[n & (kExpTab - 1)] * q[k];
+    e[k] = __hiloint2double(__double2hiint(y) + ((n >> kExpTabLog2) << 20), __double2loint(y));
   }
   if (TAIL) {
 #pragma unroll
@@ -217,23 +229,26 @@ __device__ __forceinline__ void phase_a_groups(const double2* __restrict__ p, co
 #pragma unroll
   for (int g = 0; g < NG; ++g) *reinterpret_cast<double2*>(erow + b + 2 * g) = make_double2(e[2 * g], e[2 * g + 1]);
 #pragma unroll
-  for (int k = 0; k < N; ++k) { z += e[k]; s1 = fma(e[k], x[k], s1); m = fmax(m, x[k]); }
+  for (int k = 0; k < N; ++k) {
+    z += e[k]; s1 = fma(e[k], x[k], s1);
+    const unsigned long long eb = (unsigned long long)__double_as_longlong(e[k]);
+    m = eb > m ? eb : m;
+  }
 }
-template <int NGB>
+template <int NGB, bool LOWGUARD>
 __device__ __forceinline__ void phase_a_bins(const double* __restrict__ atlas, const double* __restrict__ tab, int b0, int b1, int B,
                                              double d0, double d1, double d2, double off, double* __restrict__ erow, double& Z,
                                              double& S1, double& xmax) {
-  double z = 0.0, s1 = 0.0, m = -1.0e300;
+  double z = 0.0, s1 = 0.0;
+  unsigned long long m = 0ull;   // bits of the largest exponential (xmax carries max_b e, not max_b x, in this precision)
   const double2* p = reinterpret_cast<const double2*>(atlas);
   const int bmain = (b1 <= B) ? b1 : ((B & ~1) > b0 ? (B & ~1) : b0);
   int b = b0;
-  for (; b + 2 * NGB <= bmain; b += 2 * NGB) phase_a_groups<NGB, false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
-  for (; b < bmain; b += 2) phase_a_groups<1, false>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
-  for (; b < b1; b += 2) phase_a_groups<1, true>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
-  Z = z; S1 = s1; xmax = m;
+  for (; b + 2 * NGB <= bmain; b += 2 * NGB) phase_a_groups<NGB, false, LOWGUARD>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  for (; b < bmain; b += 2) phase_a_groups<1, false, LOWGUARD>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  for (; b < b1; b += 2) phase_a_groups<1, true, LOWGUARD>(p + 3 * (b >> 1), tab, b, B, d0, d1, d2, off, erow, z, s1, m);
+  Z = z; S1 = s1; xmax = __longlong_as_double((long long)m);
 }
-__device__ __forceinline__ float exp_of_max(float x, const double*) { return fast_exp2(x); }
-__device__ __forceinline__ double exp_of_max(double x, const double* tab) { return exp2_128<true>(x, tab); }
 
 // row maximum of the scaled similarity over ALL bins (only when the fixed shift could underflow: tiny tau)
 __device__ __forceinline__ float sim_rowmax(const float* atlas, int B, float d0, float d1, float d2) {
@@ -267,7 +282,7 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : e_pitch(cols, 4, 2);
   size_t off = (size_t)(p.TA * p.BA) * 3 * tsz;                    // phase-A atlas, 3 components per bin
   off = (off + 15) & ~(size_t)15;
-  p.o_tab = off;  off += 128 * 8;
+  p.o_tab = off;  off += (tsz == 8 ? kExpTab : 2) * 8;
   p.o_sd = off;   off += (size_t)TP * 4 * tsz;
   p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
   off = (off + 15) & ~(size_t)15;
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       s_atlas[i] = (b < B) ? (T)(P.bin_dirs[b * 3 + c] * cscale_d) : (T)0;
     }
     if (sizeof(T) == 8) {
-      if (tid < 128) s_tab[tid] = exp2((double)tid * (1.0 / 128.0));
+      for (int i = tid; i < kExpTab; i += kNT) s_tab[i] = exp2((double)i * (1.0 / kExpTab));
     }
   }
   const int binlane = tid & (L - 1);
@@ -552,7 +567,11 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     if (pi < count) {
       const T* sd = s_d + (size_t)pi * 4;
       T Z, S1, xmax;
-      phase_a_bins<(sizeof(T) == 4 ? 3 : (G >= 4 ? 2 : 4))>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+      constexpr int NGB = sizeof(T) == 4 ? 3 : (G >= 4 ? GCL_A_NG4 : 4);
+      if (sizeof(T) == 4 || (P.fixed_shift & 1))
+        phase_a_bins<NGB, false>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+      else
+        phase_a_bins<1, true>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
       T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
       zp[0] = Z; zp[1] = S1; zp[2] = xmax;
     }
@@ -561,7 +580,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     // ======================================= scale =============================================================
     if (tid == kNT - 32 && tile_is_bulk(tile0 + TP)) prefetch_bulk(tile0 + TP);   // the staging buffer is free since the front end; this warp idles here
     if (tid < count) {
-      T Z = 0, S1 = 0, xmax = (T)-1.0e30;
+      T Z = 0, S1 = 0, xmax = (T)-1.0e30;   // fp32: largest logit; fp64: largest exponential (>= 0)
       for (int a = 0; a < TA; ++a) {
         const T* zp = s_zp + ((size_t)a * TP + tid) * 3;
         Z += zp[0]; S1 += zp[1]; xmax = zp[2] > xmax ? zp[2] : xmax;
@@ -576,7 +595,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       } else {
         const double rZ = 1.0 / Zd;
         CERT(GCL_CS_SUM_ENTROPY) += log(Zd) - Num<T>::kToNat * (double)S1 * rZ - (double)B * C.eps_mass;
-        const double mr = (double)exp_of_max(xmax, s_tab) * rZ;
+        const double mr = (double)xmax * rZ;   // fp64 phase A hands over max_b e itself
         if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
       }
       const T w = wq / Z;
