@@ -271,7 +271,7 @@ __device__ __forceinline__ double sim_rowmax(const double* atlas, int B, double 
 // ---- shared-memory plan (host and device agree through these) ----------------------------------------------------------------
 struct FusedPlan {
   int G, L, TP, TA, BA, EP;   // bins/thread, bin lanes, points/tile, phase-A threads/point, bins per phase-A thread, e pitch
-  size_t o_tab, o_sd, o_zp, o_rows, o_etile, o_in, total;
+  size_t o_tab, o_sd, o_zp, o_rows, o_pt, o_etile, o_in, total;
 };
 __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, int TP) {
   FusedPlan p;
@@ -287,7 +287,9 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
   off = (off + 15) & ~(size_t)15;
   p.o_rows = off; off += (size_t)TP * kRowPitch * tsz;
-  p.o_in = off;   off += (size_t)TP * 5 * 8;
+  p.o_pt = off;   off += (size_t)(2 * TP <= kNT ? 2 : 1) * 7 * TP * tsz;   // front end -> scale step, one buffer per thread group
+  off = (off + 15) & ~(size_t)15;
+  p.o_in = off;   off += (size_t)2 * TP * 5 * 8;                            // two staging buffers of raw rows
   p.o_etile = off;
   size_t et = (size_t)TP * p.EP * tsz;
   const size_t stage = (size_t)(kNT / L) * kKC * (size_t)(G * L) * tsz;
@@ -319,13 +321,14 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   // the job record is read all through the kernel (array pointers at every prefetch, times and twist at every front end): keep
   // it in shared memory instead of going back to global memory for every field
   __shared__ gcl_job s_job;
-  __shared__ __align__(8) uint64_t s_mbar;          // completion of the bulk copies of a tile's raw rows
-  __shared__ int s_lo32;                            // low word of this CTA's first row, and whether its full tiles go by bulk copy (kept in
-  __shared__ int s_bulk_on;                         // shared memory: the <double, 4> variant has no register to spare across phase B)
+  __shared__ __align__(8) uint64_t s_mbar[2];       // completion of the bulk copies of a tile's raw rows, one per staging buffer
+  __shared__ int s_bulk_on;                         // whether this CTA's full tiles go by bulk copy (kept in shared memory: the <double, 4>
+                                                    // variant has no register to spare across phase B)
   if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
     reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
   if (tid == 0) {
-    mbar_init(smem_u32(&s_mbar), 1);
+    mbar_init(smem_u32(&s_mbar[0]), 1);
+    mbar_init(smem_u32(&s_mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   T* s_d = reinterpret_cast<T*>(smem_raw + pl.o_sd);
   T* s_zp = reinterpret_cast<T*>(smem_raw + pl.o_zp);
   T* s_rows = reinterpret_cast<T*>(smem_raw + pl.o_rows);
+  T* s_pt = reinterpret_cast<T*>(smem_raw + pl.o_pt);
   T* s_etile = reinterpret_cast<T*>(smem_raw + pl.o_etile);
   T* s_stage = s_etile;  // flush staging aliases the e-tile (a flush happens between tiles)
   double* s_in = reinterpret_cast<double*>(smem_raw + pl.o_in);
@@ -457,184 +461,236 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     acc.zero();
   };
 
-  // raw rows of tile [t0, t0 + TP) -> the tile's staging buffer, asynchronously.  Contiguous float64 rows (no PointBudget stride: the dense
-  // clouds) go as three bulk copies (TMA engine) issued by ONE thread -- points, timestamps, weights of a full tile from the CTA's even
-  // first row (16-byte alignment), arrays of rows in shared memory, completion counted by an mbarrier.  Issuing them costs that thread's
-  // warp ~400 cycles, so the thread is lane 0 of the LAST warp and the moment is the start of the previous tile's scale step, when only
-  // the first warps have work (measured with the issue on thread 0 after the front end: +2.3 % on the 1 M x 256 launch).  Everything
-  // else (strided gather, packed rows, unaligned arrays or an odd first row, a CTA's last partial tile) takes one row per thread with
-  // cp.async, after the front end.
+  // ---- tile schedule ---------------------------------------------------------------------------------------------------------
+  // Per tile only phase A and phase B use all 256 threads; the per-point steps (front end before phase A, scale between the phases)
+  // are one thread per point, i.e. TP/32 warps, and each is a long dependent fp64 chain.  Tiles therefore alternate between two
+  // thread groups (group of tile i = i & 1, threads [g TP, g TP + TP), when TP <= 128): while group g runs the scale step of tile i,
+  // the other group runs the front end of tile i + 1 in the same barrier interval.  What the scale step needs from the front end
+  // (deskewed point, direction, weight) waits in shared memory (s_pt, one buffer per group), not in registers.  With TP = 256 there
+  // is one group: scale(i) then front(i + 1) back to back, one barrier fewer per tile than a front end of its own.
+  //
+  // Raw rows are staged two tiles ahead into two buffers.  Contiguous float64 rows (no PointBudget stride: the dense clouds) go as three
+  // bulk copies (TMA engine) issued by ONE thread -- points, timestamps, weights of a full tile from the CTA's even first row (16-byte
+  // alignment), arrays of rows in shared memory, completion counted by the buffer's mbarrier.  Issuing them costs that thread's warp
+  // ~400 cycles, so the thread is lane 0 of the LAST warp and the moment is the start of the scale interval, when that warp idles for
+  // TP <= 64.  Everything else (strided gather, packed rows, unaligned arrays or an odd first row, a CTA's last partial tile) takes one
+  // row per thread with cp.async, issued by the group that will consume it.
+  const int two_groups = (2 * TP <= kNT) ? 1 : 0;
   if (tid == 0) {
-    s_lo32 = (int)lo;
     s_bulk_on = (GCL_BULK_ON && P.layout == GCL_LAYOUT_REF_F64 && stride == 1 && !(lo & 1) &&
                  ((reinterpret_cast<uintptr_t>(J.points) | reinterpret_cast<uintptr_t>(J.timestamps) | reinterpret_cast<uintptr_t>(J.weights)) & 15) == 0) ? 1 : 0;
   }
   __syncthreads();
-  // full tiles only: a CTA's last, partial tile takes the per-thread path (so the barrier's phase parity is the tile index's)
+  const size_t in_stride = (size_t)TP * 5;            // doubles per staging buffer
+  // full tiles only: a CTA's last, partial tile takes the per-thread path
   auto tile_is_bulk = [&](int64_t t0) -> bool { return t0 + TP <= hi && s_bulk_on; };
-  auto prefetch_bulk = [&](int64_t t0) {            // one thread
-    const uint32_t mb = smem_u32(&s_mbar);
+  auto prefetch_bulk = [&](int64_t t0, int ti) {      // one thread
+    const uint32_t mb = smem_u32(&s_mbar[ti & 1]);
+    double* in = s_in + (size_t)(ti & 1) * in_stride;
     mbar_arrive_expect_tx(mb, (uint32_t)TP * 40u);
-    bulk_copy_g2s(s_in, static_cast<const double*>(J.points) + t0 * 3, (uint32_t)TP * 24u, mb);
-    bulk_copy_g2s(s_in + (size_t)TP * 3, static_cast<const double*>(J.timestamps) + t0, (uint32_t)TP * 8u, mb);
-    bulk_copy_g2s(s_in + (size_t)TP * 4, static_cast<const double*>(J.weights) + t0, (uint32_t)TP * 8u, mb);
+    bulk_copy_g2s(in, static_cast<const double*>(J.points) + t0 * 3, (uint32_t)TP * 24u, mb);
+    bulk_copy_g2s(in + (size_t)TP * 3, static_cast<const double*>(J.timestamps) + t0, (uint32_t)TP * 8u, mb);
+    bulk_copy_g2s(in + (size_t)TP * 4, static_cast<const double*>(J.weights) + t0, (uint32_t)TP * 8u, mb);
   };
-  auto prefetch_tile = [&](int64_t t0) {            // the per-thread path (all threads call it)
-    if (tile_is_bulk(t0)) return;
-    const int64_t srow = t0 + tid;
-    if (tid >= TP || srow >= hi) return;
-    const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
-    const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;         // row in the points / timestamps arrays
+  // the per-thread path: called by the threads of tile ti's group with their index li in the group; ALWAYS commits a (possibly empty)
+  // cp.async group so that the wait of the front end can count groups
+  auto prefetch_rows = [&](int64_t t0, int ti, int li) {
+    const int64_t srow = t0 + li;
+    if (t0 < hi && !tile_is_bulk(t0) && srow < hi) {
+      const int64_t r = srow * stride;                                        // raw row (PointBudget gather)
+      const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;         // row in the points / timestamps arrays
+      double* in = s_in + (size_t)(ti & 1) * in_stride;
+      if (P.layout == GCL_LAYOUT_REF_F64) {
+        const double* pts = static_cast<const double*>(J.points) + rp * 3;
+        double* dst = in + (size_t)li * 5;
+        cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
+        cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
+        cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
+      } else {
+        float* base = reinterpret_cast<float*>(in);
+        cp_async16(base + (size_t)li * 4, static_cast<const float4*>(J.points) + rp);
+        cp_async4(base + (size_t)TP * 4 + li, static_cast<const float*>(J.weights) + r);
+      }
+    }
+    cp_async_commit();
+  };
+  // ======================================= front =============================================================
+  // thread li of tile ti's group: raw row -> deskew, window weight, direction; {d, shift} for phase A, point state for the scale step
+  auto front = [&](int64_t tile0, int ti, int li, bool newer_group_in_flight) {
+    const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+    const bool from_bulk = tile_is_bulk(tile0);
+    if (from_bulk) mbar_wait(smem_u32(&s_mbar[ti & 1]), (uint32_t)((ti >> 1) & 1));
+    else if (newer_group_in_flight) cp_async_wait_group<1>();
+    else cp_async_wait_group<0>();
+    if (li >= count) return;
+    const double* in_buf = s_in + (size_t)(ti & 1) * in_stride;
+    T q0, q1, q2, d0, d1, d2;
+    float xi32[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
+    const int64_t srow = tile0 + li;   // selected-row index; raw index = srow * stride (PointBudget gather)
+    double w_sel, w_time;
     if (P.layout == GCL_LAYOUT_REF_F64) {
-      const double* pts = static_cast<const double*>(J.points) + rp * 3;
-      double* dst = s_in + (size_t)tid * 5;
-      cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
-      cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
-      cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
+      double px, py, pz, tt;
+      if (from_bulk) {                            // arrays of rows
+        px = in_buf[(size_t)li * 3]; py = in_buf[(size_t)li * 3 + 1]; pz = in_buf[(size_t)li * 3 + 2];
+        tt = in_buf[(size_t)TP * 3 + li]; w_sel = in_buf[(size_t)TP * 4 + li];
+      } else {
+        const double* in = in_buf + (size_t)li * 5;  // {x, y, z, t, w}
+        px = in[0]; py = in[1]; pz = in[2]; tt = in[3]; w_sel = in[4];
+      }
+      if (sizeof(T) == 8) {
+        PointOut64 o;
+        point_front64_fast(J, C, tconst, s_tab, px, py, pz, tt, o);
+        d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+        q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+        w_time = o.w_time;
+      } else {
+        PointOut32 o;
+        point_front32(J, C, xi32, (float)px, (float)py, (float)pz, (float)(tt - J.scan_start_time), o);
+        d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+        q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+        w_time = (double)o.w_time;
+      }
     } else {
-      float* base = reinterpret_cast<float*>(s_in);
-      cp_async16(base + (size_t)tid * 4, static_cast<const float4*>(J.points) + rp);
-      cp_async4(base + (size_t)TP * 4 + tid, static_cast<const float*>(J.weights) + r);
+      const float* base = reinterpret_cast<const float*>(in_buf);
+      const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)li * 4);
+      w_sel = (double)base[(size_t)TP * 4 + li];
+      PointOut32 o;
+      point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
+      d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
+      q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
+      w_time = (double)o.w_time;
+    }
+    const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
+    const double w_desk = w_sel * w_time;
+    CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
+    CERT(GCL_CS_ROWS) += 1.0;
+    // Shift = the largest possible logit (|d.b| <= 1) when that cannot underflow, else the true row maximum
+    // (jax.nn.softmax, binning.py:69).
+    const T offv = (P.fixed_shift & 1) ? -cscale : -sim_rowmax(s_atlas, B, d0, d1, d2);
+    T* sd = s_d + (size_t)li * 4;
+    sd[0] = d0; sd[1] = d1; sd[2] = d2; sd[3] = offv;
+    T* pt = s_pt + (size_t)(two_groups ? (ti & 1) : 0) * 7 * TP + li;   // scalar-major: conflict-free
+    pt[0] = q0; pt[TP] = q1; pt[2 * TP] = q2; pt[3 * TP] = d0; pt[4 * TP] = d1; pt[5 * TP] = d2; pt[6 * TP] = (T)(w_desk * lam);
+  };
+  // ======================================= scale =============================================================
+  // thread li of tile ti's group: Z_i, certificate partials, row (w_i/Z_i) phi_i for phase B
+  auto scale = [&](int ti, int li) {
+    T Z = 0, S1 = 0, xmax = (T)-1.0e30;   // fp32: largest logit; fp64: largest exponential (>= 0)
+    for (int a = 0; a < TA; ++a) {
+      const T* zp = s_zp + ((size_t)a * TP + li) * 3;
+      Z += zp[0]; S1 += zp[1]; xmax = zp[2] > xmax ? zp[2] : xmax;
+    }
+    // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in logit units
+    const double Zd = (double)Z;
+    if (sizeof(T) == 4) {
+      const float invZ = 1.f / (float)Z;
+      CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
+      const double mr = (double)(fast_exp2((float)xmax) * invZ);
+      if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
+    } else {
+      const double rZ = 1.0 / Zd;
+      CERT(GCL_CS_SUM_ENTROPY) += log(Zd) - Num<T>::kToNat * (double)S1 * rZ - (double)B * C.eps_mass;
+      const double mr = (double)xmax * rZ;   // fp64 phase A hands over max_b e itself
+      if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
+    }
+    const T* pt = s_pt + (size_t)(two_groups ? (ti & 1) : 0) * 7 * TP + li;
+    const T q0 = pt[0], q1 = pt[TP], q2 = pt[2 * TP], d0 = pt[3 * TP], d1 = pt[4 * TP], d2 = pt[5 * TP], wq = pt[6 * TP];
+    const T w = wq / Z;
+    T f[kRowPitch];
+    f[0] = w;
+    f[1] = w * d0; f[2] = w * d1; f[3] = w * d2;
+    f[4] = f[1] * d0; f[5] = f[1] * d1; f[6] = f[1] * d2; f[7] = f[2] * d1; f[8] = f[2] * d2; f[9] = f[3] * d2;
+    f[10] = w * q0; f[11] = w * q1; f[12] = w * q2;
+    f[13] = f[10] * q0; f[14] = f[10] * q1; f[15] = f[10] * q2; f[16] = f[11] * q1; f[17] = f[11] * q2; f[18] = f[12] * q2;
+    f[19] = 0;
+    T* row = s_rows + (size_t)li * kRowPitch;
+    if (sizeof(T) == 4) {
+      float4* r4 = reinterpret_cast<float4*>(row);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) r4[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
+    } else {
+      double2* r2 = reinterpret_cast<double2*>(row);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) r2[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
     }
   };
-  if (tile_is_bulk(lo)) { if (tid == kNT - 32) prefetch_bulk(lo); } else prefetch_tile(lo);
+  // group-local index of this thread in the group of tile ti, or -1 when it is not in it
+  auto group_index = [&](int ti) -> int {
+    const int base = two_groups ? (ti & 1) * TP : 0;
+    return (tid >= base && tid < base + TP) ? tid - base : -1;
+  };
+
+  // prologue: rows of tiles 0 and 1 on their way
+  {
+    const int64_t t1 = lo + TP;
+    if (tid == kNT - 32) {
+      if (lo < hi && tile_is_bulk(lo)) prefetch_bulk(lo, 0);
+      if (t1 < hi && tile_is_bulk(t1)) prefetch_bulk(t1, 1);
+    }
+    const int l0 = group_index(0), l1 = group_index(1);
+    if (l0 >= 0) prefetch_rows(lo, 0, l0);
+    if (l1 >= 0) prefetch_rows(t1, 1, l1);
+  }
   K1T(0);   // prologue: job record, atlas, exp table, raw-weight sum
 
   int pts_since_flush = 0;
   const int flush_points = (sizeof(T) == 4) ? 512 * PS : (1 << 30);  // per-thread chain length ~512 in fp32
 
-  for (int64_t tile0 = lo; tile0 < hi; tile0 += TP) {
-    const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
-    const bool from_bulk = tile_is_bulk(tile0);
-    if (from_bulk) { if (tid < TP) mbar_wait(smem_u32(&s_mbar), (uint32_t)((((int)tile0 - s_lo32) >> (__ffs(TP) - 1)) & 1)); }   // only the front-end threads read the rows
-    else cp_async_wait_all();
-    __syncthreads();  // raw rows landed; previous tile's phase B (e-tile, rows) is finished
-    // ======================================= front =============================================================
-    T q0 = 0, q1 = 0, q2 = 0, d0 = 0, d1 = 0, d2 = 0, wq = 0;
-    if (tid < count) {
-      float xi32[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) xi32[k] = (float)J.xi_body[k];
-      const int64_t srow = tile0 + tid;   // selected-row index; raw index = srow * stride (PointBudget gather)
-      double w_sel, w_time;
-      if (P.layout == GCL_LAYOUT_REF_F64) {
-        double px, py, pz, tt;
-        if (from_bulk) {                            // arrays of rows
-          px = s_in[(size_t)tid * 3]; py = s_in[(size_t)tid * 3 + 1]; pz = s_in[(size_t)tid * 3 + 2];
-          tt = s_in[(size_t)TP * 3 + tid]; w_sel = s_in[(size_t)TP * 4 + tid];
-        } else {
-          const double* in = s_in + (size_t)tid * 5;  // {x, y, z, t, w}
-          px = in[0]; py = in[1]; pz = in[2]; tt = in[3]; w_sel = in[4];
-        }
-        if (sizeof(T) == 8) {
-          PointOut64 o;
-          point_front64_fast(J, C, tconst, s_tab, px, py, pz, tt, o);
-          d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
-          q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
-          w_time = o.w_time;
-        } else {
-          PointOut32 o;
-          point_front32(J, C, xi32, (float)px, (float)py, (float)pz, (float)(tt - J.scan_start_time), o);
-          d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
-          q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
-          w_time = (double)o.w_time;
-        }
-      } else {
-        const float* base = reinterpret_cast<const float*>(s_in);
-        const float4 xyzt = *reinterpret_cast<const float4*>(base + (size_t)tid * 4);
-        w_sel = (double)base[(size_t)TP * 4 + tid];
-        PointOut32 o;
-        point_front32(J, C, xi32, xyzt.x, xyzt.y, xyzt.z, xyzt.w, o);
-        d0 = (T)o.d[0]; d1 = (T)o.d[1]; d2 = (T)o.d[2];
-        q0 = (T)o.p0[0]; q1 = (T)o.p0[1]; q2 = (T)o.p0[2];
-        w_time = (double)o.w_time;
-      }
-      const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
-      const double w_desk = w_sel * w_time;
-      CERT(GCL_CS_SUM_W_SEL) += w_sel; CERT(GCL_CS_SUM_W_SEL_SQ) += w_sel * w_sel; CERT(GCL_CS_SUM_W_DESKEW) += w_desk;
-      CERT(GCL_CS_ROWS) += 1.0;
-      wq = (T)(w_desk * lam);
-      // Shift = the largest possible logit (|d.b| <= 1) when that cannot underflow, else the true row maximum
-      // (jax.nn.softmax, binning.py:69).
-      const T offv = (P.fixed_shift & 1) ? -cscale : -sim_rowmax(s_atlas, B, d0, d1, d2);
-      T* sd = s_d + (size_t)tid * 4;
-      sd[0] = d0; sd[1] = d1; sd[2] = d2; sd[3] = offv;
-    }
-    __syncthreads();
-    K1T(1);   // wait for the rows + front end
-    prefetch_tile(tile0 + TP);  // next tile's raw rows stream in while this tile is processed
+  // iteration ti = -1 is the front end of the first tile alone (one copy of the per-point code in the kernel: it is large)
+  const int n_tiles = (int)((hi - lo + TP - 1) / TP);
+  for (int ti = -1; ti < n_tiles; ++ti) {
+    const int64_t tile0 = lo + (int64_t)ti * TP;
+    const int count = ti < 0 ? 0 : (int)((hi - tile0 < TP) ? hi - tile0 : TP);
     // ======================================= phase A ===========================================================
-    if (pi < count) {
-      const T* sd = s_d + (size_t)pi * 4;
-      T Z, S1, xmax;
-      constexpr int NGB = sizeof(T) == 4 ? 3 : (G >= 4 ? GCL_A_NG4 : 4);
-      if (sizeof(T) == 4 || (P.fixed_shift & 1))
-        phase_a_bins<NGB, false>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
-      else
-        phase_a_bins<1, true>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
-      T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
-      zp[0] = Z; zp[1] = S1; zp[2] = xmax;
+    if (ti >= 0) {
+      if (pi < count) {
+        const T* sd = s_d + (size_t)pi * 4;
+        T Z, S1, xmax;
+        constexpr int NGB = sizeof(T) == 4 ? 3 : (G >= 4 ? GCL_A_NG4 : 4);
+        if (sizeof(T) == 4 || (P.fixed_shift & 1))
+          phase_a_bins<NGB, false>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+        else
+          phase_a_bins<1, true>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
+        T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
+        zp[0] = Z; zp[1] = S1; zp[2] = xmax;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     K1T(2);   // phase A
-    // ======================================= scale =============================================================
-    if (tid == kNT - 32 && tile_is_bulk(tile0 + TP)) prefetch_bulk(tile0 + TP);   // the staging buffer is free since the front end; this warp idles here
-    if (tid < count) {
-      T Z = 0, S1 = 0, xmax = (T)-1.0e30;   // fp32: largest logit; fp64: largest exponential (>= 0)
-      for (int a = 0; a < TA; ++a) {
-        const T* zp = s_zp + ((size_t)a * TP + tid) * 3;
-        Z += zp[0]; S1 += zp[1]; xmax = zp[2] > xmax ? zp[2] : xmax;
+    // =========================== scale of this tile | front end of the next | rows of the tile after that ======================
+    {
+      const int64_t t1 = tile0 + TP, t2 = tile0 + 2 * (int64_t)TP;
+      if (ti >= 0) {
+        if (tid == kNT - 32 && t2 < hi && tile_is_bulk(t2)) prefetch_bulk(t2, ti + 2);   // its buffer is free since the front end of this tile
+        const int ls = group_index(ti);
+        if (ls >= 0) {
+          prefetch_rows(t2, ti + 2, ls);               // same group, same buffer as this tile
+          if (ls < count) scale(ti, ls);
+        }
       }
-      // H_i = -sum_b r log(r + eps) = log Z - S1/Z - B*eps + O(B eps^2 / r)   (binning.py:70-72); S1 in logit units
-      const double Zd = (double)Z;
-      if (sizeof(T) == 4) {
-        const float invZ = 1.f / (float)Z;
-        CERT(GCL_CS_SUM_ENTROPY) += (double)(__logf((float)Z) - (float)Num<T>::kToNat * (float)S1 * invZ) - (double)B * C.eps_mass;
-        const double mr = (double)(fast_exp2((float)xmax) * invZ);
-        if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
-      } else {
-        const double rZ = 1.0 / Zd;
-        CERT(GCL_CS_SUM_ENTROPY) += log(Zd) - Num<T>::kToNat * (double)S1 * rZ - (double)B * C.eps_mass;
-        const double mr = (double)xmax * rZ;   // fp64 phase A hands over max_b e itself
-        if (mr > CERT(GCL_CS_MAX_RESP)) CERT(GCL_CS_MAX_RESP) = mr;
-      }
-      const T w = wq / Z;
-      T f[kRowPitch];
-      f[0] = w;
-      f[1] = w * d0; f[2] = w * d1; f[3] = w * d2;
-      f[4] = f[1] * d0; f[5] = f[1] * d1; f[6] = f[1] * d2; f[7] = f[2] * d1; f[8] = f[2] * d2; f[9] = f[3] * d2;
-      f[10] = w * q0; f[11] = w * q1; f[12] = w * q2;
-      f[13] = f[10] * q0; f[14] = f[10] * q1; f[15] = f[10] * q2; f[16] = f[11] * q1; f[17] = f[11] * q2; f[18] = f[12] * q2;
-      f[19] = 0;
-      T* row = s_rows + (size_t)tid * kRowPitch;
-      if (sizeof(T) == 4) {
-        float4* r4 = reinterpret_cast<float4*>(row);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) r4[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
-      } else {
-        double2* r2 = reinterpret_cast<double2*>(row);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) r2[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
-      }
+      const int lf = group_index(ti + 1);
+      if (lf >= 0 && t1 < hi) front(t1, ti + 1, lf, !two_groups);
     }
     __syncthreads();
-    K1T(3);   // scale
+    K1T(3);   // scale + next front end
+    if (ti < 0) continue;
     // ======================================= phase B ===========================================================
     {
       const T* ebase = s_etile + (size_t)binlane * VB;
 #pragma unroll 2
       for (int pt = slice; pt < count; pt += PS) acc.step(ebase + (size_t)pt * EP, L, s_rows + (size_t)pt * kRowPitch);
     }
-    K1T(4);   // phase B (this thread's share; the next barrier is charged to the front end of the next tile)
+    K1T(4);   // phase B (this thread's share; the barrier below is charged to phase A of the next tile)
     pts_since_flush += count;
+    __syncthreads();   // e-tile and rows are free for the next tile (and for the flush staging, which aliases the e-tile)
     if (pts_since_flush >= flush_points) {
-      __syncthreads();
       flush();
       pts_since_flush = 0;
     }
   }
-  __syncthreads();
-  K1T(5);   // tail barrier
+  K1T(5);   // (the loop ends on a barrier)
   if (pts_since_flush > 0) flush();
   K1T(6);   // flush
   if (!flushed)   // a CTA without rows: its record is all zeros

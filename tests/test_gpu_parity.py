@@ -239,14 +239,15 @@ def _oracle_sums(O, sc, cap, bins, tau, lam=None):
     (20001, 32768, 256, 0.1),     # odd row count, 256 bins
     (5000, 8192, 1024, 0.1),      # maximum bin count (two bin chunks in fp64)
     (3000, 4096, 100, 0.1),       # bin count that is not a multiple of the lane tile
-    (4000, 4096, 48, 0.004),      # small tau: the row-max softmax shift path
+    (4000, 4096, 48, 0.004),      # small tau: the row-max softmax shift path (fp32c)
+    (4000, 4096, 48, 0.001),      # tiny tau: the row-max shift path in fp64 too (2/tau > 600), logits far below 2^-1022
     (257, 512, 7, 0.1),           # ragged: one row past a tile, 7 bins
     (1, 16, 48, 0.1),             # single point
 ])
 @pytest.mark.parametrize("precision,tol", [("fp64", 1e-9), ("fp32c", 1e-5)])
 def test_fused_moments_vs_oracle(g, O, n_raw, cap, B, tau, precision, tol):
     if precision == "fp32c" and tau < 0.01:
-        tol = 2e-4   # |logit| up to 250: fp32 rounding of the exponent argument dominates (documented in DESIGN.md)
+        tol = 2e-4 if tau > 0.002 else 1e-3   # |logit| up to 250 (1000): fp32 rounding of the exponent argument dominates
     sc = g.synth.make_scan(n_raw, seed=1234 + n_raw % 97)
     bins = O.create_fibonacci_atlas(B)
     pb, dk, raw, fin = _oracle_sums(O, sc, cap, bins, tau)
