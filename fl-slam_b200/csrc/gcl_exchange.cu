@@ -19,6 +19,9 @@
 // Buffers alternate between two parities: rank r can only publish step s + 2 after it has completed step s + 1, which needed every
 // peer's step s + 1 record, which each peer wrote (stream order) after finishing step s -- so nobody overwrites a buffer that is
 // still being read.  Step numbers only grow; flags are never reset.
+// A block holds GCL_EXCHANGE_LANES independent copies of all that (slots, flag words, ticket, step counter): a caller that keeps the
+// tails of TWO consecutive scans in flight (gcl_scan_pipe, two tail streams) runs scan k on lane k mod 2, each lane on its own
+// stream -- the argument above then holds per lane, and the lanes share nothing.
 // The same buffers carry gcl_exchange_all_gather (hypothesis-sharded results).
 #include <cstring>
 
@@ -30,14 +33,15 @@ namespace gcl {
 struct ExchangeDev {
   unsigned char* peer[GCL_MAX_RANKS];    // every rank's exchange block as mapped into THIS process (peer[rank] = the local block)
   int world, rank;
-  unsigned long long step;               // this call's step number (1, 2, ...)
-  size_t slot_bytes;                     // bytes per (parity, rank) slot
-  size_t o_flags, o_ticket, o_error;     // offsets in a block
+  unsigned long long step;               // this call's step number on its lane (1, 2, ...)
+  int lane;
+  size_t slot_bytes;                     // bytes per (lane, parity, rank) slot
+  size_t o_flags, o_ticket, o_error;     // offsets in a block (flags, ticket: of this call's lane)
   long long timeout_clocks;
 };
 
 __device__ __forceinline__ unsigned char* slot_of(const ExchangeDev& X, int owner, int parity, int src_rank) {
-  return X.peer[owner] + ((size_t)parity * X.world + src_rank) * X.slot_bytes;
+  return X.peer[owner] + ((size_t)(X.lane * 2 + parity) * X.world + src_rank) * X.slot_bytes;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -181,19 +185,20 @@ struct gcl_exchange_s {
   unsigned char* local = nullptr;
   unsigned char* peer[GCL_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool connected = false;
-  unsigned long long step = 0;
+  unsigned long long step[GCL_EXCHANGE_LANES] = {0, 0};
   double timeout_seconds = 2.0;
   int clock_khz = 1965000;
+  int lane = 0;                // the lane the next calls run on (gcl_exchange_set_lane)
   int max_ctas = 0;            // 0 = one CTA per 128 record elements; > 0: at most this many CTAs (gcl_exchange_set_max_ctas)
   std::string err;
 };
 
-static ExchangeDev dev_view(gcl_exchange x) {
+static ExchangeDev dev_view(gcl_exchange x, int lane) {
   ExchangeDev X;
   memset(&X, 0, sizeof(X));
   for (int r = 0; r < x->world; ++r) X.peer[r] = x->peer[r];
-  X.world = x->world; X.rank = x->rank; X.step = x->step; X.slot_bytes = x->slot_bytes;
-  X.o_flags = x->o_flags; X.o_ticket = x->o_ticket; X.o_error = x->o_error;
+  X.world = x->world; X.rank = x->rank; X.step = x->step[lane]; X.lane = lane; X.slot_bytes = x->slot_bytes;
+  X.o_flags = x->o_flags + (size_t)lane * 128; X.o_ticket = x->o_ticket + (size_t)lane * 32; X.o_error = x->o_error;
   X.timeout_clocks = (long long)(x->timeout_seconds * 1e3 * (double)x->clock_khz);
   return X;
 }
@@ -209,7 +214,7 @@ int gcl_exchange_create(gcl_handle h, int world, int rank, size_t slot_bytes, gc
   gcl_exchange x = new gcl_exchange_s();
   x->world = world; x->rank = rank; x->device = h->device;
   x->slot_bytes = (slot_bytes + 255) & ~(size_t)255;
-  x->o_flags = 2 * (size_t)world * x->slot_bytes;
+  x->o_flags = 2 * GCL_EXCHANGE_LANES * (size_t)world * x->slot_bytes;   // then GCL_EXCHANGE_LANES x 128 B of flag words (8 ranks x 8 B)
   x->o_ticket = x->o_flags + 256;
   x->o_error = x->o_ticket + 64;
   x->block_bytes = x->o_error + 64;
@@ -278,6 +283,12 @@ int gcl_exchange_set_max_ctas(gcl_exchange x, int max_ctas) {
   return GCL_OK;
 }
 
+int gcl_exchange_set_lane(gcl_exchange x, int lane) {
+  if (!x || lane < 0 || lane >= GCL_EXCHANGE_LANES) return GCL_ERR_ARG;
+  x->lane = lane;
+  return GCL_OK;
+}
+
 int gcl_exchange_error_flag(gcl_exchange x) {
   if (!x) return -1;
   int v = 0;
@@ -308,8 +319,8 @@ int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, cons
   P.eps_psd = eps_psd; P.eps_mass = eps_mass; P.finalize = 1; P.from_resp = 0;
   P.reduced = reduced; P.stats = stats;
   cudaSetDevice(x->device);
-  x->step += 1;
-  const ExchangeDev X = dev_view(x);
+  x->step[x->lane] += 1;
+  const ExchangeDev X = dev_view(x, x->lane);
   unsigned chunks = (unsigned)((rec + kXEl - 1) / kXEl);
   if (x->max_ctas > 0 && chunks * (unsigned)n_jobs > (unsigned)x->max_ctas) {
     chunks = (unsigned)x->max_ctas / (unsigned)n_jobs;
@@ -331,8 +342,8 @@ int gcl_exchange_all_gather(gcl_handle h, gcl_exchange x, void* stream, const vo
     return GCL_ERR_ARG;
   }
   cudaSetDevice(x->device);
-  x->step += 1;
-  const ExchangeDev X = dev_view(x);
+  x->step[x->lane] += 1;
+  const ExchangeDev X = dev_view(x, x->lane);
   const int grid = x->world < 4 ? x->world : 4;
   exchange_all_gather_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(X, static_cast<const uint4*>(src), bytes / 16, static_cast<uint4*>(dst));
   const cudaError_t e = cudaGetLastError();
@@ -343,7 +354,7 @@ int gcl_exchange_all_gather(gcl_handle h, gcl_exchange x, void* stream, const vo
 
 const void* gcl_exchange_gathered(gcl_exchange x, int src_rank) {
   if (!x || src_rank < 0 || src_rank >= x->world) return nullptr;
-  return x->local + ((size_t)(x->step & 1) * x->world + src_rank) * x->slot_bytes;
+  return x->local + ((size_t)(x->lane * 2 + (int)(x->step[x->lane] & 1)) * x->world + src_rank) * x->slot_bytes;
 }
 
 }  // extern "C"

@@ -128,6 +128,75 @@ class PeerExchange:
             self.x = C.c_void_p()
 
 
+class ScanPipe:
+    """Consecutive scans / hypothesis batches in flight (gcl_scan_pipe, csrc/gcl_pipe.cu): one C call per submission; the moment pass
+    on one internal stream, the O(B) tail (exchange + finalise + evidence [+ gather]) alternating over ``n_tails`` high-priority
+    streams, ``n_sets`` buffer sets.  mode "sum": points sharded (needs a PeerExchange); "gather": hypotheses sharded."""
+
+    def __init__(self, pipeline, px: Optional[PeerExchange], world: int, mode: str, n_sets: int = 4, n_tails: int = 2):
+        from . import _abi, operators as ops
+        self._abi, self._ops, self.pl, self.px, self.world = _abi, ops, pipeline, px, world
+        self.mode = {"sum": 0, "gather": 1}[mode]
+        self.n_sets, self.n_tails, self.turn = int(n_sets), int(n_tails), 0
+        self.p = C.c_void_p()
+        with torch.cuda.device(pipeline.device):
+            rc = _abi.lib.gcl_scan_pipe_create(pipeline.handle, None if px is None else px.x, world, self.mode, self.n_sets, self.n_tails,
+                                               C.byref(self.p))
+        if rc != 0:
+            raise _abi.GclError(f"gcl_scan_pipe_create failed ({rc}): {_abi.lib.gcl_last_error(pipeline.handle).decode()}")
+        self._keep = [None] * self.n_sets
+        self._args: Dict[tuple, tuple] = {}
+        self._gathered: Dict[tuple, torch.Tensor] = {}
+
+    def submit(self, jobs_dev: Optional[torch.Tensor], job, n_jobs: int, ctas: int, layout: int, map_stats, poses_dev: torch.Tensor,
+               keep=None, wait_for_caller: bool = True):
+        """Enqueue one scan (or batch); returns (buffer set dict, gathered tensor or None).  Valid after ``join()``, until n_sets
+        further submissions."""
+        pl, ops, lib = self.pl, self._ops, self._abi.lib
+        i = self.turn % self.n_sets
+        self.turn += 1
+        key = (n_jobs, ctas, i)
+        a = self._args.get(key)
+        if a is None:       # the per-set pointers do not change from scan to scan: build the ctypes arguments once
+            buf = pl._buffers(n_jobs, ctas, slot=i)
+            g = None
+            if self.mode == 1 and self.world > 1:
+                g = self._gathered.setdefault(key, torch.empty((self.world, n_jobs, self._abi.GCL_EVID_DOUBLES), dtype=torch.float64,
+                                                               device=pl.device))
+            a = self._args[key] = (buf, g, tuple(ops._ptr(buf[k]) for k in ("partials", "reduced", "stats", "map_derived", "evidence")) +
+                                   (ops._ptr(g),))
+        buf, g, ptrs = a
+        self._keep[i] = (jobs_dev, job, map_stats, poses_dev, keep)      # alive until this set comes round again
+        m = map_stats
+        rc = lib.gcl_scan_pipe_submit(self.p, ops._stream() if wait_for_caller else None, 1 if wait_for_caller else 0, i,
+                                      None if jobs_dev is None else C.c_void_p(jobs_dev.data_ptr()), None if job is None else C.byref(job),
+                                      n_jobs, ctas, layout, self._precision(), self._bin_dirs(), pl.n_bins, pl.tau, pl._origin_c, pl.eps_psd,
+                                      pl.eps_mass, ops._ptr(m.S_dir), ops._ptr(m.S_dir_scatter), ops._ptr(m.N_dir), ops._ptr(m.N_pos),
+                                      ops._ptr(m.sum_p), ops._ptr(m.sum_ppT), ops._ptr(poses_dev), *ptrs)
+        if rc != 0:
+            raise self._abi.GclError(lib.gcl_scan_pipe_last_error(self.p).decode())
+        return buf, g
+
+    def _precision(self) -> int:
+        from .pipeline import PRECISIONS
+        return PRECISIONS[self.pl.precision]
+
+    def _bin_dirs(self):
+        return self._ops._ptr(self.pl.bin_dirs)
+
+    def join(self) -> None:
+        """Order the caller's current stream after everything submitted."""
+        rc = self._abi.lib.gcl_scan_pipe_join(self.p, self._ops._stream())
+        if rc != 0:
+            raise self._abi.GclError(self._abi.lib.gcl_scan_pipe_last_error(self.p).decode())
+
+    def close(self) -> None:
+        if self.p:
+            self._abi.lib.gcl_scan_pipe_destroy(self.p)       # synchronises its streams
+            self.p = C.c_void_p()
+            self._keep = [None] * self.n_sets
+
+
 class PointShardedEvidence:
     """configs[3]/[4]: one scan, points sharded over the ranks of the default process group.
 
@@ -188,59 +257,60 @@ class PointShardedEvidence:
                                  n_points_cap=pl.n_points_cap)
 
     # ---- consecutive scans pipelined: the exchange + evidence step of scan k under the moment pass of scan k + 1 -------------------
-    def run_overlapped(self, scan, n_raw_total: int, xi_bodies, poses_dev, map_stats, reserve_sms: int = 8):
+    def run_overlapped(self, scan, n_raw_total: int, xi_bodies, poses_dev, map_stats, reserve_sms: int = 8, n_tails: int = 2, job=None):
         """Same result as ``run``; the moment pass goes on one internal stream with ``reserve_sms`` SMs left free, the fused exchange +
-        finalisation (grid capped to the free SMs) and the evidence step on a second, high-priority stream -- so the O(B), single-CTA
-        tail of scan k (~50 us, latency-bound) runs beside the moment pass of scan k + 1 instead of after it.  Results alternate between
-        two buffer sets (valid until the call after next); ``join_overlapped()`` orders the caller's stream after everything submitted."""
+        finalisation (grid capped to the free SMs) and the evidence step on high-priority streams of their own -- so the O(B) tail of
+        scan k (60-70 us, latency-bound) runs beside the moment pass of scan k + 1 instead of after it, and with ``n_tails`` = 2 beside
+        the tail of scan k + 1 as well (needed once the shard's moment pass is shorter than a tail: 8 GPUs, fp32c).  One C call per scan
+        (gcl_scan_pipe_submit).  Results rotate through four buffer sets (valid until four calls later); ``join_overlapped()`` orders the
+        caller's stream after everything submitted.  ``job``: a gcl_job built earlier with ``make_sharded_job`` (saves its cost)."""
         from .pipeline import LidarScanEvidence
-        from . import _abi, operators as ops
+        from . import _abi
         pl = self.pl
         if self.px is None:
             raise ValueError("run_overlapped needs the peer exchange (exchange='peer')")
-        xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
-        H = xi.shape[0]
-        _, n_sel, (b, e), _ = self.plan(n_raw_total)
-        sms = int(_abi.lib.gcl_device_sm_count(pl.handle))
-        ctas = max(1, min(pl.plan_ctas(H, max(1, e - b)), (sms - reserve_sms) // max(1, H)))
         ov = getattr(self, "_ov", None)
-        if ov is None:
-            ov = self._ov = {"s_k1": torch.cuda.Stream(device=pl.device, priority=0), "s_rest": torch.cuda.Stream(device=pl.device, priority=-1),
-                             "free": [None, None], "turn": 0, "last": None, "keep": [None, None]}
-            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, max(1, reserve_sms))
-        cur = torch.cuda.current_stream(pl.device)
-        ov["s_k1"].wait_stream(cur); ov["s_rest"].wait_stream(cur)     # what the caller enqueued so far (uploads, poses, map) comes first
-        i = ov["turn"] & 1
-        ov["turn"] += 1
-        buf = pl._buffers(H, ctas, slot=i)
-        jobs = [pl.make_job(scan, xi[h], n_raw_total=n_raw_total, sel_range=(b, e)) for h in range(H)]
-        job, jobs_dev = (jobs[0], None) if H == 1 else (None, pl.jobs_to_device(jobs))
-        ov["keep"][i] = (jobs_dev, poses_dev, scan)
-        if ov["free"][i] is not None:
-            ov["s_k1"].wait_event(ov["free"][i])                       # the tail that read this buffer set two scans ago is done
-        with torch.cuda.stream(ov["s_k1"]):
-            pl.launch_moments(jobs_dev, job, H, ctas, scan.layout, buf["partials"])
-            ready = ov["s_k1"].record_event()
-        ov["s_rest"].wait_event(ready)
-        with torch.cuda.stream(ov["s_rest"]):
-            self.px._check(_abi.lib.gcl_sharded_reduce_finalize(
-                pl.handle, self.px.x, ops._stream(), ops._ptr(buf["partials"]), ctas, pl.rec, pl.rec * ctas,
-                None if jobs_dev is None else C.c_void_p(jobs_dev.data_ptr()), None if job is None else C.byref(job), H, pl.n_bins,
-                ops._ptr(pl.bin_dirs), pl.tau, pl._origin_c, pl.eps_psd, pl.eps_mass, ops._ptr(buf["reduced"]), ops._ptr(buf["stats"])))
-            pl.launch_chain(buf["stats"], 1, H, map_stats, buf["map_derived"], poses_dev, None, buf["evidence"])
-            ov["free"][i] = ov["last"] = ov["s_rest"].record_event()
+        if ov is None or ov["key"] != (reserve_sms, n_tails):
+            if ov is not None:
+                self.end_overlapped()
+            sms = int(_abi.lib.gcl_device_sm_count(pl.handle))
+            ov = self._ov = {"key": (reserve_sms, n_tails), "sms": sms, "pipe": ScanPipe(pl, self.px, self.world, "sum", n_sets=4, n_tails=n_tails)}
+            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, max(1, reserve_sms // n_tails))
+        jobs_dev = None
+        if job is None:
+            xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
+            H = xi.shape[0]
+            _, _, (b, e), _ = self.plan(n_raw_total)
+            jobs = [pl.make_job(scan, xi[h], n_raw_total=n_raw_total, sel_range=(b, e)) for h in range(H)]
+            job, jobs_dev = (jobs[0], None) if H == 1 else (None, pl.jobs_to_device(jobs))
+        else:
+            H = 1
+        ck = (n_raw_total, H)
+        ctas = ov.get(ck)
+        if ctas is None:
+            _, _, (b, e), _ = self.plan(n_raw_total)
+            ctas = ov[ck] = max(1, min(pl.plan_ctas(H, max(1, e - b)), (ov["sms"] - reserve_sms) // max(1, H)))
+        buf, _ = ov["pipe"].submit(jobs_dev, job, H, ctas, scan.layout, map_stats, poses_dev, keep=scan)
         return LidarScanEvidence(n_bins=pl.n_bins, n_hyp=H, stats=buf["stats"], evidence=buf["evidence"], n_input=n_raw_total,
                                  n_points_cap=pl.n_points_cap)
 
+    def make_sharded_job(self, scan, n_raw_total: int, xi_body):
+        """The gcl_job of this rank's share of ``scan`` (for ``run_overlapped(job=...)``)."""
+        _, _, (b, e), _ = self.plan(n_raw_total)
+        return self.pl.make_job(scan, np.asarray(xi_body, dtype=np.float64).reshape(6), n_raw_total=n_raw_total, sel_range=(b, e))
+
     def join_overlapped(self) -> None:
         ov = getattr(self, "_ov", None)
-        if ov is not None and ov["last"] is not None:
-            torch.cuda.current_stream(self.pl.device).wait_event(ov["last"])
+        if ov is not None:
+            ov["pipe"].join()
 
     def end_overlapped(self) -> None:
         """Back to one scan at a time (the exchange kernel's grid is no longer capped)."""
         from . import _abi
-        self.join_overlapped()
+        ov = getattr(self, "_ov", None)
+        if ov is not None:
+            ov["pipe"].join()
+            ov["pipe"].close()
         if self.px is not None:
             _abi.lib.gcl_exchange_set_max_ctas(self.px.x, 0)
         self._ov = None
@@ -349,7 +419,7 @@ def _bits_identical_across_ranks(t: torch.Tensor, world: int) -> bool:
 
 def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, warmup: int, rank: int, world: int,
                          peak_gbs: float, precision: str = "fp64", scans_per_step: int = 64, exchange: str = "peer",
-                         with_e2e: bool = True, reserve_sms: Optional[int] = None) -> Dict[str, object]:
+                         with_e2e: bool = True, reserve_sms: Optional[int] = None, n_tails: Optional[int] = None) -> Dict[str, object]:
     """BASELINE.json configs[3]: one dense cloud of n_points, sharded by points over the ranks (strong scaling).  One "step" =
     `scans_per_step` scans (each: scan_moments on this rank's rows, the fused NVLink exchange + finalisation, the evidence step);
     several copies of the input are rotated so that consecutive scans never re-read an L2-resident cloud."""
@@ -358,6 +428,9 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
         # SMs left to the exchange + evidence tail of the previous scan: enough that the tail (latency-bound, ~50-70 us) finishes
         # under the moment pass of the next scan, which shrinks with the number of ranks
         reserve_sms = {1: 2, 2: 2, 4: 4}.get(world, 6)
+    if n_tails is None:
+        # two tails in flight once the shard's moment pass can be shorter than one tail (60-70 us)
+        n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or {1: 1, 2: 1}.get(world, 2)
     sc = synth.make_scan(n_points, seed=1234 + 4, dense=True)
     pl = g.LidarEvidencePipeline(n_bins=n_bins, tau=tau, precision=precision, n_points_cap=n_points, lidar_origin=sc.lidar_origin)
     sh = PointShardedEvidence(pl, rank, world, exchange=exchange)
@@ -384,12 +457,15 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
     overlapped = sh.px is not None and reserve_sms > 0
     ctas_run = max(1, min(ctas, int(g._abi.lib.gcl_device_sm_count(pl.handle)) - reserve_sms)) if overlapped else ctas
 
+    jobs_pre = [sh.make_sharded_job(s_, n_points, sc.xi_body) for s_ in shards]     # one gcl_job per resident copy, built once
+
     def step(_k):
         # consecutive scans are pipelined: the exchange + evidence tail of scan k (three small launches' worth of latency on a few SMs)
-        # runs under the moment pass of scan k + 1
+        # runs under the moment pass of scan k + 1; one C call per scan (gcl_scan_pipe_submit)
         for _ in range(scans_per_step):
             if overlapped:
-                sh.run_overlapped(shards[it[0] % n_copies], n_points, xi, poses, ms, reserve_sms=reserve_sms)
+                c = it[0] % n_copies
+                sh.run_overlapped(shards[c], n_points, xi, poses, ms, reserve_sms=reserve_sms, n_tails=n_tails, job=jobs_pre[c])
             else:
                 sh.run(shards[it[0] % n_copies], n_points, xi, poses, ms, ctas=ctas)
             it[0] += 1
@@ -446,8 +522,9 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
         "ms_per_scan_best": float(per[0]), "points_per_sec": n_points / (ms_scan * 1e-3), "scans_per_sec": 1e3 / ms_scan,
         "scan_moments_ms": ms_k1, "rest_of_scan_ms": ms_scan - ms_k1, "pairs_per_sec": n_points * n_bins / (ms_k1 * 1e-3),
         "ms_per_scan_one_at_a_time": ms_serial_step / scans_per_step,
-        "pipelining": (f"consecutive scans pipelined on two streams: scan_moments on {ctas_run} CTAs, the exchange + evidence tail of the previous "
-                       f"scan on the {reserve_sms} SMs left free") if overlapped else "none (one scan at a time)",
+        "pipelining": (f"consecutive scans in flight (gcl_scan_pipe, one call per scan): scan_moments on {ctas_run} CTAs on one stream, the exchange + "
+                       f"evidence tails of the previous scans on {n_tails} high-priority stream(s) and the {reserve_sms} SMs left free") if overlapped
+                      else "none (one scan at a time)",
         "launches_per_step": int(launches_per_step), "launches_per_scan": launches_per_step / scans_per_step, "ctas_per_rank": ctas_run,
         "rows_per_rank": int(e - b), "input_copies_rotated": n_copies,
         "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
@@ -532,36 +609,20 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
     reserve = 8
     _, n_sel = pl.selected_rows(res[0].n_raw, cap)
     ctas_p = max(1, min(pl.plan_ctas(Hl, n_sel), (sms - reserve) // max(1, Hl)))
-    s_k1, s_rest = torch.cuda.Stream(device=pl.device, priority=0), torch.cuda.Stream(device=pl.device, priority=-1)
-    gathered2 = [gathered, torch.empty_like(gathered)] if gathered is not None else [None, None]
-    ov = {"free": [None, None], "turn": 0, "last": None}
+    n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or {1: 1, 2: 1}.get(world, 2)
+    pipe = ScanPipe(pl, px, world, "gather", n_sets=4, n_tails=n_tails)
+    ov = {"last": None}
 
     def one_pipelined(i):
-        slot = ov["turn"] & 1
-        ov["turn"] += 1
-        buf = pl._buffers(Hl, ctas_p, slot=slot)
-        jd = jobs_dev[i % n_rot]
-        if ov["free"][slot] is not None:
-            s_k1.wait_event(ov["free"][slot])                 # the tail that read this buffer set two batches ago is done
-        with torch.cuda.stream(s_k1):
-            pl.launch_moments(jd, None, Hl, ctas_p, res[i % n_rot].layout, buf["partials"])
-            ready = s_k1.record_event()
-        s_rest.wait_event(ready)
-        with torch.cuda.stream(s_rest):
-            pl.launch_finalize(buf["partials"], ctas_p, pl.rec, pl.rec * ctas_p, jd, None, Hl, True, buf["reduced"], buf["stats"])
-            pl.launch_chain(buf["stats"], 1, Hl, ms, buf["map_derived"], poses_dev, None, buf["evidence"])
-            if px is not None:
-                px.all_gather(buf["evidence"], gathered2[slot])
-            ov["free"][slot] = ov["last"] = s_rest.record_event()
+        buf, g_ = pipe.submit(jobs_dev[i % n_rot], None, Hl, ctas_p, res[i % n_rot].layout, ms, poses_dev, wait_for_caller=False)
+        ov["last"] = g_
         return buf
 
     def step(_k):
-        cur = torch.cuda.current_stream(pl.device)
-        s_k1.wait_stream(cur); s_rest.wait_stream(cur)
         for _ in range(batches_per_step):
             one_pipelined(it[0])
             it[0] += 1
-        cur.wait_event(ov["last"])
+        pipe.join()
 
     ms_step, per = _time_steps(step, steps, warmup, world)
     ms_serial_step, _ = _time_steps(step_serial, max(2, steps // 2), 1, world)
@@ -570,9 +631,11 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
     # count per job differs when SMs are reserved, which regroups the fp64 additions -- so compare to 1e-12, not bitwise)
     torch.cuda.synchronize()
     bufp = one_pipelined(0)
-    torch.cuda.current_stream(pl.device).wait_event(ov["last"])
+    pipe.join()
     torch.cuda.synchronize()
     ev_p = bufp["evidence"].clone()
+    gathered_p = ov["last"].clone() if ov["last"] is not None else None
+    pipe.close()
     # parity: hypothesis h of the batch against the same hypothesis run alone; gathered records bit-identical on every rank
     ev = one(0)
     torch.cuda.synchronize()
@@ -581,13 +644,15 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
         single = pl.run_resident(res[0], xis[h:h + 1], poses_dev[h - lo:h - lo + 1], ms)
         worst = max(worst, float((single.evidence[0] - ev.evidence[h - lo]).abs().max() / max(1e-300, float(single.evidence[0].abs().max()))))
     identical = _bits_identical_across_ranks(gathered.reshape(-1), world) if gathered is not None else True
+    if gathered_p is not None:      # the records gathered by the pipelined route: same on every rank, and this rank's own block is its evidence
+        identical = identical and _bits_identical_across_ranks(gathered_p.reshape(-1), world) and bool((gathered_p[rank] == ev_p).all())
     pipe_vs_serial = float((ev_p - ev.evidence).abs().max() / max(1e-300, float(ev.evidence.abs().max())))
     out = {"n_points": n_points, "n_points_cap": cap, "n_bins": n_bins, "n_hyp": n_hyp, "precision": precision,
            "sharding": "hypotheses" if world > 1 else "none", "ms_per_batch": ms_batch, "batches_per_step": batches_per_step,
            "ms_per_batch_one_at_a_time": ms_serial_step / batches_per_step,
-           "pipelining": f"consecutive batches pipelined on two streams: scan_moments on {ctas_p} CTAs per hypothesis x {Hl} hypotheses, the "
-                         f"finalise + evidence + gather tail of the previous batch on the {reserve} SMs left free; pipelined vs one-at-a-time "
-                         f"evidence max rel {pipe_vs_serial:.1e}",
+           "pipelining": f"consecutive batches in flight (gcl_scan_pipe, one call per batch): scan_moments on {ctas_p} CTAs per hypothesis x {Hl} "
+                         f"hypotheses on one stream, the finalise + evidence + gather tails of the previous batches on {n_tails} high-priority "
+                         f"stream(s) and the {reserve} SMs left free; pipelined vs one-at-a-time evidence max rel {pipe_vs_serial:.1e}",
            "hypothesis_scans_per_sec": n_hyp / (ms_batch * 1e-3), "points_per_sec": n_hyp * n_points / (ms_batch * 1e-3),
            "result_gather": "peer exchange (one launch, NVLink stores + flags)" if px is not None else "none",
            "parity": {"batch_vs_single_hypothesis_max_rel": worst, "gathered_bit_identical_across_ranks": bool(identical),

@@ -273,6 +273,7 @@ int gcl_scan_chain_phase(gcl_handle h, void* stream, int phase, double* stats, i
  *                         data are read in place through gcl_exchange_gathered(x, src_rank). */
 #define GCL_MAX_RANKS 8
 #define GCL_EXCHANGE_HANDLE_BYTES 64
+#define GCL_EXCHANGE_LANES 2
 typedef struct gcl_exchange_s* gcl_exchange;
 int gcl_exchange_create(gcl_handle h, int world, int rank, size_t slot_bytes, gcl_exchange* out,
                         unsigned char* ipc_handle_out /* GCL_EXCHANGE_HANDLE_BYTES */);
@@ -285,6 +286,11 @@ int gcl_exchange_error_flag(gcl_exchange x); /* synchronous read of the device-s
  * with the moment pass of scan k + 1 leaves a few SMs free for it (gcl_scan_moments with ctas_per_job < SM count) and caps the
  * exchange kernel's grid to that number, so that its CTAs do not queue behind the moment pass. */
 int gcl_exchange_set_max_ctas(gcl_exchange x, int max_ctas);
+/* A block holds GCL_EXCHANGE_LANES independent copies of the protocol state (slots, flag words, ticket, step counter).  Calls run on
+ * the lane selected here (default 0).  Calls on ONE lane must be stream-ordered among themselves; calls on different lanes may be in
+ * flight at the same time on different streams (the tails of two consecutive scans: gcl_scan_pipe).  Every rank must use the same
+ * lane for the same step. */
+int gcl_exchange_set_lane(gcl_exchange x, int lane);
 int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, const double* parts, int n_parts,
                                 int64_t part_stride_doubles, int64_t job_stride_doubles, const gcl_job* jobs_dev,
                                 const gcl_job* job_by_value_host, int n_jobs, int n_bins, const double* bin_dirs, double tau,
@@ -292,6 +298,38 @@ int gcl_sharded_reduce_finalize(gcl_handle h, gcl_exchange x, void* stream, cons
                                 double* reduced /* [n_jobs][record]: the combined record */, double* stats);
 int gcl_exchange_all_gather(gcl_handle h, gcl_exchange x, void* stream, const void* src, size_t bytes, void* dst);
 const void* gcl_exchange_gathered(gcl_exchange x, int src_rank);
+
+/* ---- consecutive scans (or hypothesis batches) in flight -------------------------------------------------------------------- */
+/* The reference processes hypotheses and scans one after another on one stream (pkg/backend/backend_node.py:2036-2119).  Per
+ * scan this library's path is three launches: gcl_scan_moments (O(N), the whole GPU), the exchange + finalisation, the evidence
+ * chain (both O(B), a few CTAs, latency-bound).  A gcl_scan_pipe keeps the O(B) tail of scan k beside the moment pass of scan k + 1
+ * (and, with n_tails = 2, beside the tail of scan k + 1 as well: scan k runs on exchange lane k mod 2) on streams of its own, so the
+ * caller makes ONE call per scan.  The caller owns the buffers: n_sets sets of
+ *   partials  [n_jobs][ctas_per_job][gcl_partial_record_doubles]      reduced [n_jobs][gcl_partial_record_doubles]
+ *   stats     [n_jobs][gcl_stats_record_doubles]                      workspace gcl_scan_chain_workspace_doubles(1, n_jobs, n_bins)
+ *   evidence  [n_jobs][GCL_EVID_DOUBLES]                              gathered [world][n_jobs][GCL_EVID_DOUBLES] (mode GATHER, world > 1)
+ * and names the set a submission writes (`set`, any order; a set is rewritten only after the tail that read it has finished).
+ * Results of a submission are valid on the caller's stream after gcl_scan_pipe_join; everything a submission reads (jobs, poses,
+ * map, scan arrays) must stay valid until n_sets further submissions or a join + synchronisation.
+ *   GCL_PIPE_SUM_RECORDS      points sharded over the ranks: tail = gcl_sharded_reduce_finalize -> chain step (needs the exchange;
+ *                             world 1 runs the same kernel without peers)
+ *   GCL_PIPE_GATHER_EVIDENCE  hypotheses sharded over the ranks: tail = gcl_reduce_finalize -> chain step -> gcl_exchange_all_gather
+ *                             of the evidence records (no exchange needed at world 1)
+ * Collective like the exchange: every rank submits the same sequence.  The map is read-only here (no pose update, no IW state). */
+#define GCL_PIPE_MAX_SETS 8
+enum { GCL_PIPE_SUM_RECORDS = 0, GCL_PIPE_GATHER_EVIDENCE = 1 };
+typedef struct gcl_scan_pipe_s* gcl_scan_pipe;
+int gcl_scan_pipe_create(gcl_handle h, gcl_exchange x, int world, int mode, int n_sets /* n_tails < n_sets <= GCL_PIPE_MAX_SETS */,
+                         int n_tails /* 1 .. GCL_EXCHANGE_LANES */, gcl_scan_pipe* out);
+void gcl_scan_pipe_destroy(gcl_scan_pipe p);
+const char* gcl_scan_pipe_last_error(gcl_scan_pipe p);
+int gcl_scan_pipe_submit(gcl_scan_pipe p, void* caller_stream, int wait_for_caller_stream, int set, const gcl_job* jobs_dev,
+                         const gcl_job* job_by_value_host, int n_jobs, int ctas_per_job, int layout, int precision,
+                         const double* bin_dirs, int n_bins, double tau, const double* lidar_origin_host, double eps_psd,
+                         double eps_mass, const double* map_S_dir, const double* map_S_dir_scatter, const double* map_N_dir,
+                         const double* map_N_pos, const double* map_sum_p, const double* map_sum_ppT, const double* pose_pred,
+                         double* partials, double* reduced, double* stats, double* workspace, double* evidence, double* gathered);
+int gcl_scan_pipe_join(gcl_scan_pipe p, void* caller_stream);
 
 /* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,

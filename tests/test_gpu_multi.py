@@ -78,6 +78,29 @@ def _worker(rank, world, port):
                 assert _rel(sc_a[:16], sc_b[:16]) < (1e-11 if c["precision"] == "fp64" else 1e-5), (c, route, h)
                 assert float((ev.evidence[h, 0:9] - ref_evid[h, 0:9]).norm()) < (1e-9 if c["precision"] == "fp64" else 1e-4), (c, route, h)
             assert S._bits_identical_across_ranks(torch.cat([ev.stats.reshape(-1), ev.evidence.reshape(-1)]), world), (c, route)
+            if route == "peer":
+                # consecutive scans in flight (gcl_scan_pipe: two tail streams on the two exchange lanes, four buffer sets): every scan
+                # equals the same scan run alone with the same grid, bit for bit, twists differing from scan to scan
+                sms = int(g._abi.lib.gcl_device_sm_count(pl.handle))
+                _, _, (b0, e0), _ = sh.plan(n_raw)
+                ctas = max(1, min(pl.plan_ctas(c["H"], max(1, e0 - b0)), (sms - 8) // c["H"]))
+                variants = [xis * (1 + 0.03 * v) for v in range(2)]
+                want = []
+                for v in range(2):
+                    e_ = sh.run(shard, n_raw, variants[v], poses, ms, ctas=ctas)
+                    want.append((e_.stats.clone(), e_.evidence.clone()))
+                order = [0, 1, 1, 0, 0, 1, 0, 1]
+                got = []
+                for k, v in enumerate(order):
+                    got.append(sh.run_overlapped(shard, n_raw, variants[v], poses, ms, reserve_sms=8, n_tails=2))
+                    if k % 4 == 3:
+                        sh.join_overlapped()
+                        torch.cuda.synchronize()
+                        for kk in range(k - 3, k + 1):
+                            assert torch.equal(got[kk].stats, want[order[kk]][0]), (c, "pipelined stats", kk)
+                            assert torch.equal(got[kk].evidence, want[order[kk]][1]), (c, "pipelined evidence", kk)
+                sh.end_overlapped()
+                assert sh.px.error_flag() == 0
             if sh.px is not None:
                 sh.px.close()
         del full
@@ -103,6 +126,19 @@ def _worker(rank, world, port):
     assert _rel(gathered.reshape(Hn, 640), allev) < 1e-9, "gathered hypothesis records differ from the unsharded batch"
     assert torch.equal(gathered[rank], mine)
     assert S._bits_identical_across_ranks(gathered.reshape(-1), world)
+    # the same through the pipe (hypothesis-batch mode: finalise -> evidence -> gather on the tail streams, lanes alternating)
+    jobs_dev = pl.jobs_to_device([pl.make_job(scan, xis[h]) for h in range(lo, hi)])
+    cj = pl.plan_ctas(hi - lo, 30_000)
+    pipe = S.ScanPipe(pl, px, world, "gather", n_sets=4, n_tails=2)
+    outs = [pipe.submit(jobs_dev, None, hi - lo, cj, scan.layout, ms, poses[lo:hi]) for _ in range(6)]
+    pipe.join()
+    torch.cuda.synchronize()
+    assert px.error_flag() == 0
+    for buf, gat in outs[2:]:
+        assert _rel(buf["evidence"], mine) < 1e-12
+        assert torch.equal(gat[rank], buf["evidence"]) and _rel(gat.reshape(Hn, 640), allev) < 1e-9
+        assert S._bits_identical_across_ranks(gat.reshape(-1), world)
+    pipe.close()
     px.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -320,6 +320,68 @@ def test_hypothesis_batch_matches_single_runs(g, O):
         assert geodesic(be[h, 0:9].reshape(3, 3), mf["R_mf"]) < 1e-8
 
 
+@pytest.mark.parametrize("precision,n_tails", [("fp64", 1), ("fp64", 2), ("fp32c", 2)])
+def test_scan_pipe_matches_one_scan_at_a_time(g, precision, n_tails):
+    """gcl_scan_pipe (consecutive scans in flight: one moment-pass stream, one or two tail streams, four buffer sets, exchange lanes) gives,
+    for every scan, bit for bit what the same launches give one after another on one stream -- points mode (world 1: the fused exchange
+    kernel without peers) with twists that differ from scan to scan, and the hypothesis-batch mode."""
+    from fl_slam_b200 import sharding as S
+    B = 128 if precision == "fp32c" else 48
+    sc = g.synth.make_scan(40_000, seed=5, dense=True)
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=0.1, precision=precision, n_points_cap=40_000, lidar_origin=sc.lidar_origin)
+    sh = S.PointShardedEvidence(pl, 0, 1, exchange="peer")
+    shard, n_raw = sh.upload_shard(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+    rng = np.random.default_rng(11)
+    ms0 = g.create_empty_map_stats(B)
+    pose = torch.from_numpy(0.03 * rng.normal(size=(1, 6))).cuda()
+    ev0 = sh.run(shard, n_raw, sc.xi_body[None], pose, ms0)
+    sa = {k: H(v) for k, v in S._stats_arrays(pl, ev0.stats[0]).items()}
+    raw = {"N": sa["N"], "s_dir": sa["s_dir"].reshape(-1, 3), "S_dir_scatter": sa["S_dir_scatter"].reshape(-1, 3, 3),
+           "sum_p": sa["sum_p"].reshape(-1, 3), "sum_ppT": sa["sum_ppT"].reshape(-1, 3, 3)}
+    ms = g.MapBinStats.from_arrays(g.synth.map_stats_from_scan_sums(raw, *g.synth.known_map_transform(2), seed=2))
+    xis = [sc.xi_body[None] * (1 + 0.05 * k) for k in range(3)]
+    sms = int(g._abi.lib.gcl_device_sm_count(pl.handle))
+    ctas = min(pl.plan_ctas(1, n_raw), sms - 8)                  # the grid run_overlapped uses with 8 SMs reserved
+    want = []
+    for xi in xis:
+        ev = sh.run(shard, n_raw, xi, pose, ms, ctas=ctas)
+        want.append((ev.stats.clone(), ev.evidence.clone()))
+    order = [0, 1, 1, 2, 0, 2, 1, 0, 2, 2]
+    got = []
+    for k, v in enumerate(order):
+        got.append(sh.run_overlapped(shard, n_raw, xis[v], pose, ms, reserve_sms=8, n_tails=n_tails))
+        if k % 4 == 3 or k == len(order) - 1:                    # four buffer sets: read the results before they are rewritten
+            sh.join_overlapped()
+            torch.cuda.synchronize()
+            for kk in range(k - (k % 4), k + 1):
+                assert torch.equal(got[kk].stats, want[order[kk]][0]), (kk, "stats")
+                assert torch.equal(got[kk].evidence, want[order[kk]][1]), (kk, "evidence")
+    sh.end_overlapped()
+    assert sh.px.error_flag() == 0
+    sh.px.close()
+    # hypothesis-batch mode (no exchange at world 1)
+    Hn = 5
+    xb = sc.xi_body[None] * (1 + 0.02 * rng.normal(size=(Hn, 6)))
+    poses = torch.from_numpy(0.02 * rng.normal(size=(Hn, 6))).cuda()
+    full = pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+    jobs = [pl.jobs_to_device([pl.make_job(full, xb[h] * (1 + 0.01 * v)) for h in range(Hn)]) for v in range(2)]
+    cj = pl.plan_ctas(Hn, n_raw)
+    refs = []
+    for v in range(2):
+        b = pl._buffers(Hn, cj, slot=7)
+        pl.launch_moments(jobs[v], None, Hn, cj, full.layout, b["partials"])
+        pl.launch_finalize(b["partials"], cj, pl.rec, pl.rec * cj, jobs[v], None, Hn, True, b["reduced"], b["stats"])
+        pl.launch_chain(b["stats"], 1, Hn, ms, b["map_derived"], poses, None, b["evidence"])
+        refs.append((b["stats"].clone(), b["evidence"].clone()))
+    pipe = S.ScanPipe(pl, None, 1, "gather", n_sets=4, n_tails=n_tails)
+    outs = [pipe.submit(jobs[v], None, Hn, cj, full.layout, ms, poses)[0] for v in (0, 1, 1, 0)]
+    pipe.join()
+    torch.cuda.synchronize()
+    for o, v in zip(outs, (0, 1, 1, 0)):
+        assert torch.equal(o["stats"], refs[v][0]) and torch.equal(o["evidence"], refs[v][1])
+    pipe.close()
+
+
 def test_recovers_known_transform(g, O):
     """map = scan statistics moved by (R*, t*)  =>  R_mf ~ R*, t_wls ~ t*."""
     sc = g.synth.make_scan(20000, seed=11)

@@ -8,7 +8,7 @@ cd "$(dirname "$0")/../fl-slam_b200/csrc"
 make -j8 > /dev/null
 mkdir -p variants
 OBJS=""
-for f in gcl_api gcl_scan_fused gcl_scan_tc gcl_scan_moments gcl_finalize gcl_exchange gcl_evidence gcl_imu gcl_ingest gcl_ops; do
+for f in gcl_api gcl_scan_fused gcl_scan_tc gcl_scan_moments gcl_finalize gcl_exchange gcl_pipe gcl_evidence gcl_imu gcl_ingest gcl_ops; do
   if [[ " $* " == *" $f.cu "* ]]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $EXTRA -c $f.cu -o variants/${NAME}_$f.o 2> variants/${NAME}_$f.o.ptxas.log || { cat variants/${NAME}_$f.o.ptxas.log; exit 1; }
     OBJS="$OBJS variants/${NAME}_$f.o"
