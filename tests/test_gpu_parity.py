@@ -213,6 +213,12 @@ def test_fused_pipeline_against_reference_goldens(g, ref_certs, name, precision,
     assert abs(certs["BinSoftAssign"][1].support.support_frac / sa["cert"]["support"]["support_frac"] - 1) < etol
     mm = cj["moment_match"]["cert"]
     assert abs(certs["ScanBinMomentMatch"][1].support.ess_total / mm["support"]["ess_total"] - 1) < 10 * ctol
+    # influence.psd_projection_delta (pkg/common/primitives.py:80-123 summed over bins, binning.py:201-204): when no eigenvalue is floored it is
+    # the round-off of V diag V^T (LAPACK there, a Jacobi sweep here), so the bar is absolute, relative to the summed matrix norms -- as in
+    # tests/test_oracle_pinning.py; when the projection does move a matrix the relative bar applies
+    psd_scale = float(np.sum(np.linalg.norm(gz["mm_Sigma_p"], axis=(1, 2))))
+    d_ref, d_got = mm["influence"]["psd_projection_delta"], certs["ScanBinMomentMatch"][1].influence.psd_projection_delta
+    assert abs(d_got - d_ref) <= (1e-6 if precision == "fp64" else 1e-3) * abs(d_ref) + (1e-12 if precision == "fp64" else 1e-5) * psd_scale, (d_got, d_ref)
     for h in range(ev.n_hyp):
         _, mf, cmf, emf = ev.certificates(h)[4]
         _, pt, cpt, ept = ev.certificates(h)[5]

@@ -71,7 +71,7 @@ s = one["extra"]["cfg2_stream"]
 e = s["e2e"]
 print(f"* resident, consecutive 200-scan batches pipelined: {s['ms_per_step']:.3f} ms per batch = {s['points_per_sec']:.3e} raw points/s "
       f"({s['processed_rows_per_sec']:.3e} processed rows/s), {s['scans_per_sec']:.3e} scans/s; one batch at a time {s['ms_per_step_one_batch_at_a_time']:.3f} ms; "
-      f"`scan_moments` {s['roofline'].get('ms_per_launch', float('nan')):.3f} ms per launch, FMA-issue fraction {s['roofline'].get('compute_frac', float('nan')):.2f}, "
+      f"`scan_moments` {s['roofline'].get('ms_per_launch', float('nan')):.3f} ms per launch, FMA-issue fraction {s['roofline'].get('compute_frac', s['roofline'].get('compute_frac_at_1965MHz', float('nan'))):.2f}, "
       f"HBM fraction {s['roofline']['frac']:.3f}.")
 print(f"* two-stage host calls (host arrays in, records out, every scan): {e['us_per_scan']:.1f} us per scan = {e['value']:.3e} points/s; blocking call "
       f"{e['blocking_call']['us_per_scan']:.1f} us (p50 {e['blocking_call']['latency_us']['p50']:.0f}, p99 {e['blocking_call']['latency_us']['p99']:.0f}); "
