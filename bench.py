@@ -47,9 +47,10 @@ TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__
 
 
 # FMA-issue ceilings of scan_moments (rates measured with tools/microbench/ffma_rate.cu):
-# FMA-pipe lane operations per (point, bin) pair = 19 accumulate + 3 similarity + softmax bookkeeping (+ the fp64 exp)
+# FMA-pipe lane operations per (point, bin) pair = 19 accumulate + 3 similarity + softmax bookkeeping (+ the fp64 exp): fp64 phase A is 12
+# FP64-pipe operations per pair since the 1/1024-octave exp table (round 2; it was 15 in round 1, i.e. 34 in all)
 FMA_LANES_PER_CLK_SM = {"fp32c": 128.0, "fp64": 64.0}
-LANE_OPS_PER_PAIR = {"fp32c": 24.0, "fp64": 34.0}
+LANE_OPS_PER_PAIR = {"fp32c": 24.0, "fp64": 31.0}
 N_SM = 148
 
 
@@ -539,7 +540,7 @@ def main():
         o["roofline"]["compute_frac"] = (o["pairs_per_sec"] / world) / pair_ceiling(other, clocks.get("sm_mhz") or 1965.0)
         o["roofline"]["compute_frac_note"] = ("pairs/s over the FMA-issue ceiling of the CUDA-core instruction mix (24 lane operations per pair); the "
                                               "tensor-core kernel moves 19 of them to tcgen05 and is bound by the issue slots of what remains "
-                                              "(DESIGN.md, K1-TC)") if other == "fp32c" else "pairs/s over the FP64 FMA-issue ceiling (34 lane operations per pair)"
+                                              "(DESIGN.md, K1-TC)") if other == "fp32c" else "pairs/s over the FP64 FMA-issue ceiling (31 lane operations per pair)"
         extra[f"cfg4_1Mx256_{other}"] = o
         if world > 1 and args.exchange == "peer":
             n = sharding.bench_points_sharded(g, n_points=HEAD_POINTS, n_bins=HEAD_BINS, tau=tau, steps=max(3, args.steps // 2), warmup=args.warmup,

@@ -521,6 +521,12 @@ struct HostTiming {
     if (!on || ++n < 64) return;
     fprintf(stderr, "[gcl host timing, us/call] stage+enqueue H2D %.1f | H2D done %.1f | scan_moments %.1f | reduce_finalize %.1f | chain %.1f | D2H+sync %.1f | copy-out %.1f\n",
             acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n);
+    // the same figures under the reference's stage labels (pkg/backend/pipeline.py:411 point_budget_ms, :581 deskew_ms; binning and the
+    // evidence operators sit under its map branch): resample, deskew, soft assign and the moment sums are ONE kernel here, so they share a label
+    fprintf(stderr, "[gcl host timing, reference labels, ms/call] upload_ms %.4f | point_budget_ms+deskew_ms+bin_soft_assign_ms+moment_sums_ms (fused scan_moments) %.4f | "
+                    "moment_match_finalize_ms %.4f | map_derived+matrix_fisher+planar_translation+iw+map_update_ms (chain) %.4f | readback_ms %.4f | total_ms %.4f\n",
+            (acc[0] + acc[1]) / n * 1e-3, acc[2] / n * 1e-3, acc[3] / n * 1e-3, acc[4] / n * 1e-3, (acc[5] + acc[6]) / n * 1e-3,
+            (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6]) / n * 1e-3);
     n = 0; for (double& a : acc) a = 0;
   }
 };
