@@ -76,9 +76,14 @@ __device__ __forceinline__ static void reduce_finalize_job(const FinalizeParams&
   for (int e = tid; nred > 0 && e < rec; e += nred) {
     const bool is_max = (e == NMOM * B + GCL_CS_MAX_RESP);
     double s = __ldcg(src + e);
-    for (int p = 1; p < P.n_parts; ++p) {
-      const double v = __ldcg(src + (size_t)p * P.part_stride + e);
-      s = is_max ? fmax(s, v) : s + v;
+    // eight loads in flight per thread (one load per trip pays the L2 latency n_parts times); the order of the additions is unchanged
+    for (int p0 = 1; p0 < P.n_parts; p0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (p0 + j < P.n_parts) ? __ldcg(src + (size_t)(p0 + j) * P.part_stride + e) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (p0 + j < P.n_parts) s = is_max ? fmax(s, v[j]) : s + v[j];
     }
     red[e] = s;
     if (red_smem) s_redrec[e] = s;

@@ -753,7 +753,10 @@ int plan_fused_tile(int n_bins, int precision, int G, int L, int minb) {
   const int tsz = precision == GCL_F64 ? 8 : 4;
   // 228 KB per SM, 1 KB reserved per CTA, ~17 KB static (certificate partials, reduction scratch)
   const size_t budget = (minb == 2 ? 94 : 200) * 1024;
-  int TP = kNT;
+  // GCL_K1_TPMAX = 16..256 (a power of two): upper limit of the tile, for A/B runs (smaller tiles at few bins let the two thread groups
+  // alternate and put several threads on a point in phase A)
+  static const int tp_max = [] { const char* e = getenv("GCL_K1_TPMAX"); const int v = e ? atoi(e) : 0; return (v >= 16 && v <= kNT && !(v & (v - 1))) ? v : kNT; }();
+  int TP = tp_max;
   while (TP > 16 && fused_plan(n_bins, tsz, G, L, TP).total > budget) TP >>= 1;
   return TP;
 }

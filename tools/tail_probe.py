@@ -72,4 +72,31 @@ for precision in ("fp32c", "fp64"):
     res["one_at_a_time_us"] = {"scan_moments": a[0], "exchange_finalize": a[1], "chain": a[2], "ctas": ctas}
     out[precision] = res
     sh.px.close()
+# the tail of a hypothesis batch as one rank of 8 sees it: 8 hypotheses x 17 CTAs, 48 bins
+for precision in ("fp64",):
+    sc = g.synth.make_scan(30000, seed=1237)
+    pl = g.LidarEvidencePipeline(n_bins=48, tau=g.synth.DEFAULT_TAU, precision=precision, n_points_cap=32768, lidar_origin=sc.lidar_origin)
+    scan = pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+    Hn, cj = 8, 17
+    rng = np.random.default_rng(1)
+    xis = sc.xi_body[None] * (1 + 0.02 * rng.normal(size=(Hn, 6)))
+    poses = torch.from_numpy(0.02 * rng.normal(size=(Hn, 6))).cuda()
+    jobs = pl.jobs_to_device([pl.make_job(scan, xis[h]) for h in range(Hn)])
+    ms = g.create_empty_map_stats(48)
+    b = pl._buffers(Hn, cj)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    tk = []
+    for k in range(60):
+        evs[0].record()
+        pl.launch_moments(jobs, None, Hn, cj, scan.layout, b["partials"])
+        evs[1].record()
+        pl.launch_finalize(b["partials"], cj, pl.rec, pl.rec * cj, jobs, None, Hn, True, b["reduced"], b["stats"])
+        evs[2].record()
+        pl.launch_chain(b["stats"], 1, Hn, ms, b["map_derived"], poses, None, b["evidence"])
+        evs[3].record()
+        torch.cuda.synchronize()
+        if k >= 20:
+            tk.append((evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])))
+    a = np.median(np.asarray(tk), axis=0) * 1e3
+    out["hyp8x17_48bins_" + precision] = {"scan_moments": a[0], "reduce_finalize": a[1], "chain": a[2]}
 print(json.dumps(out, indent=1))
