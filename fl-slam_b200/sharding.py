@@ -520,7 +520,7 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
         "sharding": "points" if world > 1 else "none", "exchange": sh.exchange if world > 1 else "none (1 rank: same fused kernel, no peers)",
         "scans_per_step": scans_per_step, "ms_per_step": ms_step, "ms_per_scan": ms_scan, "ms_per_scan_median": float(per[len(per) // 2]),
         "ms_per_scan_best": float(per[0]), "points_per_sec": n_points / (ms_scan * 1e-3), "scans_per_sec": 1e3 / ms_scan,
-        "scan_moments_ms": ms_k1, "rest_of_scan_ms": ms_scan - ms_k1, "pairs_per_sec": n_points * n_bins / (ms_k1 * 1e-3),
+        "scan_moments_ms": ms_k1, "rest_of_scan_ms": max(0.0, ms_scan - ms_k1), "pairs_per_sec": n_points * n_bins / (ms_k1 * 1e-3),
         "ms_per_scan_one_at_a_time": ms_serial_step / scans_per_step,
         "pipelining": (f"consecutive scans in flight (gcl_scan_pipe, one call per scan): scan_moments on {ctas_run} CTAs on one stream, the exchange + "
                        f"evidence tails of the previous scans on {n_tails} high-priority stream(s) and the {reserve_sms} SMs left free") if overlapped
