@@ -723,6 +723,319 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K1-WS: the fp64 kernel, warp-specialised (129..256 bins, float64 rows, fixed softmax shift)
+// ------------------------------------------------------------------------------------------------------------
+// The kernel above runs its phases one after another on the same eight warps.  Phase B is FP64-pipe bound, but phase A runs at 2.5x its
+// FP64 bound (issue slots and latency: profiles/r2_scan_moments_fp64_1Mx256.md), and through the scale interval six of the
+// eight warps idle.  Here the phases run BESIDE each other on different warps:
+//   warps 0-7   consumers: phase B of tile t (G = 4 bins x 19 accumulators per thread, as above) and the final flush; 208 registers
+//   warps 8-10  phase-A warps: lanes = the 32 points of tile t + 1, warp = a third of the bins; exponentials into the OTHER e-tile buffer
+//   warp 11     point warp: front end of tile t + 2, scale step of tile t + 1, raw rows staged two tiles ahead (cp.async)
+// Registers move between the roles with setmaxnreg (the accumulating warps take 208, the producers 88: 256 x 208 + 128 x 88 = 384 x 168, the allocation of the launch -- the pool setmaxnreg draws on).
+// Hand-offs are named barriers: FULL[buf] (point warp arrives, consumers wait), EMPTY[buf] (consumers arrive, phase-A warps wait),
+// PROD (the four producer warps, once per tile: phase A of tile t done, front end of tile t + 1 published).  Same partial-record
+// format and the same fixed summation order inside a CTA from run to run.
+constexpr int kWsTP = 32;     // points per tile
+enum { kBarFull0 = 1, kBarEmpty0 = 3, kBarProd = 5, kBarCons = 6 };
+
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct WsPlan { int BA, EP; size_t o_tab, o_sd, o_zp, o_rows, o_pt, o_in, o_etile, total; };
+__host__ __device__ inline WsPlan ws_plan(int B, int G, int L, int kWsCons, int kWsTA, int nga) {
+  WsPlan p;
+  p.BA = (((B + kWsTA - 1) / kWsTA) + 2 * nga - 1) / (2 * nga) * (2 * nga);   // whole phase-A steps of nga groups of two bins
+  const int cols = (G * L > kWsTA * p.BA) ? G * L : kWsTA * p.BA;
+  p.EP = e_pitch(cols, 4, 2);
+  size_t off = (size_t)(kWsTA * p.BA) * 3 * 8;
+  off = (off + 15) & ~(size_t)15;
+  p.o_tab = off;  off += (size_t)kExpTab * 8;
+  p.o_sd = off;   off += (size_t)2 * kWsTP * 4 * 8;
+  p.o_zp = off;   off += (size_t)2 * kWsTA * kWsTP * 3 * 8;
+  off = (off + 15) & ~(size_t)15;
+  p.o_rows = off; off += (size_t)2 * kWsTP * kRowPitch * 8;
+  p.o_pt = off;   off += (size_t)3 * 7 * kWsTP * 8;   // three buffers: the front end of tile t + 2 may run beside the scale step of tile t
+  p.o_in = off;   off += (size_t)2 * kWsTP * 5 * 8;
+  off = (off + 15) & ~(size_t)15;
+  p.o_etile = off;
+  size_t et = (size_t)2 * kWsTP * p.EP * 8;
+  const size_t stage = (size_t)(kWsCons / L) * kKC * (size_t)(G * L) * 8;
+  if (stage > et) et = stage;
+  p.total = off + et + 16;
+  return p;
+}
+
+// NCW consumer warps, TA phase-A warps (TA threads per point), one point warp; RC / RA registers of the consumers / the phase-A warps
+// (setmaxnreg; the point warp follows the phase-A warps when it shares their warpgroup, else it keeps the launch allocation);
+// NGA groups of two bins in flight per phase-A thread
+#ifdef GCL_K1_TRACE
+__device__ long long g_ws_trace[16];
+extern "C" int gcl_debug_ws_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_ws_trace, sizeof(long long) * 16); }
+#define WST_DECL long long wst_t = clock64(), wst_acc[4] = {0, 0, 0, 0}; const bool wst_on = (blockIdx.x == 1 && (threadIdx.x & 31) == 0)
+#define WST(i) do { if (wst_on) { const long long n_ = clock64(); wst_acc[i] += n_ - wst_t; wst_t = n_; } } while (0)
+#define WST_OUT(base) do { if (wst_on) for (int i_ = 0; i_ < 4; ++i_) g_ws_trace[(base) + i_] = wst_acc[i_]; } while (0)
+#else
+#define WST_DECL do { } while (0)
+#define WST(i) do { } while (0)
+#define WST_OUT(base) do { } while (0)
+#endif
+template <int G, int NCW, int TA_, int NPW, int RC, int RA, int NGA>
+__global__ void __launch_bounds__(32 * (NCW + TA_ + NPW), 1) scan_moments_ws64_kernel(const __grid_constant__ ScanParams P) {
+  using T = double;
+  constexpr int kWsCons = 32 * NCW, kWsTA = TA_, kWsProd = 32 * (TA_ + NPW), kWsNT = kWsCons + kWsProd;
+  static_assert(NCW % 4 == 0 && (TA_ + NPW) % 4 == 0 && (NPW == 1 || NPW == 2), "setmaxnreg works on warpgroups of four warps");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int B = P.n_bins, L = P.lanes;
+  __shared__ gcl_job s_job;
+  __shared__ double s_wraw[kWsNT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < (int)(sizeof(gcl_job) / sizeof(int)))
+    reinterpret_cast<int*>(&s_job)[tid] = reinterpret_cast<const int*>(P.jobs ? &P.jobs[blockIdx.y] : &P.job)[tid];
+  __syncthreads();
+  const gcl_job& J = s_job;
+  const ScanConst& C = P.c;
+  const int64_t n_raw = J.n_raw;
+  const int64_t cap = J.n_points_cap > 0 ? J.n_points_cap : 1;
+  const int64_t stride0 = (n_raw + cap - 1) / cap;
+  const int64_t stride = stride0 > 1 ? stride0 : 1;
+  const int64_t n_sel_total = (n_raw + stride - 1) / stride;
+  const int64_t sel_begin = J.sel_begin;
+  const int64_t sel_end = (J.sel_end < 0 || J.sel_end > n_sel_total) ? n_sel_total : J.sel_end;
+  const int64_t rows = sel_end > sel_begin ? sel_end - sel_begin : 0;
+  const int64_t rpc = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t lo0 = sel_begin + (int64_t)blockIdx.x * rpc;
+  const int64_t lo = lo0 < sel_end ? lo0 : sel_end;
+  const int64_t hi = (lo + rpc < sel_end) ? lo + rpc : sel_end;
+  double* part = P.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * P.rec_doubles;
+  constexpr int TP = kWsTP, TA = kWsTA;
+  const WsPlan pl = ws_plan(B, G, L, kWsCons, kWsTA, NGA);
+  const int BA = pl.BA, EP = pl.EP, PS = kWsCons / L, Bp = G * L;
+  T* s_atlas = reinterpret_cast<T*>(smem_raw);
+  double* s_tab = reinterpret_cast<double*>(smem_raw + pl.o_tab);
+  T* s_d = reinterpret_cast<T*>(smem_raw + pl.o_sd);         // [buf][TP][4]
+  T* s_zp = reinterpret_cast<T*>(smem_raw + pl.o_zp);        // [buf][TA][TP][3]
+  T* s_rows = reinterpret_cast<T*>(smem_raw + pl.o_rows);    // [buf][TP][kRowPitch]
+  T* s_pt = reinterpret_cast<T*>(smem_raw + pl.o_pt);        // [tile % 3][7][TP]
+  double* s_in = reinterpret_cast<double*>(smem_raw + pl.o_in);   // [buf][TP][5]
+  T* s_etile = reinterpret_cast<T*>(smem_raw + pl.o_etile);  // [buf][TP][EP]
+  T* s_stage = s_etile;                                      // flush staging: after the last tile
+  const double cscale_d = Num<T>::kScale / P.tau;
+
+  {  // atlas (pre-scaled, group-major as above) and exp table
+    const int nb = TA * BA;
+    constexpr int V = Num<T>::kVec;
+    for (int i = tid; i < nb * 3; i += kWsNT) {
+      const int g = i / (3 * V), rem = i - g * 3 * V, c = rem / V, b = g * V + (rem - c * V);
+      s_atlas[i] = (b < B) ? (T)(P.bin_dirs[b * 3 + c] * cscale_d) : (T)0;
+    }
+    for (int i = tid; i < kExpTab; i += kWsNT) s_tab[i] = exp2((double)i * (1.0 / kExpTab));
+  }
+  {  // sum of ALL raw weights of this CTA's raw range (mass preservation, point_budget.py:69); partials combined in a fixed order
+    double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    if (stride > 1 && hi > lo) {
+      const int64_t rlo = lo * stride;
+      const int64_t rhi = (hi >= n_sel_total) ? n_raw : hi * stride;
+      const double* w = static_cast<const double*>(J.weights);
+      int64_t r = rlo + tid;
+      for (; r + 3 * kWsNT < rhi; r += 4 * kWsNT) { p0 += w[r]; p1 += w[r + kWsNT]; p2 += w[r + 2 * kWsNT]; p3 += w[r + 3 * kWsNT]; }
+      for (; r < rhi; r += kWsNT) p0 += w[r];
+    }
+    s_wraw[tid] = (p0 + p1) + (p2 + p3);
+  }
+  __syncthreads();
+  const int n_tiles = (int)((hi - lo + TP - 1) / TP);
+
+  if (warp < kWsCons / 32) {
+    // ================================================ consumers: phase B ========================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RC));
+    constexpr int VB = Tile<T, G>::VB;
+    const int binlane = tid & (L - 1), slice = tid / L;
+    Tile<T, G> acc;
+    acc.zero();
+    WST_DECL;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const int64_t tile0 = lo + (int64_t)t * TP;
+      const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+      WST(0);
+      nb_sync(kBarFull0 + buf, kWsCons + 32);
+      WST(1);
+      const T* ebase = s_etile + (size_t)buf * TP * EP + (size_t)binlane * VB;
+      const T* rws = s_rows + (size_t)buf * TP * kRowPitch;
+#pragma unroll 2
+      for (int pt = slice; pt < count; pt += PS) acc.step(ebase + (size_t)pt * EP, L, rws + (size_t)pt * kRowPitch);
+      if (t + 2 < n_tiles) nb_arrive(kBarEmpty0 + buf, kWsCons + 32 * TA);
+    }
+    WST(0);
+    if (warp == 0) WST_OUT(0);   // consumer warp 0: [0] phase B, [1] wait FULL
+    // flush: fixed-order cross-slice sum, kKC moments at a time (the producers are done with the e-tile buffers)
+    if (n_tiles > 0) {
+#pragma unroll
+      for (int k0 = 0; k0 < GCL_NM; k0 += kKC) {
+#pragma unroll
+        for (int kc = 0; kc < kKC; ++kc) {
+          if (k0 + kc < GCL_NM) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              s_stage[((size_t)slice * kKC + kc) * Bp + (g / VB) * VB * L + VB * binlane + (g % VB)] = acc.get(g, (k0 + kc < GCL_NM) ? k0 + kc : 0);
+          }
+        }
+        nb_sync(kBarCons, kWsCons);
+        for (int e = tid; e < kKC * Bp; e += kWsCons) {
+          const int kc = e / Bp, b = e - kc * Bp, k = k0 + kc;
+          if (k < GCL_NM && b < B) {
+            double sm = 0.0;
+            for (int sl = 0; sl < PS; ++sl) sm += (double)s_stage[((size_t)sl * kKC + kc) * Bp + b];
+            part[(size_t)k * B + b] = sm;
+          }
+        }
+        nb_sync(kBarCons, kWsCons);
+      }
+    } else {
+      for (int i = tid; i < GCL_NM * B; i += kWsCons) part[i] = 0.0;
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RA));
+    if (warp < kWsCons / 32 + TA) {
+      // ============================================ phase-A warps =================================================================
+      const int pa = warp - kWsCons / 32, pi = lane;
+      nb_sync(kBarProd, kWsProd);   // front end of tile 0 published
+      WST_DECL;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        const int64_t tile0 = lo + (int64_t)t * TP;
+        const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+        WST(2);
+        if (t >= 2) nb_sync(kBarEmpty0 + buf, kWsCons + 32 * TA);   // the consumers have finished tile t - 2 in this buffer
+        WST(0);
+        if (pi < count) {
+          const T* sd = s_d + ((size_t)buf * TP + pi) * 4;
+          T Z, S1, xmax;
+          phase_a_bins<NGA, false>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3],
+                                 s_etile + ((size_t)buf * TP + pi) * EP, Z, S1, xmax);
+          T* zp = s_zp + (((size_t)buf * TA + pa) * TP + pi) * 3;
+          zp[0] = Z; zp[1] = S1; zp[2] = xmax;
+        }
+        WST(1);
+        __threadfence_block();
+        nb_sync(kBarProd, kWsProd);
+      }
+      WST(2);
+      if (pa == 0) WST_OUT(4);   // phase-A warp 0: [0] wait EMPTY, [1] phase A, [2] wait PROD
+    } else {
+      // ============================ point warp(s): front end + row staging | scale (one warp, or one warp each) ====================
+      const bool do_front = (NPW == 1) || warp == kWsCons / 32 + TA, do_scale = (NPW == 1) || !do_front;
+      const int li = lane;
+      const TimeConst tconst = time_const(J);
+      double c_sel = 0, c_sel2 = 0, c_desk = 0, c_rows = 0, c_ent = 0, c_max = 0, c_wraw = 0;
+      for (int j = 0; j < kWsNT / 32; ++j) c_wraw += s_wraw[li + 32 * j];
+      auto prefetch_rows = [&](int u) {   // tile u -> staging buffer u & 1; always commits a group
+        const int64_t srow = lo + (int64_t)u * TP + li;
+        if (u < n_tiles && srow < hi) {
+          const int64_t r = srow * stride;
+          const int64_t rp = (J.flags & GCL_JOB_COMPACT_ROWS) ? srow : r;
+          const double* pts = static_cast<const double*>(J.points) + rp * 3;
+          double* dst = s_in + ((size_t)(u & 1) * TP + li) * 5;
+          cp_async8(dst + 0, pts + 0); cp_async8(dst + 1, pts + 1); cp_async8(dst + 2, pts + 2);
+          cp_async8(dst + 3, static_cast<const double*>(J.timestamps) + rp);
+          cp_async8(dst + 4, static_cast<const double*>(J.weights) + r);
+        }
+        cp_async_commit();
+      };
+      auto front = [&](int u) {           // tile u: raw rows -> {d, shift} for phase A, point state for the scale step
+        cp_async_wait_group<1>();
+        __syncwarp();
+        const int64_t tile0 = lo + (int64_t)u * TP;
+        const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+        const int buf = u & 1;
+        if (li < count) {
+          const double* in = s_in + ((size_t)buf * TP + li) * 5;
+          const double w_sel = in[4];
+          PointOut64 o;
+          point_front64_fast(J, C, tconst, s_tab, in[0], in[1], in[2], in[3], o);
+          const int64_t srow = tile0 + li;
+          const double lam = J.point_lambda ? J.point_lambda[srow] : 1.0;
+          const double w_desk = w_sel * o.w_time;
+          c_sel += w_sel; c_sel2 += w_sel * w_sel; c_desk += w_desk; c_rows += 1.0;
+          T* sd = s_d + ((size_t)buf * TP + li) * 4;
+          sd[0] = o.d[0]; sd[1] = o.d[1]; sd[2] = o.d[2]; sd[3] = -cscale_d;   // fixed shift: the largest possible logit
+          T* pt = s_pt + (size_t)(u % 3) * 7 * TP + li;
+          pt[0] = o.p0[0]; pt[TP] = o.p0[1]; pt[2 * TP] = o.p0[2]; pt[3 * TP] = o.d[0]; pt[4 * TP] = o.d[1]; pt[5 * TP] = o.d[2];
+          pt[6 * TP] = w_desk * lam;
+        }
+        __syncwarp();
+        prefetch_rows(u + 2);             // this tile's staging buffer is free again
+      };
+      if (do_front) {
+        prefetch_rows(0);
+        prefetch_rows(1);
+        if (n_tiles > 0) front(0);
+      }
+      __threadfence_block();
+      nb_sync(kBarProd, kWsProd);
+      WST_DECL;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        const int64_t tile0 = lo + (int64_t)t * TP;
+        const int count = (int)((hi - tile0 < TP) ? hi - tile0 : TP);
+        WST(2);
+        if (do_front && t + 1 < n_tiles) front(t + 1);
+        WST(0);
+        __threadfence_block();
+        nb_sync(kBarProd, kWsProd);       // phase A of tile t is complete (and the front end of tile t + 1 is visible to the phase-A warps)
+        WST(1);
+        if (do_scale && li < count) {
+          T Z = 0, S1 = 0, xmax = 0;
+          for (int a = 0; a < TA; ++a) {
+            const T* zp = s_zp + (((size_t)buf * TA + a) * TP + li) * 3;
+            Z += zp[0]; S1 += zp[1]; xmax = zp[2] > xmax ? zp[2] : xmax;
+          }
+          const double rZ = 1.0 / Z;
+          c_ent += log(Z) - Num<T>::kToNat * S1 * rZ - (double)B * C.eps_mass;   // binning.py:70-72
+          const double mr = xmax * rZ;
+          c_max = mr > c_max ? mr : c_max;
+          const T* pt = s_pt + (size_t)(t % 3) * 7 * TP + li;
+          const T q0 = pt[0], q1 = pt[TP], q2 = pt[2 * TP], d0 = pt[3 * TP], d1 = pt[4 * TP], d2 = pt[5 * TP], wq = pt[6 * TP];
+          const T w = wq / Z;
+          T f[kRowPitch];
+          f[0] = w;
+          f[1] = w * d0; f[2] = w * d1; f[3] = w * d2;
+          f[4] = f[1] * d0; f[5] = f[1] * d1; f[6] = f[1] * d2; f[7] = f[2] * d1; f[8] = f[2] * d2; f[9] = f[3] * d2;
+          f[10] = w * q0; f[11] = w * q1; f[12] = w * q2;
+          f[13] = f[10] * q0; f[14] = f[10] * q1; f[15] = f[10] * q2; f[16] = f[11] * q1; f[17] = f[11] * q2; f[18] = f[12] * q2;
+          f[19] = 0;
+          double2* r2 = reinterpret_cast<double2*>(s_rows + ((size_t)buf * TP + li) * kRowPitch);
+#pragma unroll
+          for (int k = 0; k < 10; ++k) r2[k] = make_double2(f[2 * k], f[2 * k + 1]);
+        }
+        if (do_scale) {
+          __threadfence_block();
+          nb_arrive(kBarFull0 + buf, kWsCons + 32);
+        }
+      }
+      WST(2);
+      if (do_front) WST_OUT(8); else WST_OUT(12);   // point warp(s): [0] front end, [1] wait PROD, [2] scale
+      if (do_front) cp_async_wait_group<0>();
+      // certificate scalars of this CTA: fixed shuffle tree over the 32 lanes
+      double cv[GCL_NCERT];
+      cv[GCL_CS_SUM_W_RAW] = (stride == 1) ? c_sel : c_wraw;   // at stride 1 the raw-weight sum IS the selected-weight sum
+      cv[GCL_CS_SUM_W_SEL] = c_sel; cv[GCL_CS_SUM_W_SEL_SQ] = c_sel2; cv[GCL_CS_SUM_W_DESKEW] = c_desk;
+      cv[GCL_CS_SUM_ENTROPY] = c_ent; cv[GCL_CS_MAX_RESP] = c_max; cv[GCL_CS_ROWS] = c_rows; cv[GCL_CS_SPARE] = 0.0;
+#pragma unroll
+      for (int k = 0; k < GCL_NCERT; ++k) {
+        double v = cv[k];
+        for (int o = 16; o > 0; o >>= 1) {
+          const double other = __shfl_xor_sync(0xffffffffu, v, o);
+          v = (k == GCL_CS_MAX_RESP) ? fmax(v, other) : v + other;
+        }
+        const bool scale_owns = (k == GCL_CS_SUM_ENTROPY || k == GCL_CS_MAX_RESP);
+        if (li == 0 && (NPW == 1 || scale_owns == do_scale)) part[(size_t)GCL_NM * B + k] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------------------
 static inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -785,6 +1098,27 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   P.lanes = L; P.tile_points = TP; P.n_chunks = 1;
   const size_t smem = fused_plan(P.n_bins, precision == GCL_F64 ? 8 : 4, G, L, TP).total;
   dim3 grid(ctas_per_job, n_jobs);
+  // fp64, 129..256 bins (G = 4 on 64 bin lanes), float64 rows, fixed shift: the warp-specialised kernel on request (GCL_K1_WS = 1, 2, 3:
+  // measured 873 / 937 / 961 us against 894 us at 1 M x 256 -- see DESIGN.md; not the default)
+  static const int ws_mode = [] { const char* e = getenv("GCL_K1_WS"); return e ? atoi(e) : 0; }();
+  if (ws_mode && precision == GCL_F64 && G == 4 && L == 64 && (P.fixed_shift & 1) && P.layout == GCL_LAYOUT_REF_F64) {
+    static std::atomic<uint64_t> optin_ws{0}, optin_ws2{0};
+    if (ws_mode == 2) {        // 8 accumulating warps, 3 phase-A warps + the point warp in one warpgroup
+      auto kern = scan_moments_ws64_kernel<4, 8, 3, 1, 200, 104, 4>;
+      if (cudaError_t e = optin_dynamic_smem(kern, 204 * 1024, optin_ws2)) return e;
+      kern<<<grid, 32 * (8 + 3 + 1), ws_plan(P.n_bins, G, L, 256, 3, 4).total, stream>>>(P);
+    } else if (ws_mode == 3) { // 4 accumulating warps, 6 phase-A warps, a front-end warp and a scale warp
+      static std::atomic<uint64_t> optin_ws3{0};
+      auto kern = scan_moments_ws64_kernel<4, 4, 6, 2, 208, 144, 4>;
+      if (cudaError_t e = optin_dynamic_smem(kern, 204 * 1024, optin_ws3)) return e;
+      kern<<<grid, 32 * (4 + 6 + 2), ws_plan(P.n_bins, G, L, 128, 6, 4).total, stream>>>(P);
+    } else {                   // 4 accumulating warps (one per scheduler), 7 phase-A warps + the point warp (two producer warps per scheduler)
+      auto kern = scan_moments_ws64_kernel<4, 4, 7, 1, 208, 144, 4>;
+      if (cudaError_t e = optin_dynamic_smem(kern, 204 * 1024, optin_ws)) return e;
+      kern<<<grid, 32 * (4 + 7 + 1), ws_plan(P.n_bins, G, L, 128, 7, 4).total, stream>>>(P);
+    }
+    return cudaGetLastError();
+  }
   if (precision == GCL_F64) {
     switch (G) {
       case 2: return launch_fused_one<double, 2, 1>(P, grid, smem, stream);

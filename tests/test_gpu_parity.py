@@ -243,6 +243,8 @@ def _oracle_sums(O, sc, cap, bins, tau, lam=None):
     (30000, 8192, 48, 0.1),       # configs[1] shape: stride 4, 7500 selected, 692 padded rows
     (30000, 32768, 48, 0.1),      # configs[2] shape: stride 1
     (20001, 32768, 256, 0.1),     # odd row count, 256 bins
+    (30011, 8192, 200, 0.1),      # 129..256 bins with the PointBudget stride (stride 4, raw-weight sum) and a ragged bin count
+    (45, 64, 129, 0.1),           # fewer rows than CTAs, smallest bin count of the 64-lane tile
     (5000, 8192, 1024, 0.1),      # maximum bin count (two bin chunks in fp64)
     (3000, 4096, 100, 0.1),       # bin count that is not a multiple of the lane tile
     (4000, 4096, 48, 0.004),      # small tau: the row-max softmax shift path (fp32c)
@@ -285,14 +287,14 @@ def test_fused_moments_vs_oracle(g, O, n_raw, cap, B, tau, precision, tol):
 
 def test_fused_is_bit_reproducible(g, O):
     sc = g.synth.make_scan(30000, seed=5)
-    for precision in ("fp64", "fp32c"):
-        pl = g.LidarEvidencePipeline(n_bins=48, tau=0.1, precision=precision, n_points_cap=32768, lidar_origin=sc.lidar_origin)
+    for precision, B in (("fp64", 48), ("fp32c", 48), ("fp64", 256), ("fp32c", 256)):
+        pl = g.LidarEvidencePipeline(n_bins=B, tau=0.1, precision=precision, n_points_cap=32768, lidar_origin=sc.lidar_origin)
         scan = pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
-        ms = g.create_empty_map_stats(48)
+        ms = g.create_empty_map_stats(B)
         poses = torch.zeros(1, 6, dtype=torch.float64, device="cuda")
         a = H(pl.run_resident(scan, sc.xi_body[None], poses, ms).stats).copy()
         b = H(pl.run_resident(scan, sc.xi_body[None], poses, ms).stats).copy()
-        assert np.array_equal(a, b)
+        assert np.array_equal(a, b), (precision, B)
 
 
 def test_host_call_equals_resident_path(g):
