@@ -45,17 +45,17 @@ __global__ void __launch_bounds__(256) k(double* out, int iters, double x) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int MODE, int NACC> void run(const char* name, double fma_per_iter_per_thread, int ctas_per_sm) {
+template <int MODE, int NACC> void run(const char* name, double fma_per_iter_per_thread, int ctas_per_sm, int threads = 256) {
   double* out; cudaMalloc(&out, 148 * 8 * 256 * sizeof(double));
   const int iters = 20000;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<MODE, NACC><<<148 * ctas_per_sm, 256>>>(out, 100, 0.999);
+  k<MODE, NACC><<<148 * ctas_per_sm, threads>>>(out, 100, 0.999);
   cudaEventRecord(e0);
-  k<MODE, NACC><<<148 * ctas_per_sm, 256>>>(out, iters, 0.999);
+  k<MODE, NACC><<<148 * ctas_per_sm, threads>>>(out, iters, 0.999);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  const double total = fma_per_iter_per_thread * iters * 148.0 * ctas_per_sm * 256;
-  printf("%-44s ctas/SM %d: %.3f ms  %.2f TFMA/s  -> %.1f FMA/clk/SM @1.965GHz\n", name, ctas_per_sm, ms, total / ms * 1e-9,
+  const double total = fma_per_iter_per_thread * iters * 148.0 * ctas_per_sm * threads;
+  printf("%-44s threads %d ctas/SM %d: %.3f ms  %.2f TFMA/s  -> %.1f FMA/clk/SM @1.965GHz\n", name, threads, ctas_per_sm, ms, total / ms * 1e-9,
          total / (ms * 1e-3) / 148 / 1.965e9);
   cudaFree(out);
 }
@@ -68,5 +68,8 @@ int main() {
     run<2, 12>("DMMA, 3 A + 4 B fragments from smem per 12", 12 * 8, c);
     run<1, 12>("DFMA, 24 chains/thread", 24, c);
   }
+  // how much of the FP64 pipe can ONE warp per scheduler fill with independent DFMAs?  (128 threads = one warp per scheduler; 64 = two schedulers used)
+  run<1, 12>("DFMA, 24 chains/thread", 24, 1, 128);
+  run<0, 12>("DMMA m8n8k4, 12 accumulators/warp", 12 * 8, 1, 128);
   return 0;
 }
