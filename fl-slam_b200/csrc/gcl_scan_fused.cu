@@ -28,6 +28,9 @@
 #ifndef GCL_A_NG4
 #define GCL_A_NG4 2     // fp64, G = 4: groups of two bins in flight per thread in phase A (registers: the 76-double tile stays live)
 #endif
+#ifndef GCL_A_NGMMA
+#define GCL_A_NGMMA 4   // fp64 DMMA variant: groups of two bins in flight per thread in phase A (the accumulators are 24 doubles there)
+#endif
 #ifndef GCL_BULK_ON
 #define GCL_BULK_ON 1   // 0: every tile takes the per-thread cp.async path (A/B builds)
 #endif
@@ -36,6 +39,7 @@ namespace gcl {
 
 constexpr int kNT = 256;       // threads per CTA
 constexpr int kRowPitch = 20;  // values per scaled row: 19 moments + 1 pad (16-byte aligned rows)
+constexpr int kRowPitchMma = 24;  // ... of the DMMA variant: three 8-row fragments; 24 = 8 (mod 16) keeps the fragment loads conflict-free
 constexpr int kKC = 5;         // moments per flush pass (10 was measured: no gain, and the G = 4 fp64 variant starts to spill)
 
 template <typename T> struct Num;
@@ -273,26 +277,28 @@ struct FusedPlan {
   int G, L, TP, TA, BA, EP;   // bins/thread, bin lanes, points/tile, phase-A threads/point, bins per phase-A thread, e pitch
   size_t o_tab, o_sd, o_zp, o_rows, o_pt, o_etile, o_in, total;
 };
-__host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, int TP) {
+// mma = 1: the fp64 variant whose phase B runs on mma.sync.m8n8k4.f64 (rows of 24 values, e-tile pitch = 4 (mod 16) doubles: both
+// operand fragments load without bank conflicts)
+__host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, int TP, int mma = 0, int nt = 256) {
   FusedPlan p;
-  p.G = G; p.L = L; p.TP = TP; p.TA = kNT / TP;
+  p.G = G; p.L = L; p.TP = TP; p.TA = nt / TP;
   const int vec = tsz == 4 ? 4 : 2;
   p.BA = (((B + p.TA - 1) / p.TA) + vec - 1) / vec * vec;
   const int cols = (G * L > p.TA * p.BA) ? G * L : p.TA * p.BA;
-  p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : e_pitch(cols, 4, 2);
+  p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : (mma ? e_pitch(cols, 16, 4) : e_pitch(cols, 4, 2));
   size_t off = (size_t)(p.TA * p.BA) * 3 * tsz;                    // phase-A atlas, 3 components per bin
   off = (off + 15) & ~(size_t)15;
   p.o_tab = off;  off += (tsz == 8 ? kExpTab : 2) * 8;
   p.o_sd = off;   off += (size_t)TP * 4 * tsz;
   p.o_zp = off;   off += (size_t)p.TA * TP * 3 * tsz;
   off = (off + 15) & ~(size_t)15;
-  p.o_rows = off; off += (size_t)TP * kRowPitch * tsz;
-  p.o_pt = off;   off += (size_t)(2 * TP <= kNT ? 2 : 1) * 7 * TP * tsz;   // front end -> scale step, one buffer per thread group
+  p.o_rows = off; off += (size_t)TP * (mma ? kRowPitchMma : kRowPitch) * tsz;
+  p.o_pt = off;   off += (size_t)(2 * TP <= nt ? 2 : 1) * 7 * TP * tsz;   // front end -> scale step, one buffer per thread group
   off = (off + 15) & ~(size_t)15;
   p.o_in = off;   off += (size_t)2 * TP * 5 * 8;                            // two staging buffers of raw rows
   p.o_etile = off;
   size_t et = (size_t)TP * p.EP * tsz;
-  const size_t stage = (size_t)(kNT / L) * kKC * (size_t)(G * L) * tsz;
+  const size_t stage = mma ? 0 : (size_t)(nt / L) * kKC * (size_t)(G * L) * tsz;
   if (stage > et) et = stage;
   off += et;
   p.total = off + 16;
@@ -307,8 +313,22 @@ extern "C" int gcl_debug_k1_trace(long long* out) { return (int)cudaMemcpyFromSy
 #define K1T(i) do { } while (0)
 #endif
 
-template <typename T, int G, int MINB>
-__global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// MMA = 1 (fp64, G = 4 on 64 bin lanes, i.e. 129..256 bins): phase B as M[moment][bin] += Phi^T[moment][point] E[point][bin] on
+// mma.sync.m8n8k4.f64 (SASS DMMA).  Same FP64 rate as DFMA (tools/microbench/dmma_rate.cu: 63 FMA/clk/SM), and 19 moments pad to 24
+// rows -- but an eighth of the issue slots, and the accumulators are 24 doubles per thread instead of 76 (a warp owns 32 bins x all
+// moments over ALL points of the tile: no point slices, so the flush is a plain store), which leaves phase A the registers for eight
+// chains in flight instead of four.
+template <typename T, int G, int MINB, int MMA = 0, int NT_ = 256>
+__global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
+  static_assert(!MMA || (sizeof(T) == 8 && G == 4), "the DMMA variant is fp64, G = 4");
+  static_assert(NT_ == 256 || (MMA && NT_ == 512), "512 threads: the DMMA variant only (its accumulators leave room for 16 warps)");
+  constexpr int kNT = NT_;                   // threads per CTA (shadows the file-scope default)
+  constexpr int NTW = 256 / (NT_ / 32) / 8;  // DMMA variant: 8-bin fragments per warp (a warp owns 256 / warps bins)
+  constexpr int RP = MMA ? kRowPitchMma : kRowPitch;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int B = P.n_bins, L = P.lanes;
   __shared__ double s_red[kNT / 32][GCL_NCERT];
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   // share a point in phase A)
   int TP = P.tile_points;
   while (TP > 16 && (TP >> 1) >= rpc) TP >>= 1;
-  const FusedPlan pl = fused_plan(B, (int)sizeof(T), G, L, TP);
+  const FusedPlan pl = fused_plan(B, (int)sizeof(T), G, L, TP, MMA, kNT);
   const int TA = pl.TA, BA = pl.BA, EP = pl.EP, PS = kNT / L, Bp = G * L;
   T* s_atlas = reinterpret_cast<T*>(smem_raw);
   double* s_tab = reinterpret_cast<double*>(smem_raw + pl.o_tab);
@@ -392,6 +412,9 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
   constexpr int VB = Tile<T, G>::VB;
   Tile<T, G> acc;
   acc.zero();
+  double cm[3][NTW][2];   // DMMA variant: [moment fragment][bin fragment of this warp's 8 NTW bins][2]
+#pragma unroll
+  for (int i = 0; i < 6 * NTW; ++i) (&cm[0][0][0])[i] = 0.0;
 
   const TimeConst tconst = time_const(J);
   // per-thread certificate partials live in shared memory (they are touched once per tile; registers are for the tile)
@@ -436,6 +459,23 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
 
   // fixed-order cross-slice reduction, kKC moments at a time, carried in fp64 in this CTA's record
   auto flush = [&]() {
+    if (MMA) {   // thread (warp, lane) holds rows 8 mt + lane / 4, bins 32 warp + 8 nt + 2 (lane % 4) + {0, 1}: whole sums, stored as they are
+      const int w = tid >> 5, lane = tid & 31;
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int m = 8 * mt + (lane >> 2), b = 8 * NTW * w + 8 * nt + 2 * (lane & 3) + i;
+            if (m < GCL_NM && b < B) {
+              if (flushed) part[(size_t)m * B + b] += cm[mt][nt][i]; else part[(size_t)m * B + b] = cm[mt][nt][i];
+            }
+            cm[mt][nt][i] = 0.0;
+          }
+      flushed = true;
+      return;
+    }
 #pragma unroll
     for (int k0 = 0; k0 < GCL_NM; k0 += kKC) {
 #pragma unroll
@@ -605,7 +645,11 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     f[10] = w * q0; f[11] = w * q1; f[12] = w * q2;
     f[13] = f[10] * q0; f[14] = f[10] * q1; f[15] = f[10] * q2; f[16] = f[11] * q1; f[17] = f[11] * q2; f[18] = f[12] * q2;
     f[19] = 0;
-    T* row = s_rows + (size_t)li * kRowPitch;
+    T* row = s_rows + (size_t)li * RP;
+    if (MMA) {   // the padding rows of the third moment fragment must be zeros (they are multiplied like the others)
+      double2* r2 = reinterpret_cast<double2*>(row);
+      r2[10] = make_double2(0.0, 0.0); r2[11] = make_double2(0.0, 0.0);
+    }
     if (sizeof(T) == 4) {
       float4* r4 = reinterpret_cast<float4*>(row);
 #pragma unroll
@@ -648,13 +692,18 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
       if (pi < count) {
         const T* sd = s_d + (size_t)pi * 4;
         T Z, S1, xmax;
-        constexpr int NGB = sizeof(T) == 4 ? 3 : (G >= 4 ? GCL_A_NG4 : 4);
+        constexpr int NGB = sizeof(T) == 4 ? 3 : (MMA ? (NT_ == 512 ? 2 : GCL_A_NGMMA) : (G >= 4 ? GCL_A_NG4 : 4));
         if (sizeof(T) == 4 || (P.fixed_shift & 1))
           phase_a_bins<NGB, false>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
         else
           phase_a_bins<1, true>(s_atlas, s_tab, pa * BA, (pa + 1) * BA, B, sd[0], sd[1], sd[2], sd[3], s_etile + (size_t)pi * EP, Z, S1, xmax);
         T* zp = s_zp + ((size_t)pa * TP + pi) * 3;
         zp[0] = Z; zp[1] = S1; zp[2] = xmax;
+      } else if (MMA && pi < ((count + 3) & ~3)) {
+        // DMMA steps take four points at a time: the rows that pad a CTA's last tile multiply as zeros (stale or uninitialised
+        // shared memory could hold anything, NaN bit patterns included)
+        T* er = s_etile + (size_t)pi * EP;
+        for (int b = pa * BA; b < (pa + 1) * BA; ++b) er[b] = (T)0;
       }
       __syncthreads();
     }
@@ -668,6 +717,11 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
         if (ls >= 0) {
           prefetch_rows(t2, ti + 2, ls);               // same group, same buffer as this tile
           if (ls < count) scale(ti, ls);
+          else if (MMA && ls < ((count + 3) & ~3)) {
+            double2* r2 = reinterpret_cast<double2*>(s_rows + (size_t)ls * RP);
+#pragma unroll
+            for (int k = 0; k < RP / 2; ++k) r2[k] = make_double2(0.0, 0.0);
+          }
         }
       }
       const int lf = group_index(ti + 1);
@@ -677,7 +731,24 @@ __global__ void __launch_bounds__(kNT, MINB) scan_moments_fused_kernel(const __g
     K1T(3);   // scale + next front end
     if (ti < 0) continue;
     // ======================================= phase B ===========================================================
-    {
+    if (MMA) {
+      const int w = tid >> 5, lane = tid & 31;
+      const double* ap = reinterpret_cast<const double*>(s_rows) + (size_t)(lane & 3) * RP + (lane >> 2);
+      const double* bp = reinterpret_cast<const double*>(s_etile) + (size_t)(lane & 3) * EP + 8 * NTW * w + (lane >> 2);
+      const int nks = (count + 3) >> 2;
+#pragma unroll 2
+      for (int ks = 0; ks < nks; ++ks) {
+        double a[3], b[NTW];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) a[mt] = ap[(size_t)ks * 4 * RP + 8 * mt];
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) b[nt] = bp[(size_t)ks * 4 * EP + 8 * nt];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) dmma884(cm[mt][nt][0], cm[mt][nt][1], a[mt], b[nt]);
+      }
+    } else {
       const T* ebase = s_etile + (size_t)binlane * VB;
 #pragma unroll 2
       for (int pt = slice; pt < count; pt += PS) acc.step(ebase + (size_t)pt * EP, L, s_rows + (size_t)pt * kRowPitch);
@@ -1062,24 +1133,24 @@ void plan_fused_bins(int n_bins, int precision, int* G_out, int* L_out, int* min
 }
 
 // points per tile: as many as fit in shared memory (the kernel lowers it for CTAs that see few rows), at least 256/16
-int plan_fused_tile(int n_bins, int precision, int G, int L, int minb) {
+int plan_fused_tile(int n_bins, int precision, int G, int L, int minb, int mma = 0, int nt = 256) {
   const int tsz = precision == GCL_F64 ? 8 : 4;
-  // 228 KB per SM, 1 KB reserved per CTA, ~17 KB static (certificate partials, reduction scratch)
-  const size_t budget = (minb == 2 ? 94 : 200) * 1024;
+  // 228 KB per SM, 1 KB reserved per CTA, ~17 KB static (certificate partials, reduction scratch; 16 KB more with 512 threads)
+  const size_t budget = (minb == 2 ? 94 : (nt == 512 ? 190 : 200)) * 1024;
   // GCL_K1_TPMAX = 16..256 (a power of two): upper limit of the tile, for A/B runs (smaller tiles at few bins let the two thread groups
   // alternate and put several threads on a point in phase A)
   static const int tp_max = [] { const char* e = getenv("GCL_K1_TPMAX"); const int v = e ? atoi(e) : 0; return (v >= 16 && v <= kNT && !(v & (v - 1))) ? v : kNT; }();
   int TP = tp_max;
-  while (TP > 16 && fused_plan(n_bins, tsz, G, L, TP).total > budget) TP >>= 1;
+  while (TP > 16 && fused_plan(n_bins, tsz, G, L, TP, mma, nt).total > budget) TP >>= 1;
   return TP;
 }
 
-template <typename T, int G, int MINB>
+template <typename T, int G, int MINB, int MMA = 0, int NT_ = 256>
 static cudaError_t launch_fused_one(const ScanParams& P, dim3 grid, size_t smem, cudaStream_t stream) {
-  auto kern = scan_moments_fused_kernel<T, G, MINB>;
+  auto kern = scan_moments_fused_kernel<T, G, MINB, MMA, NT_>;
   static std::atomic<uint64_t> optin{0};  // per instantiation, one bit per device
-  if (cudaError_t e = optin_dynamic_smem(kern, 204 * 1024, optin)) return e;
-  kern<<<grid, kNT, smem, stream>>>(P);
+  if (cudaError_t e = optin_dynamic_smem(kern, (NT_ == 512 ? 192 : 204) * 1024, optin)) return e;   // + the static part (34 / 17 KB) <= 227 KB
+  kern<<<grid, NT_, smem, stream>>>(P);
   return cudaGetLastError();
 }
 
@@ -1094,9 +1165,15 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   if (tc_path_supported(P.n_bins, precision, P.fixed_shift)) return launch_scan_moments_tc(P, n_jobs, ctas_per_job, stream);
   int G, L, M;
   plan_fused_bins(P.n_bins, precision, &G, &L, &M);
-  const int TP = plan_fused_tile(P.n_bins, precision, G, L, M);
+  // fp64, 129..256 bins: phase B on mma.sync.m8n8k4.f64 on request (GCL_K1_MMA=1: 8 warps, =2: 16 warps).  Measured at 1 M x 256: 893 us and
+  // 919 us against 890-896 us of the DFMA loop -- phase B itself gains 11 % (373 against 421 us in the phase trace) and the kernel drops
+  // from 255 to 182 (104) registers, but phase A does not get faster with eight chains in flight nor with twice the warps: not the default
+  static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : 0; }();
+  const int mma = (mma_mode && precision == GCL_F64 && G == 4 && L == 64) ? 1 : 0;
+  const int nt = (mma && mma_mode == 2) ? 512 : 256;
+  const int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
   P.lanes = L; P.tile_points = TP; P.n_chunks = 1;
-  const size_t smem = fused_plan(P.n_bins, precision == GCL_F64 ? 8 : 4, G, L, TP).total;
+  const size_t smem = fused_plan(P.n_bins, precision == GCL_F64 ? 8 : 4, G, L, TP, mma, nt).total;
   dim3 grid(ctas_per_job, n_jobs);
   // fp64, 129..256 bins (G = 4 on 64 bin lanes), float64 rows, fixed shift: the warp-specialised kernel on request (GCL_K1_WS = 1, 2, 3:
   // measured 873 / 937 / 961 us against 894 us at 1 M x 256 -- see DESIGN.md; not the default)
@@ -1119,6 +1196,7 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
     }
     return cudaGetLastError();
   }
+  if (mma) return nt == 512 ? launch_fused_one<double, 4, 1, 1, 512>(P, grid, smem, stream) : launch_fused_one<double, 4, 1, 1, 256>(P, grid, smem, stream);
   if (precision == GCL_F64) {
     switch (G) {
       case 2: return launch_fused_one<double, 2, 1>(P, grid, smem, stream);

@@ -26,12 +26,13 @@ def test_fp32c_parity_with_the_kernel_choice_forced(mode):
     assert " passed" in r.stdout
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3"])
-def test_fp64_parity_with_the_warp_specialised_kernel_forced(mode):
+@pytest.mark.parametrize("switch,mode", [("GCL_K1_WS", "1"), ("GCL_K1_WS", "2"), ("GCL_K1_WS", "3"), ("GCL_K1_MMA", "1"), ("GCL_K1_MMA", "2")])
+def test_fp64_parity_with_the_opt_in_kernels_forced(switch, mode):
     """GCL_K1_WS = 1 / 2 / 3: the warp-specialised fp64 kernel (129..256 bins; three splits of the warps between accumulating, phase-A and
-    per-point roles) instead of the default kernel -- same parity bars, bit-reproducible from run to run."""
+    per-point roles); GCL_K1_MMA = 1 / 2: phase B on mma.sync.m8n8k4.f64 with 8 / 16 warps -- instead of the default kernel: same parity
+    bars, bit-reproducible from run to run."""
     pytest.importorskip("torch")
-    env = dict(os.environ, GCL_K1_WS=mode)
+    env = dict(os.environ, **{switch: mode})
     sel = "(fp64 and (fused_moments_vs_oracle or fused_pipeline_against_reference_goldens)) or bit_reproducible or full_size_properties"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-k", sel,
                         "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
