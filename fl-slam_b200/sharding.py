@@ -429,8 +429,9 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
         # under the moment pass of the next scan, which shrinks with the number of ranks
         reserve_sms = {1: 2, 2: 2, 4: 4}.get(world, 6)
     if n_tails is None:
-        # two tails in flight once the shard's moment pass can be shorter than one tail (60-70 us)
-        n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or {1: 1, 2: 1}.get(world, 2)
+        # two tails in flight: a tail (exchange capped to the few SMs left free + finalise + evidence chain) takes 60-160 us, which is
+        # longer than the fp32c moment pass of a shard from 2 GPUs on
+        n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or 2
     sc = synth.make_scan(n_points, seed=1234 + 4, dense=True)
     pl = g.LidarEvidencePipeline(n_bins=n_bins, tau=tau, precision=precision, n_points_cap=n_points, lidar_origin=sc.lidar_origin)
     sh = PointShardedEvidence(pl, rank, world, exchange=exchange)
@@ -609,7 +610,7 @@ def bench_hypothesis_sharded(g, n_points: int, cap: int, n_bins: int, n_hyp: int
     reserve = 8
     _, n_sel = pl.selected_rows(res[0].n_raw, cap)
     ctas_p = max(1, min(pl.plan_ctas(Hl, n_sel), (sms - reserve) // max(1, Hl)))
-    n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or {1: 1, 2: 1}.get(world, 2)
+    n_tails = int(os.environ.get("GCL_BENCH_TAILS", "0")) or 2
     pipe = ScanPipe(pl, px, world, "gather", n_sets=4, n_tails=n_tails)
     ov = {"last": None}
 
