@@ -275,7 +275,11 @@ class PointShardedEvidence:
                 self.end_overlapped()
             sms = int(_abi.lib.gcl_device_sm_count(pl.handle))
             ov = self._ov = {"key": (reserve_sms, n_tails), "sms": sms, "pipe": ScanPipe(pl, self.px, self.world, "sum", n_sets=4, n_tails=n_tails)}
-            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, max(1, reserve_sms // n_tails))
+            # grid cap of the exchange kernel: its CTAs must find room beside the next scan's moment pass -- as many as SMs are left free
+            # (the two tails rarely sum their partial records at the same moment; measured at 2 GPUs, fp32c: cap 1 / 2 / 4 / 8 with 2 SMs
+            # free = 0.138 / 0.135 / 0.163 / 0.139 ms per scan); GCL_EXCHANGE_CTAS overrides
+            cap = int(os.environ.get("GCL_EXCHANGE_CTAS", "0")) or max(1, reserve_sms)
+            _abi.lib.gcl_exchange_set_max_ctas(self.px.x, cap)
         jobs_dev = None
         if job is None:
             xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
