@@ -1165,11 +1165,22 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   if (tc_path_supported(P.n_bins, precision, P.fixed_shift)) return launch_scan_moments_tc(P, n_jobs, ctas_per_job, stream);
   int G, L, M;
   plan_fused_bins(P.n_bins, precision, &G, &L, &M);
-  // fp64, 129..256 bins: phase B on mma.sync.m8n8k4.f64 on request (GCL_K1_MMA=1: 8 warps, =2: 16 warps).  Measured at 1 M x 256: 893 us and
-  // 919 us against 890-896 us of the DFMA loop -- phase B itself gains 11 % (373 against 421 us in the phase trace) and the kernel drops
-  // from 255 to 182 (104) registers, but phase A does not get faster with eight chains in flight nor with twice the warps: not the default
-  static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : 0; }();
-  const int mma = (mma_mode && precision == GCL_F64 && G == 4 && L == 64) ? 1 : 0;
+  // fp64, 129..256 bins: phase B on mma.sync.m8n8k4.f64.  Measured at 1 M x 256 on 148 CTAs (7 085 rows per CTA): 894.2 us (8 warps) and
+  // 919 us (16 warps) against 889.2 us of the DFMA loop -- phase B itself gains 11 % and the kernel drops from 255 to 182 (104)
+  // registers, but phase A is no faster with eight chains in flight nor with twice the warps; on the 131 072-row shard one rank of
+  // eight sees (886 rows per CTA) 121.0 against 125.0 us: its flush is a plain store (1 us against 6).  Hence: GCL_K1_MMA unset = the
+  // DMMA variant when the job is passed by value and leaves a CTA fewer than 4 096 rows; 0 = never; 1 / 2 = always, on 8 / 16 warps.
+  static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : -1; }();
+  bool mma_wanted = mma_mode > 0;
+  if (mma_mode < 0 && !P.jobs && ctas_per_job > 0) {
+    const int64_t cap = P.job.n_points_cap > 0 ? P.job.n_points_cap : 1;
+    const int64_t st0 = (P.job.n_raw + cap - 1) / cap, st = st0 > 1 ? st0 : 1;
+    const int64_t n_sel = (P.job.n_raw + st - 1) / st;
+    const int64_t e = (P.job.sel_end < 0 || P.job.sel_end > n_sel) ? n_sel : P.job.sel_end;
+    const int64_t rows = e > P.job.sel_begin ? e - P.job.sel_begin : 0;
+    mma_wanted = rows / ctas_per_job < 4096;
+  }
+  const int mma = (mma_wanted && precision == GCL_F64 && G == 4 && L == 64) ? 1 : 0;
   const int nt = (mma && mma_mode == 2) ? 512 : 256;
   const int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
   P.lanes = L; P.tile_points = TP; P.n_chunks = 1;

@@ -50,7 +50,7 @@ def single(precision, n, bins, cap=None, iters=30):
     cap = cap or n
     sc = g.synth.make_scan(n, seed=1238, dense=n > 100000)
     pl = g.LidarEvidencePipeline(n_bins=bins, tau=tau, precision=precision, n_points_cap=cap, lidar_origin=sc.lidar_origin)
-    copies = [pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time) for _ in range(4 if n > 100000 else 1)]
+    copies = [pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time) for _ in range((4 if n > 500000 else 32) if n > 100000 else 1)]
     _, n_sel = pl.selected_rows(n, cap)
     ctas = pl.plan_ctas(1, n_sel)
     part = pl._buffers(1, ctas)["partials"]
@@ -71,6 +71,8 @@ for prec in ("fp64", "fp32c"):
         out[f"stream200x30k_48_{prec}"] = stream(prec)
     if "1M" in only:
         out[f"1Mx256_{prec}"] = single(prec, 1 << 20, 256)
+    if "shard8" in only:      # the shard one rank of eight sees of the 1 M x 256 cloud
+        out[f"131072x256_{prec}"] = single(prec, 1 << 17, 256, iters=60)
     if "single" in only:
         out[f"8192x48_{prec}"] = single(prec, 8192, 48)
         out[f"30k_cap8192x48_{prec}"] = single(prec, 30000, 48, cap=8192)
