@@ -285,8 +285,9 @@ __host__ __device__ inline FusedPlan fused_plan(int B, int tsz, int G, int L, in
   const int vec = tsz == 4 ? 4 : 2;
   p.BA = (((B + p.TA - 1) / p.TA) + vec - 1) / vec * vec;
   const int cols = (G * L > p.TA * p.BA) ? G * L : p.TA * p.BA;
-  p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : (mma ? e_pitch(cols, 16, 4) : e_pitch(cols, 4, 2));
-  size_t off = (size_t)(p.TA * p.BA) * 3 * tsz;                    // phase-A atlas, 3 components per bin
+  p.EP = tsz == 4 ? e_pitch(cols, 8, 4) : (mma == 2 ? e_pitch(cols, 16, 8) : (mma ? e_pitch(cols, 16, 4) : e_pitch(cols, 4, 2)));
+  size_t off = mma == 2 ? (size_t)(G * L) * 4 * tsz                  // DMMA phase A: [bin][bx, by, bz, 1]
+                        : (size_t)(p.TA * p.BA) * 3 * tsz;           // phase-A atlas, 3 components per bin
   off = (off + 15) & ~(size_t)15;
   p.o_tab = off;  off += (tsz == 8 ? kExpTab : 2) * 8;
   p.o_sd = off;   off += (size_t)TP * 4 * tsz;
@@ -313,6 +314,56 @@ extern "C" int gcl_debug_k1_trace(long long* out) { return (int)cudaMemcpyFromSy
 #define K1T(i) do { } while (0)
 #endif
 
+__device__ __forceinline__ void dmma884z(double& c0, double& c1, double a, double b) {   // C = 0
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+// Phase A of the MMA = 2 variant: the logits of 8 points x 8 bins per DMMA, x = [d0, d1, d2, shift] . [bx', by', bz', 1] (K = 4: one
+// instruction where the FMA chain takes six per 64 logits, and phase A is bound by dispatch slots); the lane holds the point lane / 4 and
+// bins 2 (lane % 4) + {0, 1} of each 8-bin fragment.  NG fragments in flight, then the same exponential / normaliser / entropy / maximum
+// steps as phase_a_groups.  bfrag: this lane's atlas word of the first fragment (32 doubles per fragment); erow: its e-tile words.
+template <int NG, bool TAIL>
+__device__ __forceinline__ void phase_a_mma_groups(const double* __restrict__ bfrag, const double* __restrict__ tab, double afrag, int b,
+                                                   int B, bool live, double* __restrict__ erow, double& z, double& s1, unsigned long long& m) {
+  constexpr int N = 2 * NG;
+  const double magic = 6755399441055744.0;  // 2^52 + 2^51
+  double x[N], tm[N], r[N], q[N], e[N];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) dmma884z(x[2 * g], x[2 * g + 1], afrag, bfrag[32 * g]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) tm[k] = x[k] + magic;
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = x[k] - (tm[k] - magic);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(5.169222938345892e-11, r[k], 2.2909784980688163e-07);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 6.769015435155716e-04);
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = fma(q[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int n = __double2loint(tm[k]);
+    const double y = tab[n & (kExpTab - 1)] * q[k];
+    e[k] = __hiloint2double(__double2hiint(y) + ((n >> kExpTabLog2) << 20), __double2loint(y));
+  }
+  if (TAIL) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (b + 8 * (k >> 1) + (k & 1) >= B) { e[k] = 0.0; x[k] = -1.0e300; }
+  }
+  if (!live) {   // a row that pads the CTA's last tile: zeros for phase B (its own sums are never read)
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = 0.0;
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) *reinterpret_cast<double2*>(erow + 8 * g) = make_double2(e[2 * g], e[2 * g + 1]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    z += e[k]; s1 = fma(e[k], x[k], s1);
+    const unsigned long long eb = (unsigned long long)__double_as_longlong(e[k]);
+    m = eb > m ? eb : m;
+  }
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -325,7 +376,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <typename T, int G, int MINB, int MMA = 0, int NT_ = 256>
 __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
   static_assert(!MMA || (sizeof(T) == 8 && G == 4), "the DMMA variant is fp64, G = 4");
-  static_assert(NT_ == 256 || (MMA && NT_ == 512), "512 threads: the DMMA variant only (its accumulators leave room for 16 warps)");
+  static_assert(NT_ == 256 || (MMA == 1 && NT_ == 512), "512 threads: the DMMA variant only (its accumulators leave room for 16 warps)");
   constexpr int kNT = NT_;                   // threads per CTA (shadows the file-scope default)
   constexpr int NTW = 256 / (NT_ / 32) / 8;  // DMMA variant: 8-bin fragments per warp (a warp owns 256 / warps bins)
   constexpr int RP = MMA ? kRowPitchMma : kRowPitch;
@@ -375,7 +426,7 @@ __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __g
   // points per tile: the launch's maximum (shared-memory bound), fewer when this CTA has few rows (then more threads
   // share a point in phase A)
   int TP = P.tile_points;
-  while (TP > 16 && (TP >> 1) >= rpc) TP >>= 1;
+  while (MMA != 2 && TP > 16 && (TP >> 1) >= rpc) TP >>= 1;   // (MMA = 2: eight warps x eight points, always)
   const FusedPlan pl = fused_plan(B, (int)sizeof(T), G, L, TP, MMA, kNT);
   const int TA = pl.TA, BA = pl.BA, EP = pl.EP, PS = kNT / L, Bp = G * L;
   T* s_atlas = reinterpret_cast<T*>(smem_raw);
@@ -396,6 +447,12 @@ __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __g
   {
     const int nb = TA * BA;  // padded bin count of phase A
     constexpr int V = Num<T>::kVec;
+    if (MMA == 2) {
+      for (int i = tid; i < Bp * 4; i += kNT) {   // [bin][bx', by', bz', 1]: a DMMA B fragment is 32 consecutive words
+        const int b = i >> 2, c = i & 3;
+        s_atlas[i] = (b < B) ? (c < 3 ? (T)(P.bin_dirs[b * 3 + c] * cscale_d) : (T)1) : (T)0;
+      }
+    } else
     for (int i = tid; i < nb * 3; i += kNT) {   // group-major: [group][component][lane in group]
       const int g = i / (3 * V), rem = i - g * 3 * V, c = rem / V, b = g * V + (rem - c * V);
       s_atlas[i] = (b < B) ? (T)(P.bin_dirs[b * 3 + c] * cscale_d) : (T)0;
@@ -688,7 +745,26 @@ __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __g
     const int64_t tile0 = lo + (int64_t)ti * TP;
     const int count = ti < 0 ? 0 : (int)((hi - tile0 < TP) ? hi - tile0 : TP);
     // ======================================= phase A ===========================================================
-    if (ti >= 0) {
+    if (ti >= 0 && MMA == 2) {
+      if constexpr (sizeof(T) == 8) {
+        const int w = tid >> 5, lane = tid & 31, p = 8 * w + (lane >> 2), a = lane & 3;
+        const double afrag = s_d[(size_t)p * 4 + a];               // {d0, d1, d2, shift}[a] of point p
+        const double* bf = s_atlas + (size_t)(lane >> 2) * 4 + a;  // + 32 per 8-bin fragment
+        double* er = s_etile + (size_t)p * EP + 2 * a;             // + 8 per fragment
+        const bool live = p < count;
+        double z = 0.0, s1 = 0.0;
+        unsigned long long m = 0ull;
+        const int nt_full = B >> 3, nt_all = (B + 7) >> 3;
+        constexpr int NGM = GCL_A_NGMMA;
+        int nt = 0;
+        for (; nt + NGM <= nt_full; nt += NGM) phase_a_mma_groups<NGM, false>(bf + 32 * nt, s_tab, afrag, 8 * nt + 2 * a, B, live, er + 8 * nt, z, s1, m);
+        for (; nt < nt_full; ++nt) phase_a_mma_groups<1, false>(bf + 32 * nt, s_tab, afrag, 8 * nt + 2 * a, B, live, er + 8 * nt, z, s1, m);
+        for (; nt < nt_all; ++nt) phase_a_mma_groups<1, true>(bf + 32 * nt, s_tab, afrag, 8 * nt + 2 * a, B, live, er + 8 * nt, z, s1, m);
+        T* zp = s_zp + ((size_t)a * TP + p) * 3;
+        zp[0] = z; zp[1] = s1; zp[2] = __longlong_as_double((long long)m);
+      }
+      __syncthreads();
+    } else if (ti >= 0) {
       if (pi < count) {
         const T* sd = s_d + (size_t)pi * 4;
         T Z, S1, xmax;
@@ -1180,9 +1256,12 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
     const int64_t rows = e > P.job.sel_begin ? e - P.job.sel_begin : 0;
     mma_wanted = rows / ctas_per_job < 4096;
   }
-  const int mma = (mma_wanted && precision == GCL_F64 && G == 4 && L == 64) ? 1 : 0;
+  // GCL_K1_MMA=3: phase A on DMMA as well (the similarity dot as a K = 4 product); fixed softmax shift only
+  const int mma0 = (mma_wanted && precision == GCL_F64 && G == 4 && L == 64) ? ((mma_mode == 3 && (P.fixed_shift & 1)) ? 2 : 1) : 0;
+  int mma = mma0;
   const int nt = (mma && mma_mode == 2) ? 512 : 256;
-  const int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
+  int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
+  if (mma == 2 && TP != 64) { mma = 1; TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt); }   // (its phase A is laid out for 64-point tiles)
   P.lanes = L; P.tile_points = TP; P.n_chunks = 1;
   const size_t smem = fused_plan(P.n_bins, precision == GCL_F64 ? 8 : 4, G, L, TP, mma, nt).total;
   dim3 grid(ctas_per_job, n_jobs);
@@ -1207,6 +1286,7 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
     }
     return cudaGetLastError();
   }
+  if (mma == 2) return launch_fused_one<double, 4, 1, 2, 256>(P, grid, smem, stream);
   if (mma) return nt == 512 ? launch_fused_one<double, 4, 1, 1, 512>(P, grid, smem, stream) : launch_fused_one<double, 4, 1, 1, 256>(P, grid, smem, stream);
   if (precision == GCL_F64) {
     switch (G) {
