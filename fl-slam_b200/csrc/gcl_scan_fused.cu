@@ -343,7 +343,11 @@ __device__ __forceinline__ void phase_a_mma_groups(const double* __restrict__ bf
   for (int k = 0; k < N; ++k) {
     const int n = __double2loint(tm[k]);
     const double y = tab[n & (kExpTab - 1)] * q[k];
-    e[k] = __hiloint2double(__double2hiint(y) + ((n >> kExpTabLog2) << 20), __double2loint(y));
+    // 2^(n >> 10) into the exponent field as shift + multiply-add (written as (n >> 10) << 20 it becomes shift + mask + add: one
+    // dispatch slot more per pair, and this variant has the registers for it)
+    int kq;
+    asm("shr.s32 %0, %1, %2;" : "=r"(kq) : "r"(n), "n"(kExpTabLog2));
+    e[k] = __hiloint2double(__double2hiint(y) + kq * 1048576, __double2loint(y));
   }
   if (TAIL) {
 #pragma unroll
@@ -1241,23 +1245,16 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   if (tc_path_supported(P.n_bins, precision, P.fixed_shift)) return launch_scan_moments_tc(P, n_jobs, ctas_per_job, stream);
   int G, L, M;
   plan_fused_bins(P.n_bins, precision, &G, &L, &M);
-  // fp64, 129..256 bins: phase B on mma.sync.m8n8k4.f64.  Measured at 1 M x 256 on 148 CTAs (7 085 rows per CTA): 894.2 us (8 warps) and
-  // 919 us (16 warps) against 889.2 us of the DFMA loop -- phase B itself gains 11 % and the kernel drops from 255 to 182 (104)
-  // registers, but phase A is no faster with eight chains in flight nor with twice the warps; on the 131 072-row shard one rank of
-  // eight sees (886 rows per CTA) 121.0 against 125.0 us: its flush is a plain store (1 us against 6).  Hence: GCL_K1_MMA unset = the
-  // DMMA variant when the job is passed by value and leaves a CTA fewer than 4 096 rows; 0 = never; 1 / 2 = always, on 8 / 16 warps.
-  static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : -1; }();
-  bool mma_wanted = mma_mode > 0;
-  if (mma_mode < 0 && !P.jobs && ctas_per_job > 0) {
-    const int64_t cap = P.job.n_points_cap > 0 ? P.job.n_points_cap : 1;
-    const int64_t st0 = (P.job.n_raw + cap - 1) / cap, st = st0 > 1 ? st0 : 1;
-    const int64_t n_sel = (P.job.n_raw + st - 1) / st;
-    const int64_t e = (P.job.sel_end < 0 || P.job.sel_end > n_sel) ? n_sel : P.job.sel_end;
-    const int64_t rows = e > P.job.sel_begin ? e - P.job.sel_begin : 0;
-    mma_wanted = rows / ctas_per_job < 4096;
-  }
-  // GCL_K1_MMA=3: phase A on DMMA as well (the similarity dot as a K = 4 product); fixed softmax shift only
-  const int mma0 = (mma_wanted && precision == GCL_F64 && G == 4 && L == 64) ? ((mma_mode == 3 && (P.fixed_shift & 1)) ? 2 : 1) : 0;
+  // fp64, 129..256 bins (G = 4 on 64 bin lanes): the DMMA variants of the kernel (mma.sync.m8n8k4.f64).  Measured at 1 M x 256 on 148 CTAs /
+  // on the 131 072-row shard one rank of eight sees, same box, alternating runs:
+  //   DFMA loops (MMA = 0)                                   889.3 us / 125.1 us
+  //   phase B on DMMA, 8 warps (GCL_K1_MMA=1)                894.2 us / 121.1 us   (phase B -11 %, flush a plain store; phase A unchanged)
+  //   phase B on DMMA, 16 warps (GCL_K1_MMA=2)               919 us
+  //   phases A and B on DMMA (GCL_K1_MMA=3, the default)     841.1 us / 114.5 us   (the similarity dot as a K = 4 product: phase A is
+  //                                                                                 bound by dispatch slots, and this takes 6 of 41 per pair)
+  // The default applies with the fixed softmax shift only (tiny tau takes the row-maximum path of the DFMA kernel); GCL_K1_MMA=0 = never.
+  static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : 3; }();
+  const int mma0 = (mma_mode > 0 && precision == GCL_F64 && G == 4 && L == 64) ? (mma_mode == 3 ? ((P.fixed_shift & 1) ? 2 : 0) : 1) : 0;
   int mma = mma0;
   const int nt = (mma && mma_mode == 2) ? 512 : 256;
   int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
