@@ -48,7 +48,9 @@ TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__
 
 # FMA-issue ceilings of scan_moments (rates measured with tools/microbench/ffma_rate.cu):
 # FMA-pipe lane operations per (point, bin) pair = 19 accumulate + 3 similarity + softmax bookkeeping (+ the fp64 exp): fp64 phase A is 12
-# FP64-pipe operations per pair since the 1/1024-octave exp table (round 2; it was 15 in round 1, i.e. 34 in all)
+# FP64-pipe operations per pair since the 1/1024-octave exp table (round 2; it was 15 in round 1, i.e. 34 in all).  The default fp64 kernel
+# at 129..256 bins issues part of them as DMMA (the dot as a K = 4 product with one padding lane, the 19 moments padded to 24 rows: 37 lane
+# operations per pair on the pipe); the ceiling keeps the 31 USEFUL operations, so the padding counts against the kernel
 FMA_LANES_PER_CLK_SM = {"fp32c": 128.0, "fp64": 64.0}
 LANE_OPS_PER_PAIR = {"fp32c": 24.0, "fp64": 31.0}
 N_SM = 148
