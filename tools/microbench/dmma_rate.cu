@@ -20,7 +20,20 @@ __global__ void __launch_bounds__(256) k(double* out, int iters, double x) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double a = x + lane * 1e-9, b = 1.0 - x * 1e-3;
-  for (int it = 0; it < iters; ++it) {
+  if (MODE == 3) {   // half of the warps (one of the two on every scheduler) on DMMA, the other half on DFMA, each in its own loop (a predicated
+                     // mix of both in one loop issues every instruction from every warp): do the two rates add up?  The DFMA warps run 4 x the
+                     // iterations, i.e. the same number of multiply-adds as the DMMA warps
+    if (warp & 4) {
+      for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma(c[i][0], c[i][1], a, b);
+    } else {
+      for (int it = 0; it < 4 * iters; ++it)
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) { c[i][0] = fma(c[i][0], b, a); c[i][1] = fma(c[i][1], b, a); }
+    }
+  }
+  for (int it = 0; it < (MODE == 3 ? 0 : iters); ++it) {
     if (MODE == 2) {
       double av[3], bv[4];
       const int slot = (it & 7);
@@ -71,5 +84,8 @@ int main() {
   // how much of the FP64 pipe can ONE warp per scheduler fill with independent DFMAs?  (128 threads = one warp per scheduler; 64 = two schedulers used)
   run<1, 12>("DFMA, 24 chains/thread", 24, 1, 128);
   run<0, 12>("DMMA m8n8k4, 12 accumulators/warp", 12 * 8, 1, 128);
+  // DMMA and DFMA side by side (4 warps each, one of each per scheduler): FMA per iteration per thread averaged over the two halves
+  run<3, 12>("4 warps DMMA + 4 warps DFMA (sum of both)", 12 * 8, 1);
+  run<0, 12>("DMMA alone, 4 warps (128 threads)", 12 * 8, 1, 128);
   return 0;
 }
