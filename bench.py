@@ -507,7 +507,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host = None
     if world > 1:
+        # one process per GPU: keep this rank's threads and page-locked buffers on the GPU's own NUMA node (N = 1 is left alone: the CPU
+        # baseline runs in that process and must keep every core)
+        from fl_slam_b200 import hostmem
+        host = hostmem.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
     tau = synth.DEFAULT_TAU
     peak_gbs, peak_src = load_peaks()
@@ -596,7 +601,7 @@ def main():
                                 "ctas_per_rank", "rows_per_rank")}},
                 "scans_per_sec": head["scans_per_sec"], "pairs_per_sec": head["pairs_per_sec"],
                 "processed_rows_per_sec": head["points_per_sec"], "gpu_launches": int(head["launches_per_step"] * args.steps),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "clocks": clocks, "extra": extra}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "clocks": clocks, "host_placement": host, "extra": extra}
         emit(line)
     if world > 1:
         dist.barrier()

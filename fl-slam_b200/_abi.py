@@ -95,6 +95,8 @@ def _load():
         "gcl_scan_pipe_submit": (i32, [vp, vp, i32, i32, vp, pj, i32, i32, i32, i32, vp, i32, f64, C.POINTER(f64), f64, f64, vp, vp, vp, vp,
                                        vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gcl_scan_pipe_join": (i32, [vp, vp]),
+        "gcl_scan_pipe_wait_set": (i32, [vp, i32, vp]),
+        "gcl_scan_pipe_set_readback": (i32, [vp, i32, vp, vp]),
         "gcl_sharded_reduce_finalize": (i32, [vp, vp, vp, vp, i32, i64, i64, vp, pj, i32, i32, vp, f64, C.POINTER(f64), f64, f64, vp, vp]),
         "gcl_exchange_all_gather": (i32, [vp, vp, vp, vp, sz, vp]),
         "gcl_exchange_gathered": (vp, [vp, i32]),

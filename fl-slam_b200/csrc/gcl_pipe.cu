@@ -26,6 +26,9 @@ struct gcl_scan_pipe_s {
   bool free_valid[GCL_PIPE_MAX_SETS];
   bool tail_used[GCL_EXCHANGE_LANES] = {false, false};
   cudaEvent_t ev_tail[GCL_EXCHANGE_LANES] = {nullptr, nullptr};   // end of the last tail enqueued on each lane
+  // optional read-back of a set's results into page-locked host memory at the end of its tail (gcl_scan_pipe_set_readback)
+  double* rb_stats[GCL_PIPE_MAX_SETS] = {nullptr};
+  double* rb_evidence[GCL_PIPE_MAX_SETS] = {nullptr};
   std::string err;
 };
 
@@ -134,11 +137,32 @@ int gcl_scan_pipe_submit(gcl_scan_pipe p, void* caller_stream, int wait_for_call
     rc = gcl_exchange_all_gather(h, p->x, tail, evidence, (size_t)n_jobs * GCL_EVID_DOUBLES * sizeof(double), gathered);
     if (rc != GCL_OK) { p->err = std::string("gcl_scan_pipe_submit: all_gather: ") + gcl_exchange_last_error(p->x); return rc; }
   }
+  if (p->rb_stats[set])     // the caller's page-locked copies of this set's results: part of the tail, ahead of "set free"
+    PIPE_CUDA(cudaMemcpyAsync(p->rb_stats[set], stats, (size_t)n_jobs * gcl_stats_record_doubles(n_bins) * sizeof(double), cudaMemcpyDeviceToHost, tail));
+  if (p->rb_evidence[set])
+    PIPE_CUDA(cudaMemcpyAsync(p->rb_evidence[set], evidence, (size_t)n_jobs * GCL_EVID_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, tail));
   PIPE_CUDA(cudaEventRecord(p->ev_free[set], tail));
   p->free_valid[set] = true;
   PIPE_CUDA(cudaEventRecord(p->ev_tail[lane], tail));
   p->tail_used[lane] = true;
   p->turn += 1;
+  return GCL_OK;
+}
+
+int gcl_scan_pipe_set_readback(gcl_scan_pipe p, int set, double* stats_host, double* evidence_host) {
+  if (!p || set < 0 || set >= p->n_sets) return GCL_ERR_ARG;
+  p->rb_stats[set] = stats_host;
+  p->rb_evidence[set] = evidence_host;
+  return GCL_OK;
+}
+
+int gcl_scan_pipe_wait_set(gcl_scan_pipe p, int set, void* stream) {
+  if (!p || set < 0 || set >= p->n_sets) return GCL_ERR_ARG;
+  cudaSetDevice(p->h->device);
+  if (p->free_valid[set]) {
+    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, p->ev_free[set], 0);
+    if (e != cudaSuccess) { p->err = std::string("gcl_scan_pipe_wait_set: ") + cudaGetErrorString(e); return GCL_ERR_CUDA; }
+  }
   return GCL_OK;
 }
 

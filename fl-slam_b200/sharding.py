@@ -184,6 +184,29 @@ class ScanPipe:
     def _bin_dirs(self):
         return self._ops._ptr(self.pl.bin_dirs)
 
+    def next_set(self) -> int:
+        """The buffer set the next submission writes."""
+        return self.turn % self.n_sets
+
+    def wait_set(self, i: int) -> None:
+        """Order the caller's CURRENT stream after the last submission that used set ``i`` (gcl_scan_pipe_wait_set): what the caller
+        enqueues next on that stream may overwrite the staging buffers and host outputs tied to the set."""
+        rc = self._abi.lib.gcl_scan_pipe_wait_set(self.p, int(i), self._ops._stream())
+        if rc != 0:
+            raise self._abi.GclError(self._abi.lib.gcl_scan_pipe_last_error(self.p).decode())
+
+    def set_readback(self, i: int, stats_host: Optional[torch.Tensor], evidence_host: Optional[torch.Tensor]) -> None:
+        """Page-locked host tensors every later submission on set ``i`` fills at the end of its tail (gcl_scan_pipe_set_readback)."""
+        for t in (stats_host, evidence_host):
+            if t is not None and not (t.is_pinned() and t.is_contiguous() and t.dtype == torch.float64):
+                raise ValueError("read-back buffers must be contiguous page-locked float64 tensors")
+        self._readback = getattr(self, "_readback", {})
+        self._readback[int(i)] = (stats_host, evidence_host)        # kept alive with the pipe
+        rc = self._abi.lib.gcl_scan_pipe_set_readback(self.p, int(i), None if stats_host is None else C.c_void_p(stats_host.data_ptr()),
+                                                      None if evidence_host is None else C.c_void_p(evidence_host.data_ptr()))
+        if rc != 0:
+            raise self._abi.GclError("gcl_scan_pipe_set_readback: bad arguments")
+
     def join(self) -> None:
         """Order the caller's current stream after everything submitted."""
         rc = self._abi.lib.gcl_scan_pipe_join(self.p, self._ops._stream())
@@ -256,15 +279,8 @@ class PointShardedEvidence:
         return LidarScanEvidence(n_bins=pl.n_bins, n_hyp=H, stats=buf["stats"], evidence=buf["evidence"], n_input=n_raw_total,
                                  n_points_cap=pl.n_points_cap)
 
-    # ---- consecutive scans pipelined: the exchange + evidence step of scan k under the moment pass of scan k + 1 -------------------
-    def run_overlapped(self, scan, n_raw_total: int, xi_bodies, poses_dev, map_stats, reserve_sms: int = 8, n_tails: int = 2, job=None):
-        """Same result as ``run``; the moment pass goes on one internal stream with ``reserve_sms`` SMs left free, the fused exchange +
-        finalisation (grid capped to the free SMs) and the evidence step on high-priority streams of their own -- so the O(B) tail of
-        scan k (60-70 us, latency-bound) runs beside the moment pass of scan k + 1 instead of after it, and with ``n_tails`` = 2 beside
-        the tail of scan k + 1 as well (needed once the shard's moment pass is shorter than a tail: 8 GPUs, fp32c).  One C call per scan
-        (gcl_scan_pipe_submit).  Results rotate through four buffer sets (valid until four calls later); ``join_overlapped()`` orders the
-        caller's stream after everything submitted.  ``job``: a gcl_job built earlier with ``make_sharded_job`` (saves its cost)."""
-        from .pipeline import LidarScanEvidence
+    def _ensure_overlapped(self, reserve_sms: int, n_tails: int):
+        """The scan pipe for this (reserve_sms, n_tails), created on first use."""
         from . import _abi
         pl = self.pl
         if self.px is None:
@@ -280,6 +296,19 @@ class PointShardedEvidence:
             # free = 0.138 / 0.135 / 0.163 / 0.139 ms per scan); GCL_EXCHANGE_CTAS overrides
             cap = int(os.environ.get("GCL_EXCHANGE_CTAS", "0")) or max(1, reserve_sms)
             _abi.lib.gcl_exchange_set_max_ctas(self.px.x, cap)
+        return ov
+
+    # ---- consecutive scans pipelined: the exchange + evidence step of scan k under the moment pass of scan k + 1 -------------------
+    def run_overlapped(self, scan, n_raw_total: int, xi_bodies, poses_dev, map_stats, reserve_sms: int = 8, n_tails: int = 2, job=None):
+        """Same result as ``run``; the moment pass goes on one internal stream with ``reserve_sms`` SMs left free, the fused exchange +
+        finalisation (grid capped to the free SMs) and the evidence step on high-priority streams of their own -- so the O(B) tail of
+        scan k (60-70 us, latency-bound) runs beside the moment pass of scan k + 1 instead of after it, and with ``n_tails`` = 2 beside
+        the tail of scan k + 1 as well (needed once the shard's moment pass is shorter than a tail: 8 GPUs, fp32c).  One C call per scan
+        (gcl_scan_pipe_submit).  Results rotate through four buffer sets (valid until four calls later); ``join_overlapped()`` orders the
+        caller's stream after everything submitted.  ``job``: a gcl_job built earlier with ``make_sharded_job`` (saves its cost)."""
+        from .pipeline import LidarScanEvidence
+        pl = self.pl
+        ov = self._ensure_overlapped(reserve_sms, n_tails)
         jobs_dev = None
         if job is None:
             xi = np.asarray(xi_bodies, dtype=np.float64).reshape(-1, 6)
@@ -361,6 +390,58 @@ class PointShardedEvidence:
         st["out"][0].copy_(ev.stats, non_blocking=True); st["out"][1].copy_(ev.evidence, non_blocking=True)
         st["free"][i] = cur.record_event()
         return ev
+
+
+    # ---- scans from HOST memory, consecutive scans in flight: upload of scan k + 1 under the kernels of scan k, one C call per scan ----
+    def host_stage_pipelined(self, points, timestamps, weights, scan_start_time: float, scan_end_time: float, n_hyp: int = 1,
+                             reserve_sms: int = 8, n_tails: int = 2):
+        """Page-locked copies of this rank's raw rows; per buffer set of the scan pipe (four) one device staging shard and one pair of
+        page-locked result buffers, named to the pipe as the read-back targets of that set."""
+        n_raw = int(np.asarray(points).shape[0])
+        _, _, _, (lo, hi) = self.plan(n_raw)
+        pin = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory() for a in (points, timestamps, weights)]
+        pipe = self._ensure_overlapped(reserve_sms, n_tails)["pipe"]
+        dev = [self.pl.upload_scan(points[lo:hi], timestamps[lo:hi], weights[lo:hi], scan_start_time, scan_end_time, packed=False, row_offset=lo)
+               for _ in range(pipe.n_sets)]
+        out = [(torch.empty((n_hyp, self.pl.srec), dtype=torch.float64).pin_memory(), torch.empty((n_hyp, 640), dtype=torch.float64).pin_memory())
+               for _ in range(pipe.n_sets)]
+        for k in range(pipe.n_sets):
+            pipe.set_readback(k, out[k][0], out[k][1])
+        cs = torch.cuda.Stream(device=self.pl.device)
+        cs.wait_stream(torch.cuda.current_stream(self.pl.device))    # the staging shards, poses and map the caller has enqueued so far
+        return {"pin": pin, "dev": dev, "out": out, "n_raw": n_raw, "copy": cs, "key": (reserve_sms, n_tails),
+                "h2d_bytes": int(sum(t.numel() * t.element_size() for t in pin)), "d2h_bytes": int(n_hyp * (self.pl.srec + 640) * 8)}
+
+    def run_host_pipelined(self, st, xi_bodies, poses_dev, map_stats):
+        """One scan from page-locked host arrays through the scan pipe: H2D of this rank's rows on the copy stream (once the scan that
+        used the same set four calls ago has finished), then ONE submission whose moment pass waits for the upload and whose tail ends
+        with the D2H of the stats and evidence records into ``st["out"][set]``.  Nothing here blocks the host: the upload of scan k + 1
+        runs under the kernels of scan k.  ``join_overlapped()`` + a synchronisation make the results visible; same results as
+        ``run_host`` (the same launches).  Returns (evidence view on the device, set index)."""
+        pl = self.pl
+        reserve_sms, n_tails = st["key"]
+        pipe = self._ensure_overlapped(reserve_sms, n_tails)["pipe"]
+        with torch.cuda.stream(st["copy"]):
+            i = pipe.next_set()
+            pipe.wait_set(i)
+            d = st["dev"][i]
+            d.points.copy_(st["pin"][0], non_blocking=True); d.timestamps.copy_(st["pin"][1], non_blocking=True)
+            d.weights.copy_(st["pin"][2], non_blocking=True)
+            if pl.precision == "fp32c":                      # the packed 20 B/point layout is produced on the device from the upload
+                scan = pl.upload_scan(d.points, d.timestamps, d.weights, d.scan_start_time, d.scan_end_time, packed=True, row_offset=d.row_offset)
+            else:
+                scan = d
+            ev = self.run_overlapped(scan, st["n_raw"], xi_bodies, poses_dev, map_stats, reserve_sms=reserve_sms, n_tails=n_tails)
+        return ev, i
+
+    def end_host_pipelined(self, st) -> None:
+        """Forget the read-back targets (the pipe outlives ``st``)."""
+        ov = getattr(self, "_ov", None)
+        if ov is not None:
+            ov["pipe"].join()
+            torch.cuda.synchronize(self.pl.device)
+            for k in range(ov["pipe"].n_sets):
+                ov["pipe"].set_readback(k, None, None)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -555,12 +636,43 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
             torch.cuda.synchronize()                         # the step's results are in host memory when the step ends
 
         t_e2e, _ = _time_steps(e2e_step, max(2, steps // 2), 1, world)
+        note = ("every scan: H2D of this rank's raw rows (points, timestamps, weights, float64) from page-locked host arrays on a copy "
+                "stream, the sharded evidence pass, D2H of the stats + evidence records; the upload of scan k + 1 overlaps the "
+                "kernels of scan k; host synchronisation once per step; bytes are summed over the ranks")
+        t_one, e2e_check = t_e2e, None
+        if overlapped:
+            # the same through the scan pipe (run_host_pipelined): one C call per scan, uploads ordered by the pipe's own "set free" events,
+            # the D2H of the records at the end of every tail -- consecutive scans in flight exactly as in the resident measurement
+            del st
+            stp = sh.host_stage_pipelined(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time, reserve_sms=reserve_sms,
+                                          n_tails=n_tails)
+
+            def e2e_step_pipe(_k):
+                for _ in range(scans_per_step):
+                    sh.run_host_pipelined(stp, xi, poses, ms)
+                sh.join_overlapped()
+                torch.cuda.synchronize()
+
+            t_e2e, _ = _time_steps(e2e_step_pipe, max(2, steps // 2), 1, world)
+            # every set's page-locked records equal, bit for bit, what the same submission gives on the resident copy of the cloud
+            ev_r = sh.run_overlapped(shards[0], n_points, xi, poses, ms, reserve_sms=reserve_sms, n_tails=n_tails, job=jobs_pre[0])
+            sh.join_overlapped()
+            torch.cuda.synchronize()
+            ref_stats, ref_evid = ev_r.stats.cpu(), ev_r.evidence.cpu()
+            e2e_check = {"readback_equals_resident_run_bit_for_bit": bool(all(torch.equal(o[0], ref_stats) and torch.equal(o[1], ref_evid)
+                                                                              for o in stp["out"]))}
+            sh.end_host_pipelined(stp)
+            st = stp
+            note = ("every scan: H2D of this rank's raw rows (points, timestamps, weights, float64) from page-locked host arrays on a copy "
+                    "stream, ONE gcl_scan_pipe_submit whose moment pass waits for the upload and whose tail ends with the D2H of the stats + "
+                    "evidence records into page-locked memory; consecutive scans in flight as in the resident measurement (uploads under the "
+                    "kernels of the scans before, four staging sets); host synchronisation once per step; bytes are summed over the ranks")
         out["e2e"] = {"value": n_points / (t_e2e / scans_per_step * 1e-3), "unit": "points/s",
                       "h2d_bytes_per_step": int(st["h2d_bytes"] * scans_per_step * world), "d2h_bytes_per_step": int(st["d2h_bytes"] * scans_per_step * world),
-                      "ms_per_scan": t_e2e / scans_per_step,
-                      "note": "every scan: H2D of this rank's raw rows (points, timestamps, weights, float64) from page-locked host arrays on a copy "
-                              "stream, the sharded evidence pass, D2H of the stats + evidence records; the upload of scan k + 1 overlaps the "
-                              "kernels of scan k; host synchronisation once per step; bytes are summed over the ranks"}
+                      "ms_per_scan": t_e2e / scans_per_step, "ms_per_scan_one_scan_at_a_time": t_one / scans_per_step,
+                      "h2d_gbs_per_gpu": st["h2d_bytes"] / (t_e2e / scans_per_step * 1e-3) * 1e-9, "note": note}
+        if e2e_check:
+            out["e2e"].update(e2e_check)
     if sh.px is not None:
         sh.px.close()
     return out

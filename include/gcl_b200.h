@@ -330,6 +330,15 @@ int gcl_scan_pipe_submit(gcl_scan_pipe p, void* caller_stream, int wait_for_call
                          const double* map_N_pos, const double* map_sum_p, const double* map_sum_ppT, const double* pose_pred,
                          double* partials, double* reduced, double* stats, double* workspace, double* evidence, double* gathered);
 int gcl_scan_pipe_join(gcl_scan_pipe p, void* caller_stream);
+/* Scans that arrive in HOST memory (the reference hands every scan over as NumPy arrays: pkg/backend/backend_node.py:1761-1790, and
+ * reads the results back on the host: :2106-2119).  gcl_scan_pipe_wait_set orders `stream` after the last submission that used `set`
+ * (its moment pass and its tail have finished): the caller enqueues the H2D copies of the next scan into the staging buffers it ties
+ * to that set on `stream` and then submits with caller_stream = `stream`, wait_for_caller_stream = 1 -- the upload of scan k + 1 runs
+ * under the kernels of scan k.  gcl_scan_pipe_set_readback names page-locked host buffers ([n_jobs][gcl_stats_record_doubles],
+ * [n_jobs][GCL_EVID_DOUBLES]; either may be NULL) that every later submission on `set` fills at the end of its tail; they are valid
+ * after gcl_scan_pipe_join + a synchronisation of the caller's stream, until the set is submitted again. */
+int gcl_scan_pipe_wait_set(gcl_scan_pipe p, int set, void* stream);
+int gcl_scan_pipe_set_readback(gcl_scan_pipe p, int set, double* stats_host, double* evidence_host);
 
 /* Convert the reference arrays to the packed 20 B/point layout (x,y,z,t-scan_start as float4; w as float). */
 int gcl_pack_points_f32(gcl_handle h, void* stream, const double* points, const double* timestamps,

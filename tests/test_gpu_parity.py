@@ -328,6 +328,53 @@ def test_hypothesis_batch_matches_single_runs(g, O):
         assert geodesic(be[h, 0:9].reshape(3, 3), mf["R_mf"]) < 1e-8
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32c"])
+def test_scans_from_host_memory_through_the_scan_pipe(g, precision):
+    """run_host_pipelined (page-locked host rows -> H2D on a copy stream ordered by gcl_scan_pipe_wait_set -> one gcl_scan_pipe_submit ->
+    D2H of the records at the end of the tail, gcl_scan_pipe_set_readback) hands back, for every scan of a run longer than the four
+    buffer sets, bit for bit the records run_host reads back one scan at a time -- also when the host rows CHANGE between scans."""
+    from fl_slam_b200 import sharding as S
+    B = 128 if precision == "fp32c" else 48
+    sc = g.synth.make_scan(40_000, seed=7, dense=True)
+    pl = g.LidarEvidencePipeline(n_bins=B, tau=0.1, precision=precision, n_points_cap=40_000, lidar_origin=sc.lidar_origin)
+    sh = S.PointShardedEvidence(pl, 0, 1, exchange="peer")
+    ms = g.create_empty_map_stats(B)
+    rng = np.random.default_rng(3)
+    pose = torch.from_numpy(0.03 * rng.normal(size=(1, 6))).cuda()
+    xi = sc.xi_body[None]
+    variants = [sc.points * (1.0 + 0.01 * k) for k in range(3)]     # three different clouds pass through the same page-locked rows
+    # one scan at a time (run_host on the grid the pipe uses would need ctas=...: run() plans its own grid, and the partial sums of a
+    # different grid differ in the last bits -- so the reference here is the pipe's own grid through run_overlapped on resident data)
+    want = []
+    for v in variants:
+        shard, n_raw = sh.upload_shard(v, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time)
+        ev = sh.run_overlapped(shard, n_raw, xi, pose, ms, reserve_sms=8, n_tails=2)
+        sh.join_overlapped()
+        torch.cuda.synchronize()
+        want.append((ev.stats.cpu().clone(), ev.evidence.cpu().clone()))
+    st = sh.host_stage_pipelined(variants[0], sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time, reserve_sms=8, n_tails=2)
+    order = [0, 1, 2, 2, 1, 0, 1, 2, 0, 0, 2]
+    done = 0
+    sets = []
+    for k, v in enumerate(order):
+        # rewrite the page-locked rows on the host: legal once the copy that read them has finished -- wait for the copy stream
+        st["copy"].synchronize()
+        st["pin"][0].copy_(torch.from_numpy(np.ascontiguousarray(variants[v])))
+        _, i = sh.run_host_pipelined(st, xi, pose, ms)
+        sets.append(i)
+        if k % 4 == 3 or k == len(order) - 1:                      # four sets: read before they are rewritten
+            sh.join_overlapped()
+            torch.cuda.synchronize()
+            for kk in range(done, k + 1):
+                assert torch.equal(st["out"][sets[kk]][0], want[order[kk]][0]), (kk, "stats")
+                assert torch.equal(st["out"][sets[kk]][1], want[order[kk]][1]), (kk, "evidence")
+            done = k + 1
+    sh.end_host_pipelined(st)
+    sh.end_overlapped()
+    assert sh.px.error_flag() == 0
+    sh.px.close()
+
+
 @pytest.mark.parametrize("precision,n_tails", [("fp64", 1), ("fp64", 2), ("fp32c", 2)])
 def test_scan_pipe_matches_one_scan_at_a_time(g, precision, n_tails):
     """gcl_scan_pipe (consecutive scans in flight: one moment-pass stream, one or two tail streams, four buffer sets, exchange lanes) gives,
