@@ -2,7 +2,7 @@
 """What bounds the pipelined point-sharded scan when the per-rank shard is small (the 8-GPU shard of configs[3] on ONE GPU, world = 1):
 host enqueue time per scan, the moment pass alone, the exchange + finalise + evidence tail alone, and the pipelined scan.
 
-    python tools/tail_probe.py [n_rows_per_rank] [n_bins]
+    python tools/tail_probe.py [n_rows_per_rank] [n_bins] [reserve:tails,reserve:tails,...]
 """
 import json
 import os
@@ -18,6 +18,7 @@ from fl_slam_b200.sharding import PointShardedEvidence  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+CASES = tuple(tuple(int(v) for v in c.split(":")) for c in sys.argv[3].split(",")) if len(sys.argv) > 3 else ((6, 1), (6, 2))
 out = {}
 for precision in ("fp32c", "fp64"):
     sc = g.synth.make_scan(n, seed=1238, dense=True)
@@ -30,7 +31,7 @@ for precision in ("fp32c", "fp64"):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
     jobs_pre = [sh.make_sharded_job(s_, n, sc.xi_body) for s_ in shards]
-    for reserve, tails in ((6, 1), (6, 2)):
+    for reserve, tails in CASES:
         for k in range(16):
             sh.run_overlapped(shards[k % 8], n, xi, poses, ms, reserve_sms=reserve, n_tails=tails, job=jobs_pre[k % 8])
         sh.join_overlapped(); torch.cuda.synchronize()
