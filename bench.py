@@ -37,13 +37,16 @@ HEAD_POINTS, HEAD_BINS, SCANS_PER_STEP = 1 << 20, 256, 64           # configs[3]
 REF_SAMPLE_POINTS = 1 << 16                                         # points of the same cloud one reference-arm step processes
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_moments launch of this workload, from the ncu --set full
 # capture summarised in profiles/ (None until captured)
-TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.095488e6 + 8.889856e6, "fp32c": None}
+TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 240.096e6 + 8.576e6, "fp32c": None}
 # the same for one launch of the headline workload (1M x 256, one GPU); filled from profiles/r2_*.md once captured
-HEAD_TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 42047488, "fp32c": 21088512}   # dram__bytes_read.sum + dram__bytes_write.sum
+HEAD_TRAFFIC_BYTES_PER_LAUNCH = {"fp64": 42032896, "fp32c": 21059584}   # dram__bytes_read.sum + dram__bytes_write.sum
 HEAD_TRAFFIC_SOURCE = ("profiles/r2_scan_moments_fp64_1Mx256.md, r2_scan_moments_fp32c_1Mx256.md (ncu --set full capture of one scan_moments launch of this "
-                       "workload: 1.003x / 1.006x the algorithmic bytes)")
-TRAFFIC_SOURCE = ("profiles/r1_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch; the "
-                  "stride-4 gather of 24-byte rows touches every 32-byte sector, hence ~2.3x the algorithmic bytes)")
+                       "workload: 1.002x / 1.004x the algorithmic bytes)")
+TRAFFIC_SOURCE = ("profiles/r2_scan_moments_fp64_stream200x30k_48bins.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch, captured out of "
+                  "this command with tools/capture_stream_profile.sh; the scans are resident in the reference's layout -- all ~30 000 raw rows of 24 + 8 + 8 "
+                  "bytes -- and PointBudgetResample keeps every 4th: DRAM serves 64-byte requests, so the stride-4 gather of 24-byte rows at a 96-byte "
+                  "pitch and of 8-byte times at a 32-byte pitch fetches every raw byte, 30 000 x 40 B = 1.2 MB per scan against 0.54 MB algorithmic, "
+                  "i.e. ~2.3x; the message path decodes straight into compact rows (GCL_JOB_COMPACT_ROWS) and does not pay it)")
 
 
 # FMA-issue ceilings of scan_moments (rates measured with tools/microbench/ffma_rate.cu):
