@@ -4,7 +4,8 @@ the checks, the exchange itself through the fused NVLink kernel (csrc/gcl_exchan
   * points sharded (BASELINE.json configs[3] shape, reduced): PointShardedEvidence.run on every rank == the same job unsharded
     (every raw sum is linear in the points, archive/legacy_operators/binning.py:166-173: only the grouping of the fp64 additions
     differs -> <= 1e-12), bit-identical on every rank (docs/GC_SLAM.md:1150 determinism), with stride > 1 (mass rescale after the
-    exchange, point_budget.py:80-85), several hypotheses, and the round-1 NCCL route as a cross-check;
+    exchange, point_budget.py:80-85), several hypotheses, the round-1 NCCL route as a cross-check, consecutive scans in flight through the
+    scan pipe from resident shards and from page-locked host rows;
   * hypotheses sharded (configs[2] shape): rank r's slice of the batch == the full batch's rows, gathered through the exchange.
 """
 import os
@@ -99,6 +100,20 @@ def _worker(rank, world, port):
                         for kk in range(k - 3, k + 1):
                             assert torch.equal(got[kk].stats, want[order[kk]][0]), (c, "pipelined stats", kk)
                             assert torch.equal(got[kk].evidence, want[order[kk]][1]), (c, "pipelined evidence", kk)
+                if c["H"] == 1:
+                    # the same scans from page-locked HOST rows through the pipe (run_host_pipelined: uploads ordered by
+                    # gcl_scan_pipe_wait_set, D2H of the records at the end of each tail): six scans over the four sets, every read-back
+                    # record bit-equal to the resident pipelined run, and the same bits on every rank
+                    st = sh.host_stage_pipelined(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time, reserve_sms=8,
+                                                 n_tails=2)
+                    sets = [sh.run_host_pipelined(st, variants[0], poses, ms)[1] for _ in range(6)]
+                    sh.join_overlapped()
+                    torch.cuda.synchronize()
+                    for i_ in set(sets[2:]):
+                        assert torch.equal(st["out"][i_][0], want[0][0].cpu()), (c, "host pipelined stats", i_)
+                        assert torch.equal(st["out"][i_][1], want[0][1].cpu()), (c, "host pipelined evidence", i_)
+                    assert S._bits_identical_across_ranks(torch.cat([st["out"][sets[-1]][0].reshape(-1), st["out"][sets[-1]][1].reshape(-1)]).cuda(), world)
+                    sh.end_host_pipelined(st)
                 sh.end_overlapped()
                 assert sh.px.error_flag() == 0
             if sh.px is not None:
