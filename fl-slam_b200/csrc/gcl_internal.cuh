@@ -126,6 +126,7 @@ struct ScanParams {
   int tile_points;  // fused kernel: upper bound of points per tile (shared-memory bound)
   int layout;
   int fixed_shift;
+  int stagger_ns;   // two-CTAs-per-SM variant of the fused kernel: the second half of the grid starts this much later (phases of the two CTAs of an SM apart)
 };
 
 void plan_bins(int n_bins, int precision, int* G_out, int* L_out, int* chunks_out);

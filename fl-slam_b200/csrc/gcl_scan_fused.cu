@@ -377,10 +377,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // rows -- but an eighth of the issue slots, and the accumulators are 24 doubles per thread instead of 76 (a warp owns 32 bins x all
 // moments over ALL points of the tile: no point slices, so the flush is a plain store), which leaves phase A the registers for eight
 // chains in flight instead of four.
+__device__ unsigned int g_sm_arrivals[256];   // CTAs that have started on each SM (two-CTAs-per-SM variant: parity = first or second)
+
 template <typename T, int G, int MINB, int MMA = 0, int NT_ = 256>
 __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __grid_constant__ ScanParams P) {
   static_assert(!MMA || (sizeof(T) == 8 && G == 4), "the DMMA variant is fp64, G = 4");
-  static_assert(NT_ == 256 || (MMA == 1 && NT_ == 512), "512 threads: the DMMA variant only (its accumulators leave room for 16 warps)");
+  static_assert(NT_ == 256 || (MMA == 1 && NT_ == 512) || (MMA == 2 && NT_ == 128),
+                "512 threads: the DMMA phase-B variant only (its accumulators leave room for 16 warps); 128 threads: the all-DMMA variant, two CTAs per SM");
+  static_assert(sizeof(gcl_job) / sizeof(int) <= 128, "the job record is copied by the first threads of the CTA");
   constexpr int kNT = NT_;                   // threads per CTA (shadows the file-scope default)
   constexpr int NTW = 256 / (NT_ / 32) / 8;  // DMMA variant: 8-bin fragments per warp (a warp owns 256 / warps bins)
   constexpr int RP = MMA ? kRowPitchMma : kRowPitch;
@@ -737,6 +741,22 @@ __global__ void __launch_bounds__(NT_, MINB) scan_moments_fused_kernel(const __g
     const int l0 = group_index(0), l1 = group_index(1);
     if (l0 >= 0) prefetch_rows(lo, 0, l0);
     if (l1 >= 0) prefetch_rows(t1, 1, l1);
+  }
+  if (MMA == 2 && NT_ == 128 && P.stagger_ns > 0) {
+    // the second CTA to arrive on an SM (odd arrival count: the counter only ever grows, two co-resident CTAs draw consecutive numbers)
+    // starts part of a tile late, so that one CTA's phase A meets the other's phase B from then on
+    __shared__ unsigned int s_arrival;
+    if (tid == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_arrival = atomicAdd(&g_sm_arrivals[smid & 255], 1u);
+    }
+    __syncthreads();
+    if (s_arrival & 1u) {
+      const long long t_end = clock64() + (long long)P.stagger_ns * 2;   // ~2 cycles per ns
+      while (clock64() < t_end) __nanosleep(100);
+    }
+    __syncthreads();
   }
   K1T(0);   // prologue: job record, atlas, exp table, raw-weight sum
 
@@ -1254,7 +1274,7 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
   //                                                                                 bound by dispatch slots, and this takes 6 of 41 per pair)
   // The default applies with the fixed softmax shift only (tiny tau takes the row-maximum path of the DFMA kernel); GCL_K1_MMA=0 = never.
   static const int mma_mode = [] { const char* e = getenv("GCL_K1_MMA"); return e ? atoi(e) : 3; }();
-  const int mma0 = (mma_mode > 0 && precision == GCL_F64 && G == 4 && L == 64) ? (mma_mode == 3 ? ((P.fixed_shift & 1) ? 2 : 0) : 1) : 0;
+  const int mma0 = (mma_mode > 0 && precision == GCL_F64 && G == 4 && L == 64) ? (mma_mode >= 3 ? ((P.fixed_shift & 1) ? 2 : 0) : 1) : 0;
   int mma = mma0;
   const int nt = (mma && mma_mode == 2) ? 512 : 256;
   int TP = plan_fused_tile(P.n_bins, precision, G, L, M, mma, nt);
@@ -1282,6 +1302,14 @@ cudaError_t launch_scan_moments_fused(ScanParams& P, int n_jobs, int ctas_per_jo
       kern<<<grid, 32 * (4 + 7 + 1), ws_plan(P.n_bins, G, L, 128, 7, 4).total, stream>>>(P);
     }
     return cudaGetLastError();
+  }
+  if (mma == 2 && mma_mode == 4) {
+    // two CTAs of four warps per SM on 32-point tiles (a warp owns 64 bins in phase B): the phases of the two CTAs drift apart, so the
+    // dispatch-bound phase A of one runs beside the pipe-bound phase B of the other.  The caller plans 2 x SMs CTAs per job for it.
+    P.tile_points = 32;
+    static const int stagger = [] { const char* e = getenv("GCL_K1_STAGGER_NS"); return e ? atoi(e) : 1800; }();
+    P.stagger_ns = stagger;
+    return launch_fused_one<double, 4, 2, 2, 128>(P, grid, fused_plan(P.n_bins, 8, G, L, 32, 2, 128).total, stream);
   }
   if (mma == 2) return launch_fused_one<double, 4, 1, 2, 256>(P, grid, smem, stream);
   if (mma) return nt == 512 ? launch_fused_one<double, 4, 1, 1, 512>(P, grid, smem, stream) : launch_fused_one<double, 4, 1, 1, 256>(P, grid, smem, stream);

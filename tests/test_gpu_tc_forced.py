@@ -26,11 +26,11 @@ def test_fp32c_parity_with_the_kernel_choice_forced(mode):
     assert " passed" in r.stdout
 
 
-@pytest.mark.parametrize("switch,mode", [("GCL_K1_WS", "1"), ("GCL_K1_WS", "2"), ("GCL_K1_WS", "3"), ("GCL_K1_MMA", "0"), ("GCL_K1_MMA", "1"), ("GCL_K1_MMA", "2"), ("GCL_K1_MMA", "3")])
+@pytest.mark.parametrize("switch,mode", [("GCL_K1_WS", "1"), ("GCL_K1_WS", "2"), ("GCL_K1_WS", "3"), ("GCL_K1_MMA", "0"), ("GCL_K1_MMA", "1"), ("GCL_K1_MMA", "2"), ("GCL_K1_MMA", "3"), ("GCL_K1_MMA", "4")])
 def test_fp64_parity_with_the_opt_in_kernels_forced(switch, mode):
     """GCL_K1_WS = 1 / 2 / 3: the warp-specialised fp64 kernel (129..256 bins; three splits of the warps between accumulating, phase-A and
-    per-point roles); GCL_K1_MMA = 0 / 1 / 2 / 3: mma.sync.m8n8k4.f64 never / phase B with 8 warps / phase B with 16 warps / both phases
-    (the default) -- same parity
+    per-point roles); GCL_K1_MMA = 0 / 1 / 2 / 3 / 4: mma.sync.m8n8k4.f64 never / phase B with 8 warps / phase B with 16 warps / both phases
+    (the default) / both phases with 128 threads and 32-point tiles (two CTAs per SM) -- same parity
     bars, bit-reproducible from run to run."""
     pytest.importorskip("torch")
     env = dict(os.environ, **{switch: mode})

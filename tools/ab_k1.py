@@ -52,7 +52,7 @@ def single(precision, n, bins, cap=None, iters=30):
     pl = g.LidarEvidencePipeline(n_bins=bins, tau=tau, precision=precision, n_points_cap=cap, lidar_origin=sc.lidar_origin)
     copies = [pl.upload_scan(sc.points, sc.timestamps, sc.weights, sc.scan_start_time, sc.scan_end_time) for _ in range((4 if n > 500000 else 32) if n > 100000 else 1)]
     _, n_sel = pl.selected_rows(n, cap)
-    ctas = pl.plan_ctas(1, n_sel)
+    ctas = int(os.environ.get("GCL_AB_CTAS", "0")) or pl.plan_ctas(1, n_sel)      # GCL_AB_CTAS: override the planned grid
     part = pl._buffers(1, ctas)["partials"]
     jobs = [pl.make_job(c, sc.xi_body) for c in copies]
     state = {"i": 0}
@@ -66,7 +66,7 @@ def single(precision, n, bins, cap=None, iters=30):
 
 out = {"GCL_K1_G": os.environ.get("GCL_K1_G")}
 only = sys.argv[1:] or ["stream", "1M", "single", "hyp", "16M"]
-for prec in ("fp64", "fp32c"):
+for prec in (os.environ.get("GCL_AB_PREC", "fp64,fp32c").split(",")):
     if "stream" in only:
         out[f"stream200x30k_48_{prec}"] = stream(prec)
     if "1M" in only:
