@@ -189,3 +189,21 @@ def test_message_submit_argument_checks_need_no_gpu(g):
         c(a, 9)
     with pytest.raises(ValueError):
         c(np.zeros(7), 0, 3)
+
+
+def test_numa_placement_helper_is_inert_without_nvml_or_with_one_node():
+    """fl_slam_b200.hostmem.bind_to_gpu_numa_node (multi-rank bench runs): never raises, never widens the thread's CPU set, says why
+    when it leaves the placement alone (this container: no NVML; the GPU pool: single-node VMs)."""
+    import os
+    from fl_slam_b200 import hostmem
+    before = os.sched_getaffinity(0)
+    info = hostmem.bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert set(info) >= {"applied", "numa_nodes", "cpus"} and info["numa_nodes"] >= 1
+    assert after <= before and info["cpus"] == len(after)
+    assert info["applied"] or "why" in info
+    os.environ["GCL_NUMA_BIND"] = "0"
+    try:
+        assert hostmem.bind_to_gpu_numa_node(0)["why"] == "GCL_NUMA_BIND=0"
+    finally:
+        del os.environ["GCL_NUMA_BIND"]
