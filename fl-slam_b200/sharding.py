@@ -512,7 +512,9 @@ def bench_points_sharded(g, n_points: int, n_bins: int, tau: float, steps: int, 
     if reserve_sms is None:
         # SMs left to the exchange + evidence tail of the previous scan: enough that the tail (latency-bound, ~50-70 us) finishes
         # under the moment pass of the next scan, which shrinks with the number of ranks
-        reserve_sms = {1: 2, 2: 2, 4: 4}.get(world, 6)
+        # (one GPU: the moment pass of the whole cloud is ~10 x longer than a tail, one SM is enough for it -- tools/tail_probe.py 1048576 256:
+        # 848 against 855 us per fp64 scan with 1 / 2 SMs left free, 248 against 249 in fp32c)
+        reserve_sms = {1: 1, 2: 2, 4: 4}.get(world, 6)
     if n_tails is None:
         # two tails in flight: a tail (exchange capped to the few SMs left free + finalise + evidence chain) takes 60-160 us, which is
         # longer than the fp32c moment pass of a shard from 2 GPUs on
